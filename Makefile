@@ -1,0 +1,35 @@
+# Build everything in-tree.  The .so files are git-ignored but travel to the GPU box.
+NVCC      ?= /usr/local/cuda/bin/nvcc
+CXX       ?= g++
+CC        ?= gcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v
+PKG       := kmers.anno_b200
+CSRC      := $(PKG)/csrc
+HOST      := $(PKG)/host
+
+LIB       := $(PKG)/libkmeranno.so
+SYNTH     := $(PKG)/libkasynth.so
+ORACLE    := oracle/libkaoracle.so
+CLI       := $(PKG)/bin/kmers-anno
+
+all: $(LIB) $(SYNTH) $(ORACLE)
+
+$(LIB): $(CSRC)/ka_kernels.cu $(CSRC)/ka_engine.cu $(CSRC)/ka_common.cuh $(CSRC)/ka_kernels.cuh include/kmeranno.h
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/ka_kernels.cu $(CSRC)/ka_engine.cu 2> $(PKG)/ptxas.log || (cat $(PKG)/ptxas.log; exit 1)
+	@grep -E "error|warning|spill|registers" $(PKG)/ptxas.log | grep -v "0 bytes spill" | head -40 || true
+
+$(SYNTH): $(HOST)/ka_synth.cpp
+	$(CXX) -O3 -std=c++17 -fPIC -shared -pthread -Wall -o $@ $<
+
+$(ORACLE): oracle/ka_oracle.c oracle/ka_oracle_fast.c
+	$(CC) -O2 -fPIC -shared -pthread -Wall -o $@ oracle/ka_oracle.c oracle/ka_oracle_fast.c
+
+$(CLI): $(wildcard $(HOST)/*.cpp) $(wildcard $(HOST)/*.hpp) $(LIB)
+	mkdir -p $(PKG)/bin
+	$(CXX) -O2 -std=c++17 -Wall -Iinclude -o $@ $(filter-out $(HOST)/ka_synth.cpp,$(wildcard $(HOST)/*.cpp)) -L$(PKG) -lkmeranno -Wl,-rpath,'$$ORIGIN/..' -pthread
+
+clean:
+	rm -f $(LIB) $(SYNTH) $(ORACLE) $(CLI) $(PKG)/ptxas.log
+
+.PHONY: all clean

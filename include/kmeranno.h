@@ -1,0 +1,158 @@
+/*
+ * kmeranno.h — C ABI of libkmeranno.so, the B200 (sm_100a) engine for the k-mer
+ * annotation hot path of SEEDtk/kmers.anno (`apply` command).
+ *
+ * Every entry point replaces a region of the reference's Java code.  Paths are
+ * relative to /root/reference/src/main/java/org/theseed/ :
+ *
+ *   ka_db_load       <- proteins/kmers/anno/ApplyKmerProcessor.java:99-110
+ *                       (kmerRoleMap = HashMap<String,String>; put() = last line wins;
+ *                        K taken from the k-mer text, :108)
+ *   ka_annotate      <- proteins/kmers/anno/ApplyKmerProcessor.java:122-148
+ *                       (new ProteinKmers(prot) :123, kmerRoleMap.get :130, tally
+ *                        :131-144, thresholded call :146-147)
+ *   out_role/out_hits feed reports/ApplyKmerReporter.java:75 recordFeature(feat, role, count)
+ *
+ * The library has no CPU fallback: without a usable CUDA device ka_create fails with
+ * KA_ERR_NO_DEVICE.  Nothing here prints to stdout (stdout belongs to the report,
+ * ApplyKmerProcessor.java:94); diagnostics go to ka_last_error().
+ *
+ * Ownership: the caller owns every host buffer and may free it when the call returns.
+ * The engine owns all device memory until ka_destroy().  No callbacks.
+ * Threading: an engine serialises its entry points internally (one mutex); use one
+ * engine per thread for concurrent callers (HashAnnotationProcessor.java:208 style).
+ */
+#ifndef KMERANNO_H
+#define KMERANNO_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KA_ABI_VERSION 1
+
+typedef struct ka_engine ka_engine;
+typedef struct ka_batch ka_batch;
+
+/* error codes (0 = OK, negative = failure; text via ka_last_error) */
+enum {
+    KA_OK = 0,
+    KA_ERR_INVALID = -1,   /* bad argument (NULL, K out of range, min_hits < 1 ...)       */
+    KA_ERR_NO_DEVICE = -2, /* no usable CUDA device / bad device id                       */
+    KA_ERR_CUDA = -3,      /* CUDA runtime failure                                        */
+    KA_ERR_ALPHABET = -4,  /* DB uses more than 31 distinct residue bytes: not packable   */
+    KA_ERR_K = -5,         /* K outside 1..12 (5 bits x K must fit 64 bits)               */
+    KA_ERR_NO_DB = -6,     /* annotate before a successful ka_db_load                     */
+    KA_ERR_OOM = -7,       /* host or device allocation failed                            */
+    KA_ERR_ROLE = -8,      /* negative role id in the DB (-1 is the "no call" value)      */
+    KA_ERR_OFFSETS = -9,   /* offsets not monotone / not starting at the batch base       */
+    KA_ERR_TOO_BIG = -10   /* table or batch beyond this build's limits                   */
+};
+
+/* per-sequence outcome, out_flag[] */
+enum {
+    KA_FLAG_NONE = 0,      /* no k-mer of the sequence is in the DB                       */
+    KA_FLAG_CALLED = 1,    /* unanimous role and hits >= min_hits (recordFeature fires)   */
+    KA_FLAG_AMBIGUOUS = 2, /* k-mers hit two or more roles (badPeg, :140-143)             */
+    KA_FLAG_BELOW_MIN = 3  /* unanimous role but hits < min_hits (:146)                   */
+};
+
+/* ---- engine lifetime ------------------------------------------------------------- */
+
+/* Create an engine on the listed CUDA devices (device_ids == NULL: device 0 only).
+ * On failure *out is NULL and ka_last_error(NULL) describes why. */
+int ka_create(const int* device_ids, int n_devices, ka_engine** out);
+void ka_destroy(ka_engine* e);
+
+/* Last error text of the engine (e == NULL: of the calling thread's last ka_create). */
+const char* ka_last_error(const ka_engine* e);
+
+/* Tunables, set before ka_db_load / ka_annotate.  Unknown name -> KA_ERR_INVALID.
+ *   "load_factor"   table load factor in (0,0.9], default 0.5   (next ka_db_load)
+ *   "tile_span"     residues of sequence starts per CTA tile, default 2048
+ *   "long_seq"      sequences longer than this use the long-sequence kernel, default 6144
+ *   "chunk_residues" residues per pipelined H2D chunk, default 32 Mi
+ *   "l2_persist"    1 = set an L2 persisting access-policy window on the table (default 1)
+ *   "warp_dedup"    1 = __match_any de-duplication of identical in-flight keys (default 0)
+ */
+int ka_set_option(ka_engine* e, const char* name, double value);
+
+/* ---- k-mer database (ApplyKmerProcessor.java:99-110) ------------------------------ */
+
+/* Load n k-mers of K residue bytes each (kmers = n*K bytes, no separators) with their
+ * role ids (>= 0; the Java side interns the role strings).  Line order matters only for
+ * duplicates: the LAST occurrence of a k-mer wins, as HashMap.put does (:106).
+ * Builds the open-addressed table on every device of the engine and replaces any
+ * previous DB.  Residue bytes are compared exactly (case-sensitive, no filtering): the
+ * distinct bytes of the DB (at most 31) become the 5-bit alphabet. */
+int ka_db_load(ka_engine* e, const uint8_t* kmers, const int32_t* role_ids, uint64_t n, int K);
+
+typedef struct ka_db_info {
+    int32_t K;               /* k-mer length in residues                                 */
+    int32_t n_symbols;       /* distinct residue bytes in the DB                         */
+    uint64_t n_lines;        /* k-mer lines given to ka_db_load                          */
+    uint64_t n_keys;         /* distinct k-mers stored                                   */
+    uint64_t n_buckets;      /* 32-byte buckets (2 x 16-byte slots each)                 */
+    uint64_t table_bytes;    /* device bytes of one table replica                        */
+    uint32_t max_probe;      /* longest bucket chain seen while building                 */
+    uint32_t reserved;
+} ka_db_info;
+int ka_db_get_info(ka_engine* e, ka_db_info* out);
+
+/* ---- annotate (ApplyKmerProcessor.java:122-148) ----------------------------------- */
+
+/* Annotate N sequences given as a CSR batch in HOST memory: residues[offsets[i] ..
+ * offsets[i+1]) is sequence i (offsets[0] may be non-zero; residues is indexed from 0).
+ * For each sequence: the set of DISTINCT K-windows is probed; if every hit names the
+ * same role, hits = number of distinct hitting k-mers.
+ *   out_role[i] = role id when called, else -1
+ *   out_hits[i] = distinct hitting k-mers when unanimous (called or below min), else 0
+ *   out_flag[i] = KA_FLAG_*            (may be NULL)
+ * Sequences are sharded over the engine's devices; copies are inside the call. */
+int ka_annotate(ka_engine* e, const uint8_t* residues, const uint64_t* offsets, uint64_t N,
+                int32_t min_hits, int32_t* out_role, int32_t* out_hits, uint8_t* out_flag);
+
+/* Device-resident variant, used to time the kernels with inputs already in HBM.
+ * ka_batch_upload copies a CSR batch to device `dev_index` (index into the engine's device
+ * list); ka_annotate_resident runs the kernels only (results stay on the device);
+ * ka_batch_download copies the results of the last run back. */
+int ka_batch_upload(ka_engine* e, int dev_index, const uint8_t* residues, const uint64_t* offsets,
+                    uint64_t N, ka_batch** out);
+int ka_annotate_resident(ka_engine* e, ka_batch* b, int32_t min_hits);
+int ka_batch_download(ka_engine* e, ka_batch* b, int32_t* out_role, int32_t* out_hits,
+                      uint8_t* out_flag);
+void ka_batch_free(ka_engine* e, ka_batch* b);
+
+/* ---- pinned host memory for zero-staging transfers -------------------------------- */
+void* ka_host_alloc(size_t bytes);
+void ka_host_free(void* p);
+
+/* ---- measurement ------------------------------------------------------------------ */
+typedef struct ka_stats {
+    uint64_t sequences;       /* sequences annotated by the last annotate call             */
+    uint64_t residues;        /* residues in them                                          */
+    uint64_t probes;          /* window positions: sum max(0, L_i - K + 1)                 */
+    uint64_t kernel_launches; /* kernels launched by the last annotate call                */
+    uint64_t h2d_bytes;       /* host->device bytes of the last annotate call              */
+    uint64_t d2h_bytes;       /* device->host bytes of the last annotate call              */
+    double kernel_ms;         /* device time of the annotate kernels (CUDA events; max over devices) */
+    double tile_kernel_ms;    /* device time of the tile kernel alone (sum over chunks, max over devices) */
+    double wall_ms;           /* host wall time of the last annotate call                  */
+} ka_stats;
+int ka_get_stats(ka_engine* e, ka_stats* out);
+
+/* Random-probe roofline microbenchmark: independent uniformly random `slot_bytes`-wide
+ * (16 or 32) loads over a scratch buffer of `table_bytes`, `n_probes` loads per launch,
+ * best of `reps` launches.  Returns probes per second on device dev_index. */
+int ka_probe_roofline(ka_engine* e, int dev_index, uint64_t table_bytes, uint64_t n_probes,
+                      int slot_bytes, int reps, double* probes_per_s);
+
+int ka_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KMERANNO_H */

@@ -1,0 +1,62 @@
+// ka_kernels.cuh — launcher interface between the engine (ka_engine.cu) and the kernels
+// (ka_kernels.cu).  Plain pointers only; every launcher enqueues on the given stream and
+// returns the cudaError_t of the launch.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "ka_common.cuh"
+
+namespace ka {
+
+struct BigItem {
+    uint32_t seq;                 // sequence index inside the chunk
+    uint32_t pad;
+    unsigned long long tok_base;  // first token of its de-dup region in the scratch array
+};
+
+struct AnnotParams {
+    const uint8_t* res;               // residues of the chunk; res[0] is absolute offset `base`
+    const unsigned long long* off;    // absolute offsets, n_seq + 1
+    unsigned long long base;
+    uint32_t n_seq;
+    uint32_t n_tiles;                 // floor(R / tile_span) + 1
+    uint32_t tile_span;               // residues of sequence starts per tile
+    uint32_t long_seq;                // L > long_seq goes to the long-sequence kernel
+    uint32_t ext_max;                 // tile_span + long_seq: max residue extent of a tile
+    uint32_t res_bytes;               // smem bytes reserved for the residue stage
+    uint32_t* first;                  // n_tiles + 1: first sequence starting in each tile
+    TableView tab;
+    const uint8_t* lut;               // 256-byte residue -> 5-bit code table (0 = not in DB alphabet)
+    int32_t min_hits;
+    int32_t* out_role;
+    int32_t* out_hits;
+    uint8_t* out_flag;
+    uint32_t* big_count;              // [0] number of long sequences
+    unsigned long long* tok_cursor;   // [0] tokens handed out
+    BigItem* big_list;
+    uint32_t* scratch;                // de-dup tokens of the long sequences
+    int warp_dedup;
+};
+
+size_t tile_smem_bytes(uint32_t ext_max, uint32_t* res_bytes_out);
+cudaError_t tile_kernel_set_smem(size_t bytes);
+
+cudaError_t launch_plan(const AnnotParams& p, cudaStream_t st);
+cudaError_t launch_tiles(const AnnotParams& p, size_t smem, cudaStream_t st);
+cudaError_t launch_big(const AnnotParams& p, int grid, cudaStream_t st);
+
+cudaError_t launch_alphabet_scan(const uint8_t* bytes, unsigned long long n, uint32_t* bitmap8,
+                                 cudaStream_t st);
+// errs[0] = k-mers with a byte outside the alphabet, errs[1] = negative role ids,
+// counters[0] = distinct keys stored, counters[1] = longest bucket chain
+cudaError_t launch_db_insert(const uint8_t* kmers, const int32_t* roles, unsigned long long n,
+                             unsigned long long line_base, int K, const uint8_t* lut, Slot* table,
+                             unsigned long long n_buckets, unsigned long long* counters,
+                             uint32_t* errs, cudaStream_t st);
+
+cudaError_t launch_random_probe(const uint4* buf, unsigned long long n_slots, int slot_bytes,
+                                unsigned long long n_probes, unsigned long long seed,
+                                unsigned long long* sink, cudaStream_t st);
+cudaError_t launch_fill_random(uint4* buf, unsigned long long n_uint4, cudaStream_t st);
+
+}  // namespace ka

@@ -1,0 +1,69 @@
+"""ctypes binding of libkasynth.so (host/ka_synth.cpp): seeded synthetic role families,
+proteomes and signature tables of the shapes SURVEY.md §8(d) defines.  Test/bench support."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkasynth.so")
+SEED = 20261018
+_lib = None
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        lib = C.CDLL(LIB_PATH)
+        vp = C.c_void_p
+        lib.kas_families_new.argtypes = [C.c_uint64, C.c_uint32]
+        lib.kas_families_new.restype = vp
+        lib.kas_families_free.argtypes = [vp]
+        lib.kas_families_free.restype = None
+        lib.kas_family_len.argtypes = [vp, C.c_uint32]
+        lib.kas_family_len.restype = C.c_uint64
+        lib.kas_batch_size.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_int]
+        lib.kas_batch_size.restype = C.c_uint64
+        lib.kas_batch_fill.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_int,
+                                       C.c_int, vp, vp, vp]
+        lib.kas_batch_fill.restype = None
+        lib.kas_table.argtypes = [vp, C.c_uint64, C.c_int, C.c_uint32, C.c_uint64, vp, vp]
+        lib.kas_table.restype = C.c_uint64
+        _lib = lib
+    return _lib
+
+
+class Families:
+    def __init__(self, n_roles, seed=SEED):
+        self.lib = _load()
+        self.seed = seed
+        self.n_roles = n_roles
+        self.h = self.lib.kas_families_new(seed, n_roles)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.kas_families_free(self.h)
+            self.h = None
+
+    def batch(self, g0, n_genomes, n_prot=4500, mode=0, K=8, threads=None, alloc=None):
+        """CSR batch of genomes [g0, g0+n_genomes): (residues u8, offsets u64, true_role i32).
+        `alloc(shape, dtype)` lets the caller provide pinned arrays."""
+        threads = threads or min(os.cpu_count() or 1, 32)
+        n = n_genomes * n_prot
+        alloc = alloc or (lambda shape, dtype: np.empty(shape, dtype))
+        offsets = alloc(n + 1, np.uint64)
+        true_role = np.empty(n, np.int32)
+        # sizes first (single pass inside fill computes them again; sizing is cheap)
+        total = self.lib.kas_batch_size(self.h, self.seed, g0, n_genomes, n_prot, mode, K)
+        residues = alloc(max(int(total), 1), np.uint8)
+        self.lib.kas_batch_fill(self.h, self.seed, g0, n_genomes, n_prot, mode, K, threads,
+                                residues.ctypes.data, offsets.ctypes.data, true_role.ctypes.data)
+        return residues[:int(total)], offsets, true_role
+
+    def table(self, target, K=8, members_per_role=8):
+        """(kmers u8[n*K], roles i32[n]) of up to `target` discriminating k-mers."""
+        kmers = np.empty(target * K, np.uint8)
+        roles = np.empty(target, np.int32)
+        n = self.lib.kas_table(self.h, self.seed, K, members_per_role, target,
+                               kmers.ctypes.data, roles.ctypes.data)
+        return kmers[: n * K], roles[:n]

@@ -1,0 +1,217 @@
+"""GPU parity: the CUDA path through the C ABI (libkmeranno.so) must equal the CPU oracle
+bit for bit — role call, hit count and flag of every sequence (integer work: exact)."""
+import numpy as np
+import pytest
+
+from cases import csr, py_apply, ragged_case, random_seq
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ka():
+    import kmers_anno_b200 as ka
+    return ka
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    import oracle
+    return oracle
+
+
+def assert_same(got, want, what=""):
+    for name, g, w in zip(("role", "hits", "flag"), got, want):
+        if not np.array_equal(g, w):
+            bad = np.nonzero(g != w)[0]
+            raise AssertionError(f"{what}: {name} differs on {bad.size}/{g.size} sequences; first "
+                                 f"{bad[:8]} got {g[bad[:8]]} want {w[bad[:8]]}")
+
+
+def run_case(ka, oracle, seqs, kmers, roles, K, min_hits=5, options=None, resident=False):
+    res, off = csr(seqs)
+    with ka.Engine([0]) as eng:
+        for k, v in (options or {}).items():
+            eng.set_option(k, v)
+        eng.db_load(kmers, roles, K)
+        if resident:
+            b = eng.upload(res, off)
+            eng.annotate_resident(b, min_hits)
+            got = eng.download(b)
+            b.free()
+        else:
+            got = eng.annotate(res, off, min_hits)
+        info = eng.db_info()
+    want = oracle.OracleDb(kmers, roles, K).apply(res, off, min_hits)
+    assert info["n_keys"] == oracle.OracleDb(kmers, roles, K).size()
+    assert_same(got, want, f"K={K} min_hits={min_hits} opts={options}")
+    return got
+
+
+@pytest.mark.parametrize("K", [1, 2, 5, 8, 10, 12])
+def test_ragged_all_k(ka, oracle, K):
+    seqs, kmers, roles = ragged_case(100 + K, n_seq=400, K=K)
+    got = run_case(ka, oracle, seqs, kmers, roles, K, min_hits=3)
+    # every outcome class must actually occur for the case to mean anything
+    if K >= 5:
+        assert set(np.unique(got[2])) == {0, 1, 2, 3}
+
+
+@pytest.mark.parametrize("min_hits", [1, 2, 5, 50])
+def test_min_hits(ka, oracle, min_hits):
+    seqs, kmers, roles = ragged_case(7, n_seq=300, K=8)
+    run_case(ka, oracle, seqs, kmers, roles, 8, min_hits=min_hits)
+
+
+def test_against_pure_python(ka, oracle):
+    seqs, kmers, roles = ragged_case(11, n_seq=120, K=8, max_len=300)
+    got = run_case(ka, oracle, seqs, kmers, roles, 8, min_hits=2)
+    want = py_apply(seqs, kmers, roles, 8, 2)
+    assert_same(got, want, "pure python")
+
+
+def test_duplicate_kmers_count_once(ka, oracle):
+    # a protein that is one 9-mer unit repeated: 9 distinct 8-mers however long it is
+    unit = b"ACDEFGHIK"
+    prot = unit * 40
+    kmers = [prot[i:i + 8] for i in range(9)]
+    roles = np.zeros(9, np.int32) + 4
+    got = run_case(ka, oracle, [prot, prot[:30], unit], kmers, roles, 8, min_hits=5)
+    assert got[1][0] == 9 and got[0][0] == 4 and got[2][0] == 1
+
+
+def test_last_db_line_wins(ka, oracle):
+    prot = b"MKVLAAGIVALLLAGCSSAPKE"
+    kmers = [prot[i:i + 8] for i in range(6)] * 2
+    roles = np.asarray([1] * 6 + [9] * 6, np.int32)
+    got = run_case(ka, oracle, [prot], kmers, roles, 8, min_hits=5)
+    assert got[0][0] == 9 and got[1][0] == 6
+
+
+def test_empty_and_short(ka, oracle):
+    seqs = [b"", b"", b"ACD", b"ACDEFGH", b"ACDEFGHI", b"", b"ACDEFGHIK", b""]
+    kmers = [b"ACDEFGHI", b"CDEFGHIK"]
+    got = run_case(ka, oracle, seqs, kmers, np.asarray([3, 3], np.int32), 8, min_hits=1)
+    assert list(got[1]) == [0, 0, 0, 0, 1, 0, 2, 0]
+    assert list(got[0]) == [-1, -1, -1, -1, 3, -1, 3, -1]
+
+
+def test_bytes_outside_db_alphabet(ka, oracle):
+    # case-sensitive, no filtering: 'a' != 'A', X / * never match, windows over them miss
+    kmers = [b"ACDEFGHI", b"CDEFGHIK", b"DEFGHIKL"]
+    seqs = [b"ACDEFGHIKL", b"acdefghikl", b"ACDEFGHIXKL", b"ACDEFGHI*", b"\x00\xff" * 8 + b"ACDEFGHI"]
+    got = run_case(ka, oracle, seqs, kmers, np.asarray([2, 2, 2], np.int32), 8, min_hits=1)
+    assert list(got[1]) == [3, 0, 1, 1, 1]
+
+
+def test_many_tiny_sequences_sub_batches(ka, oracle):
+    # thousands of sequences starting inside one residue tile: > MAX_TILE_SEQ per tile
+    rng = np.random.default_rng(5)
+    seqs = []
+    for i in range(6000):
+        r = rng.random()
+        seqs.append(b"" if r < 0.5 else (b"ACDEFGHI" if r < 0.75 else random_seq(rng, int(rng.integers(1, 12)))))
+    kmers = [b"ACDEFGHI"]
+    got = run_case(ka, oracle, seqs, kmers, np.asarray([7], np.int32), 8, min_hits=1)
+    assert (got[0] == 7).sum() >= 1400
+
+
+def test_long_sequences_use_big_kernel(ka, oracle):
+    lengths = [20000, 300, 7000, 5121, 5120, 64, 0, 12000]
+    seqs, kmers, roles = ragged_case(21, n_seq=len(lengths), K=8, lengths=lengths, db_frac=0.5)
+    run_case(ka, oracle, seqs, kmers, roles, 8, min_hits=3)
+    # the same inputs with a small long_seq so that most sequences take the long path
+    run_case(ka, oracle, seqs, kmers, roles, 8, min_hits=3, options={"tile_span": 256, "long_seq": 256})
+
+
+@pytest.mark.parametrize("opts", [
+    {"tile_span": 256, "long_seq": 1024},
+    {"tile_span": 4096, "long_seq": 8192},
+    {"chunk_residues": 4096},
+    {"load_factor": 0.9},
+    {"load_factor": 0.05},
+    {"l2_persist": 0},
+])
+def test_options_do_not_change_results(ka, oracle, opts):
+    seqs, kmers, roles = ragged_case(33, n_seq=500, K=8, max_len=900)
+    run_case(ka, oracle, seqs, kmers, roles, 8, min_hits=3, options=opts)
+
+
+def test_resident_path(ka, oracle):
+    seqs, kmers, roles = ragged_case(44, n_seq=500, K=10, max_len=900)
+    run_case(ka, oracle, seqs, kmers, roles, 10, min_hits=3, resident=True)
+
+
+def test_offsets_with_nonzero_base(ka, oracle):
+    seqs, kmers, roles = ragged_case(55, n_seq=200, K=8)
+    res, off = csr(seqs)
+    pad = 37
+    res2 = np.concatenate([np.full(pad, ord("A"), np.uint8), res])
+    off2 = off + np.uint64(pad)
+    with ka.Engine([0]) as eng:
+        eng.db_load(kmers, roles, 8)
+        got = eng.annotate(res2, off2, 3)
+    want = oracle.OracleDb(kmers, roles, 8).apply(res, off, 3)
+    assert_same(got, want, "nonzero base")
+
+
+def test_synthetic_proteome_c1_shape(ka, oracle):
+    """SURVEY config 1 shape: one 4,500-protein proteome vs a small family DB; the fast
+    oracle cross-checks the Java-shaped one."""
+    from kmers_anno_b200 import synth
+    fam = synth.Families(500)
+    kmers, roles = fam.table(400000, K=8)
+    res, off, true_role = fam.batch(3, 1, n_prot=4500)
+    with ka.Engine([0]) as eng:
+        eng.db_load(kmers, roles, 8)
+        got = eng.annotate(res, off, 5)
+        st = eng.stats()
+    want = oracle.OracleDb(kmers, roles, 8).apply(res, off, 5, threads=4)
+    fast = oracle.FastDb(kmers, roles, 8).apply(res, off, 5, threads=4)
+    assert_same(got, want, "C1 vs Java-shaped oracle")
+    assert_same(got, fast, "C1 vs packed oracle")
+    assert st["probes"] == oracle.count_probes(off, 8)
+    called = got[2] == 1
+    assert called.sum() > 1000 and (got[0][called] == true_role[called]).all()
+
+
+@pytest.mark.parametrize("mode,K", [(1, 8), (2, 10), (1, 12)])
+def test_skewed_lengths_c4_shape(ka, oracle, mode, K):
+    """SURVEY config 4: K sweep with log-uniform / bimodal 50..5000 aa lengths."""
+    from kmers_anno_b200 import synth
+    fam = synth.Families(300)
+    kmers, roles = fam.table(300000, K=K)
+    res, off, _ = fam.batch(1, 1, n_prot=1500, mode=mode, K=K)
+    with ka.Engine([0]) as eng:
+        eng.db_load(kmers, roles, K)
+        got = eng.annotate(res, off, 5)
+    want = oracle.OracleDb(kmers, roles, K).apply(res, off, 5, threads=4)
+    assert_same(got, want, f"C4 mode={mode} K={K}")
+    assert (got[2] == 2).sum() > 0 and (got[2] == 1).sum() > 0
+
+
+def test_error_paths(ka):
+    with ka.Engine([0]) as eng:
+        with pytest.raises(ka.KmerAnnoError) as e:
+            eng.annotate(np.zeros(8, np.uint8), np.asarray([0, 8], np.uint64), 5)
+        assert e.value.code == -6                     # KA_ERR_NO_DB
+        with pytest.raises(ka.KmerAnnoError) as e:
+            eng.db_load([b"A" * 13], np.zeros(1, np.int32), 13)
+        assert e.value.code == -5                     # KA_ERR_K
+        many = [bytes([65 + (i % 26), 97 + (i % 26)] * 4) for i in range(26)]
+        with pytest.raises(ka.KmerAnnoError) as e:
+            eng.db_load(many, np.zeros(26, np.int32), 8)
+        assert e.value.code == -4                     # KA_ERR_ALPHABET: 52 distinct bytes
+        with pytest.raises(ka.KmerAnnoError) as e:
+            eng.db_load([b"ACDEFGHI"], np.asarray([-1], np.int32), 8)
+        assert e.value.code == -8                     # KA_ERR_ROLE
+        eng.db_load([b"ACDEFGHI"], np.asarray([0], np.int32), 8)
+        with pytest.raises(ka.KmerAnnoError) as e:
+            eng.annotate(np.zeros(8, np.uint8), np.asarray([0, 8], np.uint64), 0)
+        assert e.value.code == -1                     # min_hits must be positive (:91-92)
+        with pytest.raises(ka.KmerAnnoError) as e:
+            eng.annotate(np.zeros(8, np.uint8), np.asarray([8, 0], np.uint64), 1)
+        assert e.value.code == -9                     # KA_ERR_OFFSETS
+    with pytest.raises(ka.KmerAnnoError) as e:
+        ka.Engine([99])
+    assert e.value.code == -2                         # KA_ERR_NO_DEVICE
