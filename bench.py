@@ -138,7 +138,7 @@ def cpu_baseline(a, fam, kmers, roles, threads=None):
     res, off, _ = fam.batch(10_000_000, a.cpu_genomes, n_prot=N_PROT, K=a.K)
     probes = oracle.count_probes(off, a.K)
     t0 = time.time()
-    db = oracle.OracleDb(kmers, roles, a.K, file_len_bytes=len(roles) * (a.K + 10))
+    db = oracle.OracleDb(kmers, roles, a.K, file_len_bytes=len(roles) * (a.K + 10), threads=threads)
     t_load = time.time() - t0
     t0 = time.time()
     out = db.apply(res, off, a.min_hits, threads=threads)
@@ -161,7 +161,7 @@ def run_reference(a):
     fam, kmers, roles = make_table(a)
     import oracle
     threads = os.cpu_count() or 1
-    db = oracle.OracleDb(kmers, roles, a.K, file_len_bytes=len(roles) * (a.K + 10))
+    db = oracle.OracleDb(kmers, roles, a.K, file_len_bytes=len(roles) * (a.K + 10), threads=threads)
     res, off, _ = fam.batch(10_000_000, a.cpu_genomes, n_prot=N_PROT, K=a.K)
     probes = oracle.count_probes(off, a.K)
     n_seq = off.shape[0] - 1

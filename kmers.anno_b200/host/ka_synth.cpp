@@ -215,62 +215,110 @@ void kas_batch_fill(const kas_families* f, uint64_t seed, uint64_t g0, uint64_t 
 // Signature table.  Writes up to `target` lines (kmers_out: target*K bytes, roles_out:
 // target ints) and returns the number written.  Lines come out in hash-slot order, i.e.
 // unordered, like the reference's kmerdb.tbl (BuildKmerProcessor.java:212-216).
+// The key space is split into 64 hash partitions with one private open-addressed set each,
+// so any number of threads produces the same table.
 uint64_t kas_table(const kas_families* f, uint64_t seed, int K, uint32_t members_per_role,
-                   uint64_t target, uint8_t* kmers_out, int32_t* roles_out) {
-    if (K < 1 || K > 12) return 0;
-    // open-addressed host set keyed by a 5-bit pack of the letters (generator-private)
-    uint64_t cap = 1;
-    while (cap < target * 2 + 1024) cap <<= 1;
-    std::vector<uint64_t> keys(cap, 0);
-    std::vector<int32_t> vals(cap, 0);  // role, or -2 = seen in two roles (dropped)
-    auto pack = [&](const uint8_t* s) {
+                   uint64_t target, int n_threads, uint8_t* kmers_out, int32_t* roles_out) {
+    if (K < 1 || K > 12 || target == 0) return 0;
+    if (n_threads < 1) n_threads = 1;
+    constexpr int P = 64;
+    uint64_t cap = 64;
+    while (cap < target * 3 / P + 1024) cap <<= 1;
+    std::vector<std::vector<uint64_t>> keys(P);
+    std::vector<std::vector<int32_t>> vals(P);  // role, or -2 = seen in two roles (dropped)
+    auto pack = [K](const uint8_t* s) {
         uint64_t k = 0;
         for (int j = 0; j < K; j++) k = (k << 5) | (uint64_t)(s[j] - 'A' + 1);
         return k;
     };
-    auto slot_of = [&](uint64_t k) {
+    auto hash = [](uint64_t k) {
         uint64_t h = k * 0x9E3779B97F4A7C15ull;
+        h ^= h >> 32;
+        h *= 0xD6E8FEB86659FD93ull;
         h ^= h >> 29;
-        uint64_t i = h & (cap - 1);
-        while (keys[i] != 0 && keys[i] != k) i = (i + 1) & (cap - 1);
-        return i;
+        return h;
     };
-    uint64_t n_live = 0, n_used = 0;
-    std::vector<uint8_t> buf;
-    for (uint32_t r = 0; r < f->n_roles && n_used < target; r++) {
-        uint64_t L = f->off[r + 1] - f->off[r];
-        buf.resize(L);
-        for (uint32_t m = 0; m < members_per_role; m++) {
-            write_member(f, r, m, buf.data());
-            for (uint64_t i = 0; i + K <= L && n_used < target; i++) {
-                uint64_t k = pack(buf.data() + i);
-                uint64_t sl = slot_of(k);
-                if (keys[sl] == 0) { keys[sl] = k; vals[sl] = (int32_t)r; n_live++; n_used++; }
-                else if (vals[sl] >= 0 && vals[sl] != (int32_t)r) { vals[sl] = -2; n_live--; }
+    auto run = [&](auto fn) {
+        std::vector<std::thread> th;
+        for (int t = 0; t < n_threads; t++) th.emplace_back(fn, t);
+        for (auto& x : th) x.join();
+    };
+    std::vector<uint64_t> live(P, 0), used(P, 0);
+    // phase 1: every K-window of the first members of every role; a k-mer seen in two roles
+    // is not discriminating and is dropped (BuildKmerProcessor.java:183-190)
+    run([&](int t) {
+        for (int p = t; p < P; p += n_threads) { keys[p].assign(cap, 0); vals[p].assign(cap, 0); }
+        std::vector<uint8_t> buf;
+        for (uint32_t r = 0; r < f->n_roles; r++) {
+            uint64_t L = f->off[r + 1] - f->off[r];
+            buf.resize(L);
+            for (uint32_t m = 0; m < members_per_role; m++) {
+                write_member(f, r, m, buf.data());
+                for (uint64_t i = 0; i + K <= L; i++) {
+                    uint64_t k = pack(buf.data() + i), h = hash(k);
+                    int p = (int)(h >> 58);
+                    if (p % n_threads != t) continue;
+                    if (used[p] * 4 >= cap * 3) continue;  // partition full: later windows are skipped
+                    uint64_t sl = h & (cap - 1);
+                    while (keys[p][sl] != 0 && keys[p][sl] != k) sl = (sl + 1) & (cap - 1);
+                    if (keys[p][sl] == 0) { keys[p][sl] = k; vals[p][sl] = (int32_t)r; live[p]++; used[p]++; }
+                    else if (vals[p][sl] >= 0 && vals[p][sl] != (int32_t)r) { vals[p][sl] = -2; live[p]--; }
+                }
             }
         }
+    });
+    // phase 2: top up with uniformly random k-mers (uniform letters) and random roles
+    for (int round = 0; round < 8; round++) {
+        uint64_t have = 0;
+        for (int p = 0; p < P; p++) have += live[p];
+        if (have >= target) break;
+        uint64_t need = target - have;
+        uint64_t n_cand = need + need / 64 + 256;
+        std::vector<uint64_t> cand(n_cand);
+        std::vector<int32_t> crole(n_cand);
+        const uint64_t BLK = 1 << 18;
+        uint64_t n_blk = (n_cand + BLK - 1) / BLK;
+        run([&](int t) {
+            for (uint64_t b = t; b < n_blk; b += n_threads) {
+                uint64_t s = stream(seed, 0x746f7075, (uint64_t)round, b);
+                uint64_t e = std::min(n_cand, (b + 1) * BLK);
+                for (uint64_t i = b * BLK; i < e; i++) {
+                    uint64_t k = 0, x = splitmix(s);
+                    for (int j = 0; j < K; j++) { k = (k << 5) | (uint64_t)(kLetters[x % 20] - 'A' + 1); x /= 20; }
+                    cand[i] = k;
+                    crole[i] = (int32_t)(splitmix(s) % f->n_roles);
+                }
+            }
+        });
+        run([&](int t) {
+            for (uint64_t i = 0; i < n_cand; i++) {
+                uint64_t k = cand[i], h = hash(k);
+                int p = (int)(h >> 58);
+                if (p % n_threads != t) continue;
+                if (used[p] * 8 >= cap * 7) continue;
+                uint64_t sl = h & (cap - 1);
+                while (keys[p][sl] != 0 && keys[p][sl] != k) sl = (sl + 1) & (cap - 1);
+                if (keys[p][sl] == 0) { keys[p][sl] = k; vals[p][sl] = crole[i]; live[p]++; used[p]++; }
+            }
+        });
+        if (K < 6) break;  // a small K can exhaust its key space before `target`
     }
-    // top up with uniformly random k-mers (uniform letters) and random roles
-    uint64_t s = stream(seed, 0x746f7075, 0, 0);
-    uint8_t km[16];
-    uint64_t attempts = 0;  // a small K can exhaust its key space before `target`
-    while (n_live < target && n_used < cap / 2 + cap / 4 && attempts++ < 20 * target + 1000) {
-        for (int j = 0; j < K; j++) km[j] = (uint8_t)kLetters[splitmix(s) % 20];
-        uint64_t k = pack(km);
-        uint64_t sl = slot_of(k);
-        if (keys[sl] == 0) {
-            keys[sl] = k; vals[sl] = (int32_t)(splitmix(s) % f->n_roles); n_live++; n_used++;
+    // emit partition-major in slot order, truncated at target
+    std::vector<uint64_t> start(P + 1, 0);
+    for (int p = 0; p < P; p++) start[p + 1] = start[p] + live[p];
+    run([&](int t) {
+        for (int p = t; p < P; p += n_threads) {
+            uint64_t n = start[p];
+            for (uint64_t i = 0; i < cap && n < target; i++) {
+                if (keys[p][i] == 0 || vals[p][i] < 0) continue;
+                uint64_t k = keys[p][i];
+                for (int j = K - 1; j >= 0; j--) { kmers_out[n * K + j] = (uint8_t)('A' - 1 + (k & 31)); k >>= 5; }
+                roles_out[n] = vals[p][i];
+                n++;
+            }
         }
-    }
-    uint64_t n = 0;
-    for (uint64_t i = 0; i < cap && n < target; i++) {
-        if (keys[i] == 0 || vals[i] < 0) continue;
-        uint64_t k = keys[i];
-        for (int j = K - 1; j >= 0; j--) { kmers_out[n * K + j] = (uint8_t)('A' - 1 + (k & 31)); k >>= 5; }
-        roles_out[n] = vals[i];
-        n++;
-    }
-    return n;
+    });
+    return std::min(start[P], target);
 }
 
 }  // extern "C"

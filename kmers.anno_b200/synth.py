@@ -27,7 +27,7 @@ def _load():
         lib.kas_batch_fill.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_int,
                                        C.c_int, vp, vp, vp]
         lib.kas_batch_fill.restype = None
-        lib.kas_table.argtypes = [vp, C.c_uint64, C.c_int, C.c_uint32, C.c_uint64, vp, vp]
+        lib.kas_table.argtypes = [vp, C.c_uint64, C.c_int, C.c_uint32, C.c_uint64, C.c_int, vp, vp]
         lib.kas_table.restype = C.c_uint64
         _lib = lib
     return _lib
@@ -60,10 +60,11 @@ class Families:
                                 residues.ctypes.data, offsets.ctypes.data, true_role.ctypes.data)
         return residues[:int(total)], offsets, true_role
 
-    def table(self, target, K=8, members_per_role=8):
+    def table(self, target, K=8, members_per_role=8, threads=None):
         """(kmers u8[n*K], roles i32[n]) of up to `target` discriminating k-mers."""
+        threads = threads or min(os.cpu_count() or 1, 32)
         kmers = np.empty(target * K, np.uint8)
         roles = np.empty(target, np.int32)
-        n = self.lib.kas_table(self.h, self.seed, K, members_per_role, target,
+        n = self.lib.kas_table(self.h, self.seed, K, members_per_role, target, threads,
                                kmers.ctypes.data, roles.ctypes.data)
         return kmers[: n * K], roles[:n]

@@ -27,6 +27,7 @@ def lib():
         L.orc_map_remove.argtypes = [vp, C.c_char_p, C.c_uint32]
         L.orc_map_dump.argtypes = [vp, vp, vp, vp]; L.orc_map_dump.restype = C.c_uint64
         L.orc_db_load.argtypes = [vp, vp, C.c_uint64, C.c_int, C.c_int64]; L.orc_db_load.restype = vp
+        L.orc_db_load_mt.argtypes = [vp, vp, C.c_uint64, C.c_int, C.c_int64, C.c_int]; L.orc_db_load_mt.restype = vp
         L.orc_apply.argtypes = [vp, vp, vp, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp]
         L.orc_build.argtypes = [vp, vp, C.c_uint64, vp, vp, C.c_int, C.c_int32, C.c_int, C.c_int, vp]
         L.orc_build.restype = vp
@@ -60,7 +61,7 @@ def count_probes(offsets, K):
 class OracleDb:
     """HashMap<String,String> kmerRoleMap of ApplyKmerProcessor.java:53,99-110, Java-shaped."""
 
-    def __init__(self, kmers, role_ids, K, file_len_bytes=None):
+    def __init__(self, kmers, role_ids, K, file_len_bytes=None, threads=1):
         self.L = lib()
         kmers = _kmers_array(kmers)
         role_ids = np.ascontiguousarray(role_ids, dtype=np.int32)
@@ -69,7 +70,7 @@ class OracleDb:
         if file_len_bytes is None:
             file_len_bytes = n * (K + 8)
         self.K = K
-        self.h = self.L.orc_db_load(kmers.ctypes.data, role_ids.ctypes.data, n, K, file_len_bytes)
+        self.h = self.L.orc_db_load_mt(kmers.ctypes.data, role_ids.ctypes.data, n, K, file_len_bytes, threads)
         if not self.h:
             raise MemoryError("orc_db_load failed")
 

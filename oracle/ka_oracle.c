@@ -271,6 +271,112 @@ orc_map* orc_db_load(const uint8_t* kmers, const int32_t* roles, uint64_t n, int
     return m;
 }
 
+/* Multi-threaded bulk load that produces EXACTLY the structure the sequential put() loop
+ * above produces (same table capacity, same bin contents in the same order), so that a
+ * 10^8-line DB loads in seconds.  Why it is the same structure: HashMap.resize() splits
+ * bins preserving relative order, so after any number of doublings a bin holds its nodes in
+ * insertion order — which is what inserting the lines, in line order, into a table of the
+ * final capacity gives.  Each thread owns a contiguous range of bins and walks all lines in
+ * order.  The final capacity is the first one of Java's doubling sequence whose threshold
+ * holds the number of DISTINCT keys. */
+typedef struct {
+    orc_map* m;
+    const uint8_t* kmers;
+    const int32_t* roles;
+    const uint32_t* hashes;
+    uint64_t n;
+    int K, t, T;
+    uint64_t distinct;
+} bulk_job;
+
+static void* bulk_hash_worker(void* p) {
+    bulk_job* j = (bulk_job*)p;
+    uint64_t a = j->n * (uint64_t)j->t / (uint64_t)j->T, b = j->n * (uint64_t)(j->t + 1) / (uint64_t)j->T;
+    uint32_t* hs = (uint32_t*)j->hashes;
+    for (uint64_t i = a; i < b; i++) {
+        hs[i] = jstring_hash(j->kmers + i * (uint64_t)j->K, (uint32_t)j->K);
+        jnode* nd = &j->m->nodes[i];
+        nd->hash = hs[i]; nd->next = -1; nd->value = j->roles[i]; nd->aux = 0;
+        nd->klen = (uint32_t)j->K; nd->koff = i * (uint64_t)j->K;
+    }
+    return NULL;
+}
+
+static void* bulk_link_worker(void* p) {
+    bulk_job* j = (bulk_job*)p;
+    orc_map* m = j->m;
+    uint32_t cap = m->cap;
+    uint32_t lo = (uint32_t)((uint64_t)cap * (uint64_t)j->t / (uint64_t)j->T);
+    uint32_t hi = (uint32_t)((uint64_t)cap * (uint64_t)(j->t + 1) / (uint64_t)j->T);
+    uint64_t distinct = 0;
+    for (uint64_t i = 0; i < j->n; i++) {
+        uint32_t idx = j->hashes[i] & (cap - 1);
+        if (idx < lo || idx >= hi) continue;
+        const uint8_t* k = j->kmers + i * (uint64_t)j->K;
+        int32_t e = m->table[idx], tail = -1;
+        int found = 0;
+        while (e >= 0) {
+            jnode* nd = &m->nodes[e];
+            if (nd->hash == j->hashes[i] && memcmp(m->pool + nd->koff, k, (size_t)j->K) == 0) {
+                nd->value = j->roles[i]; /* put() on an existing key: value replaced, last wins */
+                found = 1;
+                break;
+            }
+            tail = e; e = nd->next;
+        }
+        if (found) continue;
+        if (tail < 0) m->table[idx] = (int32_t)i; else m->nodes[tail].next = (int32_t)i;
+        distinct++;
+    }
+    j->distinct = distinct;
+    return NULL;
+}
+
+orc_map* orc_db_load_mt(const uint8_t* kmers, const int32_t* roles, uint64_t n, int K,
+                        int64_t file_len_bytes, int n_threads) {
+    if (n_threads < 2 || n < 100000 || n >= (uint64_t)INT32_MAX)
+        return orc_db_load(kmers, roles, n, K, file_len_bytes);
+    int64_t cap0 = file_len_bytes >= 0 ? (int64_t)(int32_t)(file_len_bytes / 30) : 0;
+    orc_map* m = orc_map_new(cap0 < 0 ? 0 : cap0);
+    if (!m) return NULL;
+    if (orc_map_reserve(m, n, n * (uint64_t)K + 1)) { orc_map_free(m); return NULL; }
+    memcpy(m->pool, kmers, n * (uint64_t)K);
+    m->pool_len = n * (uint64_t)K;
+    m->n_nodes = n;
+    uint32_t* hashes = (uint32_t*)malloc(n * sizeof(uint32_t));
+    bulk_job* jobs = (bulk_job*)calloc((size_t)n_threads, sizeof(bulk_job));
+    pthread_t* th = (pthread_t*)calloc((size_t)n_threads, sizeof(pthread_t));
+    if (!hashes || !jobs || !th) { free(hashes); free(jobs); free(th); orc_map_free(m); return NULL; }
+    for (int t = 0; t < n_threads; t++)
+        jobs[t] = (bulk_job){m, kmers, roles, hashes, n, K, t, n_threads, 0};
+    for (int t = 0; t < n_threads; t++) pthread_create(&th[t], NULL, bulk_hash_worker, &jobs[t]);
+    for (int t = 0; t < n_threads; t++) pthread_join(th[t], NULL);
+    /* Java's capacity sequence: initial, then doubling while size > threshold */
+    uint32_t cap = (uint32_t)m->threshold;
+    if (cap < 1) cap = 1;
+    uint64_t want = n; /* first guess: all lines distinct */
+    for (int pass = 0; pass < 2; pass++) {
+        uint32_t c = cap;
+        while ((uint64_t)((float)c * 0.75f) < want && c < JMAX_CAP) c <<= 1;
+        if (pass == 1 && c == m->cap) break; /* the guess was right */
+        free(m->table);
+        m->table = (int32_t*)malloc((size_t)c * sizeof(int32_t));
+        if (!m->table) { free(hashes); free(jobs); free(th); orc_map_free(m); return NULL; }
+        memset(m->table, 0xff, (size_t)c * sizeof(int32_t));
+        m->cap = c;
+        m->threshold = (int64_t)((float)c * 0.75f);
+        if (pass == 1)
+            for (uint64_t i = 0; i < n; i++) { m->nodes[i].next = -1; m->nodes[i].value = roles[i]; }
+        for (int t = 0; t < n_threads; t++) pthread_create(&th[t], NULL, bulk_link_worker, &jobs[t]);
+        uint64_t d = 0;
+        for (int t = 0; t < n_threads; t++) { pthread_join(th[t], NULL); d += jobs[t].distinct; }
+        m->size = d;
+        want = d;
+    }
+    free(hashes); free(jobs); free(th);
+    return m;
+}
+
 /* ------------------------------------------------------------------------------------
  * org.theseed.sequence.ProteinKmers (EXTERNAL, recalled — see header): the set of
  * distinct K-substrings of a protein, built with substring() + HashSet.add for
