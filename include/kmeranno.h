@@ -71,9 +71,11 @@ void ka_destroy(ka_engine* e);
 const char* ka_last_error(const ka_engine* e);
 
 /* Tunables, set before ka_db_load / ka_annotate.  Unknown name -> KA_ERR_INVALID.
- *   "load_factor"   table load factor in (0,0.9], default 0.5   (next ka_db_load)
- *   "tile_span"     residues of sequence starts per CTA tile, default 2048
- *   "long_seq"      sequences longer than this use the long-sequence kernel, default 6144
+ *   "load_factor"   table load factor in (0,0.9], default 0.4   (next ka_db_load)
+ *   "tile_span"     residues of sequence starts per CTA tile, default 1536
+ *   "long_seq"      sequences longer than this use the long-sequence kernel, default 3072
+ *   "slot_bits"     force the table slot width (32, 64, 128; 0 = smallest that fits, default)
+ *   "variant"       tile kernel shape: 0 = 8 positions x 256 threads, 1 = 4 x 256, 2 = 4 x 512
  *   "chunk_residues" residues per pipelined H2D chunk, default 32 Mi
  *   "l2_persist"    1 = set an L2 persisting access-policy window on the table (default 1)
  *   "warp_dedup"    1 = __match_any de-duplication of identical in-flight keys (default 0)
@@ -95,10 +97,10 @@ typedef struct ka_db_info {
     int32_t n_symbols;       /* distinct residue bytes in the DB                         */
     uint64_t n_lines;        /* k-mer lines given to ka_db_load                          */
     uint64_t n_keys;         /* distinct k-mers stored                                   */
-    uint64_t n_buckets;      /* 32-byte buckets (2 x 16-byte slots each)                 */
+    uint64_t n_buckets;      /* 32-byte sectors (8, 4 or 2 slots each)                   */
     uint64_t table_bytes;    /* device bytes of one table replica                        */
-    uint32_t max_probe;      /* longest bucket chain seen while building                 */
-    uint32_t reserved;
+    uint32_t max_probe;      /* longest sector chain seen while building                 */
+    uint32_t slot_bits;      /* slot width chosen for this DB: 32, 64 or 128             */
 } ka_db_info;
 int ka_db_get_info(ka_engine* e, ka_db_info* out);
 

@@ -1,11 +1,17 @@
 // ka_common.cuh — shared device/host definitions of the k-mer annotation engine (sm_100a).
 //
 // Data layout in HBM
-//   table   : n_buckets x 32-byte buckets; a bucket is ONE DRAM sector holding two 16-byte
-//             slots { u64 key ; u64 val } with val = (db line index << 32) | role id.
-//             key == 0 means empty (a packed k-mer is never 0: every 5-bit code is 1..31).
-//             Slots fill in probe order (slot 0, slot 1, next bucket ...) and are never
-//             freed, so a lookup stops at the first empty slot.
+//   table   : 2^bbits sectors of 32 bytes.  A lookup reads exactly ONE sector (one 256-bit
+//             load); B200 fetches the enclosing 128-byte line from DRAM, so one probe = one
+//             DRAM line.  The packed k-mer (5 bits per residue, w = 5K bits, every field
+//             1..31 so a key is never 0) goes through a bijective mixer on w bits; the top
+//             bbits select the sector and only the remaining rem_bits are stored
+//             (quotienting), which makes three slot widths possible:
+//               cls 32  : 8 slots/sector, slot = rem | (role+1) << rem_bits   (e.g. K=8, 1e8 keys)
+//               cls 64  : 4 slots/sector, same packing in 64 bits             (K=10/12)
+//               cls 128 : 2 slots/sector, { u64 key ; u64 (db line << 32 | role) } (fallback)
+//             0 = empty slot.  Slots fill in order inside a sector, then the next sector,
+//             and are never freed, so a lookup stops at the first sector with a free slot.
 //   batch   : CSR — residues u8[R] (+ padding), offsets u64[N+1], results i32/i32/u8 per sequence.
 #pragma once
 #include <cstdint>
@@ -14,26 +20,39 @@
 namespace ka {
 
 constexpr int KMAX = 12;            // 5 bits x 12 = 60 bits
-constexpr int TILE_THREADS = 256;   // threads per CTA of the tile kernel
-constexpr int POS_PER_THREAD = 8;   // window positions per thread per pass
-constexpr int PASS_POS = TILE_THREADS * POS_PER_THREAD;  // 2048 positions per pass
-constexpr int MAX_TILE_SEQ = 512;   // sequences handled per tile sub-batch
+constexpr int MAX_TILE_SEQ = 256;   // sequences handled per tile sub-batch
 constexpr uint32_t TOKEN_EMPTY = 0u;
 
-struct Slot {
+struct Slot128 {
     unsigned long long key;
     unsigned long long val;  // hi 32: db line index, lo 32: role id
 };
 
 struct TableView {
-    const uint4* buckets;     // n_buckets * 2 uint4 (slot0, slot1)
-    unsigned long long n_buckets;
+    const uint4* sectors;         // 2^bbits sectors, 2 uint4 each
     unsigned long long key_mask;  // (1 << 5K) - 1
+    unsigned long long rem_mask;  // (1 << rem_bits) - 1   (cls 32 / 64)
+    uint32_t bbits;               // log2(number of sectors)
+    uint32_t rem_bits;            // 5K - bbits            (cls 32 / 64)
+    uint32_t wbits;               // 5K
     int K;
+    int cls;                      // 32, 64 or 128
 };
 
-// 64-bit finaliser (two xor-shift-multiply rounds); the bucket is the high part of
-// hash * n_buckets, so n_buckets need not be a power of two.
+// Bijection on w-bit integers (xor-shift and odd multiplication are both invertible
+// modulo 2^w), mixing every input bit into the top bits that select the sector.
+__host__ __device__ __forceinline__ unsigned long long mixw(unsigned long long k, uint32_t w,
+                                                            unsigned long long mask) {
+    const uint32_t s = (w + 1) >> 1;
+    k ^= k >> s;
+    k = (k * 0xD6E8FEB86659FD93ull) & mask;
+    k ^= k >> s;
+    k = (k * 0xCA5A826395121157ull) & mask;
+    k ^= k >> s;
+    k = (k * 0x9E3779B97F4A7C15ull) & mask;
+    return k;
+}
+
 __host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
     x ^= x >> 32;
     x *= 0xD6E8FEB86659FD93ull;
@@ -43,14 +62,22 @@ __host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long 
     return x;
 }
 
-__device__ __forceinline__ unsigned long long bucket_of(unsigned long long key,
-                                                        unsigned long long n_buckets) {
-    return __umul64hi(mix64(key), n_buckets);
+// (sector, stored remainder) of a packed key.  For cls 128 the remainder is the key itself.
+__host__ __device__ __forceinline__ void locate(const TableView& t, unsigned long long key,
+                                                uint32_t& sector, unsigned long long& rem) {
+    if (t.cls == 128) {
+        sector = t.bbits ? (uint32_t)(mix64(key) >> (64 - t.bbits)) : 0u;
+        rem = key;
+    } else {
+        const unsigned long long m = mixw(key, t.wbits, t.key_mask);
+        sector = (uint32_t)(m >> t.rem_bits);
+        rem = m & t.rem_mask;
+    }
 }
 
-// One 32-byte bucket with a single 256-bit load (LDG.E.256 on sm_100a), read-only path,
-// no L1 allocation: a bucket is touched once per probe and must not evict the residue tile.
-__device__ __forceinline__ void load_bucket(const uint4* p, uint4& s0, uint4& s1) {
+// One 32-byte sector with a single 256-bit load (LDG.E.256 on sm_100a), read-only path, no
+// L1 allocation: a sector is touched once per probe and must not evict the residue tile.
+__device__ __forceinline__ void load_sector(const uint4* p, uint4& s0, uint4& s1) {
     asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(s0.x), "=r"(s0.y), "=r"(s0.z), "=r"(s0.w), "=r"(s1.x), "=r"(s1.y),
                    "=r"(s1.z), "=r"(s1.w)
@@ -60,6 +87,39 @@ __device__ __forceinline__ void load_bucket(const uint4* p, uint4& s0, uint4& s1
 __device__ __forceinline__ unsigned long long u64_of(uint32_t lo, uint32_t hi) {
     return (unsigned long long)lo | ((unsigned long long)hi << 32);
 }
+
+// Match one loaded sector against a stored remainder.
+//   returns role >= 0 and the slot index inside the sector on a hit; -1 on a miss;
+//   `full` tells whether the sector has no free slot (the chain continues).
+template <int CLS>
+__device__ __forceinline__ int match_sector(const TableView& t, const uint4& a, const uint4& b,
+                                            unsigned long long rem, uint32_t& slot_in_sector,
+                                            bool& full) {
+    int role = -1;
+    if (CLS == 32) {
+        const uint32_t r = (uint32_t)rem, m = (uint32_t)t.rem_mask;
+        const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (w[j] != 0 && ((w[j] ^ r) & m) == 0) { role = (int)(w[j] >> t.rem_bits) - 1; slot_in_sector = j; }
+        full = w[7] != 0;
+    } else if (CLS == 64) {
+        const unsigned long long w[4] = {u64_of(a.x, a.y), u64_of(a.z, a.w), u64_of(b.x, b.y), u64_of(b.z, b.w)};
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (w[j] != 0 && ((w[j] ^ rem) & t.rem_mask) == 0) { role = (int)(w[j] >> t.rem_bits) - 1; slot_in_sector = j; }
+        full = w[3] != 0;
+    } else {
+        const unsigned long long k0 = u64_of(a.x, a.y), k1 = u64_of(b.x, b.y);
+        if (k0 == rem) { role = (int)a.z; slot_in_sector = 0; }
+        else if (k1 == rem) { role = (int)b.z; slot_in_sector = 1; }
+        full = k1 != 0;
+    }
+    return role;
+}
+
+template <int CLS>
+__host__ __device__ constexpr int slots_per_sector() { return CLS == 32 ? 8 : (CLS == 64 ? 4 : 2); }
 
 // ---- mbarrier + 1-D bulk async copy (TMA engine, UBLKCP) -------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

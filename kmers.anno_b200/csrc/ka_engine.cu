@@ -41,7 +41,7 @@ struct Pipe {
 struct Device {
     int id = 0;
     int sm_count = 148;
-    Slot* table = nullptr;
+    uint4* table = nullptr;
     uint8_t* lut = nullptr;
     Pipe pipe[NPIPE];
     size_t smem_set = 0;
@@ -65,15 +65,18 @@ struct ka_engine {
     std::mutex mu;
     std::string err;
     // options
-    double load_factor = 0.5;
-    uint32_t tile_span = 2048;
-    uint32_t long_seq = 5120;
+    double load_factor = 0.4;
+    uint32_t tile_span = 1536;
+    uint32_t long_seq = 3072;
     uint64_t chunk_residues = 32ull << 20;
     int l2_persist = 1;
     int warp_dedup = 0;
+    int variant = 0;
+    int slot_bits = 0;  // 0 = choose automatically
     // db
     bool have_db = false;
     ka_db_info info{};
+    TableView geom{};   // geometry of the loaded table (sectors pointer filled per device)
     uint8_t lut[256];
     ka_stats stats{};
 };
@@ -203,10 +206,8 @@ void fill_params(ka_engine* e, Device& d, Pipe& p, uint64_t base, uint64_t n_res
     ap.n_tiles = (uint32_t)(n_res / e->tile_span + 1);
     tile_smem_bytes(ap.ext_max, &ap.res_bytes);
     ap.first = p.first;
-    ap.tab.buckets = reinterpret_cast<const uint4*>(d.table);
-    ap.tab.n_buckets = e->info.n_buckets;
-    ap.tab.K = e->info.K;
-    ap.tab.key_mask = (e->info.K * 5 >= 64) ? ~0ull : ((1ull << (5 * e->info.K)) - 1);
+    ap.tab = e->geom;
+    ap.tab.sectors = d.table;
     ap.lut = d.lut;
     ap.min_hits = min_hits;
     ap.out_role = p.role;
@@ -222,15 +223,16 @@ void fill_params(ka_engine* e, Device& d, Pipe& p, uint64_t base, uint64_t n_res
 // enqueue plan + tile + big on the pipe's stream, bracketed by timing events
 int enqueue_kernels(ka_engine* e, Device& d, Pipe& p, const AnnotParams& ap, uint64_t n_long) {
     size_t smem = tile_smem_bytes(ap.ext_max, nullptr);
-    if (d.smem_set != smem) {
-        DCK(d, tile_kernel_set_smem(smem));
-        d.smem_set = smem;
+    size_t smem_key = smem * 64 + (size_t)ap.tab.cls / 32 * 8 + (size_t)e->variant;
+    if (d.smem_set != smem_key) {
+        DCK(d, tile_kernel_set_smem(ap.tab.cls, e->variant, smem));
+        d.smem_set = smem_key;
     }
     DCK(d, cudaMemsetAsync(p.ctr, 0, 16, p.st));
     DCK(d, cudaEventRecord(p.ev_k0, p.st));
     DCK(d, launch_plan(ap, p.st));
     DCK(d, cudaEventRecord(p.ev_t0, p.st));
-    DCK(d, launch_tiles(ap, smem, p.st));
+    DCK(d, launch_tiles(ap, e->variant, smem, p.st));
     DCK(d, cudaEventRecord(p.ev_t1, p.st));
     d.launches += 2;
     if (n_long) {
@@ -239,7 +241,6 @@ int enqueue_kernels(ka_engine* e, Device& d, Pipe& p, const AnnotParams& ap, uin
         d.launches += 1;
     }
     DCK(d, cudaEventRecord(p.ev_k1, p.st));
-    (void)e;
     return KA_OK;
 }
 
@@ -339,25 +340,33 @@ int annotate_range(ka_engine* e, Device& d, const uint8_t* residues, const uint6
 }
 
 // Build the table replica of one device from the host DB arrays.
-int build_table(ka_engine* e, Device& d, const uint8_t* kmers, const int32_t* roles, uint64_t n,
-                int K, uint64_t n_buckets, uint64_t* n_keys, uint32_t* max_probe) {
+int build_table(ka_engine* e, Device& d, const TableView& geom, const uint8_t* kmers,
+                const int32_t* roles, uint64_t n, uint64_t* n_keys, uint32_t* max_probe) {
     DCK(d, cudaSetDevice(d.id));
     if (d.table) { cudaFree(d.table); d.table = nullptr; }
-    size_t bytes = (size_t)n_buckets * 32;
+    const int K = geom.K;
+    const size_t n_sectors = (size_t)1 << geom.bbits;
+    const size_t bytes = n_sectors * 32;
+    const size_t n_slots = n_sectors * (geom.cls == 32 ? 8 : (geom.cls == 64 ? 4 : 2));
     cudaError_t ce = cudaMalloc((void**)&d.table, bytes);
     if (ce != cudaSuccess) { d.table = nullptr; return dev_fail(d, KA_ERR_OOM, "table", ce); }
     cudaStream_t st = d.pipe[0].st;
-    DCK(d, cudaMemsetAsync(d.table, 0, bytes, st));
-    DCK(d, cudaMemcpyAsync(d.lut, e->lut, 256, cudaMemcpyHostToDevice, st));
+    TableView tab = geom;
+    tab.sectors = d.table;
     const uint64_t CH = 16ull << 20;  // k-mers per upload
-    uint8_t* dk = nullptr; int32_t* dr = nullptr; unsigned long long* dc = nullptr; uint32_t* de = nullptr;
+    uint8_t* dk = nullptr; int32_t* dr = nullptr; uint32_t* line_of = nullptr;
+    unsigned long long* dc = nullptr; uint32_t* de = nullptr;
     uint64_t ch = std::min<uint64_t>(CH, n ? n : 1);
+    const bool packed = geom.cls != 128;
+    // cls 32/64 keep every role on the device until db_finalize; cls 128 needs a chunk only
     if ((ce = cudaMalloc((void**)&dk, ch * K)) != cudaSuccess ||
-        (ce = cudaMalloc((void**)&dr, ch * 4)) != cudaSuccess ||
+        (ce = cudaMalloc((void**)&dr, (packed ? std::max<uint64_t>(n, 1) : ch) * 4)) != cudaSuccess ||
+        (packed && (ce = cudaMalloc((void**)&line_of, n_slots * 4)) != cudaSuccess) ||
         (ce = cudaMalloc((void**)&dc, 16)) != cudaSuccess ||
         (ce = cudaMalloc((void**)&de, 8)) != cudaSuccess) {
         if (dk) cudaFree(dk);
         if (dr) cudaFree(dr);
+        if (line_of) cudaFree(line_of);
         if (dc) cudaFree(dc);
         return dev_fail(d, KA_ERR_OOM, "DB staging", ce);
     }
@@ -365,26 +374,73 @@ int build_table(ka_engine* e, Device& d, const uint8_t* kmers, const int32_t* ro
     auto step = [&](cudaError_t c, const char* what) {
         if (c != cudaSuccess && rc == KA_OK) rc = dev_fail(d, KA_ERR_CUDA, what, c);
     };
+    step(cudaMemsetAsync(d.table, 0, bytes, st), "memset table");
+    if (packed) step(cudaMemsetAsync(line_of, 0, n_slots * 4, st), "memset line_of");
+    step(cudaMemcpyAsync(d.lut, e->lut, 256, cudaMemcpyHostToDevice, st), "H2D lut");
     step(cudaMemsetAsync(dc, 0, 16, st), "memset counters");
     step(cudaMemsetAsync(de, 0, 8, st), "memset errs");
     for (uint64_t i = 0; i < n && rc == KA_OK; i += ch) {
         uint64_t m = std::min(ch, n - i);
+        int32_t* dri = packed ? dr + i : dr;
         step(cudaMemcpyAsync(dk, kmers + i * K, m * K, cudaMemcpyHostToDevice, st), "H2D kmers");
-        step(cudaMemcpyAsync(dr, roles + i, m * 4, cudaMemcpyHostToDevice, st), "H2D roles");
-        step(launch_db_insert(dk, dr, m, i, K, d.lut, d.table, n_buckets, dc, de, st), "db_insert");
+        step(cudaMemcpyAsync(dri, roles + i, m * 4, cudaMemcpyHostToDevice, st), "H2D roles");
+        step(launch_db_insert(tab, dk, dri, m, i, d.lut, line_of, dc, de, st), "db_insert");
         step(cudaStreamSynchronize(st), "db_insert sync");
     }
+    if (rc == KA_OK) step(launch_db_finalize(tab, line_of, dr, st), "db_finalize");
+    step(cudaStreamSynchronize(st), "db_finalize sync");
     unsigned long long hc[2] = {0, 0};
     uint32_t he[2] = {0, 0};
     step(cudaMemcpy(hc, dc, 16, cudaMemcpyDeviceToHost), "D2H counters");
     step(cudaMemcpy(he, de, 8, cudaMemcpyDeviceToHost), "D2H errs");
     cudaFree(dk); cudaFree(dr); cudaFree(dc); cudaFree(de);
+    if (line_of) cudaFree(line_of);
     if (rc) return rc;
     if (he[0]) { d.err = KA_ERR_ALPHABET; d.errmsg = "k-mer byte outside the DB alphabet (internal)"; return d.err; }
     if (he[1]) { d.err = KA_ERR_ROLE; d.errmsg = "negative role id in the DB"; return d.err; }
     *n_keys = hc[0];
     *max_probe = (uint32_t)hc[1];
     return KA_OK;
+}
+
+uint32_t ceil_log2(double x) {
+    uint32_t b = 0;
+    while ((double)(1ull << b) < x && b < 62) b++;
+    return b;
+}
+
+// Pick slot class and sector count: the smallest table that holds n keys at the requested
+// load factor with remainder + role fitting the slot (see ka_common.cuh).
+bool choose_geometry(uint64_t n, int K, int32_t max_role, double lf, int force_cls, TableView& g) {
+    const uint32_t w = 5u * (uint32_t)K;
+    uint32_t role_bits = 1;
+    while (((uint64_t)max_role + 1) >> role_bits) role_bits++;
+    bool found = false;
+    uint64_t best_bytes = 0;
+    for (int cls : {32, 64, 128}) {
+        if (force_cls && cls != force_cls) continue;
+        const int S = 256 / cls;
+        uint32_t b = ceil_log2((double)(n ? n : 1) / ((double)S * lf));
+        if (b < 6) b = 6;
+        uint32_t rem_bits = 0;
+        if (cls != 128) {
+            if ((int)(w + role_bits) - cls > (int)b) b = w + role_bits - (uint32_t)cls;
+            if (b > w) b = w;
+            rem_bits = w - b;
+            if (rem_bits + role_bits > (uint32_t)cls) continue;
+        }
+        uint32_t slot_log = cls == 32 ? 3 : (cls == 64 ? 2 : 1);
+        if (b + slot_log > 31) continue;  // slot index + 1 must fit the 32-bit de-dup token
+        uint64_t bytes = 32ull << b;
+        if (!found || bytes < best_bytes) {
+            found = true; best_bytes = bytes;
+            g.cls = cls; g.bbits = b; g.rem_bits = rem_bits; g.wbits = w; g.K = K;
+            g.key_mask = (1ull << w) - 1;
+            g.rem_mask = rem_bits ? ((1ull << rem_bits) - 1) : 0;
+            g.sectors = nullptr;
+        }
+    }
+    return found;
 }
 
 template <typename F>
@@ -499,6 +555,12 @@ int ka_set_option(ka_engine* e, const char* name, double v) {
         e->l2_persist = v != 0;
     } else if (n == "warp_dedup") {
         e->warp_dedup = v != 0;
+    } else if (n == "slot_bits") {
+        if (v != 0 && v != 32 && v != 64 && v != 128) return fail(e, KA_ERR_INVALID, "slot_bits must be 0, 32, 64 or 128");
+        e->slot_bits = (int)v;
+    } else if (n == "variant") {
+        if (v < 0 || v >= N_VARIANTS) return fail(e, KA_ERR_INVALID, "variant must be 0..%d", N_VARIANTS - 1);
+        e->variant = (int)v;
     } else {
         return fail(e, KA_ERR_INVALID, "unknown option '%s'", name);
     }
@@ -550,27 +612,33 @@ int ka_db_load(ka_engine* e, const uint8_t* kmers, const int32_t* role_ids, uint
         return fail(e, KA_ERR_ALPHABET,
                     "ka_db_load: the DB uses %d distinct residue bytes; at most 31 fit the 5-bit packing", nsym);
 
-    // 2. table geometry: 2 slots per 32-byte bucket
-    uint64_t n_buckets = (uint64_t)((double)n / (2.0 * e->load_factor)) + 1;
-    if (n_buckets < 64) n_buckets = 64;
-    if (2 * n_buckets >= 0xfffffff0ull)
-        return fail(e, KA_ERR_TOO_BIG, "ka_db_load: table of %llu buckets exceeds the 32-bit slot index of this build",
-                    (unsigned long long)n_buckets);
+    // 2. table geometry (slot class, sector count) from n, K and the largest role id
+    int32_t max_role = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        if (role_ids[i] < 0) return fail(e, KA_ERR_ROLE, "ka_db_load: negative role id %d at line %llu", role_ids[i], (unsigned long long)i);
+        if (role_ids[i] > max_role) max_role = role_ids[i];
+    }
+    TableView geom;
+    if (!choose_geometry(n, K, max_role, e->load_factor, e->slot_bits, geom))
+        return fail(e, KA_ERR_TOO_BIG, "ka_db_load: %llu k-mers (K=%d, max role %d) do not fit %s of this build",
+                    (unsigned long long)n, K, max_role, e->slot_bits ? "the forced slot width" : "the 32-bit slot index");
 
     // 3. build one replica per device
     std::vector<uint64_t> nk(e->devs.size(), 0);
     std::vector<uint32_t> mp(e->devs.size(), 0);
     int rc = for_each_device(e, [&](Device& d, int i) {
-        return build_table(e, d, kmers, role_ids, n, K, n_buckets, &nk[i], &mp[i]);
+        return build_table(e, d, geom, kmers, role_ids, n, &nk[i], &mp[i]);
     });
     if (rc) return rc;
+    e->geom = geom;
     e->info.K = K;
     e->info.n_symbols = nsym;
     e->info.n_lines = n;
     e->info.n_keys = nk[0];
-    e->info.n_buckets = n_buckets;
-    e->info.table_bytes = n_buckets * 32;
+    e->info.n_buckets = 1ull << geom.bbits;
+    e->info.table_bytes = 32ull << geom.bbits;
     e->info.max_probe = mp[0];
+    e->info.slot_bits = (uint32_t)geom.cls;
     e->have_db = true;
     for (Device& d : e->devs) {
         cudaSetDevice(d.id);

@@ -11,43 +11,71 @@
 //                  and the list of long sequences.
 //   tile_kernel    one CTA per tile of whole sequences: the tile's residues are staged into
 //                  shared memory with one TMA bulk copy (cp.async.bulk + mbarrier); each
-//                  thread rolls the 5-bit packed key over 8 consecutive window positions,
-//                  issues its 8 bucket loads (one 256-bit load = one 32-byte DRAM sector
-//                  each) before consuming any, de-duplicates hitting k-mers of a sequence
+//                  thread rolls the 5-bit packed key over a run of consecutive window
+//                  positions, issues all its sector loads (one 256-bit load each = one DRAM
+//                  line) before consuming any, de-duplicates hitting k-mers of a sequence
 //                  with a shared-memory token set (HashSet semantics of ProteinKmers), and
 //                  reduces (count, min role, max role) per sequence with warp match/redux
 //                  and shared-memory atomics; the epilogue applies unanimity + min_hits.
 //   big_kernel     same per-position work for sequences too long for a tile's shared
 //                  memory: one CTA per sequence, token set in an L2-resident scratch region.
-//   db_insert      lock-free insert of the packed DB k-mers (atomicCAS on the key,
-//                  atomicMax on (line, role) so the last line wins).
+//   db_insert      lock-free insert of the packed DB k-mers (atomicCAS claims a slot,
+//                  atomicMax on the db line index makes the last line win), db_finalize
+//                  writes the winning role into every slot.
 //
-// HBM-bound integer work: no tensor cores.  Algorithmic bytes per probe = 32 (one bucket
+// HBM-bound integer work: no tensor cores.  Algorithmic bytes per probe = 32 (one table
 // sector) + 1 (the residue).
 #include "ka_kernels.cuh"
 
 namespace ka {
 
 // ------------------------------------------------------------------------------------
-// table lookup
+// table lookup: C independent probes per thread, all loads in flight before the first use
 // ------------------------------------------------------------------------------------
-
-// Continue a lookup past a full first bucket (rare at load factor <= 0.5).
-__device__ __forceinline__ int lookup_overflow(const TableView& tab, unsigned long long key,
-                                            unsigned long long b, uint32_t& slot) {
-    for (;;) {
-        b = (b + 1 == tab.n_buckets) ? 0 : b + 1;
-        uint4 s0, s1;
-        load_bucket(tab.buckets + 2 * b, s0, s1);
-        unsigned long long k0 = u64_of(s0.x, s0.y), k1 = u64_of(s1.x, s1.y);
-        if (k0 == key) { slot = (uint32_t)(2 * b); return (int)s0.z; }
-        if (k1 == key) { slot = (uint32_t)(2 * b + 1); return (int)s1.z; }
-        if (k1 == 0) return -1;  // slots fill in order: an empty slot ends the chain
+template <int CLS, int C>
+__device__ __forceinline__ void probe_batch(const TableView& tab, const unsigned long long (&rem)[C],
+                                            uint32_t (&sec)[C], unsigned okmask, int (&role)[C],
+                                            uint32_t (&tok)[C]) {
+    constexpr int S = slots_per_sector<CLS>();
+    uint4 a[C], b[C];
+#pragma unroll
+    for (int i = 0; i < C; i++)
+        if (okmask & (1u << i)) load_sector(tab.sectors + 2 * (size_t)sec[i], a[i], b[i]);
+    unsigned pend = 0;
+#pragma unroll
+    for (int i = 0; i < C; i++) {
+        role[i] = -1;
+        if (okmask & (1u << i)) {
+            uint32_t j = 0;
+            bool full;
+            const int r = match_sector<CLS>(tab, a[i], b[i], rem[i], j, full);
+            if (r >= 0) { role[i] = r; tok[i] = sec[i] * S + j + 1; }
+            else if (full) pend |= 1u << i;
+        }
+    }
+    // Rare (load factor keeps full sectors below ~1 %): the home sector had no free slot, so
+    // the key may live in the next one.  All pending positions advance together.
+    const uint32_t sec_mask = (1u << tab.bbits) - 1;
+    while (pend) {
+#pragma unroll
+        for (int i = 0; i < C; i++)
+            if (pend & (1u << i)) {
+                sec[i] = (sec[i] + 1) & sec_mask;
+                load_sector(tab.sectors + 2 * (size_t)sec[i], a[i], b[i]);
+            }
+#pragma unroll
+        for (int i = 0; i < C; i++)
+            if (pend & (1u << i)) {
+                uint32_t j = 0;
+                bool full;
+                const int r = match_sector<CLS>(tab, a[i], b[i], rem[i], j, full);
+                if (r >= 0) { role[i] = r; tok[i] = sec[i] * S + j + 1; pend &= ~(1u << i); }
+                else if (!full) pend &= ~(1u << i);
+            }
     }
 }
 
 // Insert a hit token into the sequence's open-addressed de-dup region; true = first time.
-template <bool SHARED>
 __device__ __forceinline__ bool token_insert(uint32_t* region, uint32_t n, uint32_t token) {
     uint32_t j = (uint32_t)(((unsigned long long)(token * 0x9E3779B1u) * n) >> 32);
     for (;;) {
@@ -124,8 +152,8 @@ size_t tile_smem_bytes(uint32_t ext_max, uint32_t* res_bytes_out) {
            4 * (2 * (size_t)ext_max + 4);
 }
 
-template <int C>
-__global__ void __launch_bounds__(TILE_THREADS) tile_kernel(AnnotParams p) {
+template <int CLS, int C, int THREADS>
+__global__ void __launch_bounds__(THREADS, (C == 4 && THREADS == 256) ? 3 : 2) tile_kernel(AnnotParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar;
 
@@ -148,12 +176,12 @@ __global__ void __launch_bounds__(TILE_THREADS) tile_kernel(AnnotParams p) {
     if (p.off[s1] - p.off[s1 - 1] > p.long_seq) s1--;
     if (s0 >= s1) return;
 
-    s_lut[tid] = p.lut[tid];  // TILE_THREADS == 256
+    for (uint32_t i = tid; i < 256; i += THREADS) s_lut[i] = p.lut[i];
     if (tid == 0) mbar_init(&s_bar, 1);
     __syncthreads();
 
-    const int K = p.tab.K;
-    const unsigned long long kmask = p.tab.key_mask;
+    const TableView tab = p.tab;
+    const int K = tab.K;
     uint32_t parity = 0;
 
     for (uint32_t sb = s0; sb < s1; sb += MAX_TILE_SEQ) {
@@ -169,25 +197,28 @@ __global__ void __launch_bounds__(TILE_THREADS) tile_kernel(AnnotParams p) {
             mbar_expect_tx(&s_bar, nbytes);
             bulk_g2s(s_res, p.res + g0a, nbytes, &s_bar);
         }
-        for (uint32_t i = tid; i <= ns; i += TILE_THREADS)
+        for (uint32_t i = tid; i <= ns; i += THREADS)
             s_off[i] = (uint32_t)(p.off[sb + i] - p.base - g0a);
-        for (uint32_t i = tid; i < ns; i += TILE_THREADS) {
+        for (uint32_t i = tid; i < ns; i += THREADS) {
             s_cnt[i] = 0; s_min[i] = 0x7fffffff; s_max[i] = -1;
         }
         {
             const uint32_t ntok = 2u * (ext - lead);
             const uint4 z = make_uint4(0, 0, 0, 0);
-            for (uint32_t i = tid * 4; i < ntok; i += TILE_THREADS * 4)
+            for (uint32_t i = tid * 4; i < ntok; i += THREADS * 4)
                 *reinterpret_cast<uint4*>(s_tok + i) = z;
         }
         __syncthreads();
         if (nbytes) { mbar_wait(&s_bar, parity); parity ^= 1; }
 
-        for (uint32_t pb = 0; pb < ext; pb += TILE_THREADS * C) {
-            const uint32_t P0 = pb + tid * C;
+        // passes of up to THREADS*C positions, spread evenly over the threads
+        for (uint32_t pb = lead; pb < ext; pb += THREADS * C) {
+            const uint32_t pend = min(ext, pb + THREADS * C);
+            const uint32_t run = (pend - pb + THREADS - 1) / THREADS;   // positions per thread, <= C
+            const uint32_t P0 = pb + tid * run;
             int cur = -1, cnt = 0, mn = 0x7fffffff, mx = -1;
-            if (P0 < ext) {
-                // sequence containing P0: last i with s_off[i] <= P0 (-1: lead slack)
+            if (P0 < pend) {
+                // sequence containing P0: last i with s_off[i] <= P0
                 int lo = 0, hi = (int)ns + 1;
                 while (lo < hi) {
                     int mid = (lo + hi) >> 1;
@@ -206,55 +237,47 @@ __global__ void __launch_bounds__(TILE_THREADS) tile_kernel(AnnotParams p) {
                 }
                 r += K - 1;
 
-                unsigned long long keys[C];
-                uint32_t bkt[C];
+                unsigned long long rem[C];
+                uint32_t sec[C];
                 int seqi[C];
-                uint4 v0[C], v1[C];
                 unsigned okmask = 0;
 #pragma unroll
                 for (int i = 0; i < C; i++) {
-                    uint32_t c = s_lut[r[i]];
-                    key = (key << 5) | c;
-                    vr = c ? vr + 1 : 0;
                     const uint32_t pos = P0 + i;
-                    while (si < (int)ns && pos >= s_off[si + 1]) si++;
-                    const bool ok = (si >= 0) && (si < (int)ns) && (pos + K <= s_off[si + 1]) &&
-                                    (vr >= K);
-                    keys[i] = key & kmask;
-                    seqi[i] = si;
-                    if (ok) {
-                        okmask |= 1u << i;
-                        const unsigned long long b = bucket_of(keys[i], p.tab.n_buckets);
-                        bkt[i] = (uint32_t)b;
-                        load_bucket(p.tab.buckets + 2 * b, v0[i], v1[i]);
+                    if (i < (int)run && pos < pend) {
+                        uint32_t c = s_lut[r[i]];
+                        key = (key << 5) | c;
+                        vr = c ? vr + 1 : 0;
+                        while (si < (int)ns && pos >= s_off[si + 1]) si++;
+                        const bool ok = (si >= 0) && (si < (int)ns) && (pos + K <= s_off[si + 1]) &&
+                                        (vr >= K);
+                        seqi[i] = si;
+                        if (ok) {
+                            okmask |= 1u << i;
+                            locate(tab, key & tab.key_mask, sec[i], rem[i]);
+                        }
                     }
                 }
+                int role[C];
+                uint32_t tok[C];
+                probe_batch<CLS, C>(tab, rem, sec, okmask, role, tok);
 #pragma unroll
                 for (int i = 0; i < C; i++) {
-                    if (okmask & (1u << i)) {
-                        const unsigned long long k0 = u64_of(v0[i].x, v0[i].y);
-                        const unsigned long long k1 = u64_of(v1[i].x, v1[i].y);
-                        int role = -1;
-                        uint32_t slot = 0;
-                        if (k0 == keys[i]) { role = (int)v0[i].z; slot = 2 * bkt[i]; }
-                        else if (k1 == keys[i]) { role = (int)v1[i].z; slot = 2 * bkt[i] + 1; }
-                        else if (k1 != 0) role = lookup_overflow(p.tab, keys[i], bkt[i], slot);
-                        if (role >= 0) {
-                            const int q = seqi[i];
-                            const uint32_t a = s_off[q], b = s_off[q + 1];
-                            if (token_insert<true>(s_tok + 2 * (a - lead), 2 * (b - a), slot + 1)) {
-                                if (q != cur) {
-                                    if (cur >= 0 && cnt > 0) {
-                                        atomicAdd(&s_cnt[cur], cnt);
-                                        atomicMin(&s_min[cur], mn);
-                                        atomicMax(&s_max[cur], mx);
-                                    }
-                                    cur = q; cnt = 0; mn = 0x7fffffff; mx = -1;
+                    if ((okmask & (1u << i)) && role[i] >= 0) {
+                        const int q = seqi[i];
+                        const uint32_t a = s_off[q], b = s_off[q + 1];
+                        if (token_insert(s_tok + 2 * (a - lead), 2 * (b - a), tok[i])) {
+                            if (q != cur) {
+                                if (cur >= 0 && cnt > 0) {
+                                    atomicAdd(&s_cnt[cur], cnt);
+                                    atomicMin(&s_min[cur], mn);
+                                    atomicMax(&s_max[cur], mx);
                                 }
-                                cnt++;
-                                mn = min(mn, role);
-                                mx = max(mx, role);
+                                cur = q; cnt = 0; mn = 0x7fffffff; mx = -1;
                             }
+                            cnt++;
+                            mn = min(mn, role[i]);
+                            mx = max(mx, role[i]);
                         }
                     }
                 }
@@ -271,35 +294,53 @@ __global__ void __launch_bounds__(TILE_THREADS) tile_kernel(AnnotParams p) {
             }
         }
         __syncthreads();
-        for (uint32_t i = tid; i < ns; i += TILE_THREADS)
+        for (uint32_t i = tid; i < ns; i += THREADS)
             emit_call(p, sb + i, s_cnt[i], s_min[i], s_max[i]);
         __syncthreads();
     }
 }
 
-cudaError_t tile_kernel_set_smem(size_t bytes) {
-    return cudaFuncSetAttribute(tile_kernel<POS_PER_THREAD>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+template <typename F>
+static auto with_tile_kernel(int cls, int variant, F f) {
+#define KA_VARIANTS(CLS)                                             \
+    switch (variant) {                                               \
+        case 1: return f(tile_kernel<CLS, 4, 256>, 256);             \
+        case 2: return f(tile_kernel<CLS, 4, 512>, 512);             \
+        default: return f(tile_kernel<CLS, 8, 256>, 256);            \
+    }
+    if (cls == 32) { KA_VARIANTS(32) }
+    if (cls == 64) { KA_VARIANTS(64) }
+    KA_VARIANTS(128)
+#undef KA_VARIANTS
 }
 
-cudaError_t launch_tiles(const AnnotParams& p, size_t smem, cudaStream_t st) {
+cudaError_t tile_kernel_set_smem(int cls, int variant, size_t bytes) {
+    return with_tile_kernel(cls, variant, [&](auto kern, int) {
+        return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    });
+}
+
+cudaError_t launch_tiles(const AnnotParams& p, int variant, size_t smem, cudaStream_t st) {
     if (p.n_tiles == 0) return cudaSuccess;
-    tile_kernel<POS_PER_THREAD><<<p.n_tiles, TILE_THREADS, smem, st>>>(p);
-    return cudaGetLastError();
+    return with_tile_kernel(p.tab.cls, variant, [&](auto kern, int threads) {
+        kern<<<p.n_tiles, threads, smem, st>>>(p);
+        return cudaGetLastError();
+    });
 }
 
 // ------------------------------------------------------------------------------------
 // long sequences: one CTA per sequence, token set in global scratch (L2 resident)
 // ------------------------------------------------------------------------------------
-template <int C>
-__global__ void __launch_bounds__(TILE_THREADS) big_kernel(AnnotParams p) {
+template <int CLS, int C>
+__global__ void __launch_bounds__(256) big_kernel(AnnotParams p) {
+    constexpr int THREADS = 256;
     __shared__ uint8_t s_lut[256];
     __shared__ int sh_cnt, sh_min, sh_max;
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     s_lut[tid] = p.lut[tid];
     const uint32_t nbig = *p.big_count;
-    const int K = p.tab.K;
-    const unsigned long long kmask = p.tab.key_mask;
+    const TableView tab = p.tab;
+    const int K = tab.K;
 
     for (uint32_t bi = blockIdx.x; bi < nbig; bi += gridDim.x) {
         const BigItem it = p.big_list[bi];
@@ -308,12 +349,12 @@ __global__ void __launch_bounds__(TILE_THREADS) big_kernel(AnnotParams p) {
         const unsigned long long W = L - (unsigned long long)K + 1;  // L > long_seq >= K
         uint32_t* region = p.scratch + it.tok_base;
         const uint32_t nreg = (uint32_t)(2 * L);
-        for (uint32_t i = tid; i < nreg; i += TILE_THREADS) region[i] = TOKEN_EMPTY;
+        for (uint32_t i = tid; i < nreg; i += THREADS) region[i] = TOKEN_EMPTY;
         if (tid == 0) { sh_cnt = 0; sh_min = 0x7fffffff; sh_max = -1; }
         __syncthreads();
 
         int cnt = 0, mn = 0x7fffffff, mx = -1;
-        for (unsigned long long pb = 0; pb < W; pb += TILE_THREADS * C) {
+        for (unsigned long long pb = 0; pb < W; pb += THREADS * C) {
             const unsigned long long P0 = pb + (unsigned long long)tid * C;
             if (P0 >= W) continue;
             const uint8_t* r = p.res + a + P0;
@@ -325,9 +366,8 @@ __global__ void __launch_bounds__(TILE_THREADS) big_kernel(AnnotParams p) {
                 vr = c ? vr + 1 : 0;
             }
             r += K - 1;
-            unsigned long long keys[C];
-            uint32_t bkt[C];
-            uint4 v0[C], v1[C];
+            unsigned long long rem[C];
+            uint32_t sec[C];
             unsigned okmask = 0;
 #pragma unroll
             for (int i = 0; i < C; i++) {
@@ -335,30 +375,21 @@ __global__ void __launch_bounds__(TILE_THREADS) big_kernel(AnnotParams p) {
                     uint32_t c = s_lut[__ldg(r + i)];
                     key = (key << 5) | c;
                     vr = c ? vr + 1 : 0;
-                    keys[i] = key & kmask;
                     if (vr >= K) {
                         okmask |= 1u << i;
-                        const unsigned long long b = bucket_of(keys[i], p.tab.n_buckets);
-                        bkt[i] = (uint32_t)b;
-                        load_bucket(p.tab.buckets + 2 * b, v0[i], v1[i]);
+                        locate(tab, key & tab.key_mask, sec[i], rem[i]);
                     }
                 }
             }
+            int role[C];
+            uint32_t tok[C];
+            probe_batch<CLS, C>(tab, rem, sec, okmask, role, tok);
 #pragma unroll
             for (int i = 0; i < C; i++) {
-                if (okmask & (1u << i)) {
-                    const unsigned long long k0 = u64_of(v0[i].x, v0[i].y);
-                    const unsigned long long k1 = u64_of(v1[i].x, v1[i].y);
-                    int role = -1;
-                    uint32_t slot = 0;
-                    if (k0 == keys[i]) { role = (int)v0[i].z; slot = 2 * bkt[i]; }
-                    else if (k1 == keys[i]) { role = (int)v1[i].z; slot = 2 * bkt[i] + 1; }
-                    else if (k1 != 0) role = lookup_overflow(p.tab, keys[i], bkt[i], slot);
-                    if (role >= 0 && token_insert<false>(region, nreg, slot + 1)) {
-                        cnt++;
-                        mn = min(mn, role);
-                        mx = max(mx, role);
-                    }
+                if ((okmask & (1u << i)) && role[i] >= 0 && token_insert(region, nreg, tok[i])) {
+                    cnt++;
+                    mn = min(mn, role[i]);
+                    mx = max(mx, role[i]);
                 }
             }
         }
@@ -377,7 +408,9 @@ __global__ void __launch_bounds__(TILE_THREADS) big_kernel(AnnotParams p) {
 }
 
 cudaError_t launch_big(const AnnotParams& p, int grid, cudaStream_t st) {
-    big_kernel<POS_PER_THREAD><<<grid, TILE_THREADS, 0, st>>>(p);
+    if (p.tab.cls == 32) big_kernel<32, 8><<<grid, 256, 0, st>>>(p);
+    else if (p.tab.cls == 64) big_kernel<64, 8><<<grid, 256, 0, st>>>(p);
+    else big_kernel<128, 8><<<grid, 256, 0, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -410,16 +443,18 @@ cudaError_t launch_alphabet_scan(const uint8_t* bytes, unsigned long long n, uin
 }
 
 // HashMap.put for every DB line (ApplyKmerProcessor.java:106): a duplicate k-mer keeps one
-// slot, and atomicMax over (line index << 32 | role) leaves the LAST line's role in it.
-__global__ void db_insert_kernel(const uint8_t* __restrict__ kmers,
+// slot and the LAST line's role ends up in it (atomicMax on the line index).
+template <int CLS>
+__global__ void db_insert_kernel(TableView tab, const uint8_t* __restrict__ kmers,
                                  const int32_t* __restrict__ roles, unsigned long long n,
-                                 unsigned long long line_base, int K,
-                                 const uint8_t* __restrict__ lut, Slot* table,
-                                 unsigned long long n_buckets, unsigned long long* counters,
-                                 uint32_t* errs) {
+                                 unsigned long long line_base, const uint8_t* __restrict__ lut,
+                                 uint32_t* line_of, unsigned long long* counters, uint32_t* errs) {
+    constexpr int S = slots_per_sector<CLS>();
     __shared__ uint8_t s_lut[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = lut[i];
     __syncthreads();
+    const int K = tab.K;
+    const uint32_t sec_mask = (1u << tab.bbits) - 1;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     uint32_t longest = 0;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -432,44 +467,100 @@ __global__ void db_insert_kernel(const uint8_t* __restrict__ kmers,
             bad |= (c == 0);
             key = (key << 5) | c;
         }
-        const int32_t role = roles[i];
         if (bad) { atomicAdd(&errs[0], 1u); continue; }
-        if (role < 0) { atomicAdd(&errs[1], 1u); continue; }
-        const unsigned long long val = ((line_base + i) << 32) | (uint32_t)role;
-        unsigned long long b = bucket_of(key, n_buckets);
+        if (CLS == 128 && roles[i] < 0) { atomicAdd(&errs[1], 1u); continue; }
+        uint32_t sec;
+        unsigned long long rem;
+        locate(tab, key, sec, rem);
         uint32_t chain = 1;
-        for (;;) {
-            Slot* s = table + 2 * b;
-            bool done = false;
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                if (done) break;
-                unsigned long long old = atomicCAS(&s[h].key, 0ull, key);
-                if (old == 0ull || old == key) {
-                    if (old == 0ull) atomicAdd(&counters[0], 1ull);
-                    atomicMax(&s[h].val, val);
-                    done = true;
+        bool done = false;
+        while (!done) {
+            if (CLS == 128) {
+                Slot128* s = reinterpret_cast<Slot128*>(const_cast<uint4*>(tab.sectors)) + 2 * (size_t)sec;
+                const unsigned long long val = ((line_base + i) << 32) | (uint32_t)roles[i];
+                for (int h = 0; h < 2 && !done; h++) {
+                    unsigned long long old = atomicCAS(&s[h].key, 0ull, key);
+                    if (old == 0ull || old == key) {
+                        if (old == 0ull) atomicAdd(&counters[0], 1ull);
+                        atomicMax(&s[h].val, val);
+                        done = true;
+                    }
+                }
+            } else if (CLS == 64) {
+                unsigned long long* w = reinterpret_cast<unsigned long long*>(const_cast<uint4*>(tab.sectors)) + (size_t)sec * S;
+                const unsigned long long claim = rem | (1ull << tab.rem_bits);  // role field = placeholder
+                for (int h = 0; h < S && !done; h++) {
+                    unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(w + h);
+                    if (cur == 0) cur = atomicCAS(w + h, 0ull, claim);
+                    if (cur == 0 || ((cur ^ rem) & tab.rem_mask) == 0) {
+                        if (cur == 0) atomicAdd(&counters[0], 1ull);
+                        atomicMax(&line_of[(size_t)sec * S + h], (uint32_t)(line_base + i) + 1u);
+                        done = true;
+                    }
+                }
+            } else {
+                uint32_t* w = reinterpret_cast<uint32_t*>(const_cast<uint4*>(tab.sectors)) + (size_t)sec * S;
+                const uint32_t r32 = (uint32_t)rem, m32 = (uint32_t)tab.rem_mask;
+                const uint32_t claim = r32 | (1u << tab.rem_bits);
+                for (int h = 0; h < S && !done; h++) {
+                    uint32_t cur = *reinterpret_cast<volatile uint32_t*>(w + h);
+                    if (cur == 0) cur = atomicCAS(w + h, 0u, claim);
+                    if (cur == 0 || ((cur ^ r32) & m32) == 0) {
+                        if (cur == 0) atomicAdd(&counters[0], 1ull);
+                        atomicMax(&line_of[(size_t)sec * S + h], (uint32_t)(line_base + i) + 1u);
+                        done = true;
+                    }
                 }
             }
-            if (done) break;
-            b = (b + 1 == n_buckets) ? 0 : b + 1;
-            chain++;
+            if (!done) { sec = (sec + 1) & sec_mask; chain++; }
         }
         longest = max(longest, chain);
     }
-    longest = __reduce_max_sync(__activemask(), longest);
-    if ((threadIdx.x & 31) == 0) atomicMax(&counters[1], (unsigned long long)longest);
+    if (longest) atomicMax(&counters[1], (unsigned long long)longest);
 }
 
-cudaError_t launch_db_insert(const uint8_t* kmers, const int32_t* roles, unsigned long long n,
-                             unsigned long long line_base, int K, const uint8_t* lut, Slot* table,
-                             unsigned long long n_buckets, unsigned long long* counters,
+cudaError_t launch_db_insert(const TableView& tab, const uint8_t* kmers, const int32_t* roles,
+                             unsigned long long n, unsigned long long line_base,
+                             const uint8_t* lut, uint32_t* line_of, unsigned long long* counters,
                              uint32_t* errs, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     unsigned long long want = (n + 255) / 256;
     unsigned blocks = (unsigned)(want < 148ull * 32 ? want : 148ull * 32);
-    db_insert_kernel<<<blocks, 256, 0, st>>>(kmers, roles, n, line_base, K, lut, table, n_buckets,
-                                             counters, errs);
+    if (tab.cls == 32)
+        db_insert_kernel<32><<<blocks, 256, 0, st>>>(tab, kmers, roles, n, line_base, lut, line_of, counters, errs);
+    else if (tab.cls == 64)
+        db_insert_kernel<64><<<blocks, 256, 0, st>>>(tab, kmers, roles, n, line_base, lut, line_of, counters, errs);
+    else
+        db_insert_kernel<128><<<blocks, 256, 0, st>>>(tab, kmers, roles, n, line_base, lut, line_of, counters, errs);
+    return cudaGetLastError();
+}
+
+// Write role+1 of the winning db line into the role field of every occupied slot (cls 32/64).
+template <int CLS>
+__global__ void db_finalize_kernel(TableView tab, const uint32_t* __restrict__ line_of,
+                                   const int32_t* __restrict__ all_roles) {
+    constexpr int S = slots_per_sector<CLS>();
+    const unsigned long long n_slots = (unsigned long long)S << tab.bbits;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long s = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; s < n_slots;
+         s += stride) {
+        if (CLS == 64) {
+            unsigned long long* w = reinterpret_cast<unsigned long long*>(const_cast<uint4*>(tab.sectors)) + s;
+            const unsigned long long v = *w;
+            if (v) *w = (v & tab.rem_mask) | ((unsigned long long)(all_roles[line_of[s] - 1] + 1) << tab.rem_bits);
+        } else {
+            uint32_t* w = reinterpret_cast<uint32_t*>(const_cast<uint4*>(tab.sectors)) + s;
+            const uint32_t v = *w;
+            if (v) *w = (v & (uint32_t)tab.rem_mask) | ((uint32_t)(all_roles[line_of[s] - 1] + 1) << tab.rem_bits);
+        }
+    }
+}
+
+cudaError_t launch_db_finalize(const TableView& tab, const uint32_t* line_of,
+                               const int32_t* all_roles, cudaStream_t st) {
+    if (tab.cls == 128) return cudaSuccess;
+    if (tab.cls == 32) db_finalize_kernel<32><<<148 * 16, 256, 0, st>>>(tab, line_of, all_roles);
+    else db_finalize_kernel<64><<<148 * 16, 256, 0, st>>>(tab, line_of, all_roles);
     return cudaGetLastError();
 }
 
@@ -491,11 +582,11 @@ __global__ void __launch_bounds__(256) random_probe_kernel(const uint4* __restri
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const unsigned long long idx = __umul64hi(mix64(seed + i0 + u + 1), n_slots);
-            if (BYTES == 32) load_bucket(buf + 2 * idx, a[u], b[u]);
+            if (BYTES == 32) load_sector(buf + 2 * idx, a[u], b[u]);
             else {
-                asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                    : "=r"(a[u].x), "=r"(a[u].y), "=r"(a[u].z), "=r"(a[u].w)
-                    : "l"(buf + idx));
+                asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(a[u].x), "=r"(a[u].y), "=r"(a[u].z), "=r"(a[u].w)
+                             : "l"(buf + idx));
                 b[u] = make_uint4(0, 0, 0, 0);
             }
         }

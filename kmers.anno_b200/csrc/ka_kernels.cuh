@@ -38,21 +38,28 @@ struct AnnotParams {
     int warp_dedup;
 };
 
+// tile kernel variants (option "variant"): 0 = 8 positions/thread x 256 threads,
+// 1 = 4 x 256, 2 = 4 x 512
+constexpr int N_VARIANTS = 3;
 size_t tile_smem_bytes(uint32_t ext_max, uint32_t* res_bytes_out);
-cudaError_t tile_kernel_set_smem(size_t bytes);
+cudaError_t tile_kernel_set_smem(int cls, int variant, size_t bytes);
 
 cudaError_t launch_plan(const AnnotParams& p, cudaStream_t st);
-cudaError_t launch_tiles(const AnnotParams& p, size_t smem, cudaStream_t st);
+cudaError_t launch_tiles(const AnnotParams& p, int variant, size_t smem, cudaStream_t st);
 cudaError_t launch_big(const AnnotParams& p, int grid, cudaStream_t st);
 
 cudaError_t launch_alphabet_scan(const uint8_t* bytes, unsigned long long n, uint32_t* bitmap8,
                                  cudaStream_t st);
 // errs[0] = k-mers with a byte outside the alphabet, errs[1] = negative role ids,
-// counters[0] = distinct keys stored, counters[1] = longest bucket chain
-cudaError_t launch_db_insert(const uint8_t* kmers, const int32_t* roles, unsigned long long n,
-                             unsigned long long line_base, int K, const uint8_t* lut, Slot* table,
-                             unsigned long long n_buckets, unsigned long long* counters,
+// counters[0] = distinct keys stored, counters[1] = longest sector chain.
+// cls 32/64: `roles` is unused here, the winning db line of every slot is kept in line_of
+// (atomicMax) and launch_db_finalize writes the roles; cls 128 stores (line, role) itself.
+cudaError_t launch_db_insert(const TableView& tab, const uint8_t* kmers, const int32_t* roles,
+                             unsigned long long n, unsigned long long line_base,
+                             const uint8_t* lut, uint32_t* line_of, unsigned long long* counters,
                              uint32_t* errs, cudaStream_t st);
+cudaError_t launch_db_finalize(const TableView& tab, const uint32_t* line_of,
+                               const int32_t* all_roles, cudaStream_t st);
 
 cudaError_t launch_random_probe(const uint4* buf, unsigned long long n_slots, int slot_bytes,
                                 unsigned long long n_probes, unsigned long long seed,

@@ -31,7 +31,7 @@ class KmerAnnoError(RuntimeError):
 class DbInfo(C.Structure):
     _fields_ = [("K", C.c_int32), ("n_symbols", C.c_int32), ("n_lines", C.c_uint64),
                 ("n_keys", C.c_uint64), ("n_buckets", C.c_uint64), ("table_bytes", C.c_uint64),
-                ("max_probe", C.c_uint32), ("reserved", C.c_uint32)]
+                ("max_probe", C.c_uint32), ("slot_bits", C.c_uint32)]
 
 
 class Stats(C.Structure):
@@ -164,7 +164,7 @@ class Engine:
     def db_info(self):
         info = DbInfo()
         self._check(self._lib.ka_db_get_info(self._h, C.byref(info)))
-        return {f: getattr(info, f) for f, _ in DbInfo._fields_ if f != "reserved"}
+        return {f: getattr(info, f) for f, _ in DbInfo._fields_}
 
     def annotate(self, residues, offsets, min_hits=5, out=None):
         """residues uint8[R], offsets uint64[N+1] (host).  Returns (role, hits, flag)."""

@@ -117,7 +117,7 @@ def test_many_tiny_sequences_sub_batches(ka, oracle):
 
 
 def test_long_sequences_use_big_kernel(ka, oracle):
-    lengths = [20000, 300, 7000, 5121, 5120, 64, 0, 12000]
+    lengths = [20000, 300, 7000, 3073, 3072, 64, 0, 12000]
     seqs, kmers, roles = ragged_case(21, n_seq=len(lengths), K=8, lengths=lengths, db_frac=0.5)
     run_case(ka, oracle, seqs, kmers, roles, 8, min_hits=3)
     # the same inputs with a small long_seq so that most sequences take the long path
@@ -131,10 +131,30 @@ def test_long_sequences_use_big_kernel(ka, oracle):
     {"load_factor": 0.9},
     {"load_factor": 0.05},
     {"l2_persist": 0},
+    {"variant": 1},
+    {"variant": 2},
+    {"slot_bits": 32},
+    {"slot_bits": 64},
+    {"slot_bits": 128},
+    {"slot_bits": 64, "variant": 2, "load_factor": 0.9},
+    {"slot_bits": 32, "variant": 1, "load_factor": 0.9},
 ])
 def test_options_do_not_change_results(ka, oracle, opts):
     seqs, kmers, roles = ragged_case(33, n_seq=500, K=8, max_len=900)
     run_case(ka, oracle, seqs, kmers, roles, 8, min_hits=3, options=opts)
+
+
+@pytest.mark.parametrize("K,max_role,want_bits", [(8, 400, 32), (12, 30000, 64), (12, 2**31 - 2, 128), (3, 10, 32)])
+def test_slot_class_selection(ka, oracle, K, max_role, want_bits):
+    """The engine picks the narrowest slot that holds remainder + role (ka_common.cuh)."""
+    seqs, kmers, roles = ragged_case(70 + K, n_seq=300, K=K, n_roles=12)
+    roles = (roles.astype(np.int64) * (max_role // 11)).astype(np.int32)   # spread ids up to max_role
+    res, off = csr(seqs)
+    with ka.Engine([0]) as eng:
+        eng.db_load(kmers, roles, K)
+        assert eng.db_info()["slot_bits"] == want_bits
+        got = eng.annotate(res, off, 3)
+    assert_same(got, oracle.OracleDb(kmers, roles, K).apply(res, off, 3), f"slot class K={K}")
 
 
 def test_resident_path(ka, oracle):
