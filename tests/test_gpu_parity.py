@@ -144,7 +144,7 @@ def test_options_do_not_change_results(ka, oracle, opts):
     run_case(ka, oracle, seqs, kmers, roles, 8, min_hits=3, options=opts)
 
 
-@pytest.mark.parametrize("K,max_role,want_bits", [(8, 400, 32), (12, 30000, 64), (12, 2**31 - 2, 128), (3, 10, 32)])
+@pytest.mark.parametrize("K,max_role,want_bits", [(5, 400, 32), (8, 400, 64), (12, 30000, 64), (12, 2**31 - 2, 128), (3, 10, 32)])
 def test_slot_class_selection(ka, oracle, K, max_role, want_bits):
     """The engine picks the narrowest slot that holds remainder + role (ka_common.cuh)."""
     seqs, kmers, roles = ragged_case(70 + K, n_seq=300, K=K, n_roles=12)
