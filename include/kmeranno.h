@@ -75,7 +75,7 @@ const char* ka_last_error(const ka_engine* e);
  *   "tile_span"     residues of sequence starts per CTA tile, default 1536
  *   "long_seq"      sequences longer than this use the long-sequence kernel, default 3072
  *   "slot_bits"     force the table slot width (32, 64, 128; 0 = smallest that fits, default)
- *   "variant"       tile kernel shape: 0 = 8 positions x 256 threads, 1 = 4 x 256, 2 = 4 x 512
+ *   "variant"       tile kernel shape: 0 = 8 positions x 256 threads, 1 = 4 x 256 (default), 2 = 4 x 512
  *   "chunk_residues" residues per pipelined H2D chunk, default 32 Mi
  *   "l2_persist"    1 = set an L2 persisting access-policy window on the table (default 1)
  *   "warp_dedup"    1 = __match_any de-duplication of identical in-flight keys (default 0)

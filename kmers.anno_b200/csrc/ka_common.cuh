@@ -10,8 +10,12 @@
 //               cls 32  : 8 slots/sector, slot = rem | (role+1) << rem_bits   (e.g. K=8, 1e8 keys)
 //               cls 64  : 4 slots/sector, same packing in 64 bits             (K=10/12)
 //               cls 128 : 2 slots/sector, { u64 key ; u64 (db line << 32 | role) } (fallback)
-//             0 = empty slot.  Slots fill in order inside a sector, then the next sector,
-//             and are never freed, so a lookup stops at the first sector with a free slot.
+//             0 = empty slot.  Slots fill in order inside a sector and are never freed.
+//             cls 32/64: a key whose home sector is full goes to a small OVERFLOW table that
+//             stores the whole mixed key (a remainder alone would be ambiguous outside its
+//             home sector); a lookup reads it only when the home sector is full and has no
+//             match (~1 % of probes at the default load factor; the table is L2 resident).
+//             cls 128 stores whole keys, so it simply chains to the next sector.
 //   batch   : CSR — residues u8[R] (+ padding), offsets u64[N+1], results i32/i32/u8 per sequence.
 #pragma once
 #include <cstdint>
@@ -30,6 +34,9 @@ struct Slot128 {
 
 struct TableView {
     const uint4* sectors;         // 2^bbits sectors, 2 uint4 each
+    const uint4* ovf;             // overflow table (cls 32/64): 2^ovf_bbits sectors of 2 Slot128
+    uint32_t ovf_bbits;
+    uint32_t n_primary_slots;     // slots of the primary table (de-dup tokens of overflow entries start here)
     unsigned long long key_mask;  // (1 << 5K) - 1
     unsigned long long rem_mask;  // (1 << rem_bits) - 1   (cls 32 / 64)
     uint32_t bbits;               // log2(number of sectors)

@@ -6,6 +6,7 @@
 // path below either runs the CUDA kernels or returns an error code.
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -42,6 +43,7 @@ struct Device {
     int id = 0;
     int sm_count = 148;
     uint4* table = nullptr;
+    uint4* ovf = nullptr;     // overflow table (cls 32/64)
     uint8_t* lut = nullptr;
     Pipe pipe[NPIPE];
     size_t smem_set = 0;
@@ -71,7 +73,7 @@ struct ka_engine {
     uint64_t chunk_residues = 32ull << 20;
     int l2_persist = 1;
     int warp_dedup = 0;
-    int variant = 0;
+    int variant = 1;
     int slot_bits = 0;  // 0 = choose automatically
     // db
     bool have_db = false;
@@ -208,6 +210,7 @@ void fill_params(ka_engine* e, Device& d, Pipe& p, uint64_t base, uint64_t n_res
     ap.first = p.first;
     ap.tab = e->geom;
     ap.tab.sectors = d.table;
+    ap.tab.ovf = d.ovf;
     ap.lut = d.lut;
     ap.min_hits = min_hits;
     ap.out_role = p.role;
@@ -344,15 +347,22 @@ int build_table(ka_engine* e, Device& d, const TableView& geom, const uint8_t* k
                 const int32_t* roles, uint64_t n, uint64_t* n_keys, uint32_t* max_probe) {
     DCK(d, cudaSetDevice(d.id));
     if (d.table) { cudaFree(d.table); d.table = nullptr; }
+    if (d.ovf) { cudaFree(d.ovf); d.ovf = nullptr; }
     const int K = geom.K;
     const size_t n_sectors = (size_t)1 << geom.bbits;
     const size_t bytes = n_sectors * 32;
     const size_t n_slots = n_sectors * (geom.cls == 32 ? 8 : (geom.cls == 64 ? 4 : 2));
     cudaError_t ce = cudaMalloc((void**)&d.table, bytes);
     if (ce != cudaSuccess) { d.table = nullptr; return dev_fail(d, KA_ERR_OOM, "table", ce); }
+    const size_t ovf_bytes = geom.cls == 128 ? 0 : ((size_t)64 << geom.ovf_bbits);
+    if (ovf_bytes) {
+        ce = cudaMalloc((void**)&d.ovf, ovf_bytes);
+        if (ce != cudaSuccess) { d.ovf = nullptr; return dev_fail(d, KA_ERR_OOM, "overflow table", ce); }
+    }
     cudaStream_t st = d.pipe[0].st;
     TableView tab = geom;
     tab.sectors = d.table;
+    tab.ovf = d.ovf;
     const uint64_t CH = 16ull << 20;  // k-mers per upload
     uint8_t* dk = nullptr; int32_t* dr = nullptr; uint32_t* line_of = nullptr;
     unsigned long long* dc = nullptr; uint32_t* de = nullptr;
@@ -363,7 +373,7 @@ int build_table(ka_engine* e, Device& d, const TableView& geom, const uint8_t* k
         (ce = cudaMalloc((void**)&dr, (packed ? std::max<uint64_t>(n, 1) : ch) * 4)) != cudaSuccess ||
         (packed && (ce = cudaMalloc((void**)&line_of, n_slots * 4)) != cudaSuccess) ||
         (ce = cudaMalloc((void**)&dc, 16)) != cudaSuccess ||
-        (ce = cudaMalloc((void**)&de, 8)) != cudaSuccess) {
+        (ce = cudaMalloc((void**)&de, 16)) != cudaSuccess) {
         if (dk) cudaFree(dk);
         if (dr) cudaFree(dr);
         if (line_of) cudaFree(line_of);
@@ -375,10 +385,11 @@ int build_table(ka_engine* e, Device& d, const TableView& geom, const uint8_t* k
         if (c != cudaSuccess && rc == KA_OK) rc = dev_fail(d, KA_ERR_CUDA, what, c);
     };
     step(cudaMemsetAsync(d.table, 0, bytes, st), "memset table");
+    if (ovf_bytes) step(cudaMemsetAsync(d.ovf, 0, ovf_bytes, st), "memset overflow table");
     if (packed) step(cudaMemsetAsync(line_of, 0, n_slots * 4, st), "memset line_of");
     step(cudaMemcpyAsync(d.lut, e->lut, 256, cudaMemcpyHostToDevice, st), "H2D lut");
     step(cudaMemsetAsync(dc, 0, 16, st), "memset counters");
-    step(cudaMemsetAsync(de, 0, 8, st), "memset errs");
+    step(cudaMemsetAsync(de, 0, 16, st), "memset errs");
     for (uint64_t i = 0; i < n && rc == KA_OK; i += ch) {
         uint64_t m = std::min(ch, n - i);
         int32_t* dri = packed ? dr + i : dr;
@@ -390,14 +401,15 @@ int build_table(ka_engine* e, Device& d, const TableView& geom, const uint8_t* k
     if (rc == KA_OK) step(launch_db_finalize(tab, line_of, dr, st), "db_finalize");
     step(cudaStreamSynchronize(st), "db_finalize sync");
     unsigned long long hc[2] = {0, 0};
-    uint32_t he[2] = {0, 0};
+    uint32_t he[4] = {0, 0, 0, 0};
     step(cudaMemcpy(hc, dc, 16, cudaMemcpyDeviceToHost), "D2H counters");
-    step(cudaMemcpy(he, de, 8, cudaMemcpyDeviceToHost), "D2H errs");
+    step(cudaMemcpy(he, de, 16, cudaMemcpyDeviceToHost), "D2H errs");
     cudaFree(dk); cudaFree(dr); cudaFree(dc); cudaFree(de);
     if (line_of) cudaFree(line_of);
     if (rc) return rc;
     if (he[0]) { d.err = KA_ERR_ALPHABET; d.errmsg = "k-mer byte outside the DB alphabet (internal)"; return d.err; }
     if (he[1]) { d.err = KA_ERR_ROLE; d.errmsg = "negative role id in the DB"; return d.err; }
+    if (he[2]) { d.err = KA_ERR_TOO_BIG; d.errmsg = "overflow table full"; return d.err; }  // caller retries larger
     *n_keys = hc[0];
     *max_probe = (uint32_t)hc[1];
     return KA_OK;
@@ -438,6 +450,16 @@ bool choose_geometry(uint64_t n, int K, int32_t max_role, double lf, int force_c
             g.key_mask = (1ull << w) - 1;
             g.rem_mask = rem_bits ? ((1ull << rem_bits) - 1) : 0;
             g.sectors = nullptr;
+            g.ovf = nullptr;
+            g.n_primary_slots = (uint32_t)((uint64_t)S << b);
+            // expected keys beyond S per sector under Poisson(n / sectors) arrivals
+            double lam = (double)n / (double)(1ull << b), pk = std::exp(-lam), over = 0;
+            for (int k = 1; k < S + 400; k++) {
+                pk *= lam / k;
+                if (k > S) over += (k - S) * pk;
+            }
+            double want = 4.0 * over * (double)(1ull << b) + 4096;
+            g.ovf_bbits = cls == 128 ? 0 : ceil_log2(want / 2.0);
         }
     }
     return found;
@@ -526,6 +548,7 @@ void ka_destroy(ka_engine* e) {
         cudaSetDevice(d.id);
         for (int k = 0; k < NPIPE; k++) pipe_free(d.pipe[k]);
         if (d.table) cudaFree(d.table);
+        if (d.ovf) cudaFree(d.ovf);
         if (d.lut) cudaFree(d.lut);
     }
     delete e;
@@ -626,9 +649,16 @@ int ka_db_load(ka_engine* e, const uint8_t* kmers, const int32_t* role_ids, uint
     // 3. build one replica per device
     std::vector<uint64_t> nk(e->devs.size(), 0);
     std::vector<uint32_t> mp(e->devs.size(), 0);
-    int rc = for_each_device(e, [&](Device& d, int i) {
-        return build_table(e, d, geom, kmers, role_ids, n, &nk[i], &mp[i]);
-    });
+    int rc = KA_OK;
+    for (int attempt = 0; attempt < 6; attempt++) {
+        if ((uint64_t)geom.n_primary_slots + (2ull << geom.ovf_bbits) >= 0xfffffff0ull)
+            return fail(e, KA_ERR_TOO_BIG, "ka_db_load: table exceeds the 32-bit slot index of this build");
+        rc = for_each_device(e, [&](Device& d, int i) {
+            return build_table(e, d, geom, kmers, role_ids, n, &nk[i], &mp[i]);
+        });
+        if (rc != KA_ERR_TOO_BIG) break;
+        geom.ovf_bbits += 2;  // overflow table was too small for this key set: rebuild 4x larger
+    }
     if (rc) return rc;
     e->geom = geom;
     e->info.K = K;
@@ -636,7 +666,7 @@ int ka_db_load(ka_engine* e, const uint8_t* kmers, const int32_t* role_ids, uint
     e->info.n_lines = n;
     e->info.n_keys = nk[0];
     e->info.n_buckets = 1ull << geom.bbits;
-    e->info.table_bytes = 32ull << geom.bbits;
+    e->info.table_bytes = (32ull << geom.bbits) + (geom.cls == 128 ? 0 : (64ull << geom.ovf_bbits));
     e->info.max_probe = mp[0];
     e->info.slot_bits = (uint32_t)geom.cls;
     e->have_db = true;

@@ -32,6 +32,21 @@ namespace ka {
 // ------------------------------------------------------------------------------------
 // table lookup: C independent probes per thread, all loads in flight before the first use
 // ------------------------------------------------------------------------------------
+// Overflow table (cls 32/64): whole mixed keys, 2 x Slot128 per sector, linear chaining.
+__device__ __forceinline__ int ovf_lookup(const TableView& t, unsigned long long m, uint32_t& tok) {
+    const uint32_t mask = (1u << t.ovf_bbits) - 1;
+    uint32_t s = t.ovf_bbits ? (uint32_t)(mix64(m) >> (64 - t.ovf_bbits)) : 0u;
+    for (;;) {
+        uint4 a, b;
+        load_sector(t.ovf + 2 * (size_t)s, a, b);
+        const unsigned long long k0 = u64_of(a.x, a.y), k1 = u64_of(b.x, b.y);
+        if (k0 == m) { tok = t.n_primary_slots + 2 * s + 1; return (int)a.z; }
+        if (k1 == m) { tok = t.n_primary_slots + 2 * s + 2; return (int)b.z; }
+        if (k1 == 0) return -1;
+        s = (s + 1) & mask;
+    }
+}
+
 template <int CLS, int C>
 __device__ __forceinline__ void probe_batch(const TableView& tab, const unsigned long long (&rem)[C],
                                             uint32_t (&sec)[C], unsigned okmask, int (&role)[C],
@@ -53,25 +68,34 @@ __device__ __forceinline__ void probe_batch(const TableView& tab, const unsigned
             else if (full) pend |= 1u << i;
         }
     }
-    // Rare (load factor keeps full sectors below ~1 %): the home sector had no free slot, so
-    // the key may live in the next one.  All pending positions advance together.
-    const uint32_t sec_mask = (1u << tab.bbits) - 1;
-    while (pend) {
+    // Rare (the load factor keeps full sectors near 1 %): the home sector has no free slot
+    // and no match.
+    if (CLS == 128) {
+        // whole keys are stored: follow the chain, all pending positions advance together
+        const uint32_t sec_mask = (1u << tab.bbits) - 1;
+        while (pend) {
+#pragma unroll
+            for (int i = 0; i < C; i++)
+                if (pend & (1u << i)) {
+                    sec[i] = (sec[i] + 1) & sec_mask;
+                    load_sector(tab.sectors + 2 * (size_t)sec[i], a[i], b[i]);
+                }
+#pragma unroll
+            for (int i = 0; i < C; i++)
+                if (pend & (1u << i)) {
+                    uint32_t j = 0;
+                    bool full;
+                    const int r = match_sector<CLS>(tab, a[i], b[i], rem[i], j, full);
+                    if (r >= 0) { role[i] = r; tok[i] = sec[i] * S + j + 1; pend &= ~(1u << i); }
+                    else if (!full) pend &= ~(1u << i);
+                }
+        }
+    } else if (pend) {
+        // the key, if present, is in the overflow table under its whole mixed value
 #pragma unroll
         for (int i = 0; i < C; i++)
-            if (pend & (1u << i)) {
-                sec[i] = (sec[i] + 1) & sec_mask;
-                load_sector(tab.sectors + 2 * (size_t)sec[i], a[i], b[i]);
-            }
-#pragma unroll
-        for (int i = 0; i < C; i++)
-            if (pend & (1u << i)) {
-                uint32_t j = 0;
-                bool full;
-                const int r = match_sector<CLS>(tab, a[i], b[i], rem[i], j, full);
-                if (r >= 0) { role[i] = r; tok[i] = sec[i] * S + j + 1; pend &= ~(1u << i); }
-                else if (!full) pend &= ~(1u << i);
-            }
+            if (pend & (1u << i))
+                role[i] = ovf_lookup(tab, ((unsigned long long)sec[i] << tab.rem_bits) | rem[i], tok[i]);
     }
 }
 
@@ -468,14 +492,14 @@ __global__ void db_insert_kernel(TableView tab, const uint8_t* __restrict__ kmer
             key = (key << 5) | c;
         }
         if (bad) { atomicAdd(&errs[0], 1u); continue; }
-        if (CLS == 128 && roles[i] < 0) { atomicAdd(&errs[1], 1u); continue; }
+        if (roles[i] < 0) { atomicAdd(&errs[1], 1u); continue; }
         uint32_t sec;
         unsigned long long rem;
         locate(tab, key, sec, rem);
         uint32_t chain = 1;
         bool done = false;
-        while (!done) {
-            if (CLS == 128) {
+        if (CLS == 128) {
+            while (!done) {
                 Slot128* s = reinterpret_cast<Slot128*>(const_cast<uint4*>(tab.sectors)) + 2 * (size_t)sec;
                 const unsigned long long val = ((line_base + i) << 32) | (uint32_t)roles[i];
                 for (int h = 0; h < 2 && !done; h++) {
@@ -486,7 +510,10 @@ __global__ void db_insert_kernel(TableView tab, const uint8_t* __restrict__ kmer
                         done = true;
                     }
                 }
-            } else if (CLS == 64) {
+                if (!done) { sec = (sec + 1) & sec_mask; chain++; }
+            }
+        } else {
+            if (CLS == 64) {
                 unsigned long long* w = reinterpret_cast<unsigned long long*>(const_cast<uint4*>(tab.sectors)) + (size_t)sec * S;
                 const unsigned long long claim = rem | (1ull << tab.rem_bits);  // role field = placeholder
                 for (int h = 0; h < S && !done; h++) {
@@ -512,7 +539,27 @@ __global__ void db_insert_kernel(TableView tab, const uint8_t* __restrict__ kmer
                     }
                 }
             }
-            if (!done) { sec = (sec + 1) & sec_mask; chain++; }
+            if (!done) {
+                // home sector full: the whole mixed key goes to the overflow table
+                const unsigned long long m = ((unsigned long long)sec << tab.rem_bits) | rem;
+                const unsigned long long val = ((line_base + i) << 32) | (uint32_t)roles[i];
+                const uint32_t omask = (1u << tab.ovf_bbits) - 1;
+                uint32_t os = tab.ovf_bbits ? (uint32_t)(mix64(m) >> (64 - tab.ovf_bbits)) : 0u;
+                Slot128* ovf = reinterpret_cast<Slot128*>(const_cast<uint4*>(tab.ovf));
+                while (!done && chain <= omask + 2) {
+                    Slot128* s = ovf + 2 * (size_t)os;
+                    for (int h = 0; h < 2 && !done; h++) {
+                        unsigned long long old = atomicCAS(&s[h].key, 0ull, m);
+                        if (old == 0ull || old == m) {
+                            if (old == 0ull) atomicAdd(&counters[0], 1ull);
+                            atomicMax(&s[h].val, val);
+                            done = true;
+                        }
+                    }
+                    if (!done) { os = (os + 1) & omask; chain++; }
+                }
+                if (!done) atomicAdd(&errs[2], 1u);  // overflow table full: host rebuilds it larger
+            }
         }
         longest = max(longest, chain);
     }

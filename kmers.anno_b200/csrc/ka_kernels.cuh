@@ -51,6 +51,7 @@ cudaError_t launch_big(const AnnotParams& p, int grid, cudaStream_t st);
 cudaError_t launch_alphabet_scan(const uint8_t* bytes, unsigned long long n, uint32_t* bitmap8,
                                  cudaStream_t st);
 // errs[0] = k-mers with a byte outside the alphabet, errs[1] = negative role ids,
+// errs[2] = keys that found the overflow table full,
 // counters[0] = distinct keys stored, counters[1] = longest sector chain.
 // cls 32/64: `roles` is unused here, the winning db line of every slot is kept in line_of
 // (atomicMax) and launch_db_finalize writes the roles; cls 128 stores (line, role) itself.

@@ -157,6 +157,26 @@ def test_slot_class_selection(ka, oracle, K, max_role, want_bits):
     assert_same(got, oracle.OracleDb(kmers, roles, K).apply(res, off, 3), f"slot class K={K}")
 
 
+@pytest.mark.parametrize("slot_bits,lf", [(32, 0.9), (64, 0.9), (128, 0.9), (32, 0.4)])
+def test_overflow_heavy_table(ka, oracle, slot_bits, lf):
+    """Millions of keys at a high load factor: ~13 % of the keys leave their home sector.
+    Quotiented slots keep only a remainder, so those keys must live in the overflow table
+    under their whole mixed value — every distinct key must survive and resolve exactly."""
+    from kmers_anno_b200 import synth
+    fam = synth.Families(2000)
+    kmers, roles = fam.table(3_000_000, K=8)
+    res, off, _ = fam.batch(5, 2, n_prot=4500)
+    with ka.Engine([0]) as eng:
+        eng.set_option("slot_bits", slot_bits)
+        eng.set_option("load_factor", lf)
+        eng.db_load(kmers, roles, 8)
+        info = eng.db_info()
+        got = eng.annotate(res, off, 5)
+    assert info["n_keys"] == 3_000_000 and info["slot_bits"] == slot_bits
+    want = oracle.OracleDb(kmers, roles, 8, threads=8).apply(res, off, 5, threads=8)
+    assert_same(got, want, f"overflow-heavy table slot_bits={slot_bits} lf={lf}")
+
+
 def test_resident_path(ka, oracle):
     seqs, kmers, roles = ragged_case(44, n_seq=500, K=10, max_len=900)
     run_case(ka, oracle, seqs, kmers, roles, 10, min_hits=3, resident=True)
