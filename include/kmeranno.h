@@ -72,7 +72,7 @@ const char* ka_last_error(const ka_engine* e);
 
 /* Tunables, set before ka_db_load / ka_annotate.  Unknown name -> KA_ERR_INVALID.
  *   "load_factor"   table load factor in (0,0.9], default 0.4   (next ka_db_load)
- *   "tile_span"     residues of sequence starts per CTA tile, default 1536
+ *   "tile_span"     residues of sequence starts per CTA tile, default 2048
  *   "long_seq"      sequences longer than this use the long-sequence kernel, default 3072
  *   "slot_bits"     force the table slot width (32, 64, 128; 0 = smallest that fits, default)
  *   "variant"       tile kernel shape: 0 = 8 positions x 256 threads, 1 = 4 x 256 (default), 2 = 4 x 512

@@ -68,7 +68,7 @@ struct ka_engine {
     std::string err;
     // options
     double load_factor = 0.4;
-    uint32_t tile_span = 1536;
+    uint32_t tile_span = 2048;
     uint32_t long_seq = 3072;
     uint64_t chunk_residues = 32ull << 20;
     int l2_persist = 1;
