@@ -45,15 +45,15 @@ BYTES_PER_PROBE = 33.0  # 32-byte bucket sector + 1 residue byte (SURVEY.md §8d
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--genomes", type=int, default=1000, help="proteomes per GPU per step")
     ap.add_argument("--table-kmers", type=float, default=1e8)
     ap.add_argument("--roles", type=int, default=30000)
     ap.add_argument("--K", type=int, default=8)
     ap.add_argument("--min-hits", type=int, default=5)
-    ap.add_argument("--cpu-genomes", type=int, default=48, help="proteomes in the CPU-baseline sample")
+    ap.add_argument("--cpu-genomes", type=int, default=384, help="proteomes in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--option", action="append", default=[], help="engine option name=value")
@@ -70,6 +70,10 @@ class ClockSampler:
         self.idx = gpu_index
         self.lines = []
         self.proc = None
+        self.first = 0
+
+    def mark(self):
+        self.first = len(self.lines)
 
     def start(self):
         try:
@@ -94,7 +98,7 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for l in self.lines:
+        for l in self.lines[self.first:]:
             f = [x.strip() for x in l.split(",")]
             if len(f) < 8:
                 continue
@@ -243,18 +247,18 @@ def main():
     # ---- resident loop: value --------------------------------------------------------
     batch = eng.upload(res, off)
     probes = eng.stats()["probes"]
+    sampler = ClockSampler(local)
+    sampler.start()          # nvidia-smi needs ~1 s to produce its first line: start before the warm-up
     for _ in range(a.warmup):
         eng.annotate_resident(batch, a.min_hits)
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    sampler.mark()           # samples from here on are inside the timed regions
     k_ms, t_ms, launches = 0.0, 0.0, 0
     for _ in range(a.steps):
         eng.annotate_resident(batch, a.min_hits)   # synchronises its stream before returning
         st = eng.stats()
         k_ms += st["kernel_ms"]; t_ms += st["tile_kernel_ms"]; launches += st["kernel_launches"]
     barrier()
-    clocks = sampler.stop()
     dev_role, dev_hits, dev_flag = eng.download(batch)
     batch.free()
     step_ms = max_over_ranks(k_ms / a.steps)
@@ -281,6 +285,8 @@ def main():
                "probes_per_s": total_probes / (e2e_ms * 1e-3), "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": int(st["h2d_bytes"]), "d2h_bytes_per_step": int(st["d2h_bytes"]),
                "host_memory": "pinned (ka_host_alloc)", "matches_resident_results": same}
+
+    clocks = sampler.stop()
 
     # ---- roofline of the dominant kernel ----------------------------------------------
     peak, peak_src = measured_peak()
