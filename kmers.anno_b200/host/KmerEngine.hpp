@@ -1,0 +1,53 @@
+// KmerEngine.hpp — RAII C++ face of the C ABI (include/kmeranno.h), the C++ twin of the Java
+// `org.theseed.proteins.kmers.gpu.KmerEngine` class shown in INTEGRATION.md.  It replaces the
+// `Map<String,String> kmerRoleMap` field of ApplyKmerProcessor.java:53 and the peg loop :122-148.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "kmeranno.h"
+
+namespace theseed {
+
+class KmerEngineError : public std::runtime_error {
+public:
+    KmerEngineError(int code, const std::string& msg)
+        : std::runtime_error("kmeranno error " + std::to_string(code) + ": " + msg), code(code) {}
+    int code;
+};
+
+class KmerEngine {
+public:
+    explicit KmerEngine(const std::vector<int>& devices = {0}) {
+        int rc = ka_create(devices.data(), (int)devices.size(), &h_);
+        if (rc != KA_OK) throw KmerEngineError(rc, ka_last_error(nullptr));
+    }
+    ~KmerEngine() { ka_destroy(h_); }
+    KmerEngine(const KmerEngine&) = delete;
+    KmerEngine& operator=(const KmerEngine&) = delete;
+
+    void setOption(const std::string& name, double v) { check(ka_set_option(h_, name.c_str(), v)); }
+
+    /** kmers = n*K residue bytes back to back; roles = dense role ids (one per k-mer line). */
+    void loadDb(const std::vector<uint8_t>& kmers, const std::vector<int32_t>& roles, int K) {
+        check(ka_db_load(h_, kmers.data(), roles.data(), roles.size(), K));
+    }
+    ka_db_info dbInfo() { ka_db_info i; check(ka_db_get_info(h_, &i)); return i; }
+
+    /** Annotate a CSR batch; outputs are resized to the number of sequences. */
+    void annotate(const std::vector<uint8_t>& residues, const std::vector<uint64_t>& offsets, int minHits,
+                  std::vector<int32_t>& role, std::vector<int32_t>& hits, std::vector<uint8_t>& flag) {
+        size_t n = offsets.empty() ? 0 : offsets.size() - 1;
+        role.resize(n); hits.resize(n); flag.resize(n);
+        check(ka_annotate(h_, residues.data(), offsets.data(), n, minHits, role.data(), hits.data(), flag.data()));
+    }
+    ka_stats stats() { ka_stats s; check(ka_get_stats(h_, &s)); return s; }
+
+private:
+    void check(int rc) { if (rc != KA_OK) throw KmerEngineError(rc, ka_last_error(h_)); }
+    ka_engine* h_ = nullptr;
+};
+
+}  // namespace theseed
