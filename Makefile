@@ -12,8 +12,9 @@ LIB       := $(PKG)/libkmeranno.so
 SYNTH     := $(PKG)/libkasynth.so
 ORACLE    := oracle/libkaoracle.so
 CLI       := $(PKG)/bin/kmers-anno
+SELFTEST  := $(PKG)/bin/kmers-anno-selftest
 
-all: $(LIB) $(SYNTH) $(ORACLE)
+all: $(LIB) $(SYNTH) $(ORACLE) $(CLI) $(SELFTEST)
 
 $(LIB): $(CSRC)/ka_kernels.cu $(CSRC)/ka_engine.cu $(CSRC)/ka_common.cuh $(CSRC)/ka_kernels.cuh include/kmeranno.h
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/ka_kernels.cu $(CSRC)/ka_engine.cu 2> $(PKG)/ptxas.log || (cat $(PKG)/ptxas.log; exit 1)
@@ -27,9 +28,13 @@ $(ORACLE): oracle/ka_oracle.c oracle/ka_oracle_fast.c
 
 $(CLI): $(wildcard $(HOST)/*.cpp) $(wildcard $(HOST)/*.hpp) $(LIB)
 	mkdir -p $(PKG)/bin
-	$(CXX) -O2 -std=c++17 -Wall -Iinclude -o $@ $(filter-out $(HOST)/ka_synth.cpp,$(wildcard $(HOST)/*.cpp)) -L$(PKG) -lkmeranno -Wl,-rpath,'$$ORIGIN/..' -pthread
+	$(CXX) -O2 -std=c++17 -Wall -Iinclude -o $@ $(HOST)/App.cpp $(HOST)/ApplyKmerProcessor.cpp $(HOST)/Genome.cpp -L$(PKG) -lkmeranno -Wl,-rpath,'$$ORIGIN/..' -pthread
+
+$(SELFTEST): $(HOST)/selftest.cpp $(HOST)/Genome.cpp $(wildcard $(HOST)/*.hpp)
+	mkdir -p $(PKG)/bin
+	$(CXX) -O2 -std=c++17 -Wall -Iinclude -o $@ $(HOST)/selftest.cpp $(HOST)/Genome.cpp
 
 clean:
-	rm -f $(LIB) $(SYNTH) $(ORACLE) $(CLI) $(PKG)/ptxas.log
+	rm -f $(LIB) $(SYNTH) $(ORACLE) $(CLI) $(SELFTEST) $(PKG)/ptxas.log
 
 .PHONY: all clean

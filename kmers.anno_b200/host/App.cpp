@@ -1,0 +1,34 @@
+// App.cpp — command dispatch, mirror of proteins/kmers/anno/App.java:51-84 for the verbs of the
+// GPU hot path.  `apply` runs on the engine; the reference's other verbs are outside the
+// scope of this engine and are reported as such.
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "ApplyKmerProcessor.hpp"
+
+using namespace theseed;
+
+static const char* kCommands[][2] = {
+    {"apply", "apply a discriminating-kmer database to genomes (GPU engine)"},
+};
+
+static void showCommands() {
+    std::cerr << "Available commands:\n";
+    for (auto& c : kCommands) std::cerr << "  " << c[0] << "\t" << c[1] << "\n";
+}
+
+int main(int argc, char** argv) {
+    if (argc < 2) { showCommands(); return 1; }
+    std::string command = argv[1];
+    std::vector<std::string> newArgs(argv + 2, argv + argc);   // App.java:54-55
+    if (command == "apply") {
+        ApplyKmerProcessor processor;                          // App.java:62
+        if (!processor.parseCommand(newArgs)) return 1;        // App.java:81
+        return processor.run();                                // App.java:82
+    }
+    if (command == "-h" || command == "--help") { showCommands(); return 0; }
+    std::cerr << "Invalid command " << command << ".\n";       // App.java:76
+    showCommands();
+    return 1;
+}

@@ -1,0 +1,204 @@
+// ApplyKmerProcessor.cpp — see ApplyKmerProcessor.hpp.  Line references are to
+// /root/reference/src/main/java/org/theseed/proteins/kmers/anno/ApplyKmerProcessor.java.
+#include "ApplyKmerProcessor.hpp"
+
+#include <cstdlib>
+#include <fstream>
+#include <sys/stat.h>
+
+namespace theseed {
+
+namespace {
+bool isDirectory(const std::string& p) {
+    struct stat st;
+    return stat(p.c_str(), &st) == 0 && S_ISDIR(st.st_mode);
+}
+bool canRead(const std::string& p) {
+    std::ifstream in(p);
+    return (bool)in && !isDirectory(p);
+}
+int parseInt(const std::string& opt, const std::string& v) {
+    char* end = nullptr;
+    long x = std::strtol(v.c_str(), &end, 10);
+    if (v.empty() || *end) throw ParseFailureException("\"" + v + "\" is not a valid value for \"" + opt + "\"");
+    return (int)x;
+}
+}  // namespace
+
+void ApplyKmerProcessor::usage(std::ostream& os) {
+    os << "apply [--format VERIFY|APPLY] [-m|--min N] [--devices 0,1,..] [--batch N] kmerdb.tbl roles.in.use gtoDir\n"
+          " kmerdb.tbl     discriminating kmer database\n"
+          " roles.in.use   list of roles in use\n"
+          " gtoDir         input genome directory\n"
+          " --format       reporting format (default APPLY)\n"
+          " -m (--min)     minimum number of hits required to call a role (default 5)\n"
+          " --devices      CUDA devices to shard the sequences over (default 0)\n"
+          " --batch        genomes per GPU batch (default 64)\n";
+}
+
+void ApplyKmerProcessor::setDefaults() {
+    outputType_ = ApplyKmerReporter::Type::APPLY;  // :78
+    minHits_ = 5;                                  // :79
+    devices_ = {0};
+    batchGenomes_ = 64;
+}
+
+bool ApplyKmerProcessor::parseCommand(const std::vector<std::string>& args) {
+    setDefaults();
+    std::vector<std::string> pos;
+    try {
+        for (size_t i = 0; i < args.size(); i++) {
+            const std::string& a = args[i];
+            auto value = [&]() -> const std::string& {
+                if (i + 1 >= args.size()) throw ParseFailureException("Option \"" + a + "\" takes an operand");
+                return args[++i];
+            };
+            if (a == "-h" || a == "--help") { usage(log_); return false; }
+            else if (a == "--format") outputType_ = ApplyKmerReporter::parseType(value());
+            else if (a == "-m" || a == "--min") minHits_ = parseInt(a, value());
+            else if (a == "--batch") batchGenomes_ = parseInt(a, value());
+            else if (a == "--devices") {
+                devices_.clear();
+                const std::string& v = value();
+                size_t s = 0;
+                while (s <= v.size()) {
+                    size_t e = v.find(',', s);
+                    if (e == std::string::npos) e = v.size();
+                    devices_.push_back(parseInt(a, v.substr(s, e - s)));
+                    s = e + 1;
+                }
+            } else if (a.size() > 1 && a[0] == '-') throw ParseFailureException("\"" + a + "\" is not a valid option");
+            else pos.push_back(a);
+        }
+        if (pos.size() < 3) throw ParseFailureException("Argument \"" + std::string(pos.empty() ? "kmerdb.tbl" : pos.size() == 1 ? "roles.in.use" : "gtoDir") + "\" is required");
+        if (pos.size() > 3) throw ParseFailureException("Too many arguments: " + pos[3]);
+        kmerDbFile_ = pos[0]; goodRoleFile_ = pos[1]; inDir_ = pos[2];
+        validateParms();
+    } catch (const ParseFailureException& e) {
+        log_ << e.what() << "\n";
+        usage(log_);
+        return false;
+    } catch (const std::runtime_error& e) {   // FileNotFoundException / IOException / engine errors
+        log_ << e.what() << "\n";
+        return false;
+    }
+    return true;
+}
+
+void ApplyKmerProcessor::validateParms() {
+    // Verify the input directory.  (:85-86)
+    if (!isDirectory(inDir_)) throw FileNotFoundException("Input directory " + inDir_ + " not found or invalid.");
+    // Verify the kmer database.  (:88-89)
+    if (!canRead(kmerDbFile_)) throw FileNotFoundException("Kmer database file " + kmerDbFile_ + " not found or unreadable.");
+    // Verify the minimum number of hits.  (:91-92)
+    if (minHits_ < 1) throw ParseFailureException("Min-hits must be positive.");
+    if (batchGenomes_ < 1) throw ParseFailureException("Batch size must be positive.");
+    // Initialize the reporting.  (:94-98)
+    reporter_ = ApplyKmerReporter::create(outputType_, out_);
+    if (!canRead(goodRoleFile_)) throw FileNotFoundException("Roles-to-use file " + goodRoleFile_ + " not found or unreadable.");
+    log_ << "Reading roles to use from " << goodRoleFile_ << ".\n";
+    reporter_->initReport(goodRoleFile_);
+    // Load the kmer database.  (:100-110)  TabbedLineReader(file, 2): headerless, two columns.
+    log_ << "Loading kmer database from " << kmerDbFile_ << ".\n";
+    std::string text = readFile(kmerDbFile_);
+    std::vector<uint8_t> kmers;
+    std::vector<int32_t> roles;
+    std::unordered_map<std::string, int32_t> roleIds;
+    kmers.reserve(text.size() / 2);
+    roles.reserve(text.size() / 30);  // the reference's own sizing hint (:101)
+    size_t i = 0, lineNo = 0;
+    int K = -1;
+    while (i < text.size()) {
+        size_t e = text.find('\n', i);
+        if (e == std::string::npos) e = text.size();
+        size_t len = e - i;
+        if (len && text[i + len - 1] == '\r') len--;
+        lineNo++;
+        if (len) {
+            size_t tab = text.find('\t', i);
+            if (tab == std::string::npos || tab >= i + len)
+                throw IOException("Line " + std::to_string(lineNo) + " of " + kmerDbFile_ + " has fewer than 2 columns.");
+            size_t klen = tab - i;
+            size_t rend = text.find('\t', tab + 1);
+            if (rend == std::string::npos || rend > i + len) rend = i + len;
+            // HashMap<String,String> takes k-mers of any length; one packed table needs one K
+            if (K < 0) K = (int)klen;
+            else if ((int)klen != K)
+                throw IOException("Kmer database " + kmerDbFile_ + " mixes k-mer lengths (" + std::to_string(K) + " and " +
+                                  std::to_string(klen) + " at line " + std::to_string(lineNo) + "): not supported by the GPU engine.");
+            kmers.insert(kmers.end(), text.begin() + i, text.begin() + tab);
+            std::string role(text, tab + 1, rend - tab - 1);
+            auto it = roleIds.find(role);
+            if (it == roleIds.end()) {
+                it = roleIds.emplace(role, (int32_t)roleNames_.size()).first;
+                roleNames_.push_back(role);
+            }
+            roles.push_back(it->second);
+        }
+        i = e + 1;
+    }
+    if (roles.empty()) throw IOException("Kmer database " + kmerDbFile_ + " is empty.");
+    kmerSize_ = K;                               // KmerReference.setKmerSize(kmer.length()) (:108)
+    log_ << "Kmer size is " << kmerSize_ << ".\n";
+    engine_ = std::make_unique<KmerEngine>(devices_);   // throws if there is no usable GPU: no CPU fallback
+    engine_->loadDb(kmers, roles, K);
+    ka_db_info info = engine_->dbInfo();
+    log_ << info.n_keys << " distinct kmers for " << roleNames_.size() << " roles loaded on " << devices_.size()
+         << " device(s), " << info.table_bytes / (1024 * 1024) << " MiB table, " << info.slot_bits << "-bit slots.\n";
+}
+
+void ApplyKmerProcessor::flushBatch(std::vector<std::unique_ptr<Genome>>& genomes) {
+    if (genomes.empty()) return;
+    // CSR of every peg of the batch, genome by genome, peg order preserved (:122)
+    std::vector<uint8_t> residues;
+    std::vector<uint64_t> offsets{0};
+    std::vector<std::vector<const Feature*>> pegs(genomes.size());
+    for (size_t g = 0; g < genomes.size(); g++) {
+        pegs[g] = genomes[g]->getPegs();
+        for (const Feature* f : pegs[g]) {
+            const std::string& prot = f->getProteinTranslation();
+            residues.insert(residues.end(), prot.begin(), prot.end());
+            offsets.push_back(residues.size());
+        }
+    }
+    std::vector<int32_t> role, hits;
+    std::vector<uint8_t> flag;
+    engine_->annotate(residues, offsets, minHits_, role, hits, flag);   // the peg loop :122-148 for the whole batch
+    size_t s = 0;
+    for (size_t g = 0; g < genomes.size(); g++) {
+        log_ << "Processing genome " << genomes[g]->toString() << ".\n";   // :119
+        reporter_->openGenome(*genomes[g]);                               // :120
+        for (const Feature* f : pegs[g]) {
+            if (flag[s] == KA_FLAG_CALLED)                                // :146
+                reporter_->recordFeature(*f, roleNames_[(size_t)role[s]], hits[s]);  // :147
+            s++;
+        }
+        reporter_->closeGenome();                                         // :150
+    }
+    genomes.clear();
+}
+
+void ApplyKmerProcessor::runCommand() {
+    GenomeDirectory genomes(inDir_);                                      // :116
+    log_ << genomes.size() << " genomes found in input directory.\n";     // :117
+    std::vector<std::unique_ptr<Genome>> batch;
+    for (const std::string& file : genomes.files()) {                     // :118
+        batch.push_back(std::make_unique<Genome>(file));
+        if ((int)batch.size() >= batchGenomes_) flushBatch(batch);
+    }
+    flushBatch(batch);
+    reporter_->closeReport();                                             // :153
+    reporter_->close();                                                   // :154
+}
+
+int ApplyKmerProcessor::run() {
+    try {
+        runCommand();
+        return 0;
+    } catch (const std::exception& e) {
+        log_ << "EXECUTION ERROR: " << e.what() << "\n";
+        return 1;
+    }
+}
+
+}  // namespace theseed

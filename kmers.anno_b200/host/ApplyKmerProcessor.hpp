@@ -1,0 +1,57 @@
+// ApplyKmerProcessor.hpp — C++ mirror of proteins/kmers/anno/ApplyKmerProcessor.java
+// (`apply` command), same lifecycle (setDefaults -> validateParms -> runCommand), same
+// options and positional parameters, same error behaviour; the peg loop (:122-148) runs on
+// the GPU engine and the reporter calls are replayed in the original peg order.
+//
+//   apply [--format VERIFY|APPLY] [-m|--min N] kmerdb.tbl roles.in.use gtoDir
+// added knobs (ordinary options, as SURVEY §5 asks): --devices 0,1,..  --batch genomes
+#pragma once
+#include <iostream>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "ApplyKmerReporter.hpp"
+#include "Genome.hpp"
+#include "KmerEngine.hpp"
+
+namespace theseed {
+
+class ApplyKmerProcessor {
+public:
+    explicit ApplyKmerProcessor(std::ostream& out = std::cout, std::ostream& log = std::cerr)
+        : out_(out), log_(log) {}
+
+    /** args4j-style parse; returns false (after printing usage) on -h or a bad command line. */
+    bool parseCommand(const std::vector<std::string>& args);
+    /** runCommand with the reference's exception -> message behaviour; returns the exit code. */
+    int run();
+
+    // reference lifecycle, public for the tests
+    void setDefaults();                       // ApplyKmerProcessor.java:76-80
+    void validateParms();                     // :82-111
+    void runCommand();                        // :113-155
+
+    int getKmerSize() const { return kmerSize_; }
+    static void usage(std::ostream& os);
+
+private:
+    void flushBatch(std::vector<std::unique_ptr<Genome>>& genomes);
+
+    std::ostream& out_;
+    std::ostream& log_;
+    // command-line options (:58-74)
+    ApplyKmerReporter::Type outputType_ = ApplyKmerReporter::Type::APPLY;
+    int minHits_ = 5;
+    std::string kmerDbFile_, goodRoleFile_, inDir_;
+    std::vector<int> devices_{0};
+    int batchGenomes_ = 64;
+    // state
+    std::unique_ptr<ApplyKmerReporter> reporter_;
+    std::unique_ptr<KmerEngine> engine_;       // replaces Map<String,String> kmerRoleMap (:53)
+    std::vector<std::string> roleNames_;       // dense role id -> role string
+    int kmerSize_ = 0;
+};
+
+}  // namespace theseed

@@ -18,7 +18,9 @@ def _native_built():
     nvcc cross-compiles)."""
     need = [os.path.join(ROOT, "kmers.anno_b200", "libkmeranno.so"),
             os.path.join(ROOT, "kmers.anno_b200", "libkasynth.so"),
-            os.path.join(ROOT, "oracle", "libkaoracle.so")]
+            os.path.join(ROOT, "oracle", "libkaoracle.so"),
+            os.path.join(ROOT, "kmers.anno_b200", "bin", "kmers-anno"),
+            os.path.join(ROOT, "kmers.anno_b200", "bin", "kmers-anno-selftest")]
     if not all(os.path.exists(p) for p in need):
         import __graft_entry__
         __graft_entry__.build()
