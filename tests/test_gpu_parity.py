@@ -230,6 +230,33 @@ def test_skewed_lengths_c4_shape(ka, oracle, mode, K):
     assert (got[2] == 2).sum() > 0 and (got[2] == 1).sum() > 0
 
 
+def test_multi_device_engine(ka, oracle):
+    """One engine over every visible GPU: the batch is cut into residue-balanced ranges, one
+    per device, with a replicated table; the gathered result must equal the oracle's."""
+    n_dev = 0
+    for n in (8, 4, 2):
+        try:
+            ka.Engine(list(range(n))).close()
+            n_dev = n
+            break
+        except ka.KmerAnnoError:
+            continue
+    if n_dev < 2:
+        pytest.skip("needs at least 2 GPUs")
+    from kmers_anno_b200 import synth
+    fam = synth.Families(300)
+    kmers, roles = fam.table(300000, K=8)
+    res, off, _ = fam.batch(2, 3, n_prot=2000)
+    with ka.Engine(list(range(n_dev))) as eng:
+        eng.set_option("chunk_residues", 200000)      # several chunks per device
+        eng.db_load(kmers, roles, 8)
+        got = eng.annotate(res, off, 5)
+        st = eng.stats()
+    want = oracle.OracleDb(kmers, roles, 8).apply(res, off, 5, threads=4)
+    assert_same(got, want, f"{n_dev}-device engine")
+    assert st["sequences"] == off.shape[0] - 1 and st["kernel_launches"] >= 2 * n_dev
+
+
 def test_error_paths(ka):
     with ka.Engine([0]) as eng:
         with pytest.raises(ka.KmerAnnoError) as e:
