@@ -49,7 +49,7 @@ struct Device {
     size_t smem_set = 0;
     // per-call accounting
     double kernel_ms = 0, tile_ms = 0;
-    uint64_t launches = 0, h2d = 0, d2h = 0;
+    uint64_t launches = 0, h2d = 0, d2h = 0, probes = 0;
     int err = KA_OK;
     std::string errmsg;
 };
@@ -280,7 +280,7 @@ int annotate_range(ka_engine* e, Device& d, const uint8_t* residues, const uint6
                    uint64_t s_begin, uint64_t s_end, int32_t min_hits, int32_t* out_role,
                    int32_t* out_hits, uint8_t* out_flag) {
     DCK(d, cudaSetDevice(d.id));
-    d.kernel_ms = d.tile_ms = 0; d.launches = 0; d.h2d = d.d2h = 0;
+    d.kernel_ms = d.tile_ms = 0; d.launches = 0; d.h2d = d.d2h = 0; d.probes = 0;
     int slot = 0;
     uint64_t cs = s_begin;
     while (cs < s_end) {
@@ -298,6 +298,7 @@ int annotate_range(ka_engine* e, Device& d, const uint8_t* residues, const uint6
             d.err = KA_ERR_TOO_BIG; d.errmsg = "a single sequence exceeds 2^31 residues";
             return d.err;
         }
+        d.probes += sh.probes;
         Pipe& p = d.pipe[slot];
         if (p.busy) {
             DCK(d, cudaEventSynchronize(p.done));
@@ -709,7 +710,7 @@ int ka_annotate(ka_engine* e, const uint8_t* residues, const uint64_t* offsets, 
         cut[i] = std::min<uint64_t>(std::max<uint64_t>(c, cut[i - 1]), N);
     }
     int rc = for_each_device(e, [&](Device& d, int i) {
-        if (cut[i] == cut[i + 1]) { d.kernel_ms = d.tile_ms = 0; d.launches = d.h2d = d.d2h = 0; return (int)KA_OK; }
+        if (cut[i] == cut[i + 1]) { d.kernel_ms = d.tile_ms = 0; d.launches = d.h2d = d.d2h = d.probes = 0; return (int)KA_OK; }
         return annotate_range(e, d, residues, offsets, cut[i], cut[i + 1], min_hits, out_role, out_hits, out_flag);
     });
     if (rc) {
@@ -719,12 +720,9 @@ int ka_annotate(ka_engine* e, const uint8_t* residues, const uint64_t* offsets, 
     ka_stats& s = e->stats;
     s.sequences = N;
     s.residues = total;
-    for (uint64_t i = 0; i < N; i++) {
-        uint64_t L = offsets[i + 1] - offsets[i];
-        if (L >= (uint64_t)e->info.K) s.probes += L - e->info.K + 1;
-    }
     for (Device& d : e->devs) {
         s.kernel_launches += d.launches;
+        s.probes += d.probes;
         s.h2d_bytes += d.h2d;
         s.d2h_bytes += d.d2h;
         s.kernel_ms = std::max(s.kernel_ms, d.kernel_ms);

@@ -1,0 +1,26 @@
+#!/usr/bin/env python
+"""End-to-end ka_annotate timing (pinned host buffers) vs chunk size, plus raw H2D rate."""
+import os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import kmers_anno_b200 as ka
+from kmers_anno_b200 import synth
+from kmers_anno_b200.engine import pinned_array
+genomes = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
+fam = synth.Families(30000)
+kmers, roles = fam.table(int(1e8), K=8)
+res, off, _ = fam.batch(0, genomes, n_prot=4500, alloc=pinned_array)
+n = off.shape[0] - 1
+out = (pinned_array(n, np.int32), pinned_array(n, np.int32), pinned_array(n, np.uint8))
+eng = ka.Engine([0]); eng.db_load(kmers, roles, 8)
+t = time.perf_counter(); b = eng.upload(res, off); dt = time.perf_counter() - t
+print(f"upload (sync cudaMemcpy from pinned) {len(res)/dt/1e9:.1f} GB/s", flush=True)
+eng.annotate_resident(b, 5); eng.annotate_resident(b, 5); print("resident kernel ms", eng.stats()["kernel_ms"], flush=True); b.free()
+for chunk in (4 << 20, 16 << 20, 32 << 20, 64 << 20, 256 << 20):
+    eng.set_option("chunk_residues", chunk)
+    best = 1e9
+    for r in range(4):
+        t = time.perf_counter(); eng.annotate(res, off, 5, out=out); dt = (time.perf_counter() - t) * 1e3
+        if r: best = min(best, dt)
+    st = eng.stats()
+    print(f"chunk {chunk>>20:4d} Mi: e2e {best:.2f} ms  ({n/best/1e3:.1f} M seq/s)  kernel_sum {st['kernel_ms']:.2f} ms  wall_inside {st['wall_ms']:.2f}", flush=True)
