@@ -176,8 +176,8 @@ size_t tile_smem_bytes(uint32_t ext_max, uint32_t* res_bytes_out) {
            4 * (2 * (size_t)ext_max + 4);
 }
 
-template <int CLS, int C, int THREADS>
-__global__ void __launch_bounds__(THREADS, (C == 4 && THREADS == 256) ? 3 : 2) tile_kernel(AnnotParams p) {
+template <int CLS, int C, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar;
 
@@ -328,9 +328,10 @@ template <typename F>
 static auto with_tile_kernel(int cls, int variant, F f) {
 #define KA_VARIANTS(CLS)                                             \
     switch (variant) {                                               \
-        case 1: return f(tile_kernel<CLS, 4, 256>, 256);             \
-        case 2: return f(tile_kernel<CLS, 4, 512>, 512);             \
-        default: return f(tile_kernel<CLS, 8, 256>, 256);            \
+        case 1: return f(tile_kernel<CLS, 4, 256, 3>, 256);          \
+        case 2: return f(tile_kernel<CLS, 4, 512, 2>, 512);          \
+        case 3: return f(tile_kernel<CLS, 4, 256, 4>, 256);          \
+        default: return f(tile_kernel<CLS, 8, 256, 2>, 256);         \
     }
     if (cls == 32) { KA_VARIANTS(32) }
     if (cls == 64) { KA_VARIANTS(64) }
@@ -340,7 +341,10 @@ static auto with_tile_kernel(int cls, int variant, F f) {
 
 cudaError_t tile_kernel_set_smem(int cls, int variant, size_t bytes) {
     return with_tile_kernel(cls, variant, [&](auto kern, int) {
-        return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (ce != cudaSuccess) return ce;
+        // ask for the largest shared-memory carve-out so that as many CTAs as the registers allow fit
+        return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     });
 }
 
