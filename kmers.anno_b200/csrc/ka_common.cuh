@@ -34,6 +34,7 @@ struct Slot128 {
 
 struct TableView {
     const uint4* sectors;         // 2^bbits sectors, 2 uint4 each
+    const uint16_t* sig;          // per-sector 16-bit Bloom signature (NULL = no filter), see sig_bits()
     const uint4* ovf;             // overflow table (cls 32/64): 2^ovf_bbits sectors of 2 Slot128
     uint32_t ovf_bbits;
     uint32_t n_primary_slots;     // slots of the primary table (de-dup tokens of overflow entries start here)
@@ -82,6 +83,15 @@ __host__ __device__ __forceinline__ void locate(const TableView& t, unsigned lon
     }
 }
 
+// Presence filter: every key sets two of the 16 bits of its HOME sector's signature.  The
+// 2-byte signatures of all sectors (64 MB for 2^25 sectors) stay L2 resident (persisting
+// access-policy window), so a probe whose bits are not both set is answered "absent" without
+// touching HBM — exact, a Bloom signature has no false negatives.
+__host__ __device__ __forceinline__ uint32_t sig_bits(unsigned long long rem) {
+    uint32_t h = ((uint32_t)rem ^ (uint32_t)(rem >> 32)) * 0x9E3779B1u;
+    return (1u << (h >> 28)) | (1u << ((h >> 24) & 15u));
+}
+
 // One 32-byte sector with a single 256-bit load (LDG.E.256 on sm_100a), read-only path, no
 // L1 allocation: a sector is touched once per probe and must not evict the residue tile.
 __device__ __forceinline__ void load_sector(const uint4* p, uint4& s0, uint4& s1) {
@@ -127,6 +137,10 @@ __device__ __forceinline__ int match_sector(const TableView& t, const uint4& a, 
 
 template <int CLS>
 __host__ __device__ constexpr int slots_per_sector() { return CLS == 32 ? 8 : (CLS == 64 ? 4 : 2); }
+
+// register type of a stored remainder: 32 bits are enough for 32-bit slots
+template <int CLS> struct rem_type { typedef unsigned long long type; };
+template <> struct rem_type<32> { typedef uint32_t type; };
 
 // ---- mbarrier + 1-D bulk async copy (TMA engine, UBLKCP) -------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -44,6 +44,7 @@ struct Device {
     int sm_count = 148;
     uint4* table = nullptr;
     uint4* ovf = nullptr;     // overflow table (cls 32/64)
+    uint16_t* sig = nullptr;  // per-sector presence signatures
     uint8_t* lut = nullptr;
     Pipe pipe[NPIPE];
     size_t smem_set = 0;
@@ -75,6 +76,8 @@ struct ka_engine {
     int warp_dedup = 0;
     int variant = 1;
     int slot_bits = 0;  // 0 = choose automatically
+    int filter = -1;    // -1 = on for tables of at least 2^20 sectors, 0 = off, 1 = on
+    bool have_sig = false;
     // db
     bool have_db = false;
     ka_db_info info{};
@@ -211,6 +214,7 @@ void fill_params(ka_engine* e, Device& d, Pipe& p, uint64_t base, uint64_t n_res
     ap.tab = e->geom;
     ap.tab.sectors = d.table;
     ap.tab.ovf = d.ovf;
+    ap.tab.sig = d.sig;
     ap.lut = d.lut;
     ap.min_hits = min_hits;
     ap.out_role = p.role;
@@ -265,8 +269,12 @@ void set_l2_window(ka_engine* e, Device& d, cudaStream_t st) {
     cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist);
     cudaStreamAttrValue v;
     memset(&v, 0, sizeof v);
-    size_t win = std::min<size_t>(e->info.table_bytes, (size_t)prop.accessPolicyMaxWindowSize);
-    v.accessPolicyWindow.base_ptr = d.table;
+    // with the presence filter the signatures are the hot, reusable data: pin them; otherwise
+    // pin as much of the table as the persisting carve-out holds
+    const bool sig = d.sig != nullptr;
+    size_t span = sig ? ((size_t)2 << e->geom.bbits) : (size_t)e->info.table_bytes;
+    size_t win = std::min<size_t>(span, (size_t)prop.accessPolicyMaxWindowSize);
+    v.accessPolicyWindow.base_ptr = sig ? (void*)d.sig : (void*)d.table;
     v.accessPolicyWindow.num_bytes = win;
     v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)persist / (double)win);
     v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
@@ -349,6 +357,7 @@ int build_table(ka_engine* e, Device& d, const TableView& geom, const uint8_t* k
     DCK(d, cudaSetDevice(d.id));
     if (d.table) { cudaFree(d.table); d.table = nullptr; }
     if (d.ovf) { cudaFree(d.ovf); d.ovf = nullptr; }
+    if (d.sig) { cudaFree(d.sig); d.sig = nullptr; }
     const int K = geom.K;
     const size_t n_sectors = (size_t)1 << geom.bbits;
     const size_t bytes = n_sectors * 32;
@@ -360,10 +369,17 @@ int build_table(ka_engine* e, Device& d, const TableView& geom, const uint8_t* k
         ce = cudaMalloc((void**)&d.ovf, ovf_bytes);
         if (ce != cudaSuccess) { d.ovf = nullptr; return dev_fail(d, KA_ERR_OOM, "overflow table", ce); }
     }
+    const bool use_sig = e->filter == 1 || (e->filter < 0 && geom.bbits >= 20);
+    const size_t sig_bytes = use_sig ? (n_sectors * 2 + 4) : 0;
+    if (sig_bytes) {
+        ce = cudaMalloc((void**)&d.sig, sig_bytes);
+        if (ce != cudaSuccess) { d.sig = nullptr; return dev_fail(d, KA_ERR_OOM, "signature array", ce); }
+    }
     cudaStream_t st = d.pipe[0].st;
     TableView tab = geom;
     tab.sectors = d.table;
     tab.ovf = d.ovf;
+    tab.sig = d.sig;
     const uint64_t CH = 16ull << 20;  // k-mers per upload
     uint8_t* dk = nullptr; int32_t* dr = nullptr; uint32_t* line_of = nullptr;
     unsigned long long* dc = nullptr; uint32_t* de = nullptr;
@@ -387,6 +403,7 @@ int build_table(ka_engine* e, Device& d, const TableView& geom, const uint8_t* k
     };
     step(cudaMemsetAsync(d.table, 0, bytes, st), "memset table");
     if (ovf_bytes) step(cudaMemsetAsync(d.ovf, 0, ovf_bytes, st), "memset overflow table");
+    if (sig_bytes) step(cudaMemsetAsync(d.sig, 0, sig_bytes, st), "memset signatures");
     if (packed) step(cudaMemsetAsync(line_of, 0, n_slots * 4, st), "memset line_of");
     step(cudaMemcpyAsync(d.lut, e->lut, 256, cudaMemcpyHostToDevice, st), "H2D lut");
     step(cudaMemsetAsync(dc, 0, 16, st), "memset counters");
@@ -452,6 +469,7 @@ bool choose_geometry(uint64_t n, int K, int32_t max_role, double lf, int force_c
             g.rem_mask = rem_bits ? ((1ull << rem_bits) - 1) : 0;
             g.sectors = nullptr;
             g.ovf = nullptr;
+            g.sig = nullptr;
             g.n_primary_slots = (uint32_t)((uint64_t)S << b);
             // expected keys beyond S per sector under Poisson(n / sectors) arrivals
             double lam = (double)n / (double)(1ull << b), pk = std::exp(-lam), over = 0;
@@ -550,6 +568,7 @@ void ka_destroy(ka_engine* e) {
         for (int k = 0; k < NPIPE; k++) pipe_free(d.pipe[k]);
         if (d.table) cudaFree(d.table);
         if (d.ovf) cudaFree(d.ovf);
+        if (d.sig) cudaFree(d.sig);
         if (d.lut) cudaFree(d.lut);
     }
     delete e;
@@ -579,6 +598,8 @@ int ka_set_option(ka_engine* e, const char* name, double v) {
         e->l2_persist = v != 0;
     } else if (n == "warp_dedup") {
         e->warp_dedup = v != 0;
+    } else if (n == "filter") {
+        e->filter = v < 0 ? -1 : (v != 0);
     } else if (n == "slot_bits") {
         if (v != 0 && v != 32 && v != 64 && v != 128) return fail(e, KA_ERR_INVALID, "slot_bits must be 0, 32, 64 or 128");
         e->slot_bits = (int)v;
@@ -668,6 +689,7 @@ int ka_db_load(ka_engine* e, const uint8_t* kmers, const int32_t* role_ids, uint
     e->info.n_keys = nk[0];
     e->info.n_buckets = 1ull << geom.bbits;
     e->info.table_bytes = (32ull << geom.bbits) + (geom.cls == 128 ? 0 : (64ull << geom.ovf_bbits));
+    e->have_sig = e->devs[0].sig != nullptr;
     e->info.max_probe = mp[0];
     e->info.slot_bits = (uint32_t)geom.cls;
     e->have_db = true;

@@ -47,11 +47,25 @@ __device__ __forceinline__ int ovf_lookup(const TableView& t, unsigned long long
     }
 }
 
+// On return role[i] >= 0 marks a hit and sec[i] holds its de-dup token (global slot index + 1).
 template <int CLS, int C>
-__device__ __forceinline__ void probe_batch(const TableView& tab, const unsigned long long (&rem)[C],
-                                            uint32_t (&sec)[C], unsigned okmask, int (&role)[C],
-                                            uint32_t (&tok)[C]) {
+__device__ __forceinline__ void probe_batch(const TableView& tab,
+                                            const typename rem_type<CLS>::type (&rem)[C],
+                                            uint32_t (&sec)[C], unsigned okmask, int (&role)[C]) {
     constexpr int S = slots_per_sector<CLS>();
+    if (tab.sig) {
+        // stage 0: L2-resident signatures; only probes whose two bits are set go to HBM
+        uint32_t sg[C];
+#pragma unroll
+        for (int i = 0; i < C; i++)
+            if (okmask & (1u << i)) sg[i] = __ldg(tab.sig + sec[i]);
+#pragma unroll
+        for (int i = 0; i < C; i++)
+            if (okmask & (1u << i)) {
+                const uint32_t need = sig_bits(rem[i]);
+                if ((sg[i] & need) != need) okmask &= ~(1u << i);
+            }
+    }
     uint4 a[C], b[C];
 #pragma unroll
     for (int i = 0; i < C; i++)
@@ -64,7 +78,7 @@ __device__ __forceinline__ void probe_batch(const TableView& tab, const unsigned
             uint32_t j = 0;
             bool full;
             const int r = match_sector<CLS>(tab, a[i], b[i], rem[i], j, full);
-            if (r >= 0) { role[i] = r; tok[i] = sec[i] * S + j + 1; }
+            if (r >= 0) { role[i] = r; sec[i] = sec[i] * S + j + 1; }
             else if (full) pend |= 1u << i;
         }
     }
@@ -86,7 +100,7 @@ __device__ __forceinline__ void probe_batch(const TableView& tab, const unsigned
                     uint32_t j = 0;
                     bool full;
                     const int r = match_sector<CLS>(tab, a[i], b[i], rem[i], j, full);
-                    if (r >= 0) { role[i] = r; tok[i] = sec[i] * S + j + 1; pend &= ~(1u << i); }
+                    if (r >= 0) { role[i] = r; sec[i] = sec[i] * S + j + 1; pend &= ~(1u << i); }
                     else if (!full) pend &= ~(1u << i);
                 }
         }
@@ -95,7 +109,7 @@ __device__ __forceinline__ void probe_batch(const TableView& tab, const unsigned
 #pragma unroll
         for (int i = 0; i < C; i++)
             if (pend & (1u << i))
-                role[i] = ovf_lookup(tab, ((unsigned long long)sec[i] << tab.rem_bits) | rem[i], tok[i]);
+                role[i] = ovf_lookup(tab, ((unsigned long long)sec[i] << tab.rem_bits) | rem[i], sec[i]);
     }
 }
 
@@ -261,9 +275,11 @@ __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
                 }
                 r += K - 1;
 
-                unsigned long long rem[C];
+                typename rem_type<CLS>::type rem[C];
                 uint32_t sec[C];
-                int seqi[C];
+                uint32_t seqpack = 0;   // sequence index (< MAX_TILE_SEQ = 256) of each position, one byte each
+                static_assert(C <= 4 || MAX_TILE_SEQ <= 256, "");
+                uint32_t seqpack2 = 0;
                 unsigned okmask = 0;
 #pragma unroll
                 for (int i = 0; i < C; i++) {
@@ -275,22 +291,24 @@ __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
                         while (si < (int)ns && pos >= s_off[si + 1]) si++;
                         const bool ok = (si >= 0) && (si < (int)ns) && (pos + K <= s_off[si + 1]) &&
                                         (vr >= K);
-                        seqi[i] = si;
                         if (ok) {
                             okmask |= 1u << i;
-                            locate(tab, key & tab.key_mask, sec[i], rem[i]);
+                            if (i < 4) seqpack |= (uint32_t)si << (8 * (i & 3));
+                            else seqpack2 |= (uint32_t)si << (8 * (i & 3));
+                            unsigned long long rm;
+                            locate(tab, key & tab.key_mask, sec[i], rm);
+                            rem[i] = (typename rem_type<CLS>::type)rm;
                         }
                     }
                 }
                 int role[C];
-                uint32_t tok[C];
-                probe_batch<CLS, C>(tab, rem, sec, okmask, role, tok);
+                probe_batch<CLS, C>(tab, rem, sec, okmask, role);
 #pragma unroll
                 for (int i = 0; i < C; i++) {
                     if ((okmask & (1u << i)) && role[i] >= 0) {
-                        const int q = seqi[i];
+                        const int q = (int)(((i < 4 ? seqpack : seqpack2) >> (8 * (i & 3))) & 0xffu);
                         const uint32_t a = s_off[q], b = s_off[q + 1];
-                        if (token_insert(s_tok + 2 * (a - lead), 2 * (b - a), tok[i])) {
+                        if (token_insert(s_tok + 2 * (a - lead), 2 * (b - a), sec[i])) {
                             if (q != cur) {
                                 if (cur >= 0 && cnt > 0) {
                                     atomicAdd(&s_cnt[cur], cnt);
@@ -394,7 +412,7 @@ __global__ void __launch_bounds__(256) big_kernel(AnnotParams p) {
                 vr = c ? vr + 1 : 0;
             }
             r += K - 1;
-            unsigned long long rem[C];
+            typename rem_type<CLS>::type rem[C];
             uint32_t sec[C];
             unsigned okmask = 0;
 #pragma unroll
@@ -405,16 +423,17 @@ __global__ void __launch_bounds__(256) big_kernel(AnnotParams p) {
                     vr = c ? vr + 1 : 0;
                     if (vr >= K) {
                         okmask |= 1u << i;
-                        locate(tab, key & tab.key_mask, sec[i], rem[i]);
+                        unsigned long long rm;
+                        locate(tab, key & tab.key_mask, sec[i], rm);
+                        rem[i] = (typename rem_type<CLS>::type)rm;
                     }
                 }
             }
             int role[C];
-            uint32_t tok[C];
-            probe_batch<CLS, C>(tab, rem, sec, okmask, role, tok);
+            probe_batch<CLS, C>(tab, rem, sec, okmask, role);
 #pragma unroll
             for (int i = 0; i < C; i++) {
-                if ((okmask & (1u << i)) && role[i] >= 0 && token_insert(region, nreg, tok[i])) {
+                if ((okmask & (1u << i)) && role[i] >= 0 && token_insert(region, nreg, sec[i])) {
                     cnt++;
                     mn = min(mn, role[i]);
                     mx = max(mx, role[i]);
@@ -500,6 +519,11 @@ __global__ void db_insert_kernel(TableView tab, const uint8_t* __restrict__ kmer
         uint32_t sec;
         unsigned long long rem;
         locate(tab, key, sec, rem);
+        if (tab.sig) {
+            uint32_t* word = reinterpret_cast<uint32_t*>(const_cast<uint16_t*>(tab.sig)) + (sec >> 1);
+            const uint32_t bits = sig_bits(rem) << ((sec & 1u) * 16);
+            if ((*reinterpret_cast<volatile uint32_t*>(word) & bits) != bits) atomicOr(word, bits);
+        }
         uint32_t chain = 1;
         bool done = false;
         if (CLS == 128) {

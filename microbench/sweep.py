@@ -24,15 +24,17 @@ ref = None
 last_db = None
 eng = None
 for cfg in configs:
-    db_key = cfg.get("load_factor", "")
+    DBOPTS = ("load_factor", "filter", "slot_bits")
+    db_key = tuple(cfg.get(k, "") for k in DBOPTS)
     if eng is None or db_key != last_db:
         if eng: eng.close()
         eng = ka.Engine([0])
-        if "load_factor" in cfg: eng.set_option("load_factor", float(cfg["load_factor"]))
+        for k in DBOPTS:
+            if k in cfg: eng.set_option(k, float(cfg[k]))
         t = time.time(); eng.db_load(kmers, roles, a.K); info = eng.db_info(); t_load = time.time() - t
         last_db = db_key
     for k, v in cfg.items():
-        if k != "load_factor": eng.set_option(k, float(v))
+        if k not in DBOPTS: eng.set_option(k, float(v))
     b = eng.upload(res, off)
     probes = eng.stats()["probes"]
     best = 1e9
