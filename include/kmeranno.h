@@ -74,8 +74,8 @@ const char* ka_last_error(const ka_engine* e);
  *   "load_factor"   table load factor in (0,0.9], default 0.4   (next ka_db_load)
  *   "tile_span"     residues of sequence starts per CTA tile, default 2048
  *   "long_seq"      sequences longer than this use the long-sequence kernel, default 3072
- *   "filter"        per-sector presence signatures kept in L2 (1 on, 0 off, -1 = on for tables of
- *                   at least 2^20 sectors; default -1)   (next ka_db_load)
+ *   "filter"        per-sector presence signatures kept in L2 (1 on, 0 off (default), -1 = on for
+ *                   tables of at least 2^20 sectors)   (next ka_db_load)
  *   "slot_bits"     force the table slot width (32, 64, 128; 0 = smallest that fits, default)
  *   "variant"       tile kernel shape: 0 = 8 positions x 256 threads, 1 = 4 x 256 (default), 2 = 4 x 512
  *   "chunk_residues" residues per pipelined H2D chunk, default 32 Mi

@@ -76,7 +76,8 @@ struct ka_engine {
     int warp_dedup = 0;
     int variant = 1;
     int slot_bits = 0;  // 0 = choose automatically
-    int filter = -1;    // -1 = on for tables of at least 2^20 sectors, 0 = off, 1 = on
+    int filter = 0;     // 1 = per-sector presence signatures in front of the table (measured slower
+                        // in the fused kernel: 40 vs 46 G probes/s, profiles/r01_summary.md), -1 = auto
     bool have_sig = false;
     // db
     bool have_db = false;

@@ -138,6 +138,9 @@ def test_long_sequences_use_big_kernel(ka, oracle):
     {"slot_bits": 128},
     {"slot_bits": 64, "variant": 2, "load_factor": 0.9},
     {"slot_bits": 32, "variant": 1, "load_factor": 0.9},
+    {"filter": 1},
+    {"filter": 1, "slot_bits": 32, "variant": 3, "load_factor": 0.9},
+    {"filter": 1, "slot_bits": 128, "variant": 0},
 ])
 def test_options_do_not_change_results(ka, oracle, opts):
     seqs, kmers, roles = ragged_case(33, n_seq=500, K=8, max_len=900)
@@ -157,8 +160,8 @@ def test_slot_class_selection(ka, oracle, K, max_role, want_bits):
     assert_same(got, oracle.OracleDb(kmers, roles, K).apply(res, off, 3), f"slot class K={K}")
 
 
-@pytest.mark.parametrize("slot_bits,lf", [(32, 0.9), (64, 0.9), (128, 0.9), (32, 0.4)])
-def test_overflow_heavy_table(ka, oracle, slot_bits, lf):
+@pytest.mark.parametrize("slot_bits,lf,filt", [(32, 0.9, 0), (64, 0.9, 1), (128, 0.9, 0), (32, 0.4, 1)])
+def test_overflow_heavy_table(ka, oracle, slot_bits, lf, filt):
     """Millions of keys at a high load factor: ~13 % of the keys leave their home sector.
     Quotiented slots keep only a remainder, so those keys must live in the overflow table
     under their whole mixed value — every distinct key must survive and resolve exactly."""
@@ -169,6 +172,7 @@ def test_overflow_heavy_table(ka, oracle, slot_bits, lf):
     with ka.Engine([0]) as eng:
         eng.set_option("slot_bits", slot_bits)
         eng.set_option("load_factor", lf)
+        eng.set_option("filter", filt)
         eng.db_load(kmers, roles, 8)
         info = eng.db_info()
         got = eng.annotate(res, off, 5)
