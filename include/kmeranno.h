@@ -8,6 +8,7 @@
  *   ka_db_load       <- proteins/kmers/anno/ApplyKmerProcessor.java:99-110
  *                       (kmerRoleMap = HashMap<String,String>; put() = last line wins;
  *                        K taken from the k-mer text, :108)
+ *   ka_build         <- proteins/kmers/anno/BuildKmerProcessor.java:138-223 + kmers/RoleCounter.java
  *   ka_annotate      <- proteins/kmers/anno/ApplyKmerProcessor.java:122-148
  *                       (new ProteinKmers(prot) :123, kmerRoleMap.get :130, tally
  *                        :131-144, thresholded call :146-147)
@@ -73,7 +74,7 @@ const char* ka_last_error(const ka_engine* e);
 /* Tunables, set before ka_db_load / ka_annotate.  Unknown name -> KA_ERR_INVALID.
  *   "load_factor"   table load factor in (0,0.9], default 0.4   (next ka_db_load)
  *   "tile_span"     residues of sequence starts per CTA tile, default 2048
- *   "long_seq"      sequences longer than this use the long-sequence kernel, default 3072
+ *   "long_seq"      sequences longer than this use the long-sequence kernel, default 5120
  *   "filter"        per-sector presence signatures kept in L2 (1 on, 0 off (default), -1 = on for
  *                   tables of at least 2^20 sectors)   (next ka_db_load)
  *   "slot_bits"     force the table slot width (32, 64, 128; 0 = smallest that fits, default)
@@ -129,6 +130,25 @@ int ka_annotate_resident(ka_engine* e, ka_batch* b, int32_t min_hits);
 int ka_batch_download(ka_engine* e, ka_batch* b, int32_t* out_role, int32_t* out_hits,
                       uint8_t* out_flag);
 void ka_batch_free(ka_engine* e, ka_batch* b);
+
+/* ---- build the discriminating k-mer DB (BuildKmerProcessor.java:138-223) --------------- */
+
+/* GPU restatement of the `build` command's core.  Input: every peg of the training genomes as
+ * a CSR batch, already classified by the caller (Feature.getUsefulRoles ∩ goodRoles, :158):
+ *   n_roles[i]  number of good roles of peg i (0, 1, or >= 2)
+ *   peg_role[i] the role id (>= 0) when n_roles[i] == 1, ignored otherwise
+ * Output = the k-mers that occur in at least one single-role peg (:165-173), whose
+ * single-role pegs all carry the same role (RoleCounter.isGood, :183-190) and that occur
+ * in no zero-role peg (:196-208); pegs with two or more good roles are ignored (:165).
+ * At most `cap` k-mers are written (out_kmers: cap*K bytes, out_roles: cap ints) in
+ * unspecified order — the reference's order is HashMap iteration order (:212-216).
+ * *n_out receives the number of k-mers found; if it exceeds cap the call returns
+ * KA_ERR_TOO_BIG and nothing else is guaranteed.  load_as_db != 0 also installs the result
+ * as the engine's k-mer database (as ka_db_load would), skipping the kmerdb.tbl round trip.
+ * Runs on the engine's first device. */
+int ka_build(ka_engine* e, const uint8_t* residues, const uint64_t* offsets, uint64_t N,
+             const int32_t* n_roles, const int32_t* peg_role, int K, uint64_t cap,
+             uint8_t* out_kmers, int32_t* out_roles, uint64_t* n_out, int load_as_db);
 
 /* ---- pinned host memory for zero-staging transfers -------------------------------- */
 void* ka_host_alloc(size_t bytes);

@@ -640,6 +640,90 @@ cudaError_t launch_db_finalize(const TableView& tab, const uint32_t* line_of,
 }
 
 // ------------------------------------------------------------------------------------
+// build: BuildKmerProcessor.java:138-223 on the device
+// ------------------------------------------------------------------------------------
+// One thread per residue position (grid-stride); the peg of a position is found by binary
+// search on the offsets.  The per-peg HashSet of ProteinKmers is irrelevant here: counting
+// a window twice changes neither "all the same role" nor "occurs in a zero-role peg".
+template <int PASS>
+__global__ void build_pass_kernel(const uint8_t* __restrict__ res, const unsigned long long* __restrict__ off,
+                                  uint32_t n_seq, const int32_t* __restrict__ n_roles,
+                                  const int32_t* __restrict__ peg_role, int K, const uint8_t* __restrict__ lut,
+                                  Slot128* table, unsigned long long n_slots) {
+    __shared__ uint8_t s_lut[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = lut[i];
+    __syncthreads();
+    const unsigned long long base = off[0], total = off[n_seq] - base;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long pos = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; pos < total;
+         pos += stride) {
+        // peg containing pos: last i with off[i] - base <= pos
+        uint32_t lo = 0, hi = n_seq;
+        while (lo < hi) {
+            uint32_t mid = lo + ((hi - lo) >> 1);
+            if (off[mid + 1] - base <= pos) lo = mid + 1; else hi = mid;
+        }
+        const uint32_t s = lo;
+        const int nr = n_roles[s];
+        if (PASS == 1 ? nr != 1 : nr != 0) continue;                 // :159, :165
+        if (pos + K > off[s + 1] - base) continue;                   // window must stay inside the peg
+        unsigned long long key = 0;
+        for (int j = 0; j < K; j++) key = (key << 5) | s_lut[res[pos + j]];
+        unsigned long long slot = mix64(key) & (n_slots - 1);
+        if (PASS == 1) {
+            const unsigned long long mine = (unsigned long long)(uint32_t)peg_role[s] + 1ull;
+            for (;;) {
+                unsigned long long old = atomicCAS(&table[slot].key, 0ull, key);     // computeIfAbsent :170
+                if (old == 0ull || old == key) {
+                    unsigned long long v = atomicCAS(&table[slot].val, 0ull, mine);  // new RoleCounter(pegRole)
+                    if (v != 0ull && (v & 0xffffffffull) != mine) atomicOr(&table[slot].val, BUILD_BAD);  // count(): badCount++ :171
+                    break;
+                }
+                slot = (slot + 1) & (n_slots - 1);
+            }
+        } else {
+            for (;;) {                                                               // kmerMap.remove(kmer) :201
+                const unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(&table[slot].key);
+                if (k == 0ull) break;
+                if (k == key) { atomicOr(&table[slot].val, BUILD_DEAD); break; }
+                slot = (slot + 1) & (n_slots - 1);
+            }
+        }
+    }
+}
+
+cudaError_t launch_build_pass(int pass, const uint8_t* res, const unsigned long long* off, uint32_t n_seq,
+                              const int32_t* n_roles, const int32_t* peg_role, int K, const uint8_t* lut,
+                              Slot128* table, unsigned long long n_slots, cudaStream_t st) {
+    if (n_seq == 0) return cudaSuccess;
+    if (pass == 1) build_pass_kernel<1><<<148 * 16, 256, 0, st>>>(res, off, n_seq, n_roles, peg_role, K, lut, table, n_slots);
+    else build_pass_kernel<2><<<148 * 16, 256, 0, st>>>(res, off, n_seq, n_roles, peg_role, K, lut, table, n_slots);
+    return cudaGetLastError();
+}
+
+__global__ void build_emit_kernel(const Slot128* __restrict__ table, unsigned long long n_slots, int K,
+                                  const uint8_t* __restrict__ inv_lut, unsigned long long cap,
+                                  uint8_t* out_kmers, int32_t* out_roles, unsigned long long* counter) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long s = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += stride) {
+        const unsigned long long key = table[s].key, v = table[s].val;
+        if (key == 0ull || (v & (BUILD_BAD | BUILD_DEAD))) continue;   // isGood() :186, removed :201
+        const unsigned long long idx = atomicAdd(counter, 1ull);
+        if (idx >= cap) continue;
+        unsigned long long k = key;
+        for (int j = K - 1; j >= 0; j--) { out_kmers[idx * K + j] = inv_lut[k & 31]; k >>= 5; }
+        out_roles[idx] = (int32_t)((v & 0xffffffffull) - 1);            // kmer TAB roleId :213-215
+    }
+}
+
+cudaError_t launch_build_emit(const Slot128* table, unsigned long long n_slots, int K, const uint8_t* inv_lut,
+                              unsigned long long cap, uint8_t* out_kmers, int32_t* out_roles,
+                              unsigned long long* counter, cudaStream_t st) {
+    build_emit_kernel<<<148 * 16, 256, 0, st>>>(table, n_slots, K, inv_lut, cap, out_kmers, out_roles, counter);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------
 // random-probe roofline microbenchmark
 // ------------------------------------------------------------------------------------
 template <int BYTES>

@@ -62,6 +62,19 @@ cudaError_t launch_db_insert(const TableView& tab, const uint8_t* kmers, const i
 cudaError_t launch_db_finalize(const TableView& tab, const uint32_t* line_of,
                                const int32_t* all_roles, cudaStream_t st);
 
+// ---- build (BuildKmerProcessor.java:138-223) ----
+// table: n_slots (power of two) Slot128 {key, val}; val = role + 1, bit 62 = seen under two
+// roles (RoleCounter.badCount > 0), bit 63 = occurs in a zero-role peg.
+constexpr unsigned long long BUILD_BAD = 1ull << 62, BUILD_DEAD = 1ull << 63;
+// pass = 1: insert the windows of single-role pegs; pass = 2: mark the windows of zero-role pegs
+cudaError_t launch_build_pass(int pass, const uint8_t* res, const unsigned long long* off, uint32_t n_seq,
+                              const int32_t* n_roles, const int32_t* peg_role, int K, const uint8_t* lut,
+                              Slot128* table, unsigned long long n_slots, cudaStream_t st);
+// emit the surviving k-mers (unordered); counter[0] = number found (may exceed cap)
+cudaError_t launch_build_emit(const Slot128* table, unsigned long long n_slots, int K, const uint8_t* inv_lut,
+                              unsigned long long cap, uint8_t* out_kmers, int32_t* out_roles,
+                              unsigned long long* counter, cudaStream_t st);
+
 cudaError_t launch_random_probe(const uint4* buf, unsigned long long n_slots, int slot_bytes,
                                 unsigned long long n_probes, unsigned long long seed,
                                 unsigned long long* sink, cudaStream_t st);

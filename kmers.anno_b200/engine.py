@@ -17,7 +17,7 @@ FLAG_NONE, FLAG_CALLED, FLAG_AMBIGUOUS, FLAG_BELOW_MIN = 0, 1, 2, 3
 # every symbol include/kmeranno.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
     "ka_create", "ka_destroy", "ka_last_error", "ka_set_option", "ka_db_load", "ka_db_get_info",
-    "ka_annotate", "ka_batch_upload", "ka_annotate_resident", "ka_batch_download", "ka_batch_free",
+    "ka_annotate", "ka_build", "ka_batch_upload", "ka_annotate_resident", "ka_batch_download", "ka_batch_free",
     "ka_host_alloc", "ka_host_free", "ka_get_stats", "ka_probe_roofline", "ka_abi_version",
 ]
 
@@ -63,6 +63,8 @@ def load_library():
     lib.ka_db_load.argtypes = [vp, u8p, i32p, C.c_uint64, C.c_int]
     lib.ka_db_get_info.argtypes = [vp, C.POINTER(DbInfo)]
     lib.ka_annotate.argtypes = [vp, u8p, u64p, C.c_uint64, C.c_int32, i32p, i32p, u8p]
+    lib.ka_build.argtypes = [vp, u8p, u64p, C.c_uint64, i32p, i32p, C.c_int, C.c_uint64, u8p, i32p,
+                             C.POINTER(C.c_uint64), C.c_int]
     lib.ka_batch_upload.argtypes = [vp, C.c_int, u8p, u64p, C.c_uint64, C.POINTER(vp)]
     lib.ka_annotate_resident.argtypes = [vp, vp, C.c_int32]
     lib.ka_batch_download.argtypes = [vp, vp, i32p, i32p, u8p]
@@ -177,6 +179,22 @@ class Engine:
         self._check(self._lib.ka_annotate(self._h, _ptr(residues), _ptr(offsets), n, int(min_hits),
                                           _ptr(role), _ptr(hits), _ptr(flag)))
         return role, hits, flag
+
+    def build(self, residues, offsets, n_roles, peg_role, K, load_as_db=False):
+        """GPU `build` (BuildKmerProcessor.java:138-223): returns (kmers u8[n*K], roles i32[n]), unordered."""
+        residues = np.ascontiguousarray(residues, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n_roles = np.ascontiguousarray(n_roles, dtype=np.int32)
+        peg_role = np.ascontiguousarray(peg_role, dtype=np.int32)
+        n = offsets.shape[0] - 1
+        lens = (offsets[1:] - offsets[:-1]).astype(np.int64)
+        cap = int(np.maximum(lens[n_roles == 1] - K + 1, 0).sum())
+        kmers = np.empty(max(cap * K, 1), np.uint8)
+        roles = np.empty(max(cap, 1), np.int32)
+        found = C.c_uint64()
+        self._check(self._lib.ka_build(self._h, _ptr(residues), _ptr(offsets), n, _ptr(n_roles), _ptr(peg_role),
+                                       K, cap, _ptr(kmers), _ptr(roles), C.byref(found), int(load_as_db)))
+        return kmers[: found.value * K], roles[: found.value]
 
     def upload(self, residues, offsets, dev_index=0):
         residues = np.ascontiguousarray(residues, dtype=np.uint8)

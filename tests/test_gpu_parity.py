@@ -117,7 +117,7 @@ def test_many_tiny_sequences_sub_batches(ka, oracle):
 
 
 def test_long_sequences_use_big_kernel(ka, oracle):
-    lengths = [20000, 300, 7000, 3073, 3072, 64, 0, 12000]
+    lengths = [20000, 300, 7000, 5121, 5120, 64, 0, 12000]
     seqs, kmers, roles = ragged_case(21, n_seq=len(lengths), K=8, lengths=lengths, db_frac=0.5)
     run_case(ka, oracle, seqs, kmers, roles, 8, min_hits=3)
     # the same inputs with a small long_seq so that most sequences take the long path
