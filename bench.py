@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--roles", type=int, default=30000)
     ap.add_argument("--K", type=int, default=8)
     ap.add_argument("--min-hits", type=int, default=5)
+    ap.add_argument("--mode", type=int, default=0, choices=[0, 1, 2],
+                    help="0 = C3 proteomes; 1 / 2 = config-4 skewed lengths (log-uniform / bimodal 50..5000 aa)")
     ap.add_argument("--cpu-genomes", type=int, default=384, help="proteomes in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -124,7 +126,8 @@ def measured_peak():
 
 
 def workload_name(a):
-    return (f"C3 batch: {a.genomes} synthetic proteomes x {N_PROT} proteins per GPU per step vs replicated "
+    shape = {0: "C3 batch", 1: "C4 batch (log-uniform 50..5000 aa)", 2: "C4 batch (bimodal 50..300 / 3000..5000 aa)"}[a.mode]
+    return (f"{shape}: {a.genomes} synthetic proteomes x {N_PROT} proteins per GPU per step vs replicated "
             f"C2 table ({a.table_kmers:.0e} {a.K}-mers, {a.roles} roles)")
 
 
@@ -139,7 +142,7 @@ def cpu_baseline(a, fam, kmers, roles, threads=None):
     """Java-shaped oracle on the host cores over a bounded sample of the workload."""
     import oracle
     threads = threads or (os.cpu_count() or 1)
-    res, off, _ = fam.batch(10_000_000, a.cpu_genomes, n_prot=N_PROT, K=a.K)
+    res, off, _ = fam.batch(10_000_000, a.cpu_genomes, n_prot=N_PROT, K=a.K, mode=a.mode)
     probes = oracle.count_probes(off, a.K)
     t0 = time.time()
     db = oracle.OracleDb(kmers, roles, a.K, file_len_bytes=len(roles) * (a.K + 10), threads=threads)
@@ -166,7 +169,7 @@ def run_reference(a):
     import oracle
     threads = os.cpu_count() or 1
     db = oracle.OracleDb(kmers, roles, a.K, file_len_bytes=len(roles) * (a.K + 10), threads=threads)
-    res, off, _ = fam.batch(10_000_000, a.cpu_genomes, n_prot=N_PROT, K=a.K)
+    res, off, _ = fam.batch(10_000_000, a.cpu_genomes, n_prot=N_PROT, K=a.K, mode=a.mode)
     probes = oracle.count_probes(off, a.K)
     n_seq = off.shape[0] - 1
     for _ in range(a.warmup):
@@ -239,7 +242,7 @@ def main():
     eng.db_load(kmers, roles, a.K)
     info = eng.db_info()
     # this rank's shard: genomes [rank*G, (rank+1)*G), generated straight into pinned memory
-    res, off, _ = fam.batch(rank * a.genomes, a.genomes, n_prot=N_PROT, K=a.K, alloc=pinned_array)
+    res, off, _ = fam.batch(rank * a.genomes, a.genomes, n_prot=N_PROT, K=a.K, mode=a.mode, alloc=pinned_array)
     n_seq = off.shape[0] - 1
     out = (pinned_array(n_seq, np.int32), pinned_array(n_seq, np.int32), pinned_array(n_seq, np.uint8))
     t_setup = time.time() - t_setup
@@ -306,7 +309,7 @@ def main():
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cpu, cpu_out = cpu_baseline(a, fam, kmers, roles)
         # the same sample on the GPU must give the oracle's answer (checker, not the product)
-        s_res, s_off, _ = fam.batch(10_000_000, a.cpu_genomes, n_prot=N_PROT, K=a.K)
+        s_res, s_off, _ = fam.batch(10_000_000, a.cpu_genomes, n_prot=N_PROT, K=a.K, mode=a.mode)
         g = eng.annotate(s_res, s_off, a.min_hits)
         cpu["gpu_matches_oracle_on_sample"] = bool(all(np.array_equal(x, y) for x, y in zip(g, cpu_out)))
     eng.close()
@@ -324,7 +327,7 @@ def main():
                        "table_keys": int(info["n_keys"]), "parallelism": f"replicated table, {world} shard(s)",
                        "l2": "table (>> 126 MB L2) probed at random and batch residues > L2: no flush needed",
                        "setup_s": round(t_setup, 1)},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "e2e": e2e, "gpu_launches": int(launches) * world, "clocks": clocks,
             "roofline": roofline, "rand_roofline": rand, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

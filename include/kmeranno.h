@@ -75,6 +75,9 @@ const char* ka_last_error(const ka_engine* e);
  *   "load_factor"   table load factor in (0,0.9], default 0.4   (next ka_db_load)
  *   "tile_span"     residues of sequence starts per CTA tile, default 2048
  *   "long_seq"      sequences longer than this use the long-sequence kernel, default 5120
+ *   "table_mode"    0 = table replicated on every device (default); 1 = table sharded by sector range
+ *                   over the engine's 2/4/8 devices, probes load remote sectors through NVLink
+ *                   peer memory inside the probe kernel (for tables beyond one GPU)  (next ka_db_load)
  *   "filter"        per-sector presence signatures kept in L2 (1 on, 0 off (default), -1 = on for
  *                   tables of at least 2^20 sectors)   (next ka_db_load)
  *   "slot_bits"     force the table slot width (32, 64, 128; 0 = smallest that fits, default)

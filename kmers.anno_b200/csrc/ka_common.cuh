@@ -38,6 +38,14 @@ struct TableView {
     const uint4* ovf;             // overflow table (cls 32/64): 2^ovf_bbits sectors of 2 Slot128
     uint32_t ovf_bbits;
     uint32_t n_primary_slots;     // slots of the primary table (de-dup tokens of overflow entries start here)
+    // sharded mode (table larger than one GPU's share): sector s lives on shard s >> shard_shift at
+    // local index s & shard_mask; shard_sectors[i] / shard_ovf[i] are PEER pointers (NVLink loads).
+    // n_shards == 1: `sectors` / `ovf` are used directly.
+    const uint4* const* shard_sectors;
+    const uint4* const* shard_ovf;
+    uint32_t n_shards;
+    uint32_t shard_shift;
+    uint32_t my_shard;            // build only: the shard this device fills
     unsigned long long key_mask;  // (1 << 5K) - 1
     unsigned long long rem_mask;  // (1 << rem_bits) - 1   (cls 32 / 64)
     uint32_t bbits;               // log2(number of sectors)
@@ -90,6 +98,14 @@ __host__ __device__ __forceinline__ void locate(const TableView& t, unsigned lon
 __host__ __device__ __forceinline__ uint32_t sig_bits(unsigned long long rem) {
     uint32_t h = ((uint32_t)rem ^ (uint32_t)(rem >> 32)) * 0x9E3779B1u;
     return (1u << (h >> 28)) | (1u << ((h >> 24) & 15u));
+}
+
+// address of a table sector: local HBM, or the owning GPU's HBM through NVLink peer memory
+__device__ __forceinline__ const uint4* sector_ptr(const TableView& t, uint32_t sec) {
+    if (t.n_shards <= 1) return t.sectors + 2 * (size_t)sec;
+    const uint4* base = reinterpret_cast<const uint4*>(
+        __ldg(reinterpret_cast<const unsigned long long*>(t.shard_sectors) + (sec >> t.shard_shift)));
+    return base + 2 * (size_t)(sec & ((1u << t.shard_shift) - 1));
 }
 
 // One 32-byte sector with a single 256-bit load (LDG.E.256 on sm_100a), read-only path, no

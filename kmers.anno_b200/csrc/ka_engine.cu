@@ -45,6 +45,8 @@ struct Device {
     uint4* table = nullptr;
     uint4* ovf = nullptr;     // overflow table (cls 32/64)
     uint16_t* sig = nullptr;  // per-sector presence signatures
+    const uint4** shard_sectors = nullptr;  // sharded mode: device array of peer pointers, one per shard
+    const uint4** shard_ovf = nullptr;
     uint8_t* lut = nullptr;
     Pipe pipe[NPIPE];
     size_t smem_set = 0;
@@ -79,6 +81,8 @@ struct ka_engine {
     int filter = 0;     // 1 = per-sector presence signatures in front of the table (measured slower
                         // in the fused kernel: 40 vs 46 G probes/s, profiles/r01_summary.md), -1 = auto
     bool have_sig = false;
+    int table_mode = 0; // 0 = table replicated on every device, 1 = sharded by sector range (peer loads)
+    bool peers_enabled = false;
     // db
     bool have_db = false;
     ka_db_info info{};
@@ -216,6 +220,8 @@ void fill_params(ka_engine* e, Device& d, Pipe& p, uint64_t base, uint64_t n_res
     ap.tab.sectors = d.table;
     ap.tab.ovf = d.ovf;
     ap.tab.sig = d.sig;
+    ap.tab.shard_sectors = d.shard_sectors;
+    ap.tab.shard_ovf = d.shard_ovf;
     ap.lut = d.lut;
     ap.min_hits = min_hits;
     ap.out_role = p.role;
@@ -360,7 +366,7 @@ int build_table(ka_engine* e, Device& d, const TableView& geom, const uint8_t* k
     if (d.ovf) { cudaFree(d.ovf); d.ovf = nullptr; }
     if (d.sig) { cudaFree(d.sig); d.sig = nullptr; }
     const int K = geom.K;
-    const size_t n_sectors = (size_t)1 << geom.bbits;
+    const size_t n_sectors = (size_t)1 << (geom.n_shards > 1 ? geom.shard_shift : geom.bbits);  // of this device
     const size_t bytes = n_sectors * 32;
     const size_t n_slots = n_sectors * (geom.cls == 32 ? 8 : (geom.cls == 64 ? 4 : 2));
     cudaError_t ce = cudaMalloc((void**)&d.table, bytes);
@@ -370,7 +376,7 @@ int build_table(ka_engine* e, Device& d, const TableView& geom, const uint8_t* k
         ce = cudaMalloc((void**)&d.ovf, ovf_bytes);
         if (ce != cudaSuccess) { d.ovf = nullptr; return dev_fail(d, KA_ERR_OOM, "overflow table", ce); }
     }
-    const bool use_sig = e->filter == 1 || (e->filter < 0 && geom.bbits >= 20);
+    const bool use_sig = geom.n_shards <= 1 && (e->filter == 1 || (e->filter < 0 && geom.bbits >= 20));
     const size_t sig_bytes = use_sig ? (n_sectors * 2 + 4) : 0;
     if (sig_bytes) {
         ce = cudaMalloc((void**)&d.sig, sig_bytes);
@@ -442,7 +448,7 @@ uint32_t ceil_log2(double x) {
 
 // Pick slot class and sector count: the smallest table that holds n keys at the requested
 // load factor with remainder + role fitting the slot (see ka_common.cuh).
-bool choose_geometry(uint64_t n, int K, int32_t max_role, double lf, int force_cls, TableView& g) {
+bool choose_geometry(uint64_t n, int K, int32_t max_role, double lf, int force_cls, uint32_t n_shards, TableView& g) {
     const uint32_t w = 5u * (uint32_t)K;
     uint32_t role_bits = 1;
     while (((uint64_t)max_role + 1) >> role_bits) role_bits++;
@@ -450,13 +456,18 @@ bool choose_geometry(uint64_t n, int K, int32_t max_role, double lf, int force_c
     uint64_t best_bytes = 0;
     for (int cls : {32, 64, 128}) {
         if (force_cls && cls != force_cls) continue;
+        if (n_shards > 1 && cls == 128) continue;   // chaining across shards is not supported: quotiented classes only
         const int S = 256 / cls;
         uint32_t b = ceil_log2((double)(n ? n : 1) / ((double)S * lf));
         if (b < 6) b = 6;
+        uint32_t shard_log = 0;
+        while ((1u << shard_log) < n_shards) shard_log++;
+        if (b < 6 + shard_log) b = 6 + shard_log;
         uint32_t rem_bits = 0;
         if (cls != 128) {
             if ((int)(w + role_bits) - cls > (int)b) b = w + role_bits - (uint32_t)cls;
             if (b > w) b = w;
+            if (b < shard_log) continue;
             rem_bits = w - b;
             if (rem_bits + role_bits > (uint32_t)cls) continue;
         }
@@ -479,7 +490,12 @@ bool choose_geometry(uint64_t n, int K, int32_t max_role, double lf, int force_c
                 if (k > S) over += (k - S) * pk;
             }
             double want = 4.0 * over * (double)(1ull << b) + 4096;
-            g.ovf_bbits = cls == 128 ? 0 : ceil_log2(want / 2.0);
+            g.ovf_bbits = cls == 128 ? 0 : ceil_log2(want / 2.0 / (n_shards ? n_shards : 1));
+            g.n_shards = n_shards;
+            g.shard_shift = b - shard_log;
+            g.my_shard = 0;
+            g.shard_sectors = nullptr;
+            g.shard_ovf = nullptr;
         }
     }
     return found;
@@ -570,6 +586,8 @@ void ka_destroy(ka_engine* e) {
         if (d.table) cudaFree(d.table);
         if (d.ovf) cudaFree(d.ovf);
         if (d.sig) cudaFree(d.sig);
+        if (d.shard_sectors) cudaFree((void*)d.shard_sectors);
+        if (d.shard_ovf) cudaFree((void*)d.shard_ovf);
         if (d.lut) cudaFree(d.lut);
     }
     delete e;
@@ -599,6 +617,9 @@ int ka_set_option(ka_engine* e, const char* name, double v) {
         e->l2_persist = v != 0;
     } else if (n == "warp_dedup") {
         e->warp_dedup = v != 0;
+    } else if (n == "table_mode") {
+        if (v != 0 && v != 1) return fail(e, KA_ERR_INVALID, "table_mode must be 0 (replicated) or 1 (sharded)");
+        e->table_mode = (int)v;
     } else if (n == "filter") {
         e->filter = v < 0 ? -1 : (v != 0);
     } else if (n == "slot_bits") {
@@ -671,7 +692,28 @@ static int db_load_impl(ka_engine* e, const uint8_t* kmers, const int32_t* role_
         if (role_ids[i] > max_role) max_role = role_ids[i];
     }
     TableView geom;
-    if (!choose_geometry(n, K, max_role, e->load_factor, e->slot_bits, geom))
+    const uint32_t n_shards = e->table_mode == 1 ? (uint32_t)e->devs.size() : 1u;
+    if (e->table_mode == 1) {
+        if (n_shards != 2 && n_shards != 4 && n_shards != 8)
+            return fail(e, KA_ERR_INVALID, "ka_db_load: a sharded table needs an engine on 2, 4 or 8 devices (has %u)", n_shards);
+        if (!e->peers_enabled) {
+            for (Device& a : e->devs) {
+                cudaSetDevice(a.id);
+                for (Device& b : e->devs) {
+                    if (a.id == b.id) continue;
+                    int can = 0;
+                    cudaDeviceCanAccessPeer(&can, a.id, b.id);
+                    if (!can) return fail(e, KA_ERR_NO_DEVICE, "ka_db_load: device %d cannot access device %d's memory (no NVLink/P2P)", a.id, b.id);
+                    cudaError_t pe = cudaDeviceEnablePeerAccess(b.id, 0);
+                    if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled)
+                        return fail(e, KA_ERR_CUDA, "ka_db_load: cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(pe));
+                    cudaGetLastError();
+                }
+            }
+            e->peers_enabled = true;
+        }
+    }
+    if (!choose_geometry(n, K, max_role, e->load_factor, e->slot_bits, n_shards, geom))
         return fail(e, KA_ERR_TOO_BIG, "ka_db_load: %llu k-mers (K=%d, max role %d) do not fit %s of this build",
                     (unsigned long long)n, K, max_role, e->slot_bits ? "the forced slot width" : "the 32-bit slot index");
 
@@ -680,15 +722,29 @@ static int db_load_impl(ka_engine* e, const uint8_t* kmers, const int32_t* role_
     std::vector<uint32_t> mp(e->devs.size(), 0);
     int rc = KA_OK;
     for (int attempt = 0; attempt < 6; attempt++) {
-        if ((uint64_t)geom.n_primary_slots + (2ull << geom.ovf_bbits) >= 0xfffffff0ull)
+        if ((uint64_t)geom.n_primary_slots + (uint64_t)n_shards * (2ull << geom.ovf_bbits) >= 0xfffffff0ull)
             return fail(e, KA_ERR_TOO_BIG, "ka_db_load: table exceeds the 32-bit slot index of this build");
         rc = for_each_device(e, [&](Device& d, int i) {
-            return build_table(e, d, geom, kmers, role_ids, n, &nk[i], &mp[i]);
+            TableView g = geom;
+            g.my_shard = n_shards > 1 ? (uint32_t)i : 0u;
+            return build_table(e, d, g, kmers, role_ids, n, &nk[i], &mp[i]);
         });
         if (rc != KA_ERR_TOO_BIG) break;
         geom.ovf_bbits += 2;  // overflow table was too small for this key set: rebuild 4x larger
     }
     if (rc) return rc;
+    if (n_shards > 1) {
+        // every device gets the peer pointers of all shards
+        std::vector<const uint4*> ps(8, nullptr), po(8, nullptr);
+        for (size_t i = 0; i < e->devs.size(); i++) { ps[i] = e->devs[i].table; po[i] = e->devs[i].ovf; nk[0] += i ? nk[i] : 0; mp[0] = std::max(mp[0], mp[i]); }
+        for (Device& d : e->devs) {
+            cudaSetDevice(d.id);
+            if (!d.shard_sectors && cudaMalloc((void**)&d.shard_sectors, 64) != cudaSuccess) return fail(e, KA_ERR_OOM, "shard pointer table");
+            if (!d.shard_ovf && cudaMalloc((void**)&d.shard_ovf, 64) != cudaSuccess) return fail(e, KA_ERR_OOM, "shard pointer table");
+            cudaMemcpy((void*)d.shard_sectors, ps.data(), 64, cudaMemcpyHostToDevice);
+            cudaMemcpy((void*)d.shard_ovf, po.data(), 64, cudaMemcpyHostToDevice);
+        }
+    }
     e->geom = geom;
     e->info.K = K;
     e->info.n_symbols = nsym;

@@ -36,12 +36,17 @@ namespace ka {
 __device__ __forceinline__ int ovf_lookup(const TableView& t, unsigned long long m, uint32_t& tok) {
     const uint32_t mask = (1u << t.ovf_bbits) - 1;
     uint32_t s = t.ovf_bbits ? (uint32_t)(mix64(m) >> (64 - t.ovf_bbits)) : 0u;
+    // the overflow entries of a sector live with the shard that owns the sector
+    const uint32_t shard = t.n_shards <= 1 ? 0u : (uint32_t)(m >> t.rem_bits) >> t.shard_shift;
+    const uint4* ovf = t.n_shards <= 1 ? t.ovf : reinterpret_cast<const uint4*>(
+        __ldg(reinterpret_cast<const unsigned long long*>(t.shard_ovf) + shard));
+    const uint32_t tok0 = t.n_primary_slots + shard * (2u << t.ovf_bbits);
     for (;;) {
         uint4 a, b;
-        load_sector(t.ovf + 2 * (size_t)s, a, b);
+        load_sector(ovf + 2 * (size_t)s, a, b);
         const unsigned long long k0 = u64_of(a.x, a.y), k1 = u64_of(b.x, b.y);
-        if (k0 == m) { tok = t.n_primary_slots + 2 * s + 1; return (int)a.z; }
-        if (k1 == m) { tok = t.n_primary_slots + 2 * s + 2; return (int)b.z; }
+        if (k0 == m) { tok = tok0 + 2 * s + 1; return (int)a.z; }
+        if (k1 == m) { tok = tok0 + 2 * s + 2; return (int)b.z; }
         if (k1 == 0) return -1;
         s = (s + 1) & mask;
     }
@@ -69,7 +74,7 @@ __device__ __forceinline__ void probe_batch(const TableView& tab,
     uint4 a[C], b[C];
 #pragma unroll
     for (int i = 0; i < C; i++)
-        if (okmask & (1u << i)) load_sector(tab.sectors + 2 * (size_t)sec[i], a[i], b[i]);
+        if (okmask & (1u << i)) load_sector(sector_ptr(tab, sec[i]), a[i], b[i]);
     unsigned pend = 0;
 #pragma unroll
     for (int i = 0; i < C; i++) {
@@ -92,7 +97,7 @@ __device__ __forceinline__ void probe_batch(const TableView& tab,
             for (int i = 0; i < C; i++)
                 if (pend & (1u << i)) {
                     sec[i] = (sec[i] + 1) & sec_mask;
-                    load_sector(tab.sectors + 2 * (size_t)sec[i], a[i], b[i]);
+                    load_sector(sector_ptr(tab, sec[i]), a[i], b[i]);
                 }
 #pragma unroll
             for (int i = 0; i < C; i++)
@@ -519,6 +524,14 @@ __global__ void db_insert_kernel(TableView tab, const uint8_t* __restrict__ kmer
         uint32_t sec;
         unsigned long long rem;
         locate(tab, key, sec, rem);
+        unsigned long long msec = sec;   // global sector (the overflow key keeps it)
+        if (tab.n_shards > 1) {
+            // sharded table: this device stores only the sectors of its own shard, at local indices.
+            // (cls 128 chains to the NEXT sector, which may belong to another shard: the engine
+            // only shards the quotiented classes, whose overflow stays with the home shard.)
+            if ((sec >> tab.shard_shift) != tab.my_shard) continue;
+            sec &= (1u << tab.shard_shift) - 1;
+        }
         if (tab.sig) {
             uint32_t* word = reinterpret_cast<uint32_t*>(const_cast<uint16_t*>(tab.sig)) + (sec >> 1);
             const uint32_t bits = sig_bits(rem) << ((sec & 1u) * 16);
@@ -569,7 +582,7 @@ __global__ void db_insert_kernel(TableView tab, const uint8_t* __restrict__ kmer
             }
             if (!done) {
                 // home sector full: the whole mixed key goes to the overflow table
-                const unsigned long long m = ((unsigned long long)sec << tab.rem_bits) | rem;
+                const unsigned long long m = (msec << tab.rem_bits) | rem;
                 const unsigned long long val = ((line_base + i) << 32) | (uint32_t)roles[i];
                 const uint32_t omask = (1u << tab.ovf_bbits) - 1;
                 uint32_t os = tab.ovf_bbits ? (uint32_t)(mix64(m) >> (64 - tab.ovf_bbits)) : 0u;
@@ -615,7 +628,7 @@ template <int CLS>
 __global__ void db_finalize_kernel(TableView tab, const uint32_t* __restrict__ line_of,
                                    const int32_t* __restrict__ all_roles) {
     constexpr int S = slots_per_sector<CLS>();
-    const unsigned long long n_slots = (unsigned long long)S << tab.bbits;
+    const unsigned long long n_slots = (unsigned long long)S << (tab.n_shards > 1 ? tab.shard_shift : tab.bbits);
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long s = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; s < n_slots;
          s += stride) {

@@ -261,6 +261,36 @@ def test_multi_device_engine(ka, oracle):
     assert st["sequences"] == off.shape[0] - 1 and st["kernel_launches"] >= 2 * n_dev
 
 
+@pytest.mark.parametrize("slot_bits,lf", [(0, 0.4), (32, 0.9), (64, 0.9)])
+def test_sharded_table_peer_loads(ka, oracle, slot_bits, lf):
+    """table_mode=1: the table is split by sector range over the engine's GPUs and probes read
+    remote sectors through NVLink peer memory (the config-5 shape, at test size)."""
+    n_dev = 0
+    for n in (8, 4, 2):
+        try:
+            ka.Engine(list(range(n))).close()
+            n_dev = n
+            break
+        except ka.KmerAnnoError:
+            continue
+    if n_dev < 2:
+        pytest.skip("needs at least 2 GPUs")
+    from kmers_anno_b200 import synth
+    fam = synth.Families(1000)
+    kmers, roles = fam.table(2_000_000, K=8)
+    res, off, _ = fam.batch(9, 2, n_prot=4500)
+    with ka.Engine(list(range(n_dev))) as eng:
+        eng.set_option("table_mode", 1)
+        eng.set_option("slot_bits", slot_bits)
+        eng.set_option("load_factor", lf)
+        eng.db_load(kmers, roles, 8)
+        info = eng.db_info()
+        got = eng.annotate(res, off, 5)
+    assert info["n_keys"] == 2_000_000
+    want = oracle.OracleDb(kmers, roles, 8, threads=8).apply(res, off, 5, threads=8)
+    assert_same(got, want, f"sharded table over {n_dev} GPUs slot_bits={slot_bits}")
+
+
 def test_error_paths(ka):
     with ka.Engine([0]) as eng:
         with pytest.raises(ka.KmerAnnoError) as e:
