@@ -30,7 +30,7 @@ struct Pipe {
     cudaStream_t st = nullptr;
     uint8_t* res = nullptr; size_t res_cap = 0;
     unsigned long long* off = nullptr; size_t seq_cap = 0;
-    uint32_t* first = nullptr; size_t first_cap = 0;
+    uint4* first = nullptr; size_t first_cap = 0;
     int32_t* role = nullptr; int32_t* hits = nullptr; uint8_t* flag = nullptr;
     uint32_t* ctr = nullptr;  // 16 bytes: [0] big_count, [2..3] token cursor (u64)
     BigItem* big = nullptr; size_t big_cap = 0;

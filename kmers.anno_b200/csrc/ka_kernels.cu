@@ -147,17 +147,32 @@ __device__ __forceinline__ void emit_call(const AnnotParams& p, uint32_t seq, in
 // ------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t first_seq_at(const AnnotParams& p, unsigned long long target) {
+    // first sequence i in [0, n_seq) with off[i] >= target
+    uint32_t lo = 0, hi = p.n_seq;
+    while (lo < hi) {
+        uint32_t mid = lo + ((hi - lo) >> 1);
+        if (p.off[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// One descriptor per tile so that the tile kernel starts with a single load:
+// {first sequence, number of sequences (a trailing long one removed), residue range [g0, g1)
+// relative to the chunk}.  Also the list of long sequences.
 __global__ void plan_kernel(AnnotParams p) {
     unsigned long long gid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid <= p.n_tiles) {
-        // first[t] = first sequence i in [0, n_seq) with off[i] - base >= t * tile_span
-        unsigned long long target = p.base + gid * (unsigned long long)p.tile_span;
-        uint32_t lo = 0, hi = p.n_seq;
-        while (lo < hi) {
-            uint32_t mid = lo + ((hi - lo) >> 1);
-            if (p.off[mid] < target) lo = mid + 1; else hi = mid;
-        }
-        p.first[gid] = lo;
+    if (gid < p.n_tiles) {
+        const uint32_t s0 = first_seq_at(p, p.base + gid * (unsigned long long)p.tile_span);
+        uint32_t s1 = first_seq_at(p, p.base + (gid + 1) * (unsigned long long)p.tile_span);
+        // Only the last sequence starting in a tile can be a long one (long_seq >= tile_span
+        // pushes the next start past the tile): it is left to big_kernel.
+        if (s1 > s0 && p.off[s1] - p.off[s1 - 1] > p.long_seq) s1--;
+        uint4 d;
+        d.x = s0; d.y = s1 - s0;
+        d.z = (uint32_t)(p.off[s0] - p.base);
+        d.w = (uint32_t)(p.off[s1] - p.base);
+        p.first[gid] = d;
     }
     if (gid < p.n_seq) {
         unsigned long long L = p.off[gid + 1] - p.off[gid];
@@ -210,16 +225,14 @@ __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
 
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31;
-    const uint32_t t = blockIdx.x;
-    const uint32_t s0 = p.first[t];
-    uint32_t s1 = p.first[t + 1];
-    if (s0 >= s1) return;
-    // Only the last sequence starting in a tile can be a long one (long_seq >= tile_span
-    // pushes the next start past the tile): leave it to big_kernel.
-    if (p.off[s1] - p.off[s1 - 1] > p.long_seq) s1--;
-    if (s0 >= s1) return;
+    // descriptor and LUT byte are independent loads: both in flight before the first use
+    const uint4 desc = p.first[blockIdx.x];
+    static_assert(THREADS >= 256, "one LUT byte per thread");
+    const uint8_t lut_byte = p.lut[tid & 255];
+    const uint32_t s0 = desc.x, s1 = desc.x + desc.y;
+    if (desc.y == 0) return;
 
-    for (uint32_t i = tid; i < 256; i += THREADS) s_lut[i] = p.lut[i];
+    if (tid < 256) s_lut[tid] = lut_byte;
     if (tid == 0) mbar_init(&s_bar, 1);
     __syncthreads();
 
@@ -229,7 +242,9 @@ __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
 
     for (uint32_t sb = s0; sb < s1; sb += MAX_TILE_SEQ) {
         const uint32_t ns = min((uint32_t)MAX_TILE_SEQ, s1 - sb);
-        const unsigned long long g0 = p.off[sb] - p.base, g1 = p.off[sb + ns] - p.base;
+        // the common case (one sub-batch) needs no further global load to know its residue range
+        const unsigned long long g0 = (sb == s0) ? desc.z : p.off[sb] - p.base;
+        const unsigned long long g1 = (sb + ns == s1) ? desc.w : p.off[sb + ns] - p.base;
         const unsigned long long g0a = g0 & ~15ull;
         const uint32_t lead = (uint32_t)(g0 - g0a);
         const uint32_t ext = (uint32_t)(g1 - g0a);           // stage-relative end of the residues

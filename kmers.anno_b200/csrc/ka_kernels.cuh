@@ -24,7 +24,7 @@ struct AnnotParams {
     uint32_t long_seq;                // L > long_seq goes to the long-sequence kernel
     uint32_t ext_max;                 // tile_span + long_seq: max residue extent of a tile
     uint32_t res_bytes;               // smem bytes reserved for the residue stage
-    uint32_t* first;                  // n_tiles + 1: first sequence starting in each tile
+    uint4* first;                     // n_tiles descriptors {first seq, n seqs (long tail removed), g0, g1}
     TableView tab;
     const uint8_t* lut;               // 256-byte residue -> 5-bit code table (0 = not in DB alphabet)
     int32_t min_hits;
