@@ -269,44 +269,42 @@ __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
         __syncthreads();
         if (nbytes) { mbar_wait(&s_bar, parity); parity ^= 1; }
 
-        // Every thread owns ONE contiguous run of the tile's window positions and walks it in
-        // chunks of C (C sector loads in flight per chunk): one binary search and one K-1
-        // residue warm-up per thread per tile, the rolling key carries over between chunks.
-        {
-            const uint32_t run = (ext - lead + THREADS - 1) / THREADS;
-            const uint32_t P0 = lead + tid * run;
-            const uint32_t Pend = min(ext, P0 + run);
+        // passes of up to THREADS*C positions, spread evenly over the threads
+        for (uint32_t pb = lead; pb < ext; pb += THREADS * C) {
+            const uint32_t pend = min(ext, pb + THREADS * C);
+            const uint32_t run = (pend - pb + THREADS - 1) / THREADS;   // positions per thread, <= C
+            const uint32_t P0 = pb + tid * run;
             int cur = -1, cnt = 0, mn = 0x7fffffff, mx = -1;
-            int si = -1;
-            unsigned long long key = 0;
-            int vr = 0;  // consecutive residues inside the DB alphabet
-            if (P0 < Pend) {
+            if (P0 < pend) {
                 // sequence containing P0: last i with s_off[i] <= P0
                 int lo = 0, hi = (int)ns + 1;
                 while (lo < hi) {
                     int mid = (lo + hi) >> 1;
                     if (s_off[mid] <= P0) lo = mid + 1; else hi = mid;
                 }
-                si = lo - 1;
+                int si = lo - 1;
+
                 // rolling 5-bit pack: warm up over K-1 residues, then one key per position
                 const uint8_t* r = s_res + P0;
+                unsigned long long key = 0;
+                int vr = 0;  // consecutive residues inside the DB alphabet
                 for (int j = 0; j < K - 1; j++) {
                     uint32_t c = s_lut[r[j]];
                     key = (key << 5) | c;
                     vr = c ? vr + 1 : 0;
                 }
-            }
-            for (uint32_t cb = P0; cb < Pend; cb += C) {
-                const uint8_t* r = s_res + cb + (K - 1);
+                r += K - 1;
+
                 typename rem_type<CLS>::type rem[C];
                 uint32_t sec[C];
-                uint32_t seqpack = 0, seqpack2 = 0;   // sequence index (< MAX_TILE_SEQ = 256) per position, one byte each
-                static_assert(C <= 8 && MAX_TILE_SEQ <= 256, "sequence indices are packed in bytes");
+                uint32_t seqpack = 0;   // sequence index (< MAX_TILE_SEQ = 256) of each position, one byte each
+                static_assert(C <= 4 || MAX_TILE_SEQ <= 256, "");
+                uint32_t seqpack2 = 0;
                 unsigned okmask = 0;
 #pragma unroll
                 for (int i = 0; i < C; i++) {
-                    const uint32_t pos = cb + i;
-                    if (pos < Pend) {
+                    const uint32_t pos = P0 + i;
+                    if (i < (int)run && pos < pend) {
                         uint32_t c = s_lut[r[i]];
                         key = (key << 5) | c;
                         vr = c ? vr + 1 : 0;
