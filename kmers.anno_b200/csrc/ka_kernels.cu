@@ -227,12 +227,15 @@ __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
     const uint32_t lane = tid & 31;
     // descriptor and LUT byte are independent loads: both in flight before the first use
     const uint4 desc = p.first[blockIdx.x];
-    static_assert(THREADS >= 256, "one LUT byte per thread");
-    const uint8_t lut_byte = p.lut[tid & 255];
+    uint8_t lut_byte[(256 + THREADS - 1) / THREADS];
+#pragma unroll
+    for (int i = 0; i < (256 + THREADS - 1) / THREADS; i++) lut_byte[i] = p.lut[(tid + i * THREADS) & 255];
     const uint32_t s0 = desc.x, s1 = desc.x + desc.y;
     if (desc.y == 0) return;
 
-    if (tid < 256) s_lut[tid] = lut_byte;
+#pragma unroll
+    for (int i = 0; i < (256 + THREADS - 1) / THREADS; i++)
+        if (tid + i * THREADS < 256) s_lut[tid + i * THREADS] = lut_byte[i];
     if (tid == 0) mbar_init(&s_bar, 1);
     __syncthreads();
 
@@ -369,6 +372,8 @@ static auto with_tile_kernel(int cls, int variant, F f) {
         case 1: return f(tile_kernel<CLS, 4, 256, 3>, 256);          \
         case 2: return f(tile_kernel<CLS, 4, 512, 2>, 512);          \
         case 3: return f(tile_kernel<CLS, 4, 256, 4>, 256);          \
+        case 4: return f(tile_kernel<CLS, 4, 128, 6>, 128);          \
+        case 5: return f(tile_kernel<CLS, 8, 128, 4>, 128);          \
         default: return f(tile_kernel<CLS, 8, 256, 2>, 256);         \
     }
     if (cls == 32) { KA_VARIANTS(32) }

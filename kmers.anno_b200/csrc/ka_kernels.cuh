@@ -40,7 +40,8 @@ struct AnnotParams {
 
 // tile kernel variants (option "variant"): 0 = 8 positions/thread x 256 threads,
 // 1 = 4 x 256 (3 CTAs/SM), 2 = 4 x 512, 3 = 4 x 256 capped at 64 registers (4 CTAs/SM)
-constexpr int N_VARIANTS = 4;
+// 4 = 4 x 128 (6 CTAs/SM), 5 = 8 x 128 (4 CTAs/SM)
+constexpr int N_VARIANTS = 6;
 size_t tile_smem_bytes(uint32_t ext_max, uint32_t* res_bytes_out);
 cudaError_t tile_kernel_set_smem(int cls, int variant, size_t bytes);
 
