@@ -73,15 +73,18 @@ const char* ka_last_error(const ka_engine* e);
 
 /* Tunables, set before ka_db_load / ka_annotate.  Unknown name -> KA_ERR_INVALID.
  *   "load_factor"   table load factor in (0,0.9], default 0.4   (next ka_db_load)
- *   "tile_span"     residues of sequence starts per CTA tile, default 2048
- *   "long_seq"      sequences longer than this use the long-sequence kernel, default 5120
+ *   "tile_span"     residues of sequence starts per CTA tile, default 1024
+ *   "long_seq"      sequences longer than this get a tile of their own (second tile launch), default 2048
+ *   "mid_seq"       sequences longer than this use the global-scratch long-sequence kernel, default 8192
+ *   "mid_variant"   tile kernel shape of the second launch, default 1
  *   "table_mode"    0 = table replicated on every device (default); 1 = table sharded by sector range
  *                   over the engine's 2/4/8 devices, probes load remote sectors through NVLink
  *                   peer memory inside the probe kernel (for tables beyond one GPU)  (next ka_db_load)
  *   "filter"        per-sector presence signatures kept in L2 (1 on, 0 off (default), -1 = on for
  *                   tables of at least 2^20 sectors)   (next ka_db_load)
  *   "slot_bits"     force the table slot width (32, 64, 128; 0 = smallest that fits, default)
- *   "variant"       tile kernel shape: 0 = 8 positions x 256 threads, 1 = 4 x 256 (default), 2 = 4 x 512
+ *   "variant"       tile kernel shape: 0 = 8 positions x 256 threads, 1 = 4 x 256, 2 = 4 x 512, 3 = 4 x 256 / 64 regs,
+ *                   4 = 4 x 128 (default), 5 = 8 x 128
  *   "chunk_residues" residues per pipelined H2D chunk, default 32 Mi
  *   "l2_persist"    1 = set an L2 persisting access-policy window on the table (default 1)
  *   "warp_dedup"    1 = __match_any de-duplication of identical in-flight keys (default 0)

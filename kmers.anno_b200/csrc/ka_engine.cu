@@ -34,6 +34,7 @@ struct Pipe {
     int32_t* role = nullptr; int32_t* hits = nullptr; uint8_t* flag = nullptr;
     uint32_t* ctr = nullptr;  // 16 bytes: [0] big_count, [2..3] token cursor (u64)
     BigItem* big = nullptr; size_t big_cap = 0;
+    uint4* mid = nullptr; size_t mid_cap = 0;
     uint32_t* scratch = nullptr; size_t scratch_cap = 0;
     cudaEvent_t ev_k0 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_k1 = nullptr, done = nullptr;
     bool busy = false;
@@ -49,7 +50,7 @@ struct Device {
     const uint4** shard_ovf = nullptr;
     uint8_t* lut = nullptr;
     Pipe pipe[NPIPE];
-    size_t smem_set = 0;
+    size_t smem_set = 0, smem_set_mid = 0;
     // per-call accounting
     double kernel_ms = 0, tile_ms = 0;
     uint64_t launches = 0, h2d = 0, d2h = 0, probes = 0;
@@ -61,7 +62,7 @@ struct Device {
 
 struct ka_batch {
     int dev_index = 0;
-    uint64_t n_seq = 0, n_res = 0, base = 0, long_res = 0, n_long = 0;
+    uint64_t n_seq = 0, n_res = 0, base = 0, long_res = 0, n_long = 0, n_mid = 0;
     Pipe p;  // owns device buffers of the resident batch
 };
 
@@ -71,12 +72,14 @@ struct ka_engine {
     std::string err;
     // options
     double load_factor = 0.4;
-    uint32_t tile_span = 2048;
-    uint32_t long_seq = 5120;
+    uint32_t tile_span = 1024;
+    uint32_t long_seq = 2048;
+    uint32_t mid_seq = 8192;
+    int mid_variant = 1;
     uint64_t chunk_residues = 32ull << 20;
     int l2_persist = 1;
     int warp_dedup = 0;
-    int variant = 1;
+    int variant = 4;
     int slot_bits = 0;  // 0 = choose automatically
     int filter = 0;     // 1 = per-sector presence signatures in front of the table (measured slower
                         // in the fused kernel: 40 vs 46 G probes/s, profiles/r01_summary.md), -1 = auto
@@ -148,6 +151,7 @@ void pipe_free(Pipe& p) {
     if (p.flag) cudaFree(p.flag);
     if (p.ctr) cudaFree(p.ctr);
     if (p.big) cudaFree(p.big);
+    if (p.mid) cudaFree(p.mid);
     if (p.scratch) cudaFree(p.scratch);
     if (p.ev_k0) cudaEventDestroy(p.ev_k0);
     if (p.ev_t0) cudaEventDestroy(p.ev_t0);
@@ -160,7 +164,7 @@ void pipe_free(Pipe& p) {
 
 // size the per-chunk device buffers
 int pipe_reserve(Device& d, Pipe& p, uint64_t n_res, uint64_t n_seq, uint64_t n_tiles,
-                 uint64_t n_long, uint64_t long_res) {
+                 uint64_t n_long, uint64_t long_res, uint64_t n_mid) {
     int rc;
     if ((rc = ensure(d, p.res, p.res_cap, n_res + 64, "residues"))) return rc;
     size_t want_seq = n_seq + 1;
@@ -181,23 +185,25 @@ int pipe_reserve(Device& d, Pipe& p, uint64_t n_res, uint64_t n_seq, uint64_t n_
     }
     if ((rc = ensure(d, p.first, p.first_cap, n_tiles + 2, "tile index"))) return rc;
     if ((rc = ensure(d, p.big, p.big_cap, n_long + 1, "long-sequence list"))) return rc;
+    if ((rc = ensure(d, p.mid, p.mid_cap, n_mid + 1, "mid-sequence tiles"))) return rc;
     if ((rc = ensure(d, p.scratch, p.scratch_cap, 2 * long_res + 4, "long-sequence tokens")))
         return rc;
     return KA_OK;
 }
 
 struct ChunkShape {
-    uint64_t n_res = 0, n_long = 0, long_res = 0, probes = 0;
+    uint64_t n_res = 0, n_long = 0, long_res = 0, probes = 0, n_mid = 0;
 };
 
 // validate offsets of [cs, ce) and collect shape numbers; false = offsets not monotone
-bool scan_offsets(const uint64_t* off, uint64_t cs, uint64_t ce, uint32_t long_seq, int K,
+bool scan_offsets(const uint64_t* off, uint64_t cs, uint64_t ce, uint32_t long_seq, uint32_t mid_seq, int K,
                   ChunkShape& s) {
     s = ChunkShape();
     for (uint64_t i = cs; i < ce; i++) {
         if (off[i + 1] < off[i]) return false;
         uint64_t L = off[i + 1] - off[i];
-        if (L > long_seq) { s.n_long++; s.long_res += L; }
+        if (L > mid_seq) { s.n_long++; s.long_res += L; }
+        else if (L > long_seq) s.n_mid++;
         if (L >= (uint64_t)K) s.probes += L - K + 1;
     }
     s.n_res = off[ce] - off[cs];
@@ -212,6 +218,9 @@ void fill_params(ka_engine* e, Device& d, Pipe& p, uint64_t base, uint64_t n_res
     ap.n_seq = (uint32_t)n_seq;
     ap.tile_span = e->tile_span;
     ap.long_seq = e->long_seq;
+    ap.mid_seq = std::max(e->mid_seq, e->long_seq);
+    ap.mid_desc = p.mid;
+    ap.mid_count = p.ctr + 1;
     ap.ext_max = e->tile_span + e->long_seq;
     ap.n_tiles = (uint32_t)(n_res / e->tile_span + 1);
     tile_smem_bytes(ap.ext_max, &ap.res_bytes);
@@ -235,7 +244,7 @@ void fill_params(ka_engine* e, Device& d, Pipe& p, uint64_t base, uint64_t n_res
 }
 
 // enqueue plan + tile + big on the pipe's stream, bracketed by timing events
-int enqueue_kernels(ka_engine* e, Device& d, Pipe& p, const AnnotParams& ap, uint64_t n_long) {
+int enqueue_kernels(ka_engine* e, Device& d, Pipe& p, const AnnotParams& ap, uint64_t n_long, uint64_t n_mid) {
     size_t smem = tile_smem_bytes(ap.ext_max, nullptr);
     size_t smem_key = smem * 64 + (size_t)ap.tab.cls / 32 * 8 + (size_t)e->variant;
     if (d.smem_set != smem_key) {
@@ -247,8 +256,23 @@ int enqueue_kernels(ka_engine* e, Device& d, Pipe& p, const AnnotParams& ap, uin
     DCK(d, launch_plan(ap, p.st));
     DCK(d, cudaEventRecord(p.ev_t0, p.st));
     DCK(d, launch_tiles(ap, e->variant, smem, p.st));
-    DCK(d, cudaEventRecord(p.ev_t1, p.st));
     d.launches += 2;
+    if (n_mid) {
+        // sequences of long_seq < L <= mid_seq: one tile each, same kernel, larger shared-memory shape
+        AnnotParams am = ap;
+        am.first = p.mid;
+        am.n_tiles = (uint32_t)n_mid;
+        am.ext_max = ap.mid_seq;
+        size_t smem_mid = tile_smem_bytes(am.ext_max, &am.res_bytes);
+        size_t key_mid = smem_mid * 64 + (size_t)am.tab.cls / 32 * 8 + (size_t)e->mid_variant;
+        if (d.smem_set_mid != key_mid) {
+            DCK(d, tile_kernel_set_smem(am.tab.cls, e->mid_variant, smem_mid));
+            d.smem_set_mid = key_mid;
+        }
+        DCK(d, launch_tiles(am, e->mid_variant, smem_mid, p.st));
+        d.launches += 1;
+    }
+    DCK(d, cudaEventRecord(p.ev_t1, p.st));
     if (n_long) {
         int grid = (int)std::min<uint64_t>(n_long, (uint64_t)d.sm_count * 4);
         DCK(d, launch_big(ap, grid, p.st));
@@ -305,7 +329,7 @@ int annotate_range(ka_engine* e, Device& d, const uint8_t* residues, const uint6
         if (ce <= cs) ce = cs + 1;
         if (ce - cs > 0xfffffff0ull) ce = cs + 0xfffffff0ull;
         ChunkShape sh;
-        if (!scan_offsets(offsets, cs, ce, e->long_seq, e->info.K, sh)) {
+        if (!scan_offsets(offsets, cs, ce, e->long_seq, e->mid_seq, e->info.K, sh)) {
             d.err = KA_ERR_OFFSETS; d.errmsg = "offsets are not monotone";
             return d.err;
         }
@@ -323,7 +347,7 @@ int annotate_range(ka_engine* e, Device& d, const uint8_t* residues, const uint6
         }
         uint64_t n = ce - cs;
         uint64_t n_tiles = sh.n_res / e->tile_span + 1;
-        int rc = pipe_reserve(d, p, sh.n_res, n, n_tiles, sh.n_long, sh.long_res);
+        int rc = pipe_reserve(d, p, sh.n_res, n, n_tiles, sh.n_long, sh.long_res, sh.n_mid);
         if (rc) return rc;
         if (sh.n_res)
             DCK(d, cudaMemcpyAsync(p.res, residues + offsets[cs], sh.n_res, cudaMemcpyHostToDevice, p.st));
@@ -332,7 +356,7 @@ int annotate_range(ka_engine* e, Device& d, const uint8_t* residues, const uint6
         AnnotParams ap;
         fill_params(e, d, p, offsets[cs], sh.n_res, n, min_hits, ap);
         if (!out_flag) ap.out_flag = p.flag;  // kernel always writes flags; host may skip them
-        rc = enqueue_kernels(e, d, p, ap, sh.n_long);
+        rc = enqueue_kernels(e, d, p, ap, sh.n_long, sh.n_mid);
         if (rc) return rc;
         DCK(d, cudaMemcpyAsync(out_role + cs, p.role, n * 4, cudaMemcpyDeviceToHost, p.st));
         DCK(d, cudaMemcpyAsync(out_hits + cs, p.hits, n * 4, cudaMemcpyDeviceToHost, p.st));
@@ -610,6 +634,12 @@ int ka_set_option(ka_engine* e, const char* name, double v) {
         if (v < 256 || v > (1 << 20)) return fail(e, KA_ERR_INVALID, "long_seq must be in [256, 2^20]");
         e->long_seq = (uint32_t)v;
         if (e->long_seq < e->tile_span) e->long_seq = e->tile_span;
+    } else if (n == "mid_seq") {
+        if (v < 256 || v > 49152) return fail(e, KA_ERR_INVALID, "mid_seq must be in [256, 49152]");
+        e->mid_seq = (uint32_t)v;
+    } else if (n == "mid_variant") {
+        if (v < 0 || v >= N_VARIANTS) return fail(e, KA_ERR_INVALID, "mid_variant must be 0..%d", N_VARIANTS - 1);
+        e->mid_variant = (int)v;
     } else if (n == "chunk_residues") {
         if (v < 4096 || v > (double)(1ull << 30)) return fail(e, KA_ERR_INVALID, "chunk_residues must be in [4096, 2^30]");
         e->chunk_residues = (uint64_t)v;
@@ -631,8 +661,9 @@ int ka_set_option(ka_engine* e, const char* name, double v) {
     } else {
         return fail(e, KA_ERR_INVALID, "unknown option '%s'", name);
     }
-    if (tile_smem_bytes(e->tile_span + e->long_seq, nullptr) > 227 * 1024)
-        return fail(e, KA_ERR_INVALID, "tile_span + long_seq needs more than 227 KB of shared memory");
+    if (tile_smem_bytes(e->tile_span + e->long_seq, nullptr) > 227 * 1024 ||
+        tile_smem_bytes(std::max(e->mid_seq, e->long_seq), nullptr) > 227 * 1024)
+        return fail(e, KA_ERR_INVALID, "tile_span + long_seq (or mid_seq) needs more than 227 KB of shared memory");
     return KA_OK;
 }
 
@@ -829,12 +860,12 @@ int ka_batch_upload(ka_engine* e, int dev_index, const uint8_t* residues, const 
     Device& d = e->devs[dev_index];
     cudaSetDevice(d.id);
     ChunkShape sh;
-    if (!scan_offsets(offsets, 0, N, e->long_seq, e->info.K, sh)) return fail(e, KA_ERR_OFFSETS, "ka_batch_upload: offsets are not monotone");
+    if (!scan_offsets(offsets, 0, N, e->long_seq, e->mid_seq, e->info.K, sh)) return fail(e, KA_ERR_OFFSETS, "ka_batch_upload: offsets are not monotone");
     ka_batch* b = new ka_batch();
     b->dev_index = dev_index; b->n_seq = N; b->n_res = sh.n_res; b->base = offsets[0];
-    b->long_res = sh.long_res; b->n_long = sh.n_long;
+    b->long_res = sh.long_res; b->n_long = sh.n_long; b->n_mid = sh.n_mid;
     int rc = pipe_init(d, b->p);
-    if (rc == KA_OK) rc = pipe_reserve(d, b->p, sh.n_res, N, sh.n_res / e->tile_span + 1, sh.n_long, sh.long_res);
+    if (rc == KA_OK) rc = pipe_reserve(d, b->p, sh.n_res, N, sh.n_res / e->tile_span + 1, sh.n_long, sh.long_res, sh.n_mid);
     cudaError_t ce = cudaSuccess;
     if (rc == KA_OK && sh.n_res) ce = cudaMemcpy(b->p.res, residues + offsets[0], sh.n_res, cudaMemcpyHostToDevice);
     if (rc == KA_OK && ce == cudaSuccess) ce = cudaMemcpy(b->p.off, offsets, (N + 1) * 8, cudaMemcpyHostToDevice);
@@ -862,7 +893,7 @@ int ka_annotate_resident(ka_engine* e, ka_batch* b, int32_t min_hits) {
     d.kernel_ms = d.tile_ms = 0; d.launches = 0;
     AnnotParams ap;
     fill_params(e, d, b->p, b->base, b->n_res, b->n_seq, min_hits, ap);
-    int rc = enqueue_kernels(e, d, b->p, ap, b->n_long);
+    int rc = enqueue_kernels(e, d, b->p, ap, b->n_long, b->n_mid);
     if (rc == KA_OK) {
         cudaError_t ce = cudaStreamSynchronize(b->p.st);
         if (ce != cudaSuccess) rc = dev_fail(d, KA_ERR_CUDA, "annotate kernels", ce);

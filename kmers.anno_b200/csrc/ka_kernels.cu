@@ -176,11 +176,19 @@ __global__ void plan_kernel(AnnotParams p) {
     }
     if (gid < p.n_seq) {
         unsigned long long L = p.off[gid + 1] - p.off[gid];
-        if (L > p.long_seq) {
+        if (L > p.mid_seq) {
             uint32_t idx = atomicAdd(p.big_count, 1u);
             unsigned long long tb = atomicAdd(p.tok_cursor, 2ull * L);
             BigItem it; it.seq = (uint32_t)gid; it.pad = 0; it.tok_base = tb;
             p.big_list[idx] = it;
+        } else if (L > p.long_seq) {
+            // a tile of its own, run by the second tile launch (larger shared-memory configuration)
+            uint32_t idx = atomicAdd(p.mid_count, 1u);
+            uint4 d;
+            d.x = (uint32_t)gid; d.y = 1;
+            d.z = (uint32_t)(p.off[gid] - p.base);
+            d.w = (uint32_t)(p.off[gid + 1] - p.base);
+            p.mid_desc[idx] = d;
         }
     }
 }
@@ -202,12 +210,13 @@ cudaError_t launch_plan(const AnnotParams& p, cudaStream_t st) {
 //   [+256)                               residue -> code LUT
 //   [+4*(MAX_TILE_SEQ+4))                s_off: sequence starts relative to the stage
 //   [+3 * 4*MAX_TILE_SEQ)                s_cnt, s_min, s_max
-//   [+4*(2*ext_max+4))                   token set
+//   [+4*(tok_cap(ext_max)+4*MAX_TILE_SEQ+8))  token set: sequence q starting at residue a owns
+//                                        [tok_cap(a)+4q, +tok_cap(L)+4), never full (hits <= L-K+1)
 size_t tile_smem_bytes(uint32_t ext_max, uint32_t* res_bytes_out) {
     uint32_t res_bytes = (ext_max + 16 + 32 + 15) & ~15u;  // lead slack + K-1 over-read
     if (res_bytes_out) *res_bytes_out = res_bytes;
     return (size_t)res_bytes + 256 + 4 * (MAX_TILE_SEQ + 4) + 3 * 4 * MAX_TILE_SEQ +
-           4 * (2 * (size_t)ext_max + 4);
+           4 * ((size_t)tok_cap(ext_max) + 4 * MAX_TILE_SEQ + 8);
 }
 
 template <int CLS, int C, int THREADS, int MINB>
@@ -264,7 +273,7 @@ __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
             s_cnt[i] = 0; s_min[i] = 0x7fffffff; s_max[i] = -1;
         }
         {
-            const uint32_t ntok = 2u * (ext - lead);
+            const uint32_t ntok = tok_cap(ext - lead) + 4u * ns + 4u;
             const uint4 z = make_uint4(0, 0, 0, 0);
             for (uint32_t i = tid * 4; i < ntok; i += THREADS * 4)
                 *reinterpret_cast<uint4*>(s_tok + i) = z;
@@ -331,7 +340,7 @@ __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
                     if ((okmask & (1u << i)) && role[i] >= 0) {
                         const int q = (int)(((i < 4 ? seqpack : seqpack2) >> (8 * (i & 3))) & 0xffu);
                         const uint32_t a = s_off[q], b = s_off[q + 1];
-                        if (token_insert(s_tok + 2 * (a - lead), 2 * (b - a), sec[i])) {
+                        if (token_insert(s_tok + tok_cap(a - lead) + 4u * (uint32_t)q, tok_cap(b - a) + 4u, sec[i])) {
                             if (q != cur) {
                                 if (cur >= 0 && cnt > 0) {
                                     atomicAdd(&s_cnt[cur], cnt);

@@ -21,7 +21,10 @@ struct AnnotParams {
     uint32_t n_seq;
     uint32_t n_tiles;                 // floor(R / tile_span) + 1
     uint32_t tile_span;               // residues of sequence starts per tile
-    uint32_t long_seq;                // L > long_seq goes to the long-sequence kernel
+    uint32_t long_seq;                // L > long_seq leaves the residue tiles: one tile of its own (mid) or big_kernel
+    uint32_t mid_seq;                 // long_seq < L <= mid_seq: a single-sequence tile in the second tile launch
+    uint4* mid_desc;                  // descriptors of those single-sequence tiles
+    uint32_t* mid_count;              // [0] how many
     uint32_t ext_max;                 // tile_span + long_seq: max residue extent of a tile
     uint32_t res_bytes;               // smem bytes reserved for the residue stage
     uint4* first;                     // n_tiles descriptors {first seq, n seqs (long tail removed), g0, g1}
@@ -43,6 +46,8 @@ struct AnnotParams {
 // 4 = 4 x 128 (6 CTAs/SM), 5 = 8 x 128 (4 CTAs/SM)
 constexpr int N_VARIANTS = 6;
 size_t tile_smem_bytes(uint32_t ext_max, uint32_t* res_bytes_out);
+// de-dup token capacity of x window positions: x + x/4 (worst-case load factor 0.8)
+__host__ __device__ inline uint32_t tok_cap(uint32_t x) { return x + (x >> 2); }
 cudaError_t tile_kernel_set_smem(int cls, int variant, size_t bytes);
 
 cudaError_t launch_plan(const AnnotParams& p, cudaStream_t st);

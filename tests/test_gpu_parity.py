@@ -117,7 +117,7 @@ def test_many_tiny_sequences_sub_batches(ka, oracle):
 
 
 def test_long_sequences_use_big_kernel(ka, oracle):
-    lengths = [20000, 300, 7000, 5121, 5120, 64, 0, 12000]
+    lengths = [20000, 300, 7000, 2049, 2048, 64, 0, 12000, 8192, 8193, 2047, 5000]
     seqs, kmers, roles = ragged_case(21, n_seq=len(lengths), K=8, lengths=lengths, db_frac=0.5)
     run_case(ka, oracle, seqs, kmers, roles, 8, min_hits=3)
     # the same inputs with a small long_seq so that most sequences take the long path
@@ -126,7 +126,9 @@ def test_long_sequences_use_big_kernel(ka, oracle):
 
 @pytest.mark.parametrize("opts", [
     {"tile_span": 256, "long_seq": 1024},
-    {"tile_span": 4096, "long_seq": 8192},
+    {"tile_span": 4096, "long_seq": 8192, "mid_seq": 8192, "variant": 1},
+    {"tile_span": 512, "long_seq": 512, "mid_seq": 600},
+    {"mid_seq": 2048},
     {"chunk_residues": 4096},
     {"load_factor": 0.9},
     {"load_factor": 0.05},
