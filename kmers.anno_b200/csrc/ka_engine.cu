@@ -269,7 +269,14 @@ int enqueue_kernels(ka_engine* e, Device& d, Pipe& p, const AnnotParams& ap, uin
             DCK(d, tile_kernel_set_smem(am.tab.cls, e->mid_variant, smem_mid));
             d.smem_set_mid = key_mid;
         }
-        DCK(d, launch_tiles(am, e->mid_variant, smem_mid, p.st));
+        {
+            cudaError_t ce = launch_tiles(am, e->mid_variant, smem_mid, p.st);
+            if (ce != cudaSuccess) {
+                char buf[256];
+                snprintf(buf, sizeof buf, "mid tile launch (tiles %u, smem %zu, variant %d, cls %d)", am.n_tiles, smem_mid, e->mid_variant, am.tab.cls);
+                return dev_fail(d, KA_ERR_CUDA, buf, ce);
+            }
+        }
         d.launches += 1;
     }
     DCK(d, cudaEventRecord(p.ev_t1, p.st));
