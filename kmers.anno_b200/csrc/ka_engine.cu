@@ -50,7 +50,7 @@ struct Device {
     const uint4** shard_ovf = nullptr;
     uint8_t* lut = nullptr;
     Pipe pipe[NPIPE];
-    size_t smem_set = 0, smem_set_mid = 0;
+    size_t smem_set = 0;   // opt-in shared-memory limit once the tile kernels are configured
     // per-call accounting
     double kernel_ms = 0, tile_ms = 0;
     uint64_t launches = 0, h2d = 0, d2h = 0, probes = 0;
@@ -246,11 +246,15 @@ void fill_params(ka_engine* e, Device& d, Pipe& p, uint64_t base, uint64_t n_res
 // enqueue plan + tile + big on the pipe's stream, bracketed by timing events
 int enqueue_kernels(ka_engine* e, Device& d, Pipe& p, const AnnotParams& ap, uint64_t n_long, uint64_t n_mid) {
     size_t smem = tile_smem_bytes(ap.ext_max, nullptr);
-    size_t smem_key = smem * 64 + (size_t)ap.tab.cls / 32 * 8 + (size_t)e->variant;
-    if (d.smem_set != smem_key) {
-        DCK(d, tile_kernel_set_smem(ap.tab.cls, e->variant, smem));
-        d.smem_set = smem_key;
+    if (!d.smem_set) {
+        // every tile-kernel instantiation may use up to the opt-in shared-memory limit of the device
+        int optin = 0;
+        DCK(d, cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d.id));
+        for (int cls : {32, 64, 128})
+            for (int v = 0; v < N_VARIANTS; v++) DCK(d, tile_kernel_set_smem(cls, v, (size_t)optin));
+        d.smem_set = (size_t)optin;
     }
+    if (smem > d.smem_set) return dev_fail(d, KA_ERR_INVALID, "tile shared memory exceeds the device limit", cudaErrorInvalidValue);
     DCK(d, cudaMemsetAsync(p.ctr, 0, 16, p.st));
     DCK(d, cudaEventRecord(p.ev_k0, p.st));
     DCK(d, launch_plan(ap, p.st));
@@ -264,11 +268,7 @@ int enqueue_kernels(ka_engine* e, Device& d, Pipe& p, const AnnotParams& ap, uin
         am.n_tiles = (uint32_t)n_mid;
         am.ext_max = ap.mid_seq;
         size_t smem_mid = tile_smem_bytes(am.ext_max, &am.res_bytes);
-        size_t key_mid = smem_mid * 64 + (size_t)am.tab.cls / 32 * 8 + (size_t)e->mid_variant;
-        if (d.smem_set_mid != key_mid) {
-            DCK(d, tile_kernel_set_smem(am.tab.cls, e->mid_variant, smem_mid));
-            d.smem_set_mid = key_mid;
-        }
+        if (smem_mid > d.smem_set) return dev_fail(d, KA_ERR_INVALID, "mid tile shared memory exceeds the device limit", cudaErrorInvalidValue);
         {
             cudaError_t ce = launch_tiles(am, e->mid_variant, smem_mid, p.st);
             if (ce != cudaSuccess) {
