@@ -251,8 +251,8 @@ int enqueue_kernels(ka_engine* e, Device& d, Pipe& p, const AnnotParams& ap, uin
         int optin = 0;
         DCK(d, cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d.id));
         for (int cls : {32, 64, 128})
-            for (int v = 0; v < N_VARIANTS; v++) DCK(d, tile_kernel_set_smem(cls, v, (size_t)optin));
-        d.smem_set = (size_t)optin;
+            for (int v = 0; v < N_VARIANTS; v++) DCK(d, tile_kernel_set_smem(cls, v, (size_t)optin - 2048));  // minus the static part
+        d.smem_set = (size_t)optin - 2048;
     }
     if (smem > d.smem_set) return dev_fail(d, KA_ERR_INVALID, "tile shared memory exceeds the device limit", cudaErrorInvalidValue);
     DCK(d, cudaMemsetAsync(p.ctr, 0, 16, p.st));
