@@ -73,7 +73,7 @@ const char* ka_last_error(const ka_engine* e);
 
 /* Tunables, set before ka_db_load / ka_annotate.  Unknown name -> KA_ERR_INVALID.
  *   "load_factor"   table load factor in (0,0.9], default 0.4   (next ka_db_load)
- *   "tile_span"     residues of sequence starts per CTA tile, default 1024
+ *   "tile_span"     residues of sequence starts per CTA tile, default 1536
  *   "long_seq"      sequences longer than this get a tile of their own (second tile launch), default 2048
  *   "mid_seq"       sequences longer than this use the global-scratch long-sequence kernel, default 8192
  *   "mid_variant"   tile kernel shape of the second launch, default 1

@@ -72,7 +72,7 @@ struct ka_engine {
     std::string err;
     // options
     double load_factor = 0.4;
-    uint32_t tile_span = 1024;
+    uint32_t tile_span = 1536;
     uint32_t long_seq = 2048;
     uint32_t mid_seq = 8192;
     int mid_variant = 1;
