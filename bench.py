@@ -40,6 +40,10 @@ sys.path.insert(0, ROOT)
 SEED = 20261018
 N_PROT = 4500
 BYTES_PER_PROBE = 33.0  # 32-byte bucket sector + 1 residue byte
+# dram__bytes_read.sum + dram__bytes_write.sum of tile_kernel<32,4,128,6> from the ncu --set full
+# capture of `bench.py --genomes 60` (profiles/r01_summary.md §E): 8.423 GB for 88.1 M probes.
+# B200 fills a whole 128-byte line per L2 miss, hence ~3x the algorithmic bytes.
+NCU_DRAM_BYTES_PER_PROBE = 8.423e9 / 88.1e6
 
 
 def parse():
@@ -295,7 +299,9 @@ def main():
     peak, peak_src = measured_peak()
     achieved = BYTES_PER_PROBE * probes / (tile_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_PROBE * probes,
+                "traffic_note": "ncu dram bytes per probe (95.6 B, 60-proteome capture) x probes of this launch",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_probe": BYTES_PER_PROBE, "probes_per_launch": int(probes),
                 "kernel_ms": tile_ms}
     rand = None
