@@ -41,9 +41,9 @@ SEED = 20261018
 N_PROT = 4500
 BYTES_PER_PROBE = 33.0  # 32-byte bucket sector + 1 residue byte
 # dram__bytes_read.sum + dram__bytes_write.sum of tile_kernel<32,4,128,6> from the ncu --set full
-# capture of `bench.py --genomes 60` (profiles/r01_summary.md §E): 8.423 GB for 88.1 M probes.
+# capture of `bench.py --genomes 60` (profiles/r01_summary.md §E): 8.426 GB (8.417 read + 0.009 write) for 88.1 M probes.
 # B200 fills a whole 128-byte line per L2 miss, hence ~3x the algorithmic bytes.
-NCU_DRAM_BYTES_PER_PROBE = 8.423e9 / 88.1e6
+NCU_DRAM_BYTES_PER_PROBE = 8.426e9 / 88.1e6
 
 
 def parse():
