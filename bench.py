@@ -209,6 +209,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
     if world > 1:
+        # NCCL's version banner goes to stdout (NCCL_DEBUG=VERSION); stdout carries only the JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
