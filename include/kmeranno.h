@@ -87,7 +87,6 @@ const char* ka_last_error(const ka_engine* e);
  *                   4 = 4 x 128 (default), 5 = 8 x 128
  *   "chunk_residues" residues per pipelined H2D chunk, default 32 Mi
  *   "l2_persist"    1 = set an L2 persisting access-policy window on the table (default 1)
- *   "warp_dedup"    1 = __match_any de-duplication of identical in-flight keys (default 0)
  */
 int ka_set_option(ka_engine* e, const char* name, double value);
 

@@ -78,7 +78,6 @@ struct ka_engine {
     int mid_variant = 1;
     uint64_t chunk_residues = 32ull << 20;
     int l2_persist = 1;
-    int warp_dedup = 0;
     int variant = 4;
     int slot_bits = 0;  // 0 = choose automatically
     int filter = 0;     // 1 = per-sector presence signatures in front of the table (measured slower
@@ -240,7 +239,6 @@ void fill_params(ka_engine* e, Device& d, Pipe& p, uint64_t base, uint64_t n_res
     ap.tok_cursor = reinterpret_cast<unsigned long long*>(p.ctr + 2);
     ap.big_list = p.big;
     ap.scratch = p.scratch;
-    ap.warp_dedup = e->warp_dedup;
 }
 
 // enqueue plan + tile + big on the pipe's stream, bracketed by timing events
@@ -652,8 +650,6 @@ int ka_set_option(ka_engine* e, const char* name, double v) {
         e->chunk_residues = (uint64_t)v;
     } else if (n == "l2_persist") {
         e->l2_persist = v != 0;
-    } else if (n == "warp_dedup") {
-        e->warp_dedup = v != 0;
     } else if (n == "table_mode") {
         if (v != 0 && v != 1) return fail(e, KA_ERR_INVALID, "table_mode must be 0 (replicated) or 1 (sharded)");
         e->table_mode = (int)v;

@@ -38,7 +38,6 @@ struct AnnotParams {
     unsigned long long* tok_cursor;   // [0] tokens handed out
     BigItem* big_list;
     uint32_t* scratch;                // de-dup tokens of the long sequences
-    int warp_dedup;
 };
 
 // tile kernel variants (option "variant"): 0 = 8 positions/thread x 256 threads,
