@@ -385,6 +385,8 @@ static auto with_tile_kernel(int cls, int variant, F f) {
         case 3: return f(tile_kernel<CLS, 4, 256, 4>, 256);          \
         case 4: return f(tile_kernel<CLS, 4, 128, 6>, 128);          \
         case 5: return f(tile_kernel<CLS, 8, 128, 4>, 128);          \
+        case 6: return f(tile_kernel<CLS, 4, 128, 8>, 128);          \
+        case 7: return f(tile_kernel<CLS, 2, 128, 10>, 128);         \
         default: return f(tile_kernel<CLS, 8, 256, 2>, 256);         \
     }
     if (cls == 32) { KA_VARIANTS(32) }

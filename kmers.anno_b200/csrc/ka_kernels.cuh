@@ -43,7 +43,8 @@ struct AnnotParams {
 // tile kernel variants (option "variant"): 0 = 8 positions/thread x 256 threads,
 // 1 = 4 x 256 (3 CTAs/SM), 2 = 4 x 512, 3 = 4 x 256 capped at 64 registers (4 CTAs/SM)
 // 4 = 4 x 128 (6 CTAs/SM), 5 = 8 x 128 (4 CTAs/SM)
-constexpr int N_VARIANTS = 6;
+// 6 = 4 x 128 capped at 64 registers (8 CTAs/SM), 7 = 2 x 128 (10 CTAs/SM)
+constexpr int N_VARIANTS = 8;
 size_t tile_smem_bytes(uint32_t ext_max, uint32_t* res_bytes_out);
 // de-dup token capacity of x window positions: x + x/4 (worst-case load factor 0.8)
 __host__ __device__ inline uint32_t tok_cap(uint32_t x) { return x + (x >> 2); }
