@@ -1,15 +1,17 @@
 // App.cpp — command dispatch, mirror of proteins/kmers/anno/App.java:51-84 for the verbs of the
-// GPU hot path.  `apply` runs on the engine; the reference's other verbs are outside the
+// GPU hot path.  `build` and `apply` run on the engine; the reference's other verbs are outside the
 // scope of this engine and are reported as such.
 #include <iostream>
 #include <string>
 #include <vector>
 
 #include "ApplyKmerProcessor.hpp"
+#include "BuildKmerProcessor.hpp"
 
 using namespace theseed;
 
 static const char* kCommands[][2] = {
+    {"build", "build a discriminating-kmer database from annotated genomes (GPU engine)"},
     {"apply", "apply a discriminating-kmer database to genomes (GPU engine)"},
 };
 
@@ -26,6 +28,11 @@ int main(int argc, char** argv) {
         ApplyKmerProcessor processor;                          // App.java:62
         if (!processor.parseCommand(newArgs)) return 1;        // App.java:81
         return processor.run();                                // App.java:82
+    }
+    if (command == "build") {
+        BuildKmerProcessor processor;                          // App.java:61
+        if (!processor.parseCommand(newArgs)) return 1;
+        return processor.run();
     }
     if (command == "-h" || command == "--help") { showCommands(); return 0; }
     std::cerr << "Invalid command " << command << ".\n";       // App.java:76

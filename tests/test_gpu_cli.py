@@ -61,3 +61,28 @@ def test_apply_many_genomes_order_and_batching(tmp_path):
     out, _ = run(["--batch", "2", DB, ROLES, str(tmp_path)])
     vec = open(os.path.join(GOLD, "small.apply.tsv")).read().split("\t", 1)[1]
     assert out == "".join(f"{g}\t{vec}" for g in sorted(ids))
+
+
+def test_build_verb_then_apply(tmp_path):
+    """`build` over the reference's small genome reproduces the golden kmerdb.tbl (as a set of
+    lines; the reference's order is HashMap order) and `apply` on its output the golden report."""
+    gid, pegs = load_small()
+    gdir = tmp_path / "genomes"
+    gdir.mkdir()
+    write_gto(str(gdir / f"{gid}.gto"), gid, pegs)
+    r = subprocess.run([CLI, "build", ROLES, ROLES, str(gdir)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = sorted(r.stdout.splitlines())
+    want = sorted(open(DB).read().splitlines())
+    assert len(got) == 23796 and got == want
+    assert "discriminating kmers remaining" in r.stderr
+    db = tmp_path / "kmerdb.tbl"
+    db.write_text(r.stdout)
+    out, _ = run(["--format", "VERIFY", str(db), ROLES, str(gdir)])
+    assert out == open(os.path.join(GOLD, "small.verify.tsv")).read()
+    # -K changes the k-mer length of the DB and apply follows it
+    r = subprocess.run([CLI, "build", "-K", "10", ROLES, ROLES, str(gdir)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and all(len(l.split("\t")[0]) == 10 for l in r.stdout.splitlines())
+    db.write_text(r.stdout)
+    _, err = run([str(db), ROLES, str(gdir)])
+    assert "Kmer size is 10." in err

@@ -13,6 +13,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
 BIN = os.path.join(ROOT, "kmers.anno_b200", "bin")
+ROLES_FILE = os.path.join(GOLD, "small.roles.in.use")
 
 
 def test_abi_library_exports_every_declared_symbol():
@@ -57,6 +58,10 @@ def test_cli_argument_errors_follow_the_reference():
     assert r.returncode == 1 and "--format" in r.stderr
     r = subprocess.run([cli, "apply", db], capture_output=True, text=True)
     assert r.returncode == 1 and "is required" in r.stderr
+    r = subprocess.run([cli, "build", ROLES_FILE, "noroles", GOLD], capture_output=True, text=True)
+    assert r.returncode == 1 and "Good-role file noroles not found or unreadable." in r.stderr
+    r = subprocess.run([cli, "build", ROLES_FILE, ROLES_FILE, "nodir"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Genome directory nodir not found or invalid." in r.stderr
     r = subprocess.run([cli, "nosuchverb"], capture_output=True, text=True)
     assert r.returncode == 1 and "Invalid command nosuchverb." in r.stderr
 
