@@ -3,7 +3,7 @@ NVCC      ?= /usr/local/cuda/bin/nvcc
 CXX       ?= g++
 CC        ?= gcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v
+NVFLAGS   := $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v $(if $(DEBUG),-DKA_DEBUG,)
 PKG       := kmers.anno_b200
 CSRC      := $(PKG)/csrc
 HOST      := $(PKG)/host

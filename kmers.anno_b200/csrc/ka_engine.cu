@@ -137,7 +137,8 @@ int pipe_init(Device& d, Pipe& p) {
     DCK(d, cudaEventCreate(&p.ev_t1));
     DCK(d, cudaEventCreate(&p.ev_k1));
     DCK(d, cudaEventCreateWithFlags(&p.done, cudaEventDisableTiming));
-    DCK(d, cudaMalloc((void**)&p.ctr, 16));
+    DCK(d, cudaMalloc((void**)&p.ctr, 32));
+    DCK(d, cudaMemset(p.ctr, 0, 32));
     return KA_OK;
 }
 
@@ -239,6 +240,7 @@ void fill_params(ka_engine* e, Device& d, Pipe& p, uint64_t base, uint64_t n_res
     ap.tok_cursor = reinterpret_cast<unsigned long long*>(p.ctr + 2);
     ap.big_list = p.big;
     ap.scratch = p.scratch;
+    ap.dbg = p.ctr + 4;
 }
 
 // enqueue plan + tile + big on the pipe's stream, bracketed by timing events
@@ -288,6 +290,17 @@ int enqueue_kernels(ka_engine* e, Device& d, Pipe& p, const AnnotParams& ap, uin
 }
 
 int collect_times(Device& d, Pipe& p) {
+#ifdef KA_DEBUG
+    uint32_t dbg = 0;
+    DCK(d, cudaMemcpy(&dbg, p.ctr + 4, 4, cudaMemcpyDeviceToHost));
+    if (dbg) {
+        char buf[96];
+        snprintf(buf, sizeof buf, "KA_DEBUG bounds check failed in a kernel (codes 0x%x)", dbg);
+        d.err = KA_ERR_CUDA; d.errmsg = buf;
+        cudaMemset(p.ctr + 4, 0, 4);
+        return d.err;
+    }
+#endif
     float a = 0, b = 0;
     DCK(d, cudaEventElapsedTime(&a, p.ev_k0, p.ev_k1));
     DCK(d, cudaEventElapsedTime(&b, p.ev_t0, p.ev_t1));

@@ -27,6 +27,15 @@
 // sector) + 1 (the residue).
 #include "ka_kernels.cuh"
 
+// `make DEBUG=1` compiles bounds checks into the kernels (compute-sanitizer is not available on
+// the GPU pool): a failed check ORs its code into p.dbg[0] and the engine turns that into an
+// error; indices are clamped so that the kernel itself stays in bounds.
+#ifdef KA_DEBUG
+#define KA_CHECK(cond, code) do { if (!(cond)) atomicOr(p.dbg, (code)); } while (0)
+#else
+#define KA_CHECK(cond, code) do { } while (0)
+#endif
+
 namespace ka {
 
 // ------------------------------------------------------------------------------------
@@ -261,6 +270,8 @@ __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
         const uint32_t lead = (uint32_t)(g0 - g0a);
         const uint32_t ext = (uint32_t)(g1 - g0a);           // stage-relative end of the residues
         const uint32_t nbytes = (ext + 15u) & ~15u;
+        KA_CHECK(nbytes + 32 <= p.res_bytes, 1u);                               // residue stage holds the tile
+        KA_CHECK(tok_cap(ext - lead) + 4u * ns + 8u <= tok_cap(p.ext_max) + 4u * MAX_TILE_SEQ + 8u, 2u);  // token set too
 
         // stage the residues of sequences [sb, sb+ns) with one bulk copy
         if (tid == 0 && nbytes) {
@@ -295,6 +306,7 @@ __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
                     if (s_off[mid] <= P0) lo = mid + 1; else hi = mid;
                 }
                 int si = lo - 1;                       // >= 0: P0 >= lead = s_off[0]
+                KA_CHECK(si >= 0 && si < (int)ns, 32u);
                 uint32_t nb = s_off[si + 1];           // end of the sequence holding the current position
 
                 // rolling 5-bit pack: warm up over K-1 residues, then one key per position
@@ -321,7 +333,7 @@ __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
                         uint32_t c = s_lut[r[i]];
                         key = (key << 5) | c;
                         vr = c ? vr + 1 : 0;
-                        while (pos >= nb) { si++; nb = s_off[si + 1]; }   // pos < ext = s_off[ns]: si stays < ns
+                        while (pos >= nb) { si++; KA_CHECK(si < (int)ns, 4u); nb = s_off[si + 1]; }   // pos < ext = s_off[ns]: si stays < ns
                         if (pos + K <= nb && vr >= K) {
                             okmask |= 1u << i;
                             if (i < 4) seqpack |= (uint32_t)si << (8 * (i & 3));
@@ -339,6 +351,8 @@ __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
                     if ((okmask & (1u << i)) && role[i] >= 0) {
                         const int q = (int)(((i < 4 ? seqpack : seqpack2) >> (8 * (i & 3))) & 0xffu);
                         const uint32_t a = s_off[q], b = s_off[q + 1];
+                        KA_CHECK(q >= 0 && q < (int)ns && b >= a && a >= lead, 8u);
+                        KA_CHECK(tok_cap(a - lead) + 4u * (uint32_t)q + tok_cap(b - a) + 4u <= tok_cap(p.ext_max) + 4u * MAX_TILE_SEQ + 8u, 16u);
                         if (token_insert(s_tok + tok_cap(a - lead) + 4u * (uint32_t)q, tok_cap(b - a) + 4u, sec[i])) {
                             if (q != cur) {
                                 if (cur >= 0 && cnt > 0) {

@@ -38,6 +38,7 @@ struct AnnotParams {
     unsigned long long* tok_cursor;   // [0] tokens handed out
     BigItem* big_list;
     uint32_t* scratch;                // de-dup tokens of the long sequences
+    uint32_t* dbg;                    // KA_DEBUG builds: [0] OR of the codes of failed bounds checks
 };
 
 // tile kernel variants (option "variant"): 0 = 8 positions/thread x 256 threads,
