@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -1046,7 +1047,11 @@ int ka_build(ka_engine* e, const uint8_t* residues, const uint64_t* offsets, uin
 
 void* ka_host_alloc(size_t bytes) {
     void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    // KA_PINNED_WC=1: write-combined pinned memory (no CPU cache snooping on the DMA reads; the
+    // host must then only WRITE these buffers) — an experiment knob for multi-GPU ingest
+    const char* wc = getenv("KA_PINNED_WC");
+    unsigned flags = cudaHostAllocPortable | ((wc && wc[0] == '1') ? cudaHostAllocWriteCombined : 0u);
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, flags) != cudaSuccess) return nullptr;
     return p;
 }
 
