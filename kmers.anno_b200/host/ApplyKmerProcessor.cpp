@@ -2,9 +2,12 @@
 // /root/reference/src/main/java/org/theseed/proteins/kmers/anno/ApplyKmerProcessor.java.
 #include "ApplyKmerProcessor.hpp"
 
+#include <atomic>
 #include <cstdlib>
 #include <fstream>
+#include <future>
 #include <sys/stat.h>
+#include <thread>
 
 namespace theseed {
 
@@ -33,7 +36,8 @@ void ApplyKmerProcessor::usage(std::ostream& os) {
           " --format       reporting format (default APPLY)\n"
           " -m (--min)     minimum number of hits required to call a role (default 5)\n"
           " --devices      CUDA devices to shard the sequences over (default 0)\n"
-          " --batch        genomes per GPU batch (default 64)\n";
+          " --batch        genomes per GPU batch (default 64)\n"
+          " --threads      genome-parsing threads (default: hardware threads)\n";
 }
 
 void ApplyKmerProcessor::setDefaults() {
@@ -41,6 +45,7 @@ void ApplyKmerProcessor::setDefaults() {
     minHits_ = 5;                                  // :79
     devices_ = {0};
     batchGenomes_ = 64;
+    loadThreads_ = (int)std::max(1u, std::thread::hardware_concurrency());
 }
 
 bool ApplyKmerProcessor::parseCommand(const std::vector<std::string>& args) {
@@ -57,6 +62,7 @@ bool ApplyKmerProcessor::parseCommand(const std::vector<std::string>& args) {
             else if (a == "--format") outputType_ = ApplyKmerReporter::parseType(value());
             else if (a == "-m" || a == "--min") minHits_ = parseInt(a, value());
             else if (a == "--batch") batchGenomes_ = parseInt(a, value());
+            else if (a == "--threads") loadThreads_ = parseInt(a, value());
             else if (a == "--devices") {
                 devices_.clear();
                 const std::string& v = value();
@@ -181,12 +187,37 @@ void ApplyKmerProcessor::flushBatch(std::vector<std::unique_ptr<Genome>>& genome
 void ApplyKmerProcessor::runCommand() {
     GenomeDirectory genomes(inDir_);                                      // :116
     log_ << genomes.size() << " genomes found in input directory.\n";     // :117
-    std::vector<std::unique_ptr<Genome>> batch;
-    for (const std::string& file : genomes.files()) {                     // :118
-        batch.push_back(std::make_unique<Genome>(file));
-        if ((int)batch.size() >= batchGenomes_) flushBatch(batch);
+    const std::vector<std::string>& files = genomes.files();
+    // Ingest pipeline: the genomes of batch i+1 are parsed by `loadThreads_` threads while the
+    // GPU annotates batch i; reports are still written in directory order (:118).
+    auto loadBatch = [&](size_t b0) {
+        size_t n = std::min(files.size() - b0, (size_t)batchGenomes_);
+        std::vector<std::unique_ptr<Genome>> out(n);
+        std::vector<std::string> errors(n);
+        std::atomic<size_t> next{0};
+        auto work = [&] {
+            for (size_t i = next++; i < n; i = next++) {
+                try { out[i] = std::make_unique<Genome>(files[b0 + i]); }
+                catch (const std::exception& e) { errors[i] = e.what(); }
+            }
+        };
+        size_t nt = std::min<size_t>(std::max(1, loadThreads_), n);
+        std::vector<std::thread> th;
+        for (size_t t = 1; t < nt; t++) th.emplace_back(work);
+        work();
+        for (auto& t : th) t.join();
+        for (size_t i = 0; i < n; i++)
+            if (!out[i]) throw IOException("Error loading " + files[b0 + i] + ": " + errors[i]);
+        return out;
+    };
+    std::future<std::vector<std::unique_ptr<Genome>>> pending;
+    if (!files.empty()) pending = std::async(std::launch::async, loadBatch, (size_t)0);
+    for (size_t b0 = 0; b0 < files.size(); b0 += (size_t)batchGenomes_) {
+        std::vector<std::unique_ptr<Genome>> batch = pending.get();
+        size_t nextStart = b0 + (size_t)batchGenomes_;
+        if (nextStart < files.size()) pending = std::async(std::launch::async, loadBatch, nextStart);
+        flushBatch(batch);
     }
-    flushBatch(batch);
     reporter_->closeReport();                                             // :153
     reporter_->close();                                                   // :154
 }

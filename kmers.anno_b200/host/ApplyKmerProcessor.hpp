@@ -4,7 +4,8 @@
 // the GPU engine and the reporter calls are replayed in the original peg order.
 //
 //   apply [--format VERIFY|APPLY] [-m|--min N] kmerdb.tbl roles.in.use gtoDir
-// added knobs (ordinary options, as SURVEY §5 asks): --devices 0,1,..  --batch genomes
+// added knobs (ordinary options, as SURVEY §5 asks): --devices 0,1,..  --batch genomes  --threads n
+// Genomes of the next batch are parsed by a thread pool while the GPU annotates the current one.
 #pragma once
 #include <iostream>
 #include <memory>
@@ -47,6 +48,7 @@ private:
     std::string kmerDbFile_, goodRoleFile_, inDir_;
     std::vector<int> devices_{0};
     int batchGenomes_ = 64;
+    int loadThreads_ = 1;
     // state
     std::unique_ptr<ApplyKmerReporter> reporter_;
     std::unique_ptr<KmerEngine> engine_;       // replaces Map<String,String> kmerRoleMap (:53)
