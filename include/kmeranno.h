@@ -83,8 +83,7 @@ const char* ka_last_error(const ka_engine* e);
  *   "filter"        per-sector presence signatures kept in L2 (1 on, 0 off (default), -1 = on for
  *                   tables of at least 2^20 sectors)   (next ka_db_load)
  *   "slot_bits"     force the table slot width (32, 64, 128; 0 = smallest that fits, default)
- *   "variant"       tile kernel shape: 0 = 8 positions x 256 threads, 1 = 4 x 256, 2 = 4 x 512, 3 = 4 x 256 / 64 regs,
- *                   4 = 4 x 128 (default), 5 = 8 x 128
+ *   "variant"       tile kernel shape: 0 = 4 positions x 128 threads (default), 1 = 4 x 256, 2 = 8 x 256
  *   "chunk_residues" residues per pipelined H2D chunk, default 32 Mi
  *   "l2_persist"    1 = set an L2 persisting access-policy window on the table (default 1)
  */

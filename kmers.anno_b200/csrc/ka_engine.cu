@@ -79,7 +79,7 @@ struct ka_engine {
     int mid_variant = 1;
     uint64_t chunk_residues = 32ull << 20;
     int l2_persist = 1;
-    int variant = 4;
+    int variant = 0;
     int slot_bits = 0;  // 0 = choose automatically
     int filter = 0;     // 1 = per-sector presence signatures in front of the table (measured slower
                         // in the fused kernel: 40 vs 46 G probes/s, profiles/r01_summary.md), -1 = auto

@@ -395,13 +395,8 @@ static auto with_tile_kernel(int cls, int variant, F f) {
 #define KA_VARIANTS(CLS)                                             \
     switch (variant) {                                               \
         case 1: return f(tile_kernel<CLS, 4, 256, 3>, 256);          \
-        case 2: return f(tile_kernel<CLS, 4, 512, 2>, 512);          \
-        case 3: return f(tile_kernel<CLS, 4, 256, 4>, 256);          \
-        case 4: return f(tile_kernel<CLS, 4, 128, 6>, 128);          \
-        case 5: return f(tile_kernel<CLS, 8, 128, 4>, 128);          \
-        case 6: return f(tile_kernel<CLS, 4, 128, 8>, 128);          \
-        case 7: return f(tile_kernel<CLS, 2, 128, 10>, 128);         \
-        default: return f(tile_kernel<CLS, 8, 256, 2>, 256);         \
+        case 2: return f(tile_kernel<CLS, 8, 256, 2>, 256);          \
+        default: return f(tile_kernel<CLS, 4, 128, 6>, 128);         \
     }
     if (cls == 32) { KA_VARIANTS(32) }
     if (cls == 64) { KA_VARIANTS(64) }

@@ -41,11 +41,11 @@ struct AnnotParams {
     uint32_t* dbg;                    // KA_DEBUG builds: [0] OR of the codes of failed bounds checks
 };
 
-// tile kernel variants (option "variant"): 0 = 8 positions/thread x 256 threads,
-// 1 = 4 x 256 (3 CTAs/SM), 2 = 4 x 512, 3 = 4 x 256 capped at 64 registers (4 CTAs/SM)
-// 4 = 4 x 128 (6 CTAs/SM), 5 = 8 x 128 (4 CTAs/SM)
-// 6 = 4 x 128 capped at 64 registers (8 CTAs/SM), 7 = 2 x 128 (10 CTAs/SM)
-constexpr int N_VARIANTS = 8;
+// tile kernel shapes (option "variant"): 0 = 4 window positions per thread x 128 threads
+// (7 CTAs/SM, default), 1 = 4 x 256 (default of the mid-sequence launch), 2 = 8 x 256.
+// Shapes that were measured and dropped (64-register caps, 512 threads, 2 or 8 positions x 128)
+// are listed in profiles/r01_summary.md.
+constexpr int N_VARIANTS = 3;
 size_t tile_smem_bytes(uint32_t ext_max, uint32_t* res_bytes_out);
 // de-dup token capacity of x window positions: x + x/4 (worst-case load factor 0.8)
 __host__ __device__ inline uint32_t tok_cap(uint32_t x) { return x + (x >> 2); }

@@ -141,8 +141,8 @@ def test_long_sequences_use_big_kernel(ka, oracle):
     {"slot_bits": 64, "variant": 2, "load_factor": 0.9},
     {"slot_bits": 32, "variant": 1, "load_factor": 0.9},
     {"filter": 1},
-    {"filter": 1, "slot_bits": 32, "variant": 3, "load_factor": 0.9},
-    {"filter": 1, "slot_bits": 128, "variant": 0},
+    {"filter": 1, "slot_bits": 32, "variant": 1, "load_factor": 0.9},
+    {"filter": 1, "slot_bits": 128, "variant": 2, "mid_variant": 0},
 ])
 def test_options_do_not_change_results(ka, oracle, opts):
     seqs, kmers, roles = ragged_case(33, n_seq=500, K=8, max_len=900)
