@@ -61,6 +61,7 @@ def parse():
                     help="0 = C3 proteomes; 1 / 2 = config-4 skewed lengths (log-uniform / bimodal 50..5000 aa)")
     ap.add_argument("--cpu-genomes", type=int, default=384, help="proteomes in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-best", action="store_true", help="skip the packed-integer 'best CPU' line")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--option", action="append", default=[], help="engine option name=value")
     return ap.parse_args()
@@ -174,7 +175,29 @@ def cpu_baseline(a, fam, kmers, roles, threads=None):
     out = db.apply(res, off, a.min_hits, threads=threads)
     dt = time.time() - t0
     n_seq = off.shape[0] - 1
+    # the reference `apply` itself is single-threaded (ApplyKmerProcessor.java:118): same oracle, one
+    # thread, on a tenth of the sample
+    n1 = max(N_PROT, (n_seq // 10) // N_PROT * N_PROT)
+    t0 = time.time()
+    db.apply(res[: int(off[n1])], off[: n1 + 1], a.min_hits, threads=1)
+    dt1 = time.time() - t0
+    one = {"value": n1 / dt1, "unit": "sequences/s", "cores": 1, "sample": f"{n1} proteins, {dt1:.2f} s"}
+    # "best reasonable CPU" context line: packed 64-bit keys, open addressing, all cores
+    best = None
+    if not a.no_cpu_best:
+        t0 = time.time()
+        fdb = oracle.FastDb(kmers, roles, a.K)
+        t_fl = time.time() - t0
+        t0 = time.time()
+        fout = fdb.apply(res, off, a.min_hits, threads=threads)
+        dtf = time.time() - t0
+        best = {"value": n_seq / dtf, "unit": "sequences/s", "probes_per_s": probes / dtf, "cores": threads,
+                "sample": f"same sample, packed-integer C port (oracle/ka_oracle_fast.c), {dtf:.2f} s; table build {t_fl:.1f} s not timed",
+                "matches_java_shaped_oracle": bool(all(np.array_equal(x, y) for x, y in zip(fout, out)))}
+        del fdb
     return {"value": n_seq / dt, "unit": "sequences/s", "probes_per_s": probes / dt, "cores": threads,
+            "one_thread": one, "best_cpu_packed": best,
+            "note": "all three lines are C proxies of the Java path, not a JVM run (no JVM in this image)",
             "kind": "port",
             "sample": f"{a.cpu_genomes} proteomes ({n_seq} proteins, {probes} probes) of the same generator, "
                       f"Java-shaped C oracle (String keys, HashMap/HashSet restatement), {threads} threads, "
