@@ -84,6 +84,7 @@ struct ka_engine {
     int filter = 0;     // 1 = per-sector presence signatures in front of the table (measured slower
                         // in the fused kernel: 40 vs 46 G probes/s, profiles/r01_summary.md), -1 = auto
     bool have_sig = false;
+    int two_phase = 1;  // with signatures: 1 = two-phase tile kernel, 0 = signature test inside the fused kernel
     int table_mode = 0; // 0 = table replicated on every device, 1 = sharded by sector range (peer loads)
     bool peers_enabled = false;
     // db
@@ -253,6 +254,7 @@ int enqueue_kernels(ka_engine* e, Device& d, Pipe& p, const AnnotParams& ap, uin
         DCK(d, cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d.id));
         for (int cls : {32, 64, 128})
             for (int v = 0; v < N_VARIANTS; v++) DCK(d, tile_kernel_set_smem(cls, v, (size_t)optin - 2048));  // minus the static part
+        for (int cls : {32, 64, 128}) DCK(d, tile_kernel_filt_set_smem(cls, (size_t)optin - 2048));
         d.smem_set = (size_t)optin - 2048;
     }
     if (smem > d.smem_set) return dev_fail(d, KA_ERR_INVALID, "tile shared memory exceeds the device limit", cudaErrorInvalidValue);
@@ -260,7 +262,13 @@ int enqueue_kernels(ka_engine* e, Device& d, Pipe& p, const AnnotParams& ap, uin
     DCK(d, cudaEventRecord(p.ev_k0, p.st));
     DCK(d, launch_plan(ap, p.st));
     DCK(d, cudaEventRecord(p.ev_t0, p.st));
-    DCK(d, launch_tiles(ap, e->variant, smem, p.st));
+    if (ap.tab.sig && e->two_phase) {
+        size_t smem_f = tile_smem_bytes_filt(ap.ext_max, nullptr);
+        if (smem_f > d.smem_set) return dev_fail(d, KA_ERR_INVALID, "tile shared memory exceeds the device limit", cudaErrorInvalidValue);
+        DCK(d, launch_tiles_filt(ap, smem_f, p.st));
+    } else {
+        DCK(d, launch_tiles(ap, e->variant, smem, p.st));
+    }
     d.launches += 2;
     if (n_mid) {
         // sequences of long_seq < L <= mid_seq: one tile each, same kernel, larger shared-memory shape
@@ -664,6 +672,8 @@ int ka_set_option(ka_engine* e, const char* name, double v) {
         e->chunk_residues = (uint64_t)v;
     } else if (n == "l2_persist") {
         e->l2_persist = v != 0;
+    } else if (n == "two_phase") {
+        e->two_phase = v != 0;
     } else if (n == "table_mode") {
         if (v != 0 && v != 1) return fail(e, KA_ERR_INVALID, "table_mode must be 0 (replicated) or 1 (sharded)");
         e->table_mode = (int)v;

@@ -51,6 +51,11 @@ size_t tile_smem_bytes(uint32_t ext_max, uint32_t* res_bytes_out);
 __host__ __device__ inline uint32_t tok_cap(uint32_t x) { return x + (x >> 2); }
 cudaError_t tile_kernel_set_smem(int cls, int variant, size_t bytes);
 
+// two-phase tile kernel used when the table has presence signatures (tab.sig != NULL)
+size_t tile_smem_bytes_filt(uint32_t ext_max, uint32_t* res_bytes_out);
+cudaError_t tile_kernel_filt_set_smem(int cls, size_t bytes);
+cudaError_t launch_tiles_filt(const AnnotParams& p, size_t smem, cudaStream_t st);
+
 cudaError_t launch_plan(const AnnotParams& p, cudaStream_t st);
 cudaError_t launch_tiles(const AnnotParams& p, int variant, size_t smem, cudaStream_t st);
 cudaError_t launch_big(const AnnotParams& p, int grid, cudaStream_t st);
