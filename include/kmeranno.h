@@ -82,6 +82,8 @@ const char* ka_last_error(const ka_engine* e);
  *                   peer memory inside the probe kernel (for tables beyond one GPU)  (next ka_db_load)
  *   "filter"        per-sector presence signatures kept in L2 (1 on, 0 off (default), -1 = on for
  *                   tables of at least 2^20 sectors)   (next ka_db_load)
+ *   "two_phase"     with "filter": 1 = two-phase tile kernel (signature test and candidate compaction,
+ *                   then probes of the survivors only), 0 = test inside the fused kernel (default)
  *   "slot_bits"     force the table slot width (32, 64, 128; 0 = smallest that fits, default)
  *   "variant"       tile kernel shape: 0 = 4 positions x 128 threads (default), 1 = 4 x 256, 2 = 8 x 256
  *   "chunk_residues" residues per pipelined H2D chunk, default 32 Mi

@@ -84,7 +84,8 @@ struct ka_engine {
     int filter = 0;     // 1 = per-sector presence signatures in front of the table (measured slower
                         // in the fused kernel: 40 vs 46 G probes/s, profiles/r01_summary.md), -1 = auto
     bool have_sig = false;
-    int two_phase = 1;  // with signatures: 1 = two-phase tile kernel, 0 = signature test inside the fused kernel
+    int two_phase = 0;  // with signatures: 1 = two-phase tile kernel (measured slower, kept as an experiment),
+                        // 0 = signature test inside the fused kernel
     int table_mode = 0; // 0 = table replicated on every device, 1 = sharded by sector range (peer loads)
     bool peers_enabled = false;
     // db

@@ -141,8 +141,10 @@ def test_long_sequences_use_big_kernel(ka, oracle):
     {"slot_bits": 64, "variant": 2, "load_factor": 0.9},
     {"slot_bits": 32, "variant": 1, "load_factor": 0.9},
     {"filter": 1},
-    {"filter": 1, "two_phase": 0},
-    {"filter": 1, "tile_span": 256, "long_seq": 300, "mid_seq": 700},
+    {"filter": 1, "two_phase": 1},
+    {"filter": 1, "two_phase": 1, "slot_bits": 64},
+    {"filter": 1, "two_phase": 1, "slot_bits": 128, "load_factor": 0.9},
+    {"filter": 1, "two_phase": 1, "tile_span": 256, "long_seq": 300, "mid_seq": 700},
     {"filter": 1, "slot_bits": 32, "variant": 1, "load_factor": 0.9},
     {"filter": 1, "slot_bits": 128, "variant": 2, "mid_variant": 0},
 ])
