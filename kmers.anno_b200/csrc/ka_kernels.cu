@@ -7,8 +7,8 @@
 //   line wins).
 //
 // Kernels
-//   plan_kernel    first sequence of every residue tile (binary search on the CSR offsets)
-//                  and the list of long sequences.
+//   plan_kernel    one 16-byte descriptor per residue tile (binary searches on the CSR offsets),
+//                  single-sequence tiles for mid-length sequences, the list of long sequences.
 //   tile_kernel    one CTA per tile of whole sequences: the tile's residues are staged into
 //                  shared memory with one TMA bulk copy (cp.async.bulk + mbarrier); each
 //                  thread rolls the 5-bit packed key over a run of consecutive window
@@ -29,7 +29,7 @@
 
 // `make DEBUG=1` compiles bounds checks into the kernels (compute-sanitizer is not available on
 // the GPU pool): a failed check ORs its code into p.dbg[0] and the engine turns that into an
-// error; indices are clamped so that the kernel itself stays in bounds.
+// error (tests/ run once under this build: no check fires).
 #ifdef KA_DEBUG
 #define KA_CHECK(cond, code) do { if (!(cond)) atomicOr(p.dbg, (code)); } while (0)
 #else
