@@ -79,7 +79,10 @@ const char* ka_last_error(const ka_engine* e);
  *   "mid_variant"   tile kernel shape of the second launch, default 1
  *   "table_mode"    0 = table replicated on every device (default); 1 = table sharded by sector range
  *                   over the engine's 2/4/8 devices, probes load remote sectors through NVLink
- *                   peer memory inside the probe kernel (for tables beyond one GPU)  (next ka_db_load)
+ *                   peer memory inside the probe kernel (for tables beyond one GPU); 2 = same sharding,
+ *                   but the k-mer keys are ROUTED: NCCL send/recv all-to-all of 8-byte keys to the
+ *                   owning GPU, local probe there, 8-byte answers back in request order (sequences
+ *                   longer than mid_seq are rejected in this mode)  (next ka_db_load)
  *   "filter"        per-sector presence signatures kept in L2 (1 on, 0 off (default), -1 = on for
  *                   tables of at least 2^20 sectors)   (next ka_db_load)
  *   "two_phase"     with "filter": 1 = two-phase tile kernel (signature test and candidate compaction,

@@ -5,7 +5,12 @@
 // ApplyKmerProcessor.java:99-110 (DB load) and :122-148 (peg loop).  No CPU fallback: every
 // path below either runs the CUDA kernels or returns an error code.
 #include <algorithm>
+#include <array>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <dlfcn.h>
+#include <nccl.h>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -49,9 +54,16 @@ struct Device {
     uint16_t* sig = nullptr;  // per-sector presence signatures
     const uint4** shard_sectors = nullptr;  // sharded mode: device array of peer pointers, one per shard
     const uint4** shard_ovf = nullptr;
+    // routed mode (table_mode 2)
+    ncclComm_t comm = nullptr;
+    unsigned long long *r_keys = nullptr, *r_send = nullptr, *r_recv = nullptr, *r_ans_recv = nullptr,
+                       *r_ans_sorted = nullptr, *r_ans_pos = nullptr, *r_small = nullptr;  // r_small: 8 counts, 8 offsets, 8 cursors
+    uint32_t* r_pos = nullptr;
+    size_t r_cap_pos = 0, r_cap_recv = 0;
     uint8_t* lut = nullptr;
     Pipe pipe[NPIPE];
     size_t smem_set = 0;   // opt-in shared-memory limit once the tile kernels are configured
+    bool route_smem_set = false;
     // per-call accounting
     double kernel_ms = 0, tile_ms = 0;
     uint64_t launches = 0, h2d = 0, d2h = 0, probes = 0;
@@ -88,6 +100,7 @@ struct ka_engine {
                         // 0 = signature test inside the fused kernel
     int table_mode = 0; // 0 = table replicated on every device, 1 = sharded by sector range (peer loads)
     bool peers_enabled = false;
+    bool nccl_ready = false;
     // db
     bool have_db = false;
     ka_db_info info{};
@@ -553,6 +566,236 @@ bool choose_geometry(uint64_t n, int K, int32_t max_role, double lf, int force_c
     return found;
 }
 
+// ---- NCCL, loaded on demand: only the routed sharded table needs it -------------------------
+struct NcclApi {
+    void* h = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    bool load() {
+        if (h) return true;
+        h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+        if (!h) return false;
+        GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
+        CommInitAll = (decltype(CommInitAll))dlsym(h, "ncclCommInitAll");
+        CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+        GroupStart = (decltype(GroupStart))dlsym(h, "ncclGroupStart");
+        GroupEnd = (decltype(GroupEnd))dlsym(h, "ncclGroupEnd");
+        Send = (decltype(Send))dlsym(h, "ncclSend");
+        Recv = (decltype(Recv))dlsym(h, "ncclRecv");
+        return GetErrorString && CommInitAll && CommDestroy && GroupStart && GroupEnd && Send && Recv;
+    }
+};
+NcclApi g_nccl;
+
+class Barrier {
+public:
+    explicit Barrier(int n) : n_(n) {}
+    void wait() {
+        std::unique_lock<std::mutex> lk(m_);
+        const int gen = gen_;
+        if (++count_ == n_) { count_ = 0; gen_++; cv_.notify_all(); }
+        else cv_.wait(lk, [&] { return gen != gen_; });
+    }
+private:
+    std::mutex m_;
+    std::condition_variable cv_;
+    int n_, count_ = 0, gen_ = 0;
+};
+
+struct RouteShared {
+    Barrier bar;
+    std::vector<std::array<unsigned long long, 8>> counts;   // counts[d][o]: keys device d sends to owner o this round
+    std::vector<size_t> n_chunks;
+    std::atomic<int> abort{0};                                // a device could not size its receive buffers
+    explicit RouteShared(int n) : bar(n), counts(n), n_chunks(n, 0) {}
+};
+
+int route_reserve(Device& d, size_t n_pos, size_t n_recv) {
+    if (n_pos > d.r_cap_pos) {
+        for (void* q : {(void*)d.r_keys, (void*)d.r_send, (void*)d.r_ans_sorted, (void*)d.r_ans_pos, (void*)d.r_pos}) if (q) cudaFree(q);
+        d.r_keys = d.r_send = d.r_ans_sorted = d.r_ans_pos = nullptr; d.r_pos = nullptr; d.r_cap_pos = 0;
+        size_t n = n_pos + n_pos / 8 + 1024;
+        cudaError_t ce;
+        if ((ce = cudaMalloc((void**)&d.r_keys, n * 8)) != cudaSuccess || (ce = cudaMalloc((void**)&d.r_send, n * 8)) != cudaSuccess ||
+            (ce = cudaMalloc((void**)&d.r_ans_sorted, n * 8)) != cudaSuccess || (ce = cudaMalloc((void**)&d.r_ans_pos, n * 8)) != cudaSuccess ||
+            (ce = cudaMalloc((void**)&d.r_pos, n * 4)) != cudaSuccess)
+            return dev_fail(d, KA_ERR_OOM, "routing buffers", ce);
+        d.r_cap_pos = n;
+    }
+    if (n_recv > d.r_cap_recv) {
+        if (d.r_recv) cudaFree(d.r_recv);
+        if (d.r_ans_recv) cudaFree(d.r_ans_recv);
+        d.r_recv = d.r_ans_recv = nullptr; d.r_cap_recv = 0;
+        size_t n = n_recv + n_recv / 8 + 1024;
+        cudaError_t ce;
+        if ((ce = cudaMalloc((void**)&d.r_recv, n * 8)) != cudaSuccess || (ce = cudaMalloc((void**)&d.r_ans_recv, n * 8)) != cudaSuccess)
+            return dev_fail(d, KA_ERR_OOM, "routing receive buffers", ce);
+        d.r_cap_recv = n;
+    }
+    if (!d.r_small && cudaMalloc((void**)&d.r_small, 24 * 8) != cudaSuccess) return dev_fail(d, KA_ERR_OOM, "routing counters", cudaErrorMemoryAllocation);
+    return KA_OK;
+}
+
+#define NCK(d, call)                                                                    \
+    do {                                                                                \
+        ncclResult_t _nr = (call);                                                      \
+        if (_nr != ncclSuccess && (d).err == KA_OK) {                                   \
+            (d).err = KA_ERR_CUDA; (d).errmsg = std::string("NCCL: ") + g_nccl.GetErrorString(_nr); \
+        }                                                                               \
+    } while (0)
+
+// Routed sharded table: every device extracts the keys of its own sequences, the keys travel to
+// the GPU that owns their table sector (NCCL send/recv all-to-all over NVLink), the owner probes
+// its local shard, the answers travel back in request order and the requester tallies.
+// All devices walk the same number of rounds (empty rounds send nothing) so that the
+// point-to-point calls always match.  A failure on one device is remembered but the device keeps
+// taking part with empty rounds: nobody is left waiting in a collective.
+int annotate_routed_range(ka_engine* e, Device& d, int idx, RouteShared& sh, const uint8_t* residues,
+                          const uint64_t* offsets, uint64_t s_begin, uint64_t s_end, int32_t min_hits,
+                          int32_t* out_role, int32_t* out_hits, uint8_t* out_flag) {
+    const int nd = (int)e->devs.size();
+    cudaSetDevice(d.id);
+    d.kernel_ms = d.tile_ms = 0; d.launches = 0; d.h2d = d.d2h = 0; d.probes = 0;
+    d.err = KA_OK; d.errmsg.clear();
+    std::vector<std::pair<uint64_t, uint64_t>> chunks;
+    for (uint64_t cs = s_begin; cs < s_end;) {
+        uint64_t lim = offsets[cs] + e->chunk_residues;
+        uint64_t ce = std::upper_bound(offsets + cs + 1, offsets + s_end + 1, lim) - offsets - 1;
+        if (ce <= cs) ce = cs + 1;
+        chunks.push_back({cs, ce});
+        cs = ce;
+    }
+    sh.n_chunks[idx] = chunks.size();
+    sh.bar.wait();
+    size_t rounds = 0;
+    for (size_t c : sh.n_chunks) rounds = std::max(rounds, c);
+    Pipe& p = d.pipe[0];
+    cudaStream_t st = p.st;
+    auto cuda_ok = [&](cudaError_t ce, const char* what) {
+        if (ce != cudaSuccess && d.err == KA_OK) dev_fail(d, KA_ERR_CUDA, what, ce);
+        return ce == cudaSuccess;
+    };
+    if (!d.smem_set) {
+        int optin = 0;
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d.id);
+        for (int cls : {32, 64, 128})
+            for (int v = 0; v < N_VARIANTS; v++) cuda_ok(tile_kernel_set_smem(cls, v, (size_t)optin - 2048), "tile kernel shared memory");
+        for (int cls : {32, 64, 128}) cuda_ok(tile_kernel_filt_set_smem(cls, (size_t)optin - 2048), "tile kernel shared memory");
+        d.smem_set = (size_t)optin - 2048;
+    }
+    if (!d.route_smem_set) { cuda_ok(tile_kernel_mode_set_smem(d.smem_set), "routed tile kernel shared memory"); d.route_smem_set = true; }
+
+    for (size_t r = 0; r < rounds; r++) {
+        bool has = r < chunks.size() && d.err == KA_OK;
+        uint64_t cs = 0, ce = 0, n = 0;
+        ChunkShape shp;
+        AnnotParams ap;
+        size_t smem = 0, smem_mid = 0;
+        AnnotParams am;
+        std::array<unsigned long long, 8> cnt{};
+        if (has) {
+            cs = chunks[r].first; ce = chunks[r].second; n = ce - cs;
+            if (!scan_offsets(offsets, cs, ce, e->long_seq, e->mid_seq, e->info.K, shp)) { d.err = KA_ERR_OFFSETS; d.errmsg = "offsets are not monotone"; has = false; }
+            else if (shp.n_long) { d.err = KA_ERR_TOO_BIG; d.errmsg = "routed table mode: a sequence is longer than mid_seq (raise the mid_seq option)"; has = false; }
+            else if (shp.n_res > 0x7fffffffull) { d.err = KA_ERR_TOO_BIG; d.errmsg = "chunk exceeds 2^31 residues"; has = false; }
+        }
+        if (has) {
+            d.probes += shp.probes;
+            if (pipe_reserve(d, p, shp.n_res, n, shp.n_res / e->tile_span + 1, 0, 0, shp.n_mid) || route_reserve(d, shp.n_res + 64, 0)) has = false;
+        }
+        if (has) {
+            if (shp.n_res) cuda_ok(cudaMemcpyAsync(p.res, residues + offsets[cs], shp.n_res, cudaMemcpyHostToDevice, st), "H2D residues");
+            cuda_ok(cudaMemcpyAsync(p.off, offsets + cs, (n + 1) * 8, cudaMemcpyHostToDevice, st), "H2D offsets");
+            d.h2d += shp.n_res + (n + 1) * 8;
+            fill_params(e, d, p, offsets[cs], shp.n_res, n, min_hits, ap);
+            ap.route_keys = d.r_keys;
+            ap.route_ans = d.r_ans_pos;
+            smem = tile_smem_bytes(ap.ext_max, nullptr);
+            am = ap;
+            am.first = p.mid; am.n_tiles = (uint32_t)shp.n_mid; am.ext_max = ap.mid_seq;
+            smem_mid = tile_smem_bytes(am.ext_max, &am.res_bytes);
+            cuda_ok(cudaMemsetAsync(p.ctr, 0, 16, st), "memset");
+            cuda_ok(cudaMemsetAsync(d.r_keys, 0xff, (shp.n_res + 64) * 8, st), "memset keys");
+            cuda_ok(cudaMemsetAsync(d.r_small, 0, 24 * 8, st), "memset counters");
+            cuda_ok(cudaEventRecord(p.ev_k0, st), "event");
+            cuda_ok(launch_plan(ap, st), "plan");
+            cuda_ok(launch_tiles_mode(ap, 0, 1, smem, st), "extract tiles");
+            if (shp.n_mid) cuda_ok(launch_tiles_mode(am, 1, 1, smem_mid, st), "extract mid tiles");
+            cuda_ok(launch_route_count(d.r_keys, shp.n_res, ap.tab, d.r_small, st), "route count");
+            cuda_ok(cudaMemcpyAsync(cnt.data(), d.r_small, 64, cudaMemcpyDeviceToHost, st), "D2H counts");
+            cuda_ok(cudaStreamSynchronize(st), "extract sync");
+            d.launches += 3 + (shp.n_mid ? 1 : 0);
+            if (d.err != KA_OK) { has = false; cnt.fill(0); }
+        }
+        sh.counts[idx] = cnt;
+        sh.bar.wait();                     // every device's counts of this round are visible
+        unsigned long long send_off[9] = {0}, recv_cnt[8] = {0}, recv_off[9] = {0};
+        for (int o = 0; o < nd; o++) send_off[o + 1] = send_off[o] + sh.counts[idx][o];
+        for (int o = 0; o < nd; o++) { recv_cnt[o] = sh.counts[o][idx]; recv_off[o + 1] = recv_off[o] + recv_cnt[o]; }
+        const unsigned long long total_send = send_off[nd], total_recv = recv_off[nd];
+        bool recv_ok = route_reserve(d, 0, total_recv + 64) == KA_OK && d.r_small;
+        if (!recv_ok) { sh.abort.store(1); if (d.err == KA_OK) d.err = KA_ERR_OOM; }
+        sh.bar.wait();                     // nobody overwrites counts before everyone has read them
+        if (sh.abort.load()) {
+            // a peer cannot receive: every device skips the exchange of this and all later rounds
+            if (d.err == KA_OK) { d.err = KA_ERR_OOM; d.errmsg = "routed table mode: a peer device ran out of memory"; }
+            recv_ok = false; has = false;
+        }
+        if (has) {
+            cuda_ok(cudaMemcpyAsync(d.r_small + 8, send_off, 64, cudaMemcpyHostToDevice, st), "H2D offsets");
+            cuda_ok(launch_route_scatter(d.r_keys, shp.n_res, ap.tab, d.r_small + 8, d.r_small + 16, d.r_send, d.r_pos, st), "route scatter");
+            d.launches += 1;
+        }
+        if (recv_ok) {
+            // keys to their owners
+            NCK(d, g_nccl.GroupStart());
+            for (int o = 0; o < nd; o++) {
+                if (o == idx) continue;
+                if (sh.counts[idx][o]) NCK(d, g_nccl.Send(d.r_send + send_off[o], sh.counts[idx][o], ncclUint64, o, d.comm, st));
+                if (recv_cnt[o]) NCK(d, g_nccl.Recv(d.r_recv + recv_off[o], recv_cnt[o], ncclUint64, o, d.comm, st));
+            }
+            NCK(d, g_nccl.GroupEnd());
+            if (recv_cnt[idx]) cuda_ok(cudaMemcpyAsync(d.r_recv + recv_off[idx], d.r_send + send_off[idx], recv_cnt[idx] * 8, cudaMemcpyDeviceToDevice, st), "self keys");
+            // the owner answers from its local shard
+            TableView tab = e->geom;
+            tab.sectors = d.table; tab.ovf = d.ovf; tab.sig = nullptr; tab.my_shard = (uint32_t)idx;
+            cuda_ok(launch_route_lookup(d.r_recv, total_recv, tab, d.r_ans_recv, st), "route lookup");
+            d.launches += 1;
+            // answers back to the requesters, in request order
+            NCK(d, g_nccl.GroupStart());
+            for (int o = 0; o < nd; o++) {
+                if (o == idx) continue;
+                if (recv_cnt[o]) NCK(d, g_nccl.Send(d.r_ans_recv + recv_off[o], recv_cnt[o], ncclUint64, o, d.comm, st));
+                if (sh.counts[idx][o]) NCK(d, g_nccl.Recv(d.r_ans_sorted + send_off[o], sh.counts[idx][o], ncclUint64, o, d.comm, st));
+            }
+            NCK(d, g_nccl.GroupEnd());
+            if (recv_cnt[idx]) cuda_ok(cudaMemcpyAsync(d.r_ans_sorted + send_off[idx], d.r_ans_recv + recv_off[idx], recv_cnt[idx] * 8, cudaMemcpyDeviceToDevice, st), "self answers");
+        }
+        if (has) {
+            cuda_ok(cudaMemsetAsync(d.r_ans_pos, 0xff, (shp.n_res + 64) * 8, st), "memset answers");
+            cuda_ok(launch_route_unpermute(d.r_ans_sorted, d.r_pos, total_send, d.r_ans_pos, st), "route unpermute");
+            cuda_ok(cudaEventRecord(p.ev_t0, st), "event");
+            cuda_ok(launch_tiles_mode(ap, 0, 2, smem, st), "tally tiles");
+            if (shp.n_mid) cuda_ok(launch_tiles_mode(am, 1, 2, smem_mid, st), "tally mid tiles");
+            cuda_ok(cudaEventRecord(p.ev_t1, st), "event");
+            cuda_ok(cudaEventRecord(p.ev_k1, st), "event");
+            d.launches += 2 + (shp.n_mid ? 1 : 0);
+            cuda_ok(cudaMemcpyAsync(out_role + cs, p.role, n * 4, cudaMemcpyDeviceToHost, st), "D2H role");
+            cuda_ok(cudaMemcpyAsync(out_hits + cs, p.hits, n * 4, cudaMemcpyDeviceToHost, st), "D2H hits");
+            d.d2h += n * 8;
+            if (out_flag) { cuda_ok(cudaMemcpyAsync(out_flag + cs, p.flag, n, cudaMemcpyDeviceToHost, st), "D2H flag"); d.d2h += n; }
+        }
+        cuda_ok(cudaStreamSynchronize(st), "round sync");
+        if (has && d.err == KA_OK) collect_times(d, p);
+    }
+    return d.err;
+}
+
 template <typename F>
 int for_each_device(ka_engine* e, F f) {
     if (e->devs.size() == 1) {
@@ -638,6 +881,9 @@ void ka_destroy(ka_engine* e) {
         if (d.table) cudaFree(d.table);
         if (d.ovf) cudaFree(d.ovf);
         if (d.sig) cudaFree(d.sig);
+        if (d.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d.comm);
+        for (void* q : {(void*)d.r_keys, (void*)d.r_send, (void*)d.r_recv, (void*)d.r_ans_recv, (void*)d.r_ans_sorted,
+                        (void*)d.r_ans_pos, (void*)d.r_small, (void*)d.r_pos}) if (q) cudaFree(q);
         if (d.shard_sectors) cudaFree((void*)d.shard_sectors);
         if (d.shard_ovf) cudaFree((void*)d.shard_ovf);
         if (d.lut) cudaFree(d.lut);
@@ -676,7 +922,7 @@ int ka_set_option(ka_engine* e, const char* name, double v) {
     } else if (n == "two_phase") {
         e->two_phase = v != 0;
     } else if (n == "table_mode") {
-        if (v != 0 && v != 1) return fail(e, KA_ERR_INVALID, "table_mode must be 0 (replicated) or 1 (sharded)");
+        if (v != 0 && v != 1 && v != 2) return fail(e, KA_ERR_INVALID, "table_mode must be 0 (replicated), 1 (sharded, peer loads) or 2 (sharded, routed)");
         e->table_mode = (int)v;
     } else if (n == "filter") {
         e->filter = v < 0 ? -1 : (v != 0);
@@ -751,8 +997,8 @@ static int db_load_impl(ka_engine* e, const uint8_t* kmers, const int32_t* role_
         if (role_ids[i] > max_role) max_role = role_ids[i];
     }
     TableView geom;
-    const uint32_t n_shards = e->table_mode == 1 ? (uint32_t)e->devs.size() : 1u;
-    if (e->table_mode == 1) {
+    const uint32_t n_shards = e->table_mode >= 1 ? (uint32_t)e->devs.size() : 1u;
+    if (e->table_mode >= 1) {
         if (n_shards != 2 && n_shards != 4 && n_shards != 8)
             return fail(e, KA_ERR_INVALID, "ka_db_load: a sharded table needs an engine on 2, 4 or 8 devices (has %u)", n_shards);
         if (!e->peers_enabled) {
@@ -804,6 +1050,16 @@ static int db_load_impl(ka_engine* e, const uint8_t* kmers, const int32_t* role_
             cudaMemcpy((void*)d.shard_ovf, po.data(), 64, cudaMemcpyHostToDevice);
         }
     }
+    if (e->table_mode == 2 && !e->nccl_ready) {
+        if (!g_nccl.load()) return fail(e, KA_ERR_NO_DEVICE, "ka_db_load: table_mode 2 needs libnccl.so.2 (%s)", dlerror() ? dlerror() : "symbols missing");
+        std::vector<ncclComm_t> comms(e->devs.size());
+        std::vector<int> ids;
+        for (Device& d : e->devs) ids.push_back(d.id);
+        ncclResult_t nr = g_nccl.CommInitAll(comms.data(), (int)ids.size(), ids.data());
+        if (nr != ncclSuccess) return fail(e, KA_ERR_CUDA, "ka_db_load: ncclCommInitAll: %s", g_nccl.GetErrorString(nr));
+        for (size_t i = 0; i < e->devs.size(); i++) e->devs[i].comm = comms[i];
+        e->nccl_ready = true;
+    }
     e->geom = geom;
     e->info.K = K;
     e->info.n_symbols = nsym;
@@ -853,10 +1109,19 @@ int ka_annotate(ka_engine* e, const uint8_t* residues, const uint64_t* offsets, 
         uint64_t c = std::lower_bound(offsets, offsets + N + 1, target) - offsets;
         cut[i] = std::min<uint64_t>(std::max<uint64_t>(c, cut[i - 1]), N);
     }
-    int rc = for_each_device(e, [&](Device& d, int i) {
-        if (cut[i] == cut[i + 1]) { d.kernel_ms = d.tile_ms = 0; d.launches = d.h2d = d.d2h = d.probes = 0; return (int)KA_OK; }
-        return annotate_range(e, d, residues, offsets, cut[i], cut[i + 1], min_hits, out_role, out_hits, out_flag);
-    });
+    int rc;
+    if (e->table_mode == 2) {
+        // routed sharded table: every device must walk every round, even with an empty range
+        RouteShared shared((int)nd);
+        rc = for_each_device(e, [&](Device& d, int i) {
+            return annotate_routed_range(e, d, i, shared, residues, offsets, cut[i], cut[i + 1], min_hits, out_role, out_hits, out_flag);
+        });
+    } else {
+        rc = for_each_device(e, [&](Device& d, int i) {
+            if (cut[i] == cut[i + 1]) { d.kernel_ms = d.tile_ms = 0; d.launches = d.h2d = d.d2h = d.probes = 0; return (int)KA_OK; }
+            return annotate_range(e, d, residues, offsets, cut[i], cut[i + 1], min_hits, out_role, out_hits, out_flag);
+        });
+    }
     if (rc) {
         for (Device& d : e->devs) { cudaSetDevice(d.id); cudaDeviceSynchronize(); for (auto& p : d.pipe) p.busy = false; }
         return rc;
@@ -883,6 +1148,7 @@ int ka_batch_upload(ka_engine* e, int dev_index, const uint8_t* residues, const 
     std::lock_guard<std::mutex> lk(e->mu);
     if (!e->have_db) return fail(e, KA_ERR_NO_DB, "ka_batch_upload: load the k-mer database first");
     if (dev_index < 0 || dev_index >= (int)e->devs.size()) return fail(e, KA_ERR_INVALID, "ka_batch_upload: bad device index");
+    if (e->table_mode == 2) return fail(e, KA_ERR_INVALID, "ka_batch_upload: resident batches are not available with the routed table (table_mode 2)");
     if (N == 0 || !offsets) return fail(e, KA_ERR_INVALID, "ka_batch_upload: empty batch");
     if (N > 0xfffffff0ull) return fail(e, KA_ERR_TOO_BIG, "ka_batch_upload: too many sequences");
     Device& d = e->devs[dev_index];

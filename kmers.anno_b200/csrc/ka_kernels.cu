@@ -228,7 +228,7 @@ size_t tile_smem_bytes(uint32_t ext_max, uint32_t* res_bytes_out) {
            4 * ((size_t)tok_cap(ext_max) + 4 * MAX_TILE_SEQ + 8);
 }
 
-template <int CLS, int C, int THREADS, int MINB>
+template <int CLS, int C, int THREADS, int MINB, int MODE = 0>
 __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar;
@@ -345,7 +345,29 @@ __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
                     }
                 }
                 int role[C];
-                probe_batch<CLS, C>(tab, rem, sec, okmask, role);
+                if (MODE == 1) {
+                    // routed mode, step 1: only publish the mixed key of every position of this run
+                    // (chunk-relative residue index = stage origin + position)
+#pragma unroll
+                    for (int i = 0; i < C; i++)
+                        if (i < (int)run && P0 + i < pend)
+                            p.route_keys[g0a + P0 + i] = (okmask & (1u << i))
+                                ? (((unsigned long long)sec[i] << tab.rem_bits) | (unsigned long long)rem[i]) : ROUTE_INVALID;
+                    okmask = 0;
+                } else if (MODE == 2) {
+                    // routed mode, last step: the owning GPUs have answered (role << 32 | token)
+                    unsigned long long ans[C];
+#pragma unroll
+                    for (int i = 0; i < C; i++)
+                        if (okmask & (1u << i)) ans[i] = __ldg(p.route_ans + g0a + P0 + i);
+#pragma unroll
+                    for (int i = 0; i < C; i++) {
+                        role[i] = -1;
+                        if (okmask & (1u << i)) { role[i] = (int)(ans[i] >> 32); sec[i] = (uint32_t)ans[i]; }
+                    }
+                } else {
+                    probe_batch<CLS, C>(tab, rem, sec, okmask, role);
+                }
 #pragma unroll
                 for (int i = 0; i < C; i++) {
                     if ((okmask & (1u << i)) && role[i] >= 0) {
@@ -384,8 +406,9 @@ __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
             }
         }
         __syncthreads();
-        for (uint32_t i = tid; i < ns; i += THREADS)
-            emit_call(p, sb + i, s_cnt[i], s_min[i], s_max[i]);
+        if (MODE != 1)
+            for (uint32_t i = tid; i < ns; i += THREADS)
+                emit_call(p, sb + i, s_cnt[i], s_min[i], s_max[i]);
         __syncthreads();
     }
 }
@@ -674,6 +697,181 @@ cudaError_t launch_tiles(const AnnotParams& p, int variant, size_t smem, cudaStr
         kern<<<p.n_tiles, threads, smem, st>>>(p);
         return cudaGetLastError();
     });
+}
+
+cudaError_t launch_tiles_mode(const AnnotParams& p, int variant, int mode, size_t smem, cudaStream_t st) {
+    if (mode == 0) return launch_tiles(p, variant, smem, st);
+    if (p.n_tiles == 0) return cudaSuccess;
+    if (p.tab.cls == 128 || variant > 1) return cudaErrorInvalidValue;   // routed tables are quotiented; shapes 0 and 1
+#define KA_MODE_LAUNCH(CLS)                                                                         \
+    if (variant == 0 && mode == 1) tile_kernel<CLS, 4, 128, 6, 1><<<p.n_tiles, 128, smem, st>>>(p);  \
+    else if (variant == 0)         tile_kernel<CLS, 4, 128, 6, 2><<<p.n_tiles, 128, smem, st>>>(p);  \
+    else if (mode == 1)            tile_kernel<CLS, 4, 256, 3, 1><<<p.n_tiles, 256, smem, st>>>(p);  \
+    else                           tile_kernel<CLS, 4, 256, 3, 2><<<p.n_tiles, 256, smem, st>>>(p);
+    if (p.tab.cls == 32) { KA_MODE_LAUNCH(32) } else { KA_MODE_LAUNCH(64) }
+#undef KA_MODE_LAUNCH
+    return cudaGetLastError();
+}
+
+cudaError_t tile_kernel_mode_set_smem(size_t bytes) {
+    cudaError_t ce = cudaSuccess;
+#define KA_MODE_ATTR(K)                                                                                   \
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); \
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    KA_MODE_ATTR((tile_kernel<32, 4, 128, 6, 1>)) KA_MODE_ATTR((tile_kernel<32, 4, 128, 6, 2>))
+    KA_MODE_ATTR((tile_kernel<32, 4, 256, 3, 1>)) KA_MODE_ATTR((tile_kernel<32, 4, 256, 3, 2>))
+    KA_MODE_ATTR((tile_kernel<64, 4, 128, 6, 1>)) KA_MODE_ATTR((tile_kernel<64, 4, 128, 6, 2>))
+    KA_MODE_ATTR((tile_kernel<64, 4, 256, 3, 1>)) KA_MODE_ATTR((tile_kernel<64, 4, 256, 3, 2>))
+#undef KA_MODE_ATTR
+    return ce;
+}
+
+// ------------------------------------------------------------------------------------
+// routed sharded table (table_mode 2): all-to-all of keys, owners probe, answers come back
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t route_owner(const TableView& t, unsigned long long m) {
+    return (uint32_t)(m >> t.rem_bits) >> t.shard_shift;
+}
+
+__global__ void route_count_kernel(const unsigned long long* __restrict__ keys, unsigned long long n,
+                                   TableView tab, unsigned long long* counts) {
+    __shared__ unsigned long long sh[8];
+    if (threadIdx.x < 8) sh[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t mine[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long m = keys[i];
+        const uint32_t o = m == ROUTE_INVALID ? 0xffffffffu : route_owner(tab, m);
+#pragma unroll
+        for (int k = 0; k < 8; k++) mine[k] += (o == (uint32_t)k);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint32_t w = __reduce_add_sync(0xffffffffu, mine[k]);
+        if ((threadIdx.x & 31) == 0 && w) atomicAdd(&sh[k], (unsigned long long)w);
+    }
+    __syncthreads();
+    if (threadIdx.x < 8 && sh[threadIdx.x]) atomicAdd(&counts[threadIdx.x], sh[threadIdx.x]);
+}
+
+cudaError_t launch_route_count(const unsigned long long* keys, unsigned long long n, TableView tab,
+                               unsigned long long* counts, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    route_count_kernel<<<148 * 8, 256, 0, st>>>(keys, n, tab, counts);
+    return cudaGetLastError();
+}
+
+__global__ void route_scatter_kernel(const unsigned long long* __restrict__ keys, unsigned long long n,
+                                     TableView tab, const unsigned long long* __restrict__ offsets,
+                                     unsigned long long* cursor, unsigned long long* send_keys, uint32_t* send_pos) {
+    const uint32_t lane = threadIdx.x & 31;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const unsigned long long n_round = (n + 31) & ~31ull;   // whole warps stay in the loop for the ballots
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        const unsigned long long m = i < n ? keys[i] : ROUTE_INVALID;
+        const uint32_t o = m == ROUTE_INVALID ? 0xffffffffu : route_owner(tab, m);
+        for (uint32_t k = 0; k < tab.n_shards; k++) {
+            const unsigned b = __ballot_sync(0xffffffffu, o == k);
+            if (!b) continue;
+            unsigned long long base = 0;
+            if (lane == (uint32_t)(__ffs(b) - 1)) base = atomicAdd(&cursor[k], (unsigned long long)__popc(b));
+            base = __shfl_sync(0xffffffffu, base, __ffs(b) - 1);
+            if (o == k) {
+                const unsigned long long w = offsets[k] + base + __popc(b & ((1u << lane) - 1));
+                send_keys[w] = m;
+                send_pos[w] = (uint32_t)i;
+            }
+        }
+    }
+}
+
+cudaError_t launch_route_scatter(const unsigned long long* keys, unsigned long long n, TableView tab,
+                                 const unsigned long long* offsets, unsigned long long* cursor,
+                                 unsigned long long* send_keys, uint32_t* send_pos, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    route_scatter_kernel<<<148 * 8, 256, 0, st>>>(keys, n, tab, offsets, cursor, send_keys, send_pos);
+    return cudaGetLastError();
+}
+
+// every received key belongs to this device's shard: one sector load from local HBM each
+template <int CLS>
+__global__ void __launch_bounds__(256) route_lookup_kernel(const unsigned long long* __restrict__ keys,
+                                                           unsigned long long n, TableView tab,
+                                                           unsigned long long* ans) {
+    constexpr int S = slots_per_sector<CLS>();
+    constexpr int U = 4;
+    typedef typename rem_type<CLS>::type rem_t;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const uint32_t local_mask = (1u << tab.shard_shift) - 1;
+    for (unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += stride * U) {
+        uint4 a[U], b[U];
+        uint32_t sec[U];
+        rem_t rem[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const unsigned long long i = i0 + u * stride;
+            if (i < n) {
+                const unsigned long long m = keys[i];
+                sec[u] = (uint32_t)(m >> tab.rem_bits);
+                rem[u] = (rem_t)(m & tab.rem_mask);
+                load_sector(tab.sectors + 2 * (size_t)(sec[u] & local_mask), a[u], b[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const unsigned long long i = i0 + u * stride;
+            if (i < n) {
+                uint32_t j = 0, tok = 0;
+                bool full;
+                int role = match_sector<CLS>(tab, a[u], b[u], rem[u], j, full);
+                if (role >= 0) tok = sec[u] * S + j + 1;
+                else if (full) {
+                    // the overflow entries of a sector live on its owner: local as well
+                    const unsigned long long m = ((unsigned long long)sec[u] << tab.rem_bits) | (unsigned long long)rem[u];
+                    const uint32_t mask = (1u << tab.ovf_bbits) - 1;
+                    uint32_t s = tab.ovf_bbits ? (uint32_t)(mix64(m) >> (64 - tab.ovf_bbits)) : 0u;
+                    const uint32_t tok0 = tab.n_primary_slots + tab.my_shard * (2u << tab.ovf_bbits);
+                    for (;;) {
+                        uint4 xa, xb;
+                        load_sector(tab.ovf + 2 * (size_t)s, xa, xb);
+                        const unsigned long long k0 = u64_of(xa.x, xa.y), k1 = u64_of(xb.x, xb.y);
+                        if (k0 == m) { tok = tok0 + 2 * s + 1; role = (int)xa.z; break; }
+                        if (k1 == m) { tok = tok0 + 2 * s + 2; role = (int)xb.z; break; }
+                        if (k1 == 0) break;
+                        s = (s + 1) & mask;
+                    }
+                }
+                ans[i] = role >= 0 ? (((unsigned long long)(uint32_t)role << 32) | tok) : ROUTE_MISS;
+            }
+        }
+    }
+}
+
+cudaError_t launch_route_lookup(const unsigned long long* keys, unsigned long long n, TableView tab,
+                                unsigned long long* ans, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    unsigned long long want = (n + 256ull * 4 - 1) / (256ull * 4);
+    unsigned blocks = (unsigned)(want < 148ull * 16 ? want : 148ull * 16);
+    if (tab.cls == 32) route_lookup_kernel<32><<<blocks, 256, 0, st>>>(keys, n, tab, ans);
+    else if (tab.cls == 64) route_lookup_kernel<64><<<blocks, 256, 0, st>>>(keys, n, tab, ans);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+__global__ void route_unpermute_kernel(const unsigned long long* __restrict__ ans_sorted,
+                                       const uint32_t* __restrict__ send_pos, unsigned long long n,
+                                       unsigned long long* ans_by_pos) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        ans_by_pos[send_pos[i]] = ans_sorted[i];
+}
+
+cudaError_t launch_route_unpermute(const unsigned long long* ans_sorted, const uint32_t* send_pos,
+                                   unsigned long long n, unsigned long long* ans_by_pos, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    route_unpermute_kernel<<<148 * 8, 256, 0, st>>>(ans_sorted, send_pos, n, ans_by_pos);
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------

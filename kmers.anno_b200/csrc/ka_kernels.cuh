@@ -39,6 +39,11 @@ struct AnnotParams {
     BigItem* big_list;
     uint32_t* scratch;                // de-dup tokens of the long sequences
     uint32_t* dbg;                    // KA_DEBUG builds: [0] OR of the codes of failed bounds checks
+    // routed mode (table_mode 2): the tile kernel either only EXTRACTS the mixed key of every window
+    // position into route_keys[chunk-relative residue index] (ROUTE_INVALID = no window), or TALLIES
+    // from route_ans[same index] = (role << 32 | de-dup token) answered by the owning GPU.
+    unsigned long long* route_keys;
+    const unsigned long long* route_ans;
 };
 
 // tile kernel shapes (option "variant"): 0 = 4 window positions per thread x 128 threads
@@ -55,6 +60,25 @@ cudaError_t tile_kernel_set_smem(int cls, int variant, size_t bytes);
 size_t tile_smem_bytes_filt(uint32_t ext_max, uint32_t* res_bytes_out);
 cudaError_t tile_kernel_filt_set_smem(int cls, size_t bytes);
 cudaError_t launch_tiles_filt(const AnnotParams& p, size_t smem, cudaStream_t st);
+
+constexpr unsigned long long ROUTE_INVALID = ~0ull;
+constexpr unsigned long long ROUTE_MISS = ~0ull;          // answer of a key that is not in the table
+// mode 0 = probe the table, 1 = extract keys only, 2 = tally from routed answers (variants 0 and 1 only)
+cudaError_t launch_tiles_mode(const AnnotParams& p, int variant, int mode, size_t smem, cudaStream_t st);
+cudaError_t tile_kernel_mode_set_smem(size_t bytes);
+// per-owner counts of the valid keys of keys[0..n) (owner = sector >> shard_shift); counts[8] accumulates
+cudaError_t launch_route_count(const unsigned long long* keys, unsigned long long n, TableView tab,
+                               unsigned long long* counts, cudaStream_t st);
+// bucket the valid keys by owner: send_keys/send_pos at offsets[o] + running cursor[o]
+cudaError_t launch_route_scatter(const unsigned long long* keys, unsigned long long n, TableView tab,
+                                 const unsigned long long* offsets, unsigned long long* cursor,
+                                 unsigned long long* send_keys, uint32_t* send_pos, cudaStream_t st);
+// owner side: answer every received key from the local shard
+cudaError_t launch_route_lookup(const unsigned long long* keys, unsigned long long n, TableView tab,
+                                unsigned long long* ans, cudaStream_t st);
+// requester side: ans_by_pos[send_pos[i]] = ans_sorted[i]
+cudaError_t launch_route_unpermute(const unsigned long long* ans_sorted, const uint32_t* send_pos,
+                                   unsigned long long n, unsigned long long* ans_by_pos, cudaStream_t st);
 
 cudaError_t launch_plan(const AnnotParams& p, cudaStream_t st);
 cudaError_t launch_tiles(const AnnotParams& p, int variant, size_t smem, cudaStream_t st);

@@ -13,7 +13,7 @@ res, off, _ = fam.batch(0, genomes, n_prot=4500, alloc=pinned_array)
 n = off.shape[0] - 1
 out = (pinned_array(n, np.int32), pinned_array(n, np.int32), pinned_array(n, np.uint8))
 ref = None
-for mode in (0, 1):
+for mode in (0, 1, 2):
     eng = ka.Engine(list(range(n_dev)))
     eng.set_option("table_mode", mode)
     t = time.time(); eng.db_load(kmers, roles, 8); tl = time.time() - t
@@ -25,6 +25,6 @@ for mode in (0, 1):
     st = eng.stats()
     sig = hash(out[0].tobytes()) ^ hash(out[1].tobytes())
     if ref is None: ref = sig
-    print(f"mode {mode} ({'sharded' if mode else 'replicated'}) on {n_dev} GPUs: db load {tl:.1f}s table/GPU {info['table_bytes']/1e6/(n_dev if mode else 1):.0f} MB; "
+    print(f"mode {mode} ({('replicated', 'sharded / peer loads', 'sharded / NCCL routed')[mode]}) on {n_dev} GPUs: db load {tl:.1f}s table/GPU {info['table_bytes']/1e6/(n_dev if mode else 1):.0f} MB; "
           f"e2e {best:.2f} ms {st['probes']/best/1e6:.1f} G probes/s  kernel max {st['kernel_ms']:.2f} ms  same={sig==ref}", flush=True)
     eng.close()

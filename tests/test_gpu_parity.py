@@ -297,6 +297,43 @@ def test_sharded_table_peer_loads(ka, oracle, slot_bits, lf):
     assert_same(got, want, f"sharded table over {n_dev} GPUs slot_bits={slot_bits}")
 
 
+@pytest.mark.parametrize("slot_bits,lf,chunk", [(0, 0.4, 32 << 20), (32, 0.9, 300000), (64, 0.9, 1 << 20)])
+def test_routed_table_nccl_all_to_all(ka, oracle, slot_bits, lf, chunk):
+    """table_mode=2: same sharding, but the keys are routed to the owning GPU with NCCL send/recv
+    (all-to-all), probed there and the answers come back in request order."""
+    n_dev = 0
+    for n in (8, 4, 2):
+        try:
+            ka.Engine(list(range(n))).close()
+            n_dev = n
+            break
+        except ka.KmerAnnoError:
+            continue
+    if n_dev < 2:
+        pytest.skip("needs at least 2 GPUs")
+    from kmers_anno_b200 import synth
+    fam = synth.Families(1000)
+    kmers, roles = fam.table(2_000_000, K=8)
+    res, off, _ = fam.batch(9, 2, n_prot=4500)
+    # uneven ranges: a long tail of empty sequences gives the last device fewer rounds than the first
+    off = np.concatenate([off, np.full(5000, off[-1], np.uint64)])
+    with ka.Engine(list(range(n_dev))) as eng:
+        eng.set_option("table_mode", 2)
+        eng.set_option("slot_bits", slot_bits)
+        eng.set_option("load_factor", lf)
+        eng.set_option("chunk_residues", chunk)
+        eng.db_load(kmers, roles, 8)
+        got = eng.annotate(res, off, 5)
+        got2 = eng.annotate(res, off, 1)
+        with pytest.raises(ka.KmerAnnoError):           # longer than mid_seq: rejected in this mode, no hang
+            eng.annotate(np.full(9000, 65, np.uint8), np.asarray([0, 9000], np.uint64), 5)
+        again = eng.annotate(res, off, 5)               # the engine stays usable
+    want = oracle.OracleDb(kmers, roles, 8, threads=8).apply(res, off, 5, threads=8)
+    assert_same(got, want, f"routed table over {n_dev} GPUs slot_bits={slot_bits}")
+    assert_same(again, want, "routed table, second call")
+    assert_same(got2, oracle.OracleDb(kmers, roles, 8, threads=8).apply(res, off, 1, threads=8), "routed, min_hits 1")
+
+
 def test_error_paths(ka):
     with ka.Engine([0]) as eng:
         with pytest.raises(ka.KmerAnnoError) as e:
