@@ -13,9 +13,10 @@ res, off, _ = fam.batch(0, genomes, n_prot=4500, alloc=pinned_array)
 n = off.shape[0] - 1
 out = (pinned_array(n, np.int32), pinned_array(n, np.int32), pinned_array(n, np.uint8))
 ref = None
-for mode in (0, 1, 2):
+for mode, chunk in ((0, 32 << 20), (1, 32 << 20), (2, 32 << 20), (2, 8 << 20), (2, 4 << 20), (2, 2 << 20), (2, 1 << 20)):
     eng = ka.Engine(list(range(n_dev)))
     eng.set_option("table_mode", mode)
+    eng.set_option("chunk_residues", chunk)
     t = time.time(); eng.db_load(kmers, roles, 8); tl = time.time() - t
     info = eng.db_info()
     best = 1e9
@@ -25,6 +26,6 @@ for mode in (0, 1, 2):
     st = eng.stats()
     sig = hash(out[0].tobytes()) ^ hash(out[1].tobytes())
     if ref is None: ref = sig
-    print(f"mode {mode} ({('replicated', 'sharded / peer loads', 'sharded / NCCL routed')[mode]}) on {n_dev} GPUs: db load {tl:.1f}s table/GPU {info['table_bytes']/1e6/(n_dev if mode else 1):.0f} MB; "
+    print(f"chunk {chunk>>20:2d} Mi mode {mode} ({('replicated', 'sharded / peer loads', 'sharded / NCCL routed')[mode]}) on {n_dev} GPUs: db load {tl:.1f}s table/GPU {info['table_bytes']/1e6/(n_dev if mode else 1):.0f} MB; "
           f"e2e {best:.2f} ms {st['probes']/best/1e6:.1f} G probes/s  kernel max {st['kernel_ms']:.2f} ms  same={sig==ref}", flush=True)
     eng.close()
