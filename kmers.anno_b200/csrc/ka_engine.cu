@@ -690,6 +690,11 @@ int annotate_routed_range(ka_engine* e, Device& d, int idx, RouteShared& sh, con
     }
     if (!d.route_smem_set) { cuda_ok(tile_kernel_mode_set_smem(d.smem_set), "routed tile kernel shared memory"); d.route_smem_set = true; }
 
+    const bool trace = idx == 0 && getenv("KA_ROUTE_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev(12, nullptr);
+    if (trace) for (auto& ev : tev) cudaEventCreate(&ev);
+    double tsum[11] = {0};
+    auto mark = [&](int k) { if (trace) cudaEventRecord(tev[k], st); };
     for (size_t r = 0; r < rounds; r++) {
         bool has = r < chunks.size() && d.err == KA_OK;
         uint64_t cs = 0, ce = 0, n = 0;
@@ -723,10 +728,13 @@ int annotate_routed_range(ka_engine* e, Device& d, int idx, RouteShared& sh, con
             cuda_ok(cudaMemsetAsync(d.r_keys, 0xff, (shp.n_res + 64) * 8, st), "memset keys");
             cuda_ok(cudaMemsetAsync(d.r_small, 0, 24 * 8, st), "memset counters");
             cuda_ok(cudaEventRecord(p.ev_k0, st), "event");
+            mark(0);
             cuda_ok(launch_plan(ap, st), "plan");
             cuda_ok(launch_tiles_mode(ap, 0, 1, smem, st), "extract tiles");
             if (shp.n_mid) cuda_ok(launch_tiles_mode(am, 1, 1, smem_mid, st), "extract mid tiles");
+            mark(1);
             cuda_ok(launch_route_count(d.r_keys, shp.n_res, ap.tab, d.r_small, st), "route count");
+            mark(2);
             cuda_ok(cudaMemcpyAsync(cnt.data(), d.r_small, 64, cudaMemcpyDeviceToHost, st), "D2H counts");
             cuda_ok(cudaStreamSynchronize(st), "extract sync");
             d.launches += 3 + (shp.n_mid ? 1 : 0);
@@ -748,7 +756,9 @@ int annotate_routed_range(ka_engine* e, Device& d, int idx, RouteShared& sh, con
         }
         if (has) {
             cuda_ok(cudaMemcpyAsync(d.r_small + 8, send_off, 64, cudaMemcpyHostToDevice, st), "H2D offsets");
+            mark(3);
             cuda_ok(launch_route_scatter(d.r_keys, shp.n_res, ap.tab, d.r_small + 8, d.r_small + 16, d.r_send, d.r_pos, st), "route scatter");
+            mark(4);
             d.launches += 1;
         }
         if (recv_ok) {
@@ -764,7 +774,9 @@ int annotate_routed_range(ka_engine* e, Device& d, int idx, RouteShared& sh, con
             // the owner answers from its local shard
             TableView tab = e->geom;
             tab.sectors = d.table; tab.ovf = d.ovf; tab.sig = nullptr; tab.my_shard = (uint32_t)idx;
+            mark(5);
             cuda_ok(launch_route_lookup(d.r_recv, total_recv, tab, d.r_ans_recv, st), "route lookup");
+            mark(6);
             d.launches += 1;
             // answers back to the requesters, in request order
             NCK(d, g_nccl.GroupStart());
@@ -777,13 +789,16 @@ int annotate_routed_range(ka_engine* e, Device& d, int idx, RouteShared& sh, con
             if (recv_cnt[idx]) cuda_ok(cudaMemcpyAsync(d.r_ans_sorted + send_off[idx], d.r_ans_recv + recv_off[idx], recv_cnt[idx] * 8, cudaMemcpyDeviceToDevice, st), "self answers");
         }
         if (has) {
+            mark(7);
             cuda_ok(cudaMemsetAsync(d.r_ans_pos, 0xff, (shp.n_res + 64) * 8, st), "memset answers");
             cuda_ok(launch_route_unpermute(d.r_ans_sorted, d.r_pos, total_send, d.r_ans_pos, st), "route unpermute");
+            mark(8);
             cuda_ok(cudaEventRecord(p.ev_t0, st), "event");
             cuda_ok(launch_tiles_mode(ap, 0, 2, smem, st), "tally tiles");
             if (shp.n_mid) cuda_ok(launch_tiles_mode(am, 1, 2, smem_mid, st), "tally mid tiles");
             cuda_ok(cudaEventRecord(p.ev_t1, st), "event");
             cuda_ok(cudaEventRecord(p.ev_k1, st), "event");
+            mark(9);
             d.launches += 2 + (shp.n_mid ? 1 : 0);
             cuda_ok(cudaMemcpyAsync(out_role + cs, p.role, n * 4, cudaMemcpyDeviceToHost, st), "D2H role");
             cuda_ok(cudaMemcpyAsync(out_hits + cs, p.hits, n * 4, cudaMemcpyDeviceToHost, st), "D2H hits");
@@ -792,6 +807,16 @@ int annotate_routed_range(ka_engine* e, Device& d, int idx, RouteShared& sh, con
         }
         cuda_ok(cudaStreamSynchronize(st), "round sync");
         if (has && d.err == KA_OK) collect_times(d, p);
+        if (trace && has) {
+            const int pairs[9][2] = {{0, 1}, {1, 2}, {3, 4}, {4, 5}, {5, 6}, {6, 7}, {7, 8}, {8, 9}, {0, 9}};
+            for (int k = 0; k < 9; k++) { float ms = 0; if (cudaEventElapsedTime(&ms, tev[pairs[k][0]], tev[pairs[k][1]]) == cudaSuccess) tsum[k] += ms; }
+            cudaGetLastError();
+        }
+    }
+    if (trace) {
+        fprintf(stderr, "[route trace dev0, %zu rounds] extract %.2f count %.2f scatter %.2f exchange-keys %.2f lookup %.2f exchange-answers %.2f unpermute %.2f tally %.2f | first-to-last %.2f ms\n",
+                rounds, tsum[0], tsum[1], tsum[2], tsum[3], tsum[4], tsum[5], tsum[6], tsum[7], tsum[8]);
+        for (auto& ev : tev) cudaEventDestroy(ev);
     }
     return d.err;
 }
