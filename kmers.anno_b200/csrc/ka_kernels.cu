@@ -338,9 +338,11 @@ __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
                             okmask |= 1u << i;
                             if (i < 4) seqpack |= (uint32_t)si << (8 * (i & 3));
                             else seqpack2 |= (uint32_t)si << (8 * (i & 3));
-                            unsigned long long rm;
-                            locate(tab, key & tab.key_mask, sec[i], rm);
-                            rem[i] = (typename rem_type<CLS>::type)rm;
+                            if (MODE != 2) {
+                                unsigned long long rm;
+                                locate(tab, key & tab.key_mask, sec[i], rm);
+                                rem[i] = (typename rem_type<CLS>::type)rm;
+                            }
                         }
                     }
                 }
@@ -762,27 +764,55 @@ cudaError_t launch_route_count(const unsigned long long* keys, unsigned long lon
     return cudaGetLastError();
 }
 
-__global__ void route_scatter_kernel(const unsigned long long* __restrict__ keys, unsigned long long n,
+// One CTA buckets a tile of 256 x 16 keys: owners are counted with ballots into shared memory,
+// ONE global atomicAdd per owner and CTA reserves the output ranges, then every warp writes its
+// keys at (range + rank inside the CTA).
+__global__ void __launch_bounds__(256) route_scatter_kernel(const unsigned long long* __restrict__ keys, unsigned long long n,
                                      TableView tab, const unsigned long long* __restrict__ offsets,
                                      unsigned long long* cursor, unsigned long long* send_keys, uint32_t* send_pos) {
-    const uint32_t lane = threadIdx.x & 31;
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    const unsigned long long n_round = (n + 31) & ~31ull;   // whole warps stay in the loop for the ballots
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-        const unsigned long long m = i < n ? keys[i] : ROUTE_INVALID;
-        const uint32_t o = m == ROUTE_INVALID ? 0xffffffffu : route_owner(tab, m);
-        for (uint32_t k = 0; k < tab.n_shards; k++) {
-            const unsigned b = __ballot_sync(0xffffffffu, o == k);
-            if (!b) continue;
-            unsigned long long base = 0;
-            if (lane == (uint32_t)(__ffs(b) - 1)) base = atomicAdd(&cursor[k], (unsigned long long)__popc(b));
-            base = __shfl_sync(0xffffffffu, base, __ffs(b) - 1);
-            if (o == k) {
-                const unsigned long long w = offsets[k] + base + __popc(b & ((1u << lane) - 1));
-                send_keys[w] = m;
-                send_pos[w] = (uint32_t)i;
+    constexpr int PER = 16;                       // keys per thread, strided by 256 inside the tile
+    __shared__ uint32_t s_cnt[8][8];              // [warp][owner]
+    __shared__ unsigned long long s_base[8][8];   // [warp][owner] first output index
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned long long tile = 256ull * PER;
+    for (unsigned long long t0 = (unsigned long long)blockIdx.x * tile; t0 < n; t0 += (unsigned long long)gridDim.x * tile) {
+        unsigned long long m[PER];
+        uint32_t own[PER];
+        uint32_t wcnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            // a warp reads 32 consecutive keys at a time: ranks follow the position order inside a warp
+            const unsigned long long i = t0 + (unsigned long long)warp * (32 * PER) + k * 32 + lane;
+            m[k] = i < n ? keys[i] : ROUTE_INVALID;
+            own[k] = m[k] == ROUTE_INVALID ? 0xffffffffu : route_owner(tab, m[k]);
+            for (uint32_t o = 0; o < tab.n_shards; o++) wcnt[o] += __popc(__ballot_sync(0xffffffffu, own[k] == o));
+        }
+        if (lane < 8) s_cnt[warp][lane] = wcnt[lane];
+        __syncthreads();
+        if (threadIdx.x < 8) {
+            const uint32_t o = threadIdx.x;
+            uint32_t tot = 0;
+            for (int w = 0; w < 8; w++) tot += s_cnt[w][o];
+            unsigned long long base = tot ? atomicAdd(&cursor[o], (unsigned long long)tot) : 0ull;
+            base += offsets[o];
+            for (int w = 0; w < 8; w++) { s_base[w][o] = base; base += s_cnt[w][o]; }
+        }
+        __syncthreads();
+        uint32_t done[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const unsigned long long i = t0 + (unsigned long long)warp * (32 * PER) + k * 32 + lane;
+            for (uint32_t o = 0; o < tab.n_shards; o++) {
+                const unsigned b = __ballot_sync(0xffffffffu, own[k] == o);
+                if (own[k] == o) {
+                    const unsigned long long w = s_base[warp][o] + done[o] + __popc(b & ((1u << lane) - 1));
+                    send_keys[w] = m[k];
+                    send_pos[w] = (uint32_t)i;
+                }
+                done[o] += __popc(b);
             }
         }
+        __syncthreads();
     }
 }
 
@@ -790,7 +820,8 @@ cudaError_t launch_route_scatter(const unsigned long long* keys, unsigned long l
                                  const unsigned long long* offsets, unsigned long long* cursor,
                                  unsigned long long* send_keys, uint32_t* send_pos, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
-    route_scatter_kernel<<<148 * 8, 256, 0, st>>>(keys, n, tab, offsets, cursor, send_keys, send_pos);
+    unsigned long long want = (n + 256ull * 16 - 1) / (256ull * 16);
+    route_scatter_kernel<<<(unsigned)(want < 148ull * 8 ? want : 148ull * 8), 256, 0, st>>>(keys, n, tab, offsets, cursor, send_keys, send_pos);
     return cudaGetLastError();
 }
 
