@@ -13,7 +13,7 @@ res, off, _ = fam.batch(0, genomes, n_prot=4500, alloc=pinned_array)
 n = off.shape[0] - 1
 out = (pinned_array(n, np.int32), pinned_array(n, np.int32), pinned_array(n, np.uint8))
 ref = None
-for mode, chunk in ((0, 32 << 20), (1, 32 << 20), (2, 32 << 20), (2, 8 << 20), (2, 4 << 20), (2, 2 << 20), (2, 1 << 20)):
+for mode, chunk in ((0, 32 << 20), (1, 32 << 20), (2, 32 << 20), (2, 8 << 20)):
     eng = ka.Engine(list(range(n_dev)))
     eng.set_option("table_mode", mode)
     eng.set_option("chunk_residues", chunk)
