@@ -107,41 +107,80 @@ void ApplyKmerProcessor::validateParms() {
     // Load the kmer database.  (:100-110)  TabbedLineReader(file, 2): headerless, two columns.
     log_ << "Loading kmer database from " << kmerDbFile_ << ".\n";
     std::string text = readFile(kmerDbFile_);
+    // The file is cut at line boundaries into one slice per thread; every slice is parsed into
+    // its own k-mer bytes / local role ids, then the role strings are interned globally (the ids
+    // are internal: any consistent numbering gives the same report).
+    struct Slice {
+        size_t begin = 0, end = 0, firstLine = 0;
+        std::vector<uint8_t> kmers;
+        std::vector<int32_t> roles;
+        std::vector<std::string> names;
+        std::unordered_map<std::string, int32_t> ids;
+        int K = -1;
+        std::string error;
+    };
+    size_t nt = std::max<size_t>(1, std::min<size_t>((size_t)loadThreads_, text.size() / (1 << 20) + 1));
+    std::vector<Slice> slices(nt);
+    for (size_t t = 0; t < nt; t++) {
+        size_t b0 = text.size() * t / nt;
+        if (t && b0 < text.size()) { b0 = text.find('\n', b0); b0 = b0 == std::string::npos ? text.size() : b0 + 1; }
+        slices[t].begin = t ? b0 : 0;
+        if (t) slices[t - 1].end = slices[t].begin;
+    }
+    slices[nt - 1].end = text.size();
+    auto parse = [&](Slice& sl) {
+        sl.kmers.reserve((sl.end - sl.begin) / 2);
+        sl.roles.reserve((sl.end - sl.begin) / 30 + 16);   // the reference's own sizing hint (:101)
+        size_t i = sl.begin, lineNo = 0;
+        std::string role;
+        while (i < sl.end) {
+            size_t e = text.find('\n', i);
+            if (e == std::string::npos || e > sl.end) e = sl.end;
+            size_t len = e - i;
+            if (len && text[i + len - 1] == '\r') len--;
+            lineNo++;
+            if (len) {
+                size_t tab = text.find('\t', i);
+                if (tab == std::string::npos || tab >= i + len) { sl.error = "a line has fewer than 2 columns"; sl.firstLine = lineNo; return; }
+                size_t klen = tab - i;
+                size_t rend = text.find('\t', tab + 1);
+                if (rend == std::string::npos || rend > i + len) rend = i + len;
+                // HashMap<String,String> takes k-mers of any length; one packed table needs one K
+                if (sl.K < 0) sl.K = (int)klen;
+                else if ((int)klen != sl.K) { sl.error = "mixed k-mer lengths (" + std::to_string(sl.K) + " and " + std::to_string(klen) + ")"; sl.firstLine = lineNo; return; }
+                sl.kmers.insert(sl.kmers.end(), text.begin() + i, text.begin() + tab);
+                role.assign(text, tab + 1, rend - tab - 1);
+                auto it = sl.ids.find(role);
+                if (it == sl.ids.end()) { it = sl.ids.emplace(role, (int32_t)sl.names.size()).first; sl.names.push_back(role); }
+                sl.roles.push_back(it->second);
+            }
+            i = e + 1;
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        for (size_t t = 1; t < nt; t++) th.emplace_back(parse, std::ref(slices[t]));
+        parse(slices[0]);
+        for (auto& x : th) x.join();
+    }
     std::vector<uint8_t> kmers;
     std::vector<int32_t> roles;
     std::unordered_map<std::string, int32_t> roleIds;
-    kmers.reserve(text.size() / 2);
-    roles.reserve(text.size() / 30);  // the reference's own sizing hint (:101)
-    size_t i = 0, lineNo = 0;
     int K = -1;
-    while (i < text.size()) {
-        size_t e = text.find('\n', i);
-        if (e == std::string::npos) e = text.size();
-        size_t len = e - i;
-        if (len && text[i + len - 1] == '\r') len--;
-        lineNo++;
-        if (len) {
-            size_t tab = text.find('\t', i);
-            if (tab == std::string::npos || tab >= i + len)
-                throw IOException("Line " + std::to_string(lineNo) + " of " + kmerDbFile_ + " has fewer than 2 columns.");
-            size_t klen = tab - i;
-            size_t rend = text.find('\t', tab + 1);
-            if (rend == std::string::npos || rend > i + len) rend = i + len;
-            // HashMap<String,String> takes k-mers of any length; one packed table needs one K
-            if (K < 0) K = (int)klen;
-            else if ((int)klen != K)
-                throw IOException("Kmer database " + kmerDbFile_ + " mixes k-mer lengths (" + std::to_string(K) + " and " +
-                                  std::to_string(klen) + " at line " + std::to_string(lineNo) + "): not supported by the GPU engine.");
-            kmers.insert(kmers.end(), text.begin() + i, text.begin() + tab);
-            std::string role(text, tab + 1, rend - tab - 1);
-            auto it = roleIds.find(role);
-            if (it == roleIds.end()) {
-                it = roleIds.emplace(role, (int32_t)roleNames_.size()).first;
-                roleNames_.push_back(role);
-            }
-            roles.push_back(it->second);
+    for (Slice& sl : slices) {
+        if (!sl.error.empty()) throw IOException("Kmer database " + kmerDbFile_ + ": " + sl.error + " (not supported by the GPU engine).");
+        if (sl.K < 0) continue;
+        if (K < 0) K = sl.K;
+        else if (sl.K != K) throw IOException("Kmer database " + kmerDbFile_ + " mixes k-mer lengths (" + std::to_string(K) + " and " + std::to_string(sl.K) + "): not supported by the GPU engine.");
+        std::vector<int32_t> remap(sl.names.size());
+        for (size_t j = 0; j < sl.names.size(); j++) {
+            auto it = roleIds.find(sl.names[j]);
+            if (it == roleIds.end()) { it = roleIds.emplace(sl.names[j], (int32_t)roleNames_.size()).first; roleNames_.push_back(sl.names[j]); }
+            remap[j] = it->second;
         }
-        i = e + 1;
+        kmers.insert(kmers.end(), sl.kmers.begin(), sl.kmers.end());
+        for (int32_t r : sl.roles) roles.push_back(remap[(size_t)r]);
+        sl.kmers.clear(); sl.kmers.shrink_to_fit(); sl.roles.clear(); sl.roles.shrink_to_fit();
     }
     if (roles.empty()) throw IOException("Kmer database " + kmerDbFile_ + " is empty.");
     kmerSize_ = K;                               // KmerReference.setKmerSize(kmer.length()) (:108)
