@@ -3,6 +3,7 @@
 #include "ApplyKmerProcessor.hpp"
 
 #include <atomic>
+#include <chrono>
 #include <cstdlib>
 #include <fstream>
 #include <future>
@@ -12,6 +13,10 @@
 namespace theseed {
 
 namespace {
+double nowSeconds() {
+    static const auto t0 = std::chrono::steady_clock::now();
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
 bool isDirectory(const std::string& p) {
     struct stat st;
     return stat(p.c_str(), &st) == 0 && S_ISDIR(st.st_mode);
@@ -105,7 +110,7 @@ void ApplyKmerProcessor::validateParms() {
     log_ << "Reading roles to use from " << goodRoleFile_ << ".\n";
     reporter_->initReport(goodRoleFile_);
     // Load the kmer database.  (:100-110)  TabbedLineReader(file, 2): headerless, two columns.
-    log_ << "Loading kmer database from " << kmerDbFile_ << ".\n";
+    log_ << "Loading kmer database from " << kmerDbFile_ << ".  (t=" << nowSeconds() << " s)\n";
     std::string text = readFile(kmerDbFile_);
     // The file is cut at line boundaries into one slice per thread; every slice is parsed into
     // its own k-mer bytes / local role ids, then the role strings are interned globally (the ids
@@ -184,12 +189,12 @@ void ApplyKmerProcessor::validateParms() {
     }
     if (roles.empty()) throw IOException("Kmer database " + kmerDbFile_ + " is empty.");
     kmerSize_ = K;                               // KmerReference.setKmerSize(kmer.length()) (:108)
-    log_ << "Kmer size is " << kmerSize_ << ".\n";
+    log_ << "Kmer size is " << kmerSize_ << ".  (" << roles.size() << " lines parsed, t=" << nowSeconds() << " s)\n";
     engine_ = std::make_unique<KmerEngine>(devices_);   // throws if there is no usable GPU: no CPU fallback
     engine_->loadDb(kmers, roles, K);
     ka_db_info info = engine_->dbInfo();
     log_ << info.n_keys << " distinct kmers for " << roleNames_.size() << " roles loaded on " << devices_.size()
-         << " device(s), " << info.table_bytes / (1024 * 1024) << " MiB table, " << info.slot_bits << "-bit slots.\n";
+         << " device(s), " << info.table_bytes / (1024 * 1024) << " MiB table, " << info.slot_bits << "-bit slots.  (t=" << nowSeconds() << " s)\n";
 }
 
 void ApplyKmerProcessor::flushBatch(std::vector<std::unique_ptr<Genome>>& genomes) {
@@ -259,6 +264,7 @@ void ApplyKmerProcessor::runCommand() {
     }
     reporter_->closeReport();                                             // :153
     reporter_->close();                                                   // :154
+    log_ << "All done.  (t=" << nowSeconds() << " s)\n";
 }
 
 int ApplyKmerProcessor::run() {

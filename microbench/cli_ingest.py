@@ -38,5 +38,7 @@ for threads in (1, 4, 16):
     dt = time.time() - t
     assert r.returncode == 0, r.stderr[-500:]
     outs.append(r.stdout)
+    marks = [l for l in r.stderr.decode().splitlines() if "t=" in l]
+    print("   ", " | ".join(m[-40:] for m in marks))
     print(f"--threads {threads:2d}: {dt:.2f} s wall for the whole command ({n_genomes*4500/dt/1e3:.0f} k proteins/s incl. DB load), report {len(r.stdout)} bytes", flush=True)
 print("reports identical:", all(o == outs[0] for o in outs))
