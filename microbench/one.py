@@ -7,7 +7,8 @@ from kmers_anno_b200 import synth
 genomes = int(sys.argv[1]); opts = dict(kv.split("=") for kv in sys.argv[2:])
 fam = synth.Families(30000)
 kmers, roles = fam.table(int(1e8), K=8)
-res, off, _ = fam.batch(0, genomes, n_prot=4500)
+bseed = int(opts.pop("batch_seed", 0))   # non-zero: proteins from unrelated families (nearly all misses)
+res, off, _ = (synth.Families(30000, seed=bseed) if bseed else fam).batch(0, genomes, n_prot=4500)
 eng = ka.Engine([0])
 for k, v in opts.items(): eng.set_option(k, float(v))
 eng.db_load(kmers, roles, 8)
