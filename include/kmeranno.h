@@ -87,6 +87,9 @@ const char* ka_last_error(const ka_engine* e);
  *                   tables of at least 2^20 sectors)   (next ka_db_load)
  *   "two_phase"     with "filter": 1 = two-phase tile kernel (signature test and candidate compaction,
  *                   then probes of the survivors only), 0 = test inside the fused kernel (default)
+ *   "wide"          1 = use the wide-table kernels (64-bit sector indices, the mixed key as de-dup
+ *                   token) on any table; 0 (default) = only when the table has more than 2^32 - 16
+ *                   slots, e.g. more than ~34 GB of 64-bit slots   (next ka_db_load)
  *   "slot_bits"     force the table slot width (32, 64, 128; 0 = smallest that fits, default)
  *   "variant"       tile kernel shape: 0 = 4 positions x 128 threads (default), 1 = 4 x 256, 2 = 8 x 256
  *   "chunk_residues" residues per pipelined H2D chunk, default 32 Mi
@@ -182,6 +185,14 @@ int ka_get_stats(ka_engine* e, ka_stats* out);
  * best of `reps` launches.  Returns probes per second on device dev_index. */
 int ka_probe_roofline(ka_engine* e, int dev_index, uint64_t table_bytes, uint64_t n_probes,
                       int slot_bytes, int reps, double* probes_per_s);
+
+/* Synthetic k-mer database for the oversized-table configuration (table larger than one GPU,
+ * BASELINE.json configs[4]): n lines generated ON THE DEVICES, so the host never holds them.
+ * Line i (0-based) is the K-mer whose j-th residue is "ACDEFGHIKLMNPQRSTVWY"[((x >> 5j) & 31) % 20]
+ * with x = mix64(seed + i * 0x9E3779B97F4A7C15) (mix64: x ^= x>>32; x *= 0xD6E8FEB86659FD93; twice;
+ * x ^= x>>32), and its role id is i % n_roles.  Duplicate k-mers keep the last line, as in
+ * ka_db_load.  Measurement / test entry point: it replaces no reference code. */
+int ka_db_load_synthetic(ka_engine* e, uint64_t n, int K, int32_t n_roles, uint64_t seed);
 
 int ka_abi_version(void);
 

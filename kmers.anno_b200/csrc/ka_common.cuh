@@ -16,6 +16,9 @@
 //             home sector); a lookup reads it only when the home sector is full and has no
 //             match (~1 % of probes at the default load factor; the table is L2 resident).
 //             cls 128 stores whole keys, so it simply chains to the next sector.
+//             WIDE tables (more than 2^32 - 16 slots, e.g. > 34 GB of 64-bit slots, or forced by
+//             the "wide" option) use 64-bit sector indices and the mixed key itself as the de-dup
+//             token; the narrow form keeps 32-bit sector indices and slot-index tokens in registers.
 //   batch   : CSR — residues u8[R] (+ padding), offsets u64[N+1], results i32/i32/u8 per sequence.
 #pragma once
 #include <cstdint>
@@ -37,7 +40,8 @@ struct TableView {
     const uint16_t* sig;          // per-sector 16-bit Bloom signature (NULL = no filter), see sig_bits()
     const uint4* ovf;             // overflow table (cls 32/64): 2^ovf_bbits sectors of 2 Slot128
     uint32_t ovf_bbits;
-    uint32_t n_primary_slots;     // slots of the primary table (de-dup tokens of overflow entries start here)
+    uint32_t n_primary_slots;     // slots of the primary table (de-dup tokens of overflow entries start here; narrow only)
+    uint32_t wide;                // 1 = 64-bit sector indices and tokens (see above)
     // sharded mode (table larger than one GPU's share): sector s lives on shard s >> shard_shift at
     // local index s & shard_mask; shard_sectors[i] / shard_ovf[i] are PEER pointers (NVLink loads).
     // n_shards == 1: `sectors` / `ovf` are used directly.
@@ -101,11 +105,18 @@ __host__ __device__ __forceinline__ uint32_t sig_bits(unsigned long long rem) {
 }
 
 // address of a table sector: local HBM, or the owning GPU's HBM through NVLink peer memory
-__device__ __forceinline__ const uint4* sector_ptr(const TableView& t, uint32_t sec) {
+// (SEC = uint32_t for narrow tables, unsigned long long for wide ones)
+template <typename SEC>
+__device__ __forceinline__ const uint4* sector_ptr(const TableView& t, SEC sec) {
     if (t.n_shards <= 1) return t.sectors + 2 * (size_t)sec;
     const uint4* base = reinterpret_cast<const uint4*>(
         __ldg(reinterpret_cast<const unsigned long long*>(t.shard_sectors) + (sec >> t.shard_shift)));
-    return base + 2 * (size_t)(sec & ((1u << t.shard_shift) - 1));
+    return base + 2 * (size_t)(sec & (((SEC)1 << t.shard_shift) - 1));
+}
+
+// shard owning a mixed key (sharded tables are quotiented: sector = mixed >> rem_bits)
+__host__ __device__ __forceinline__ uint32_t shard_of(const TableView& t, unsigned long long mixed) {
+    return (uint32_t)((mixed >> t.rem_bits) >> t.shard_shift);
 }
 
 // One 32-byte sector with a single 256-bit load (LDG.E.256 on sm_100a), read-only path, no

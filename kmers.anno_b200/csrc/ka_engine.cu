@@ -99,6 +99,7 @@ struct ka_engine {
     int two_phase = 0;  // with signatures: 1 = two-phase tile kernel (measured slower, kept as an experiment),
                         // 0 = signature test inside the fused kernel
     int table_mode = 0; // 0 = table replicated on every device, 1 = sharded by sector range (peer loads)
+    int wide = 0;       // 1 = force the wide-table kernels (64-bit sector indices and tokens) on any table
     bool peers_enabled = false;
     bool nccl_ready = false;
     // db
@@ -180,7 +181,7 @@ void pipe_free(Pipe& p) {
 
 // size the per-chunk device buffers
 int pipe_reserve(Device& d, Pipe& p, uint64_t n_res, uint64_t n_seq, uint64_t n_tiles,
-                 uint64_t n_long, uint64_t long_res, uint64_t n_mid) {
+                 uint64_t n_long, uint64_t long_res, uint64_t n_mid, bool wide) {
     int rc;
     if ((rc = ensure(d, p.res, p.res_cap, n_res + 64, "residues"))) return rc;
     size_t want_seq = n_seq + 1;
@@ -202,7 +203,7 @@ int pipe_reserve(Device& d, Pipe& p, uint64_t n_res, uint64_t n_seq, uint64_t n_
     if ((rc = ensure(d, p.first, p.first_cap, n_tiles + 2, "tile index"))) return rc;
     if ((rc = ensure(d, p.big, p.big_cap, n_long + 1, "long-sequence list"))) return rc;
     if ((rc = ensure(d, p.mid, p.mid_cap, n_mid + 1, "mid-sequence tiles"))) return rc;
-    if ((rc = ensure(d, p.scratch, p.scratch_cap, 2 * long_res + 4, "long-sequence tokens")))
+    if ((rc = ensure(d, p.scratch, p.scratch_cap, (wide ? 2 : 1) * (2 * long_res + 4), "long-sequence tokens")))
         return rc;
     return KA_OK;
 }
@@ -239,7 +240,7 @@ void fill_params(ka_engine* e, Device& d, Pipe& p, uint64_t base, uint64_t n_res
     ap.mid_count = p.ctr + 1;
     ap.ext_max = e->tile_span + e->long_seq;
     ap.n_tiles = (uint32_t)(n_res / e->tile_span + 1);
-    tile_smem_bytes(ap.ext_max, &ap.res_bytes);
+    tile_smem_bytes(ap.ext_max, &ap.res_bytes, false);
     ap.first = p.first;
     ap.tab = e->geom;
     ap.tab.sectors = d.table;
@@ -261,7 +262,8 @@ void fill_params(ka_engine* e, Device& d, Pipe& p, uint64_t base, uint64_t n_res
 
 // enqueue plan + tile + big on the pipe's stream, bracketed by timing events
 int enqueue_kernels(ka_engine* e, Device& d, Pipe& p, const AnnotParams& ap, uint64_t n_long, uint64_t n_mid) {
-    size_t smem = tile_smem_bytes(ap.ext_max, nullptr);
+    const bool wide = ap.tab.wide != 0;
+    size_t smem = tile_smem_bytes(ap.ext_max, nullptr, wide);
     if (!d.smem_set) {
         // every tile-kernel instantiation may use up to the opt-in shared-memory limit of the device
         int optin = 0;
@@ -269,6 +271,7 @@ int enqueue_kernels(ka_engine* e, Device& d, Pipe& p, const AnnotParams& ap, uin
         for (int cls : {32, 64, 128})
             for (int v = 0; v < N_VARIANTS; v++) DCK(d, tile_kernel_set_smem(cls, v, (size_t)optin - 2048));  // minus the static part
         for (int cls : {32, 64, 128}) DCK(d, tile_kernel_filt_set_smem(cls, (size_t)optin - 2048));
+        DCK(d, tile_kernel_mode_set_smem((size_t)optin - 2048));
         d.smem_set = (size_t)optin - 2048;
     }
     if (smem > d.smem_set) return dev_fail(d, KA_ERR_INVALID, "tile shared memory exceeds the device limit", cudaErrorInvalidValue);
@@ -276,7 +279,7 @@ int enqueue_kernels(ka_engine* e, Device& d, Pipe& p, const AnnotParams& ap, uin
     DCK(d, cudaEventRecord(p.ev_k0, p.st));
     DCK(d, launch_plan(ap, p.st));
     DCK(d, cudaEventRecord(p.ev_t0, p.st));
-    if (ap.tab.sig && e->two_phase) {
+    if (ap.tab.sig && e->two_phase && !wide) {
         size_t smem_f = tile_smem_bytes_filt(ap.ext_max, nullptr);
         if (smem_f > d.smem_set) return dev_fail(d, KA_ERR_INVALID, "tile shared memory exceeds the device limit", cudaErrorInvalidValue);
         DCK(d, launch_tiles_filt(ap, smem_f, p.st));
@@ -290,7 +293,7 @@ int enqueue_kernels(ka_engine* e, Device& d, Pipe& p, const AnnotParams& ap, uin
         am.first = p.mid;
         am.n_tiles = (uint32_t)n_mid;
         am.ext_max = ap.mid_seq;
-        size_t smem_mid = tile_smem_bytes(am.ext_max, &am.res_bytes);
+        size_t smem_mid = tile_smem_bytes(am.ext_max, &am.res_bytes, wide);
         if (smem_mid > d.smem_set) return dev_fail(d, KA_ERR_INVALID, "mid tile shared memory exceeds the device limit", cudaErrorInvalidValue);
         {
             cudaError_t ce = launch_tiles(am, e->mid_variant, smem_mid, p.st);
@@ -388,7 +391,7 @@ int annotate_range(ka_engine* e, Device& d, const uint8_t* residues, const uint6
         }
         uint64_t n = ce - cs;
         uint64_t n_tiles = sh.n_res / e->tile_span + 1;
-        int rc = pipe_reserve(d, p, sh.n_res, n, n_tiles, sh.n_long, sh.long_res, sh.n_mid);
+        int rc = pipe_reserve(d, p, sh.n_res, n, n_tiles, sh.n_long, sh.long_res, sh.n_mid, e->geom.wide != 0);
         if (rc) return rc;
         if (sh.n_res)
             DCK(d, cudaMemcpyAsync(p.res, residues + offsets[cs], sh.n_res, cudaMemcpyHostToDevice, p.st));
@@ -423,9 +426,22 @@ int annotate_range(ka_engine* e, Device& d, const uint8_t* residues, const uint6
     return KA_OK;
 }
 
-// Build the table replica of one device from the host DB arrays.
-int build_table(ka_engine* e, Device& d, const TableView& geom, const uint8_t* kmers,
-                const int32_t* roles, uint64_t n, uint64_t* n_keys, uint32_t* max_probe) {
+// Source of the DB lines: host arrays, or the synthetic generator (kmers == NULL).
+struct DbSource {
+    const uint8_t* kmers = nullptr;
+    const int32_t* roles = nullptr;
+    uint64_t n = 0;
+    uint64_t seed = 0;        // synthetic only
+    uint32_t n_roles = 0;     // synthetic only
+    uint32_t role_bits = 1;   // bits of the largest role id
+    bool synthetic = false;
+};
+
+// Build the table replica (or shard) of one device from the DB lines.
+int build_table(ka_engine* e, Device& d, const TableView& geom, const DbSource& src, uint64_t* n_keys, uint32_t* max_probe) {
+    const uint8_t* kmers = src.kmers;
+    const int32_t* roles = src.roles;
+    const uint64_t n = src.n;
     DCK(d, cudaSetDevice(d.id));
     if (d.table) { cudaFree(d.table); d.table = nullptr; }
     if (d.ovf) { cudaFree(d.ovf); d.ovf = nullptr; }
@@ -441,7 +457,7 @@ int build_table(ka_engine* e, Device& d, const TableView& geom, const uint8_t* k
         ce = cudaMalloc((void**)&d.ovf, ovf_bytes);
         if (ce != cudaSuccess) { d.ovf = nullptr; return dev_fail(d, KA_ERR_OOM, "overflow table", ce); }
     }
-    const bool use_sig = geom.n_shards <= 1 && (e->filter == 1 || (e->filter < 0 && geom.bbits >= 20));
+    const bool use_sig = geom.n_shards <= 1 && !geom.wide && (e->filter == 1 || (e->filter < 0 && geom.bbits >= 20));
     const size_t sig_bytes = use_sig ? (n_sectors * 2 + 4) : 0;
     if (sig_bytes) {
         ce = cudaMalloc((void**)&d.sig, sig_bytes);
@@ -452,20 +468,20 @@ int build_table(ka_engine* e, Device& d, const TableView& geom, const uint8_t* k
     tab.sectors = d.table;
     tab.ovf = d.ovf;
     tab.sig = d.sig;
-    const uint64_t CH = 16ull << 20;  // k-mers per upload
-    uint8_t* dk = nullptr; int32_t* dr = nullptr; uint32_t* line_of = nullptr;
+    const uint64_t CH = (src.synthetic ? 64ull : 16ull) << 20;  // k-mers per upload / per generator launch
+    uint8_t* dk = nullptr; int32_t* dr = nullptr; unsigned long long* best = nullptr;
     unsigned long long* dc = nullptr; uint32_t* de = nullptr;
     uint64_t ch = std::min<uint64_t>(CH, n ? n : 1);
     const bool packed = geom.cls != 128;
-    // cls 32/64 keep every role on the device until db_finalize; cls 128 needs a chunk only
+    // cls 32/64: 8 bytes per primary slot hold the winning (line, role) until db_finalize
     if ((ce = cudaMalloc((void**)&dk, ch * K)) != cudaSuccess ||
-        (ce = cudaMalloc((void**)&dr, (packed ? std::max<uint64_t>(n, 1) : ch) * 4)) != cudaSuccess ||
-        (packed && (ce = cudaMalloc((void**)&line_of, n_slots * 4)) != cudaSuccess) ||
+        (ce = cudaMalloc((void**)&dr, ch * 4)) != cudaSuccess ||
+        (packed && (ce = cudaMalloc((void**)&best, n_slots * 8)) != cudaSuccess) ||
         (ce = cudaMalloc((void**)&dc, 16)) != cudaSuccess ||
         (ce = cudaMalloc((void**)&de, 16)) != cudaSuccess) {
         if (dk) cudaFree(dk);
         if (dr) cudaFree(dr);
-        if (line_of) cudaFree(line_of);
+        if (best) cudaFree(best);
         if (dc) cudaFree(dc);
         return dev_fail(d, KA_ERR_OOM, "DB staging", ce);
     }
@@ -476,26 +492,29 @@ int build_table(ka_engine* e, Device& d, const TableView& geom, const uint8_t* k
     step(cudaMemsetAsync(d.table, 0, bytes, st), "memset table");
     if (ovf_bytes) step(cudaMemsetAsync(d.ovf, 0, ovf_bytes, st), "memset overflow table");
     if (sig_bytes) step(cudaMemsetAsync(d.sig, 0, sig_bytes, st), "memset signatures");
-    if (packed) step(cudaMemsetAsync(line_of, 0, n_slots * 4, st), "memset line_of");
+    if (packed) step(cudaMemsetAsync(best, 0, n_slots * 8, st), "memset best");
     step(cudaMemcpyAsync(d.lut, e->lut, 256, cudaMemcpyHostToDevice, st), "H2D lut");
     step(cudaMemsetAsync(dc, 0, 16, st), "memset counters");
     step(cudaMemsetAsync(de, 0, 16, st), "memset errs");
     for (uint64_t i = 0; i < n && rc == KA_OK; i += ch) {
         uint64_t m = std::min(ch, n - i);
-        int32_t* dri = packed ? dr + i : dr;
-        step(cudaMemcpyAsync(dk, kmers + i * K, m * K, cudaMemcpyHostToDevice, st), "H2D kmers");
-        step(cudaMemcpyAsync(dri, roles + i, m * 4, cudaMemcpyHostToDevice, st), "H2D roles");
-        step(launch_db_insert(tab, dk, dri, m, i, d.lut, line_of, dc, de, st), "db_insert");
+        if (!src.synthetic) {
+            step(cudaMemcpyAsync(dk, kmers + i * K, m * K, cudaMemcpyHostToDevice, st), "H2D kmers");
+            step(cudaMemcpyAsync(dr, roles + i, m * 4, cudaMemcpyHostToDevice, st), "H2D roles");
+        } else {
+            step(launch_db_generate(i, m, K, src.seed, src.n_roles, dk, dr, st), "db_generate");
+        }
+        step(launch_db_insert(tab, dk, dr, m, i, d.lut, best, src.role_bits, dc, de, st), "db_insert");
         step(cudaStreamSynchronize(st), "db_insert sync");
     }
-    if (rc == KA_OK) step(launch_db_finalize(tab, line_of, dr, st), "db_finalize");
+    if (rc == KA_OK) step(launch_db_finalize(tab, best, src.role_bits, st), "db_finalize");
     step(cudaStreamSynchronize(st), "db_finalize sync");
     unsigned long long hc[2] = {0, 0};
     uint32_t he[4] = {0, 0, 0, 0};
     step(cudaMemcpy(hc, dc, 16, cudaMemcpyDeviceToHost), "D2H counters");
     step(cudaMemcpy(he, de, 16, cudaMemcpyDeviceToHost), "D2H errs");
     cudaFree(dk); cudaFree(dr); cudaFree(dc); cudaFree(de);
-    if (line_of) cudaFree(line_of);
+    if (best) cudaFree(best);
     if (rc) return rc;
     if (he[0]) { d.err = KA_ERR_ALPHABET; d.errmsg = "k-mer byte outside the DB alphabet (internal)"; return d.err; }
     if (he[1]) { d.err = KA_ERR_ROLE; d.errmsg = "negative role id in the DB"; return d.err; }
@@ -513,7 +532,7 @@ uint32_t ceil_log2(double x) {
 
 // Pick slot class and sector count: the smallest table that holds n keys at the requested
 // load factor with remainder + role fitting the slot (see ka_common.cuh).
-bool choose_geometry(uint64_t n, int K, int32_t max_role, double lf, int force_cls, uint32_t n_shards, TableView& g) {
+bool choose_geometry(uint64_t n, int K, int32_t max_role, double lf, int force_cls, uint32_t n_shards, bool force_wide, TableView& g) {
     const uint32_t w = 5u * (uint32_t)K;
     uint32_t role_bits = 1;
     while (((uint64_t)max_role + 1) >> role_bits) role_bits++;
@@ -537,7 +556,13 @@ bool choose_geometry(uint64_t n, int K, int32_t max_role, double lf, int force_c
             if (rem_bits + role_bits > (uint32_t)cls) continue;
         }
         uint32_t slot_log = cls == 32 ? 3 : (cls == 64 ? 2 : 1);
-        if (b + slot_log > 31) continue;  // slot index + 1 must fit the 32-bit de-dup token
+        // narrow tables: slot index + 1 must fit the 32-bit de-dup token; beyond that the quotiented
+        // classes switch to the wide kernels (64-bit sector indices, the key is the token)
+        bool wide = force_wide && cls != 128;
+        if (b + slot_log > 31) {
+            if (cls == 128 || b > 40) continue;
+            wide = true;
+        }
         uint64_t bytes = 32ull << b;
         if (!found || bytes < best_bytes) {
             found = true; best_bytes = bytes;
@@ -547,7 +572,8 @@ bool choose_geometry(uint64_t n, int K, int32_t max_role, double lf, int force_c
             g.sectors = nullptr;
             g.ovf = nullptr;
             g.sig = nullptr;
-            g.n_primary_slots = (uint32_t)((uint64_t)S << b);
+            g.n_primary_slots = wide ? 0u : (uint32_t)((uint64_t)S << b);
+            g.wide = wide ? 1u : 0u;
             // expected keys beyond S per sector under Poisson(n / sectors) arrivals
             double lam = (double)n / (double)(1ull << b), pk = std::exp(-lam), over = 0;
             for (int k = 1; k < S + 400; k++) {
@@ -686,9 +712,9 @@ int annotate_routed_range(ka_engine* e, Device& d, int idx, RouteShared& sh, con
         for (int cls : {32, 64, 128})
             for (int v = 0; v < N_VARIANTS; v++) cuda_ok(tile_kernel_set_smem(cls, v, (size_t)optin - 2048), "tile kernel shared memory");
         for (int cls : {32, 64, 128}) cuda_ok(tile_kernel_filt_set_smem(cls, (size_t)optin - 2048), "tile kernel shared memory");
+        cuda_ok(tile_kernel_mode_set_smem((size_t)optin - 2048), "routed tile kernel shared memory");
         d.smem_set = (size_t)optin - 2048;
     }
-    if (!d.route_smem_set) { cuda_ok(tile_kernel_mode_set_smem(d.smem_set), "routed tile kernel shared memory"); d.route_smem_set = true; }
 
     const bool trace = idx == 0 && getenv("KA_ROUTE_TRACE") != nullptr;
     std::vector<cudaEvent_t> tev(12, nullptr);
@@ -711,7 +737,7 @@ int annotate_routed_range(ka_engine* e, Device& d, int idx, RouteShared& sh, con
         }
         if (has) {
             d.probes += shp.probes;
-            if (pipe_reserve(d, p, shp.n_res, n, shp.n_res / e->tile_span + 1, 0, 0, shp.n_mid) || route_reserve(d, shp.n_res + 64, 0)) has = false;
+            if (pipe_reserve(d, p, shp.n_res, n, shp.n_res / e->tile_span + 1, 0, 0, shp.n_mid, e->geom.wide != 0) || route_reserve(d, shp.n_res + 64, 0)) has = false;
         }
         if (has) {
             if (shp.n_res) cuda_ok(cudaMemcpyAsync(p.res, residues + offsets[cs], shp.n_res, cudaMemcpyHostToDevice, st), "H2D residues");
@@ -720,10 +746,11 @@ int annotate_routed_range(ka_engine* e, Device& d, int idx, RouteShared& sh, con
             fill_params(e, d, p, offsets[cs], shp.n_res, n, min_hits, ap);
             ap.route_keys = d.r_keys;
             ap.route_ans = d.r_ans_pos;
-            smem = tile_smem_bytes(ap.ext_max, nullptr);
+            smem = tile_smem_bytes(ap.ext_max, nullptr, ap.tab.wide != 0);
             am = ap;
             am.first = p.mid; am.n_tiles = (uint32_t)shp.n_mid; am.ext_max = ap.mid_seq;
-            smem_mid = tile_smem_bytes(am.ext_max, &am.res_bytes);
+            smem_mid = tile_smem_bytes(am.ext_max, &am.res_bytes, ap.tab.wide != 0);
+            if (std::max(smem, smem_mid) > d.smem_set && d.err == KA_OK) { d.err = KA_ERR_INVALID; d.errmsg = "tile shared memory exceeds the device limit"; }
             cuda_ok(cudaMemsetAsync(p.ctr, 0, 16, st), "memset");
             cuda_ok(cudaMemsetAsync(d.r_keys, 0xff, (shp.n_res + 64) * 8, st), "memset keys");
             cuda_ok(cudaMemsetAsync(d.r_small, 0, 24 * 8, st), "memset counters");
@@ -949,6 +976,8 @@ int ka_set_option(ka_engine* e, const char* name, double v) {
     } else if (n == "table_mode") {
         if (v != 0 && v != 1 && v != 2) return fail(e, KA_ERR_INVALID, "table_mode must be 0 (replicated), 1 (sharded, peer loads) or 2 (sharded, routed)");
         e->table_mode = (int)v;
+    } else if (n == "wide") {
+        e->wide = v != 0;
     } else if (n == "filter") {
         e->filter = v < 0 ? -1 : (v != 0);
     } else if (n == "slot_bits") {
@@ -960,30 +989,42 @@ int ka_set_option(ka_engine* e, const char* name, double v) {
     } else {
         return fail(e, KA_ERR_INVALID, "unknown option '%s'", name);
     }
-    if (tile_smem_bytes(e->tile_span + e->long_seq, nullptr) > 227 * 1024 ||
-        tile_smem_bytes(std::max(e->mid_seq, e->long_seq), nullptr) > 227 * 1024)
+    if (tile_smem_bytes(e->tile_span + e->long_seq, nullptr, e->wide != 0) > 225 * 1024 ||
+        tile_smem_bytes(std::max(e->mid_seq, e->long_seq), nullptr, e->wide != 0) > 225 * 1024)
         return fail(e, KA_ERR_INVALID, "tile_span + long_seq (or mid_seq) needs more than 227 KB of shared memory");
     return KA_OK;
 }
 
-static int db_load_impl(ka_engine* e, const uint8_t* kmers, const int32_t* role_ids, uint64_t n, int K);
+static int db_load_impl(ka_engine* e, const uint8_t* kmers, const int32_t* role_ids, uint64_t n, int K,
+                        uint64_t syn_seed = 0, int32_t syn_roles = 0);
 
 int ka_db_load(ka_engine* e, const uint8_t* kmers, const int32_t* role_ids, uint64_t n, int K) {
     if (!e) return KA_ERR_INVALID;
     std::lock_guard<std::mutex> lk(e->mu);
+    if (n && (!kmers || !role_ids)) return fail(e, KA_ERR_INVALID, "ka_db_load: NULL input");
     return db_load_impl(e, kmers, role_ids, n, K);
 }
 
-static int db_load_impl(ka_engine* e, const uint8_t* kmers, const int32_t* role_ids, uint64_t n, int K) {
+int ka_db_load_synthetic(ka_engine* e, uint64_t n, int K, int32_t n_roles, uint64_t seed) {
+    if (!e) return KA_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (n == 0 || n_roles < 1) return fail(e, KA_ERR_INVALID, "ka_db_load_synthetic: n and n_roles must be positive");
+    return db_load_impl(e, nullptr, nullptr, n, K, seed, n_roles);
+}
+
+// syn_roles > 0: the lines come from the synthetic generator (syn_seed, syn_roles), kmers/role_ids unused
+static int db_load_impl(ka_engine* e, const uint8_t* kmers, const int32_t* role_ids, uint64_t n, int K,
+                        uint64_t syn_seed, int32_t syn_roles) {
     if (K < 1 || K > KMAX) return fail(e, KA_ERR_K, "K = %d: this engine packs 5 bits per residue, K must be 1..%d", K, KMAX);
-    if (n && (!kmers || !role_ids)) return fail(e, KA_ERR_INVALID, "ka_db_load: NULL input");
-    if (n >= (1ull << 32)) return fail(e, KA_ERR_TOO_BIG, "ka_db_load: more than 2^32-1 DB lines");
     e->have_db = false;
 
     // 1. alphabet: the distinct bytes of the DB, scanned on device 0
     Device& d0 = e->devs[0];
     uint32_t bitmap[8] = {0};
-    {
+    const bool synthetic = syn_roles > 0;
+    if (synthetic) {
+        for (const char* a = "ACDEFGHIKLMNPQRSTVWY"; *a; a++) bitmap[(uint8_t)*a >> 5] |= 1u << ((uint8_t)*a & 31);
+    } else {
         cudaSetDevice(d0.id);
         cudaStream_t st = d0.pipe[0].st;
         uint32_t* dbm = nullptr; uint8_t* dk = nullptr;
@@ -1016,10 +1057,22 @@ static int db_load_impl(ka_engine* e, const uint8_t* kmers, const int32_t* role_
                     "ka_db_load: the DB uses %d distinct residue bytes; at most 31 fit the 5-bit packing", nsym);
 
     // 2. table geometry (slot class, sector count) from n, K and the largest role id
-    int32_t max_role = 0;
-    for (uint64_t i = 0; i < n; i++) {
+    int32_t max_role = synthetic ? syn_roles - 1 : 0;
+    for (uint64_t i = 0; !synthetic && i < n; i++) {
         if (role_ids[i] < 0) return fail(e, KA_ERR_ROLE, "ka_db_load: negative role id %d at line %llu", role_ids[i], (unsigned long long)i);
         if (role_ids[i] > max_role) max_role = role_ids[i];
+    }
+    DbSource src;
+    src.kmers = synthetic ? nullptr : kmers; src.roles = role_ids; src.n = n; src.seed = syn_seed; src.n_roles = (uint32_t)syn_roles;
+    src.synthetic = synthetic;
+    while (((uint64_t)max_role + 1) >> src.role_bits) src.role_bits++;
+    {
+        // a slot keeps (line + 1) << role_bits | role in 64 bits while the DB streams in
+        uint32_t line_bits = 1;
+        while (line_bits < 64 && ((n + 1) >> line_bits)) line_bits++;
+        if (line_bits + src.role_bits > 64)
+            return fail(e, KA_ERR_TOO_BIG, "ka_db_load: %llu lines with role ids up to %d exceed the 64-bit (line, role) word",
+                        (unsigned long long)n, max_role);
     }
     TableView geom;
     const uint32_t n_shards = e->table_mode >= 1 ? (uint32_t)e->devs.size() : 1u;
@@ -1043,21 +1096,23 @@ static int db_load_impl(ka_engine* e, const uint8_t* kmers, const int32_t* role_
             e->peers_enabled = true;
         }
     }
-    if (!choose_geometry(n, K, max_role, e->load_factor, e->slot_bits, n_shards, geom))
-        return fail(e, KA_ERR_TOO_BIG, "ka_db_load: %llu k-mers (K=%d, max role %d) do not fit %s of this build",
-                    (unsigned long long)n, K, max_role, e->slot_bits ? "the forced slot width" : "the 32-bit slot index");
+    if (!choose_geometry(n, K, max_role, e->load_factor, e->slot_bits, n_shards, e->wide != 0, geom))
+        return fail(e, KA_ERR_TOO_BIG, "ka_db_load: %llu k-mers (K=%d, max role %d) do not fit %s",
+                    (unsigned long long)n, K, max_role, e->slot_bits ? "the forced slot width" : "any slot class of this build");
 
     // 3. build one replica per device
     std::vector<uint64_t> nk(e->devs.size(), 0);
     std::vector<uint32_t> mp(e->devs.size(), 0);
     int rc = KA_OK;
     for (int attempt = 0; attempt < 6; attempt++) {
-        if ((uint64_t)geom.n_primary_slots + (uint64_t)n_shards * (2ull << geom.ovf_bbits) >= 0xfffffff0ull)
-            return fail(e, KA_ERR_TOO_BIG, "ka_db_load: table exceeds the 32-bit slot index of this build");
+        if (!geom.wide && (uint64_t)geom.n_primary_slots + (uint64_t)n_shards * (2ull << geom.ovf_bbits) >= 0xfffffff0ull) {
+            if (geom.cls == 128) return fail(e, KA_ERR_TOO_BIG, "ka_db_load: table exceeds the 32-bit slot index of the 128-bit slot class");
+            geom.wide = 1; geom.n_primary_slots = 0;   // overflow entries pushed the token range past 32 bits
+        }
         rc = for_each_device(e, [&](Device& d, int i) {
             TableView g = geom;
             g.my_shard = n_shards > 1 ? (uint32_t)i : 0u;
-            return build_table(e, d, g, kmers, role_ids, n, &nk[i], &mp[i]);
+            return build_table(e, d, g, src, &nk[i], &mp[i]);
         });
         if (rc != KA_ERR_TOO_BIG) break;
         geom.ovf_bbits += 2;  // overflow table was too small for this key set: rebuild 4x larger
@@ -1184,7 +1239,7 @@ int ka_batch_upload(ka_engine* e, int dev_index, const uint8_t* residues, const 
     b->dev_index = dev_index; b->n_seq = N; b->n_res = sh.n_res; b->base = offsets[0];
     b->long_res = sh.long_res; b->n_long = sh.n_long; b->n_mid = sh.n_mid;
     int rc = pipe_init(d, b->p);
-    if (rc == KA_OK) rc = pipe_reserve(d, b->p, sh.n_res, N, sh.n_res / e->tile_span + 1, sh.n_long, sh.long_res, sh.n_mid);
+    if (rc == KA_OK) rc = pipe_reserve(d, b->p, sh.n_res, N, sh.n_res / e->tile_span + 1, sh.n_long, sh.long_res, sh.n_mid, e->geom.wide != 0);
     cudaError_t ce = cudaSuccess;
     if (rc == KA_OK && sh.n_res) ce = cudaMemcpy(b->p.res, residues + offsets[0], sh.n_res, cudaMemcpyHostToDevice);
     if (rc == KA_OK && ce == cudaSuccess) ce = cudaMemcpy(b->p.off, offsets, (N + 1) * 8, cudaMemcpyHostToDevice);

@@ -26,6 +26,7 @@
 // HBM-bound integer work: no tensor cores.  Algorithmic bytes per probe = 32 (one table
 // sector) + 1 (the residue).
 #include "ka_kernels.cuh"
+#include <type_traits>
 
 // `make DEBUG=1` compiles bounds checks into the kernels (compute-sanitizer is not available on
 // the GPU pool): a failed check ORs its code into p.dbg[0] and the engine turns that into an
@@ -46,7 +47,7 @@ __device__ __forceinline__ int ovf_lookup(const TableView& t, unsigned long long
     const uint32_t mask = (1u << t.ovf_bbits) - 1;
     uint32_t s = t.ovf_bbits ? (uint32_t)(mix64(m) >> (64 - t.ovf_bbits)) : 0u;
     // the overflow entries of a sector live with the shard that owns the sector
-    const uint32_t shard = t.n_shards <= 1 ? 0u : (uint32_t)(m >> t.rem_bits) >> t.shard_shift;
+    const uint32_t shard = t.n_shards <= 1 ? 0u : shard_of(t, m);
     const uint4* ovf = t.n_shards <= 1 ? t.ovf : reinterpret_cast<const uint4*>(
         __ldg(reinterpret_cast<const unsigned long long*>(t.shard_ovf) + shard));
     const uint32_t tok0 = t.n_primary_slots + shard * (2u << t.ovf_bbits);
@@ -138,6 +139,45 @@ __device__ __forceinline__ bool token_insert(uint32_t* region, uint32_t n, uint3
     }
 }
 
+// Wide tables: the de-dup token is the mixed key itself (64 bits), same open addressing.
+__device__ __forceinline__ bool token_insert(unsigned long long* region, uint32_t n, unsigned long long token) {
+    uint32_t j = (uint32_t)(((unsigned long long)(((uint32_t)token ^ (uint32_t)(token >> 32)) * 0x9E3779B1u) * n) >> 32);
+    for (;;) {
+        unsigned long long old = atomicCAS(region + j, 0ull, token);
+        if (old == 0ull) return true;
+        if (old == token) return false;
+        j = (j + 1 == n) ? 0 : j + 1;
+    }
+}
+
+// probe_batch for wide tables (cls 32/64): m[i] is the whole mixed key (sector = m >> rem_bits,
+// which may need more than 32 bits); the key is its own token, so only the roles come back.
+template <int CLS, int C>
+__device__ __forceinline__ void probe_batch_wide(const TableView& tab, const unsigned long long (&m)[C],
+                                                 unsigned okmask, int (&role)[C]) {
+    uint4 a[C], b[C];
+#pragma unroll
+    for (int i = 0; i < C; i++)
+        if (okmask & (1u << i)) load_sector(sector_ptr(tab, m[i] >> tab.rem_bits), a[i], b[i]);
+    unsigned pend = 0;
+#pragma unroll
+    for (int i = 0; i < C; i++) {
+        role[i] = -1;
+        if (okmask & (1u << i)) {
+            uint32_t j = 0;
+            bool full;
+            const int r = match_sector<CLS>(tab, a[i], b[i], m[i] & tab.rem_mask, j, full);
+            if (r >= 0) role[i] = r;
+            else if (full) pend |= 1u << i;
+        }
+    }
+    if (pend) {
+#pragma unroll
+        for (int i = 0; i < C; i++)
+            if (pend & (1u << i)) { uint32_t unused; role[i] = ovf_lookup(tab, m[i], unused); }
+    }
+}
+
 // The reference's decision (ApplyKmerProcessor.java:146-147) from the reduced tally.
 __device__ __forceinline__ void emit_call(const AnnotParams& p, uint32_t seq, int cnt, int rmin,
                                           int rmax) {
@@ -221,15 +261,19 @@ cudaError_t launch_plan(const AnnotParams& p, cudaStream_t st) {
 //   [+3 * 4*MAX_TILE_SEQ)                s_cnt, s_min, s_max
 //   [+4*(tok_cap(ext_max)+4*MAX_TILE_SEQ+8))  token set: sequence q starting at residue a owns
 //                                        [tok_cap(a)+4q, +tok_cap(L)+4), never full (hits <= L-K+1)
-size_t tile_smem_bytes(uint32_t ext_max, uint32_t* res_bytes_out) {
+// (tokens are 8 bytes each for wide tables)
+size_t tile_smem_bytes(uint32_t ext_max, uint32_t* res_bytes_out, bool wide) {
     uint32_t res_bytes = (ext_max + 16 + 32 + 15) & ~15u;  // lead slack + K-1 over-read
     if (res_bytes_out) *res_bytes_out = res_bytes;
     return (size_t)res_bytes + 256 + 4 * (MAX_TILE_SEQ + 4) + 3 * 4 * MAX_TILE_SEQ +
-           4 * ((size_t)tok_cap(ext_max) + 4 * MAX_TILE_SEQ + 8);
+           (wide ? 8 : 4) * ((size_t)tok_cap(ext_max) + 4 * MAX_TILE_SEQ + 8);
 }
 
-template <int CLS, int C, int THREADS, int MINB, int MODE = 0>
+template <int CLS, int C, int THREADS, int MINB, int MODE = 0, bool WIDE = false>
 __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
+    static_assert(!WIDE || CLS != 128, "wide tables are quotiented");
+    typedef typename std::conditional<WIDE, unsigned long long, uint32_t>::type tok_t;
+    typedef typename std::conditional<WIDE, unsigned long long, typename rem_type<CLS>::type>::type rem_t;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar;
 
@@ -239,7 +283,7 @@ __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
     int* s_cnt = (int*)(s_off + MAX_TILE_SEQ + 4);
     int* s_min = s_cnt + MAX_TILE_SEQ;
     int* s_max = s_min + MAX_TILE_SEQ;
-    uint32_t* s_tok = (uint32_t*)(s_max + MAX_TILE_SEQ);
+    tok_t* s_tok = (tok_t*)(s_max + MAX_TILE_SEQ);   // 16-byte aligned: res_bytes is, and so is the rest
 
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = tid & 31;
@@ -284,10 +328,10 @@ __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
             s_cnt[i] = 0; s_min[i] = 0x7fffffff; s_max[i] = -1;
         }
         {
-            const uint32_t ntok = tok_cap(ext - lead) + 4u * ns + 4u;
+            const uint32_t ntok = (tok_cap(ext - lead) + 4u * ns + 4u) * (uint32_t)(sizeof(tok_t) / 4);   // in 32-bit words
             const uint4 z = make_uint4(0, 0, 0, 0);
             for (uint32_t i = tid * 4; i < ntok; i += THREADS * 4)
-                *reinterpret_cast<uint4*>(s_tok + i) = z;
+                *reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(s_tok) + i) = z;
         }
         __syncthreads();
         if (nbytes) { mbar_wait(&s_bar, parity); parity ^= 1; }
@@ -320,8 +364,8 @@ __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
                 }
                 r += K - 1;
 
-                typename rem_type<CLS>::type rem[C];
-                uint32_t sec[C];
+                rem_t rem[C];           // stored remainder; wide tables: the whole mixed key
+                uint32_t sec[C];        // home sector, then the de-dup token (narrow tables only)
                 uint32_t seqpack = 0;   // sequence index (< MAX_TILE_SEQ = 256) of each position, one byte each
                 static_assert(C <= 4 || MAX_TILE_SEQ <= 256, "");
                 uint32_t seqpack2 = 0;
@@ -338,10 +382,12 @@ __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
                             okmask |= 1u << i;
                             if (i < 4) seqpack |= (uint32_t)si << (8 * (i & 3));
                             else seqpack2 |= (uint32_t)si << (8 * (i & 3));
-                            if (MODE != 2) {
+                            if (WIDE) {
+                                rem[i] = mixw(key & tab.key_mask, tab.wbits, tab.key_mask);
+                            } else if (MODE != 2) {
                                 unsigned long long rm;
                                 locate(tab, key & tab.key_mask, sec[i], rm);
-                                rem[i] = (typename rem_type<CLS>::type)rm;
+                                rem[i] = (rem_t)rm;
                             }
                         }
                     }
@@ -353,8 +399,8 @@ __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
 #pragma unroll
                     for (int i = 0; i < C; i++)
                         if (i < (int)run && P0 + i < pend)
-                            p.route_keys[g0a + P0 + i] = (okmask & (1u << i))
-                                ? (((unsigned long long)sec[i] << tab.rem_bits) | (unsigned long long)rem[i]) : ROUTE_INVALID;
+                            p.route_keys[g0a + P0 + i] = !(okmask & (1u << i)) ? ROUTE_INVALID
+                                : (WIDE ? (unsigned long long)rem[i] : (((unsigned long long)sec[i] << tab.rem_bits) | (unsigned long long)rem[i]));
                     okmask = 0;
                 } else if (MODE == 2) {
                     // routed mode, last step: the owning GPUs have answered (role << 32 | token)
@@ -367,17 +413,21 @@ __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
                         role[i] = -1;
                         if (okmask & (1u << i)) { role[i] = (int)(ans[i] >> 32); sec[i] = (uint32_t)ans[i]; }
                     }
+                } else if constexpr (WIDE) {
+                    probe_batch_wide<CLS, C>(tab, rem, okmask, role);
                 } else {
                     probe_batch<CLS, C>(tab, rem, sec, okmask, role);
                 }
 #pragma unroll
                 for (int i = 0; i < C; i++) {
                     if ((okmask & (1u << i)) && role[i] >= 0) {
+                        tok_t token;
+                        if constexpr (WIDE) token = rem[i]; else token = sec[i];
                         const int q = (int)(((i < 4 ? seqpack : seqpack2) >> (8 * (i & 3))) & 0xffu);
                         const uint32_t a = s_off[q], b = s_off[q + 1];
                         KA_CHECK(q >= 0 && q < (int)ns && b >= a && a >= lead, 8u);
                         KA_CHECK(tok_cap(a - lead) + 4u * (uint32_t)q + tok_cap(b - a) + 4u <= tok_cap(p.ext_max) + 4u * MAX_TILE_SEQ + 8u, 16u);
-                        if (token_insert(s_tok + tok_cap(a - lead) + 4u * (uint32_t)q, tok_cap(b - a) + 4u, sec[i])) {
+                        if (token_insert(s_tok + tok_cap(a - lead) + 4u * (uint32_t)q, tok_cap(b - a) + 4u, token)) {
                             if (q != cur) {
                                 if (cur >= 0 && cnt > 0) {
                                     atomicAdd(&s_cnt[cur], cnt);
@@ -430,7 +480,7 @@ __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
 constexpr int FILT_THREADS = 128, FA = 8, FB = 4, FILT_CAND = FILT_THREADS * FA;
 
 size_t tile_smem_bytes_filt(uint32_t ext_max, uint32_t* res_bytes_out) {
-    return tile_smem_bytes(ext_max, res_bytes_out) + 8 + (size_t)FILT_CAND * (4 + 8 + 1) + 16;
+    return tile_smem_bytes(ext_max, res_bytes_out, false) + 8 + (size_t)FILT_CAND * (4 + 8 + 1) + 16;
 }
 
 template <int CLS>
@@ -695,6 +745,7 @@ cudaError_t tile_kernel_set_smem(int cls, int variant, size_t bytes) {
 
 cudaError_t launch_tiles(const AnnotParams& p, int variant, size_t smem, cudaStream_t st) {
     if (p.n_tiles == 0) return cudaSuccess;
+    if (p.tab.wide) return launch_tiles_mode(p, variant, 0, smem, st);
     return with_tile_kernel(p.tab.cls, variant, [&](auto kern, int threads) {
         kern<<<p.n_tiles, threads, smem, st>>>(p);
         return cudaGetLastError();
@@ -702,15 +753,22 @@ cudaError_t launch_tiles(const AnnotParams& p, int variant, size_t smem, cudaStr
 }
 
 cudaError_t launch_tiles_mode(const AnnotParams& p, int variant, int mode, size_t smem, cudaStream_t st) {
-    if (mode == 0) return launch_tiles(p, variant, smem, st);
+    if (mode == 0 && !p.tab.wide) return launch_tiles(p, variant, smem, st);
     if (p.n_tiles == 0) return cudaSuccess;
-    if (p.tab.cls == 128 || variant > 1) return cudaErrorInvalidValue;   // routed tables are quotiented; shapes 0 and 1
-#define KA_MODE_LAUNCH(CLS)                                                                         \
-    if (variant == 0 && mode == 1) tile_kernel<CLS, 4, 128, 6, 1><<<p.n_tiles, 128, smem, st>>>(p);  \
-    else if (variant == 0)         tile_kernel<CLS, 4, 128, 6, 2><<<p.n_tiles, 128, smem, st>>>(p);  \
-    else if (mode == 1)            tile_kernel<CLS, 4, 256, 3, 1><<<p.n_tiles, 256, smem, st>>>(p);  \
-    else                           tile_kernel<CLS, 4, 256, 3, 2><<<p.n_tiles, 256, smem, st>>>(p);
-    if (p.tab.cls == 32) { KA_MODE_LAUNCH(32) } else { KA_MODE_LAUNCH(64) }
+    if (p.tab.cls == 128) return cudaErrorInvalidValue;   // routed and wide tables are quotiented
+    if (variant > 1) variant = 1;                          // shapes 0 (4 x 128) and 1 (4 x 256)
+#define KA_MODE_LAUNCH(CLS, W)                                                                          \
+    if (variant == 0) {                                                                                 \
+        if (mode == 0)      tile_kernel<CLS, 4, 128, 6, 0, W><<<p.n_tiles, 128, smem, st>>>(p);          \
+        else if (mode == 1) tile_kernel<CLS, 4, 128, 6, 1, W><<<p.n_tiles, 128, smem, st>>>(p);          \
+        else                tile_kernel<CLS, 4, 128, 6, 2, W><<<p.n_tiles, 128, smem, st>>>(p);          \
+    } else {                                                                                            \
+        if (mode == 0)      tile_kernel<CLS, 4, 256, 3, 0, W><<<p.n_tiles, 256, smem, st>>>(p);          \
+        else if (mode == 1) tile_kernel<CLS, 4, 256, 3, 1, W><<<p.n_tiles, 256, smem, st>>>(p);          \
+        else                tile_kernel<CLS, 4, 256, 3, 2, W><<<p.n_tiles, 256, smem, st>>>(p);          \
+    }
+    if (p.tab.wide) { if (p.tab.cls == 32) { KA_MODE_LAUNCH(32, true) } else { KA_MODE_LAUNCH(64, true) } }
+    else            { if (p.tab.cls == 32) { KA_MODE_LAUNCH(32, false) } else { KA_MODE_LAUNCH(64, false) } }
 #undef KA_MODE_LAUNCH
     return cudaGetLastError();
 }
@@ -720,10 +778,12 @@ cudaError_t tile_kernel_mode_set_smem(size_t bytes) {
 #define KA_MODE_ATTR(K)                                                                                   \
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); \
     if (ce == cudaSuccess) ce = cudaFuncSetAttribute(K, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    KA_MODE_ATTR((tile_kernel<32, 4, 128, 6, 1>)) KA_MODE_ATTR((tile_kernel<32, 4, 128, 6, 2>))
-    KA_MODE_ATTR((tile_kernel<32, 4, 256, 3, 1>)) KA_MODE_ATTR((tile_kernel<32, 4, 256, 3, 2>))
-    KA_MODE_ATTR((tile_kernel<64, 4, 128, 6, 1>)) KA_MODE_ATTR((tile_kernel<64, 4, 128, 6, 2>))
-    KA_MODE_ATTR((tile_kernel<64, 4, 256, 3, 1>)) KA_MODE_ATTR((tile_kernel<64, 4, 256, 3, 2>))
+#define KA_MODE_ATTR6(CLS, W)                                                                   \
+    KA_MODE_ATTR((tile_kernel<CLS, 4, 128, 6, 0, W>)) KA_MODE_ATTR((tile_kernel<CLS, 4, 256, 3, 0, W>))   \
+    KA_MODE_ATTR((tile_kernel<CLS, 4, 128, 6, 1, W>)) KA_MODE_ATTR((tile_kernel<CLS, 4, 256, 3, 1, W>))   \
+    KA_MODE_ATTR((tile_kernel<CLS, 4, 128, 6, 2, W>)) KA_MODE_ATTR((tile_kernel<CLS, 4, 256, 3, 2, W>))
+    KA_MODE_ATTR6(32, false) KA_MODE_ATTR6(64, false) KA_MODE_ATTR6(32, true) KA_MODE_ATTR6(64, true)
+#undef KA_MODE_ATTR6
 #undef KA_MODE_ATTR
     return ce;
 }
@@ -732,7 +792,7 @@ cudaError_t tile_kernel_mode_set_smem(size_t bytes) {
 // routed sharded table (table_mode 2): all-to-all of keys, owners probe, answers come back
 // ------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t route_owner(const TableView& t, unsigned long long m) {
-    return (uint32_t)(m >> t.rem_bits) >> t.shard_shift;
+    return shard_of(t, m);
 }
 
 __global__ void route_count_kernel(const unsigned long long* __restrict__ keys, unsigned long long n,
@@ -834,17 +894,17 @@ __global__ void __launch_bounds__(256) route_lookup_kernel(const unsigned long l
     constexpr int U = 4;
     typedef typename rem_type<CLS>::type rem_t;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    const uint32_t local_mask = (1u << tab.shard_shift) - 1;
+    const unsigned long long local_mask = (1ull << tab.shard_shift) - 1;
     for (unsigned long long i0 = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += stride * U) {
         uint4 a[U], b[U];
-        uint32_t sec[U];
+        unsigned long long sec[U];
         rem_t rem[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const unsigned long long i = i0 + u * stride;
             if (i < n) {
                 const unsigned long long m = keys[i];
-                sec[u] = (uint32_t)(m >> tab.rem_bits);
+                sec[u] = m >> tab.rem_bits;
                 rem[u] = (rem_t)(m & tab.rem_mask);
                 load_sector(tab.sectors + 2 * (size_t)(sec[u] & local_mask), a[u], b[u]);
             }
@@ -856,10 +916,12 @@ __global__ void __launch_bounds__(256) route_lookup_kernel(const unsigned long l
                 uint32_t j = 0, tok = 0;
                 bool full;
                 int role = match_sector<CLS>(tab, a[u], b[u], rem[u], j, full);
-                if (role >= 0) tok = sec[u] * S + j + 1;
+                // (narrow tables: the token is the global slot index + 1; wide tables ignore it, the
+                // requester uses the key itself)
+                if (role >= 0) tok = (uint32_t)sec[u] * S + j + 1;
                 else if (full) {
                     // the overflow entries of a sector live on its owner: local as well
-                    const unsigned long long m = ((unsigned long long)sec[u] << tab.rem_bits) | (unsigned long long)rem[u];
+                    const unsigned long long m = (sec[u] << tab.rem_bits) | (unsigned long long)rem[u];
                     const uint32_t mask = (1u << tab.ovf_bbits) - 1;
                     uint32_t s = tab.ovf_bbits ? (uint32_t)(mix64(m) >> (64 - tab.ovf_bbits)) : 0u;
                     const uint32_t tok0 = tab.n_primary_slots + tab.my_shard * (2u << tab.ovf_bbits);
@@ -908,9 +970,11 @@ cudaError_t launch_route_unpermute(const unsigned long long* ans_sorted, const u
 // ------------------------------------------------------------------------------------
 // long sequences: one CTA per sequence, token set in global scratch (L2 resident)
 // ------------------------------------------------------------------------------------
-template <int CLS, int C>
+template <int CLS, int C, bool WIDE>
 __global__ void __launch_bounds__(256) big_kernel(AnnotParams p) {
     constexpr int THREADS = 256;
+    typedef typename std::conditional<WIDE, unsigned long long, uint32_t>::type tok_t;
+    typedef typename std::conditional<WIDE, unsigned long long, typename rem_type<CLS>::type>::type rem_t;
     __shared__ uint8_t s_lut[256];
     __shared__ int sh_cnt, sh_min, sh_max;
     const uint32_t tid = threadIdx.x, lane = tid & 31;
@@ -924,9 +988,9 @@ __global__ void __launch_bounds__(256) big_kernel(AnnotParams p) {
         const unsigned long long a = p.off[it.seq] - p.base;
         const unsigned long long L = p.off[it.seq + 1] - p.off[it.seq];
         const unsigned long long W = L - (unsigned long long)K + 1;  // L > long_seq >= K
-        uint32_t* region = p.scratch + it.tok_base;
+        tok_t* region = reinterpret_cast<tok_t*>(p.scratch) + it.tok_base;
         const uint32_t nreg = (uint32_t)(2 * L);
-        for (uint32_t i = tid; i < nreg; i += THREADS) region[i] = TOKEN_EMPTY;
+        for (uint32_t i = tid; i < nreg; i += THREADS) region[i] = 0;
         if (tid == 0) { sh_cnt = 0; sh_min = 0x7fffffff; sh_max = -1; }
         __syncthreads();
 
@@ -943,7 +1007,7 @@ __global__ void __launch_bounds__(256) big_kernel(AnnotParams p) {
                 vr = c ? vr + 1 : 0;
             }
             r += K - 1;
-            typename rem_type<CLS>::type rem[C];
+            rem_t rem[C];
             uint32_t sec[C];
             unsigned okmask = 0;
 #pragma unroll
@@ -954,17 +1018,24 @@ __global__ void __launch_bounds__(256) big_kernel(AnnotParams p) {
                     vr = c ? vr + 1 : 0;
                     if (vr >= K) {
                         okmask |= 1u << i;
-                        unsigned long long rm;
-                        locate(tab, key & tab.key_mask, sec[i], rm);
-                        rem[i] = (typename rem_type<CLS>::type)rm;
+                        if (WIDE) {
+                            rem[i] = mixw(key & tab.key_mask, tab.wbits, tab.key_mask);
+                        } else {
+                            unsigned long long rm;
+                            locate(tab, key & tab.key_mask, sec[i], rm);
+                            rem[i] = (rem_t)rm;
+                        }
                     }
                 }
             }
             int role[C];
-            probe_batch<CLS, C>(tab, rem, sec, okmask, role);
+            if constexpr (WIDE) probe_batch_wide<CLS, C>(tab, rem, okmask, role);
+            else probe_batch<CLS, C>(tab, rem, sec, okmask, role);
 #pragma unroll
             for (int i = 0; i < C; i++) {
-                if ((okmask & (1u << i)) && role[i] >= 0 && token_insert(region, nreg, sec[i])) {
+                tok_t token;
+                if constexpr (WIDE) token = rem[i]; else token = sec[i];
+                if ((okmask & (1u << i)) && role[i] >= 0 && token_insert(region, nreg, token)) {
                     cnt++;
                     mn = min(mn, role[i]);
                     mx = max(mx, role[i]);
@@ -986,9 +1057,13 @@ __global__ void __launch_bounds__(256) big_kernel(AnnotParams p) {
 }
 
 cudaError_t launch_big(const AnnotParams& p, int grid, cudaStream_t st) {
-    if (p.tab.cls == 32) big_kernel<32, 8><<<grid, 256, 0, st>>>(p);
-    else if (p.tab.cls == 64) big_kernel<64, 8><<<grid, 256, 0, st>>>(p);
-    else big_kernel<128, 8><<<grid, 256, 0, st>>>(p);
+    if (p.tab.wide) {
+        if (p.tab.cls == 32) big_kernel<32, 8, true><<<grid, 256, 0, st>>>(p);
+        else if (p.tab.cls == 64) big_kernel<64, 8, true><<<grid, 256, 0, st>>>(p);
+        else return cudaErrorInvalidValue;
+    } else if (p.tab.cls == 32) big_kernel<32, 8, false><<<grid, 256, 0, st>>>(p);
+    else if (p.tab.cls == 64) big_kernel<64, 8, false><<<grid, 256, 0, st>>>(p);
+    else big_kernel<128, 8, false><<<grid, 256, 0, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -1020,19 +1095,42 @@ cudaError_t launch_alphabet_scan(const uint8_t* bytes, unsigned long long n, uin
     return cudaGetLastError();
 }
 
+// Synthetic DB lines for the oversized-table configuration (ka_db_load_synthetic): line i is the
+// K-mer whose j-th residue is AA[(x >> 5j) & 31 mod 20], x = mix64(seed + i * golden), with role
+// i mod n_roles.  The host can regenerate any line (kmers.anno_b200/synth.py: synthetic_db_lines).
+__global__ void db_generate_kernel(unsigned long long first, unsigned long long n, int K,
+                                   unsigned long long seed, uint32_t n_roles, uint8_t* kmers, int32_t* roles) {
+    const char* AA = "ACDEFGHIKLMNPQRSTVWY";
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+        const unsigned long long i = first + t;
+        unsigned long long x = mix64(seed + i * 0x9E3779B97F4A7C15ull);
+        for (int j = 0; j < K; j++) { kmers[t * K + j] = (uint8_t)AA[(x & 31u) % 20u]; x >>= 5; }
+        roles[t] = (int32_t)(i % n_roles);
+    }
+}
+
+cudaError_t launch_db_generate(unsigned long long first, unsigned long long n, int K, unsigned long long seed,
+                               uint32_t n_roles, uint8_t* kmers, int32_t* roles, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    db_generate_kernel<<<148 * 16, 256, 0, st>>>(first, n, K, seed, n_roles, kmers, roles);
+    return cudaGetLastError();
+}
+
 // HashMap.put for every DB line (ApplyKmerProcessor.java:106): a duplicate k-mer keeps one
-// slot and the LAST line's role ends up in it (atomicMax on the line index).
+// slot and the LAST line's role ends up in it: atomicMax on best[slot] = (line + 1) << role_bits | role.
 template <int CLS>
 __global__ void db_insert_kernel(TableView tab, const uint8_t* __restrict__ kmers,
                                  const int32_t* __restrict__ roles, unsigned long long n,
                                  unsigned long long line_base, const uint8_t* __restrict__ lut,
-                                 uint32_t* line_of, unsigned long long* counters, uint32_t* errs) {
+                                 unsigned long long* best, uint32_t role_bits,
+                                 unsigned long long* counters, uint32_t* errs) {
     constexpr int S = slots_per_sector<CLS>();
     __shared__ uint8_t s_lut[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = lut[i];
     __syncthreads();
     const int K = tab.K;
-    const uint32_t sec_mask = (1u << tab.bbits) - 1;
+    const unsigned long long sec_mask = (1ull << tab.bbits) - 1;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     uint32_t longest = 0;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -1047,17 +1145,25 @@ __global__ void db_insert_kernel(TableView tab, const uint8_t* __restrict__ kmer
         }
         if (bad) { atomicAdd(&errs[0], 1u); continue; }
         if (roles[i] < 0) { atomicAdd(&errs[1], 1u); continue; }
-        uint32_t sec;
-        unsigned long long rem;
-        locate(tab, key, sec, rem);
-        unsigned long long msec = sec;   // global sector (the overflow key keeps it)
+        unsigned long long sec, rem;     // 64-bit sector index: wide tables have more than 2^32 sectors
+        if (CLS == 128) {
+            uint32_t s32;
+            locate(tab, key, s32, rem);
+            sec = s32;
+        } else {
+            const unsigned long long m = mixw(key, tab.wbits, tab.key_mask);
+            sec = m >> tab.rem_bits;
+            rem = m & tab.rem_mask;
+        }
+        const unsigned long long msec = sec;   // global sector (the overflow key keeps it)
         if (tab.n_shards > 1) {
             // sharded table: this device stores only the sectors of its own shard, at local indices.
             // (cls 128 chains to the NEXT sector, which may belong to another shard: the engine
             // only shards the quotiented classes, whose overflow stays with the home shard.)
             if ((sec >> tab.shard_shift) != tab.my_shard) continue;
-            sec &= (1u << tab.shard_shift) - 1;
+            sec &= (1ull << tab.shard_shift) - 1;
         }
+        const unsigned long long mine = ((line_base + i + 1) << role_bits) | (unsigned long long)(uint32_t)roles[i];
         if (tab.sig) {
             uint32_t* word = reinterpret_cast<uint32_t*>(const_cast<uint16_t*>(tab.sig)) + (sec >> 1);
             const uint32_t bits = sig_bits(rem) << ((sec & 1u) * 16);
@@ -1068,12 +1174,11 @@ __global__ void db_insert_kernel(TableView tab, const uint8_t* __restrict__ kmer
         if (CLS == 128) {
             while (!done) {
                 Slot128* s = reinterpret_cast<Slot128*>(const_cast<uint4*>(tab.sectors)) + 2 * (size_t)sec;
-                const unsigned long long val = ((line_base + i) << 32) | (uint32_t)roles[i];
                 for (int h = 0; h < 2 && !done; h++) {
                     unsigned long long old = atomicCAS(&s[h].key, 0ull, key);
                     if (old == 0ull || old == key) {
                         if (old == 0ull) atomicAdd(&counters[0], 1ull);
-                        atomicMax(&s[h].val, val);
+                        atomicMax(&s[h].val, mine);
                         done = true;
                     }
                 }
@@ -1088,7 +1193,7 @@ __global__ void db_insert_kernel(TableView tab, const uint8_t* __restrict__ kmer
                     if (cur == 0) cur = atomicCAS(w + h, 0ull, claim);
                     if (cur == 0 || ((cur ^ rem) & tab.rem_mask) == 0) {
                         if (cur == 0) atomicAdd(&counters[0], 1ull);
-                        atomicMax(&line_of[(size_t)sec * S + h], (uint32_t)(line_base + i) + 1u);
+                        atomicMax(&best[(size_t)sec * S + h], mine);
                         done = true;
                     }
                 }
@@ -1101,7 +1206,7 @@ __global__ void db_insert_kernel(TableView tab, const uint8_t* __restrict__ kmer
                     if (cur == 0) cur = atomicCAS(w + h, 0u, claim);
                     if (cur == 0 || ((cur ^ r32) & m32) == 0) {
                         if (cur == 0) atomicAdd(&counters[0], 1ull);
-                        atomicMax(&line_of[(size_t)sec * S + h], (uint32_t)(line_base + i) + 1u);
+                        atomicMax(&best[(size_t)sec * S + h], mine);
                         done = true;
                     }
                 }
@@ -1109,7 +1214,6 @@ __global__ void db_insert_kernel(TableView tab, const uint8_t* __restrict__ kmer
             if (!done) {
                 // home sector full: the whole mixed key goes to the overflow table
                 const unsigned long long m = (msec << tab.rem_bits) | rem;
-                const unsigned long long val = ((line_base + i) << 32) | (uint32_t)roles[i];
                 const uint32_t omask = (1u << tab.ovf_bbits) - 1;
                 uint32_t os = tab.ovf_bbits ? (uint32_t)(mix64(m) >> (64 - tab.ovf_bbits)) : 0u;
                 Slot128* ovf = reinterpret_cast<Slot128*>(const_cast<uint4*>(tab.ovf));
@@ -1119,7 +1223,7 @@ __global__ void db_insert_kernel(TableView tab, const uint8_t* __restrict__ kmer
                         unsigned long long old = atomicCAS(&s[h].key, 0ull, m);
                         if (old == 0ull || old == m) {
                             if (old == 0ull) atomicAdd(&counters[0], 1ull);
-                            atomicMax(&s[h].val, val);
+                            atomicMax(&s[h].val, mine);
                             done = true;
                         }
                     }
@@ -1135,24 +1239,24 @@ __global__ void db_insert_kernel(TableView tab, const uint8_t* __restrict__ kmer
 
 cudaError_t launch_db_insert(const TableView& tab, const uint8_t* kmers, const int32_t* roles,
                              unsigned long long n, unsigned long long line_base,
-                             const uint8_t* lut, uint32_t* line_of, unsigned long long* counters,
-                             uint32_t* errs, cudaStream_t st) {
+                             const uint8_t* lut, unsigned long long* best, uint32_t role_bits,
+                             unsigned long long* counters, uint32_t* errs, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     unsigned long long want = (n + 255) / 256;
     unsigned blocks = (unsigned)(want < 148ull * 32 ? want : 148ull * 32);
     if (tab.cls == 32)
-        db_insert_kernel<32><<<blocks, 256, 0, st>>>(tab, kmers, roles, n, line_base, lut, line_of, counters, errs);
+        db_insert_kernel<32><<<blocks, 256, 0, st>>>(tab, kmers, roles, n, line_base, lut, best, role_bits, counters, errs);
     else if (tab.cls == 64)
-        db_insert_kernel<64><<<blocks, 256, 0, st>>>(tab, kmers, roles, n, line_base, lut, line_of, counters, errs);
+        db_insert_kernel<64><<<blocks, 256, 0, st>>>(tab, kmers, roles, n, line_base, lut, best, role_bits, counters, errs);
     else
-        db_insert_kernel<128><<<blocks, 256, 0, st>>>(tab, kmers, roles, n, line_base, lut, line_of, counters, errs);
+        db_insert_kernel<128><<<blocks, 256, 0, st>>>(tab, kmers, roles, n, line_base, lut, best, role_bits, counters, errs);
     return cudaGetLastError();
 }
 
 // Write role+1 of the winning db line into the role field of every occupied slot (cls 32/64).
 template <int CLS>
-__global__ void db_finalize_kernel(TableView tab, const uint32_t* __restrict__ line_of,
-                                   const int32_t* __restrict__ all_roles) {
+__global__ void db_finalize_kernel(TableView tab, const unsigned long long* __restrict__ best, uint32_t role_bits) {
+    const unsigned long long role_mask = (1ull << role_bits) - 1;
     constexpr int S = slots_per_sector<CLS>();
     const unsigned long long n_slots = (unsigned long long)S << (tab.n_shards > 1 ? tab.shard_shift : tab.bbits);
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
@@ -1161,20 +1265,34 @@ __global__ void db_finalize_kernel(TableView tab, const uint32_t* __restrict__ l
         if (CLS == 64) {
             unsigned long long* w = reinterpret_cast<unsigned long long*>(const_cast<uint4*>(tab.sectors)) + s;
             const unsigned long long v = *w;
-            if (v) *w = (v & tab.rem_mask) | ((unsigned long long)(all_roles[line_of[s] - 1] + 1) << tab.rem_bits);
+            if (v) *w = (v & tab.rem_mask) | (((best[s] & role_mask) + 1) << tab.rem_bits);
         } else {
             uint32_t* w = reinterpret_cast<uint32_t*>(const_cast<uint4*>(tab.sectors)) + s;
             const uint32_t v = *w;
-            if (v) *w = (v & (uint32_t)tab.rem_mask) | ((uint32_t)(all_roles[line_of[s] - 1] + 1) << tab.rem_bits);
+            if (v) *w = (v & (uint32_t)tab.rem_mask) | ((uint32_t)((best[s] & role_mask) + 1) << tab.rem_bits);
         }
     }
 }
 
-cudaError_t launch_db_finalize(const TableView& tab, const uint32_t* line_of,
-                               const int32_t* all_roles, cudaStream_t st) {
-    if (tab.cls == 128) return cudaSuccess;
-    if (tab.cls == 32) db_finalize_kernel<32><<<148 * 16, 256, 0, st>>>(tab, line_of, all_roles);
-    else db_finalize_kernel<64><<<148 * 16, 256, 0, st>>>(tab, line_of, all_roles);
+// whole-key slots (cls 128 table, overflow table): val = (line + 1) << role_bits | role  ->  role
+__global__ void db_finalize_slot128_kernel(Slot128* slots, unsigned long long n_slots, uint32_t role_bits) {
+    const unsigned long long role_mask = (1ull << role_bits) - 1;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long s = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += stride)
+        if (slots[s].key) slots[s].val &= role_mask;
+}
+
+cudaError_t launch_db_finalize(const TableView& tab, const unsigned long long* best, uint32_t role_bits, cudaStream_t st) {
+    if (tab.cls == 128) {
+        db_finalize_slot128_kernel<<<148 * 16, 256, 0, st>>>(reinterpret_cast<Slot128*>(const_cast<uint4*>(tab.sectors)),
+                                                             2ull << tab.bbits, role_bits);
+        return cudaGetLastError();
+    }
+    if (tab.cls == 32) db_finalize_kernel<32><<<148 * 16, 256, 0, st>>>(tab, best, role_bits);
+    else db_finalize_kernel<64><<<148 * 16, 256, 0, st>>>(tab, best, role_bits);
+    if (tab.ovf)
+        db_finalize_slot128_kernel<<<148 * 4, 256, 0, st>>>(reinterpret_cast<Slot128*>(const_cast<uint4*>(tab.ovf)),
+                                                            2ull << tab.ovf_bbits, role_bits);
     return cudaGetLastError();
 }
 

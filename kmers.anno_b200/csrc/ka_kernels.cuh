@@ -37,7 +37,7 @@ struct AnnotParams {
     uint32_t* big_count;              // [0] number of long sequences
     unsigned long long* tok_cursor;   // [0] tokens handed out
     BigItem* big_list;
-    uint32_t* scratch;                // de-dup tokens of the long sequences
+    uint32_t* scratch;                // de-dup tokens of the long sequences (8-byte tokens for wide tables)
     uint32_t* dbg;                    // KA_DEBUG builds: [0] OR of the codes of failed bounds checks
     // routed mode (table_mode 2): the tile kernel either only EXTRACTS the mixed key of every window
     // position into route_keys[chunk-relative residue index] (ROUTE_INVALID = no window), or TALLIES
@@ -51,7 +51,7 @@ struct AnnotParams {
 // Shapes that were measured and dropped (64-register caps, 512 threads, 2 or 8 positions x 128)
 // are listed in profiles/r01_summary.md.
 constexpr int N_VARIANTS = 3;
-size_t tile_smem_bytes(uint32_t ext_max, uint32_t* res_bytes_out);
+size_t tile_smem_bytes(uint32_t ext_max, uint32_t* res_bytes_out, bool wide);
 // de-dup token capacity of x window positions: x + x/4 (worst-case load factor 0.8)
 __host__ __device__ inline uint32_t tok_cap(uint32_t x) { return x + (x >> 2); }
 cudaError_t tile_kernel_set_smem(int cls, int variant, size_t bytes);
@@ -63,7 +63,8 @@ cudaError_t launch_tiles_filt(const AnnotParams& p, size_t smem, cudaStream_t st
 
 constexpr unsigned long long ROUTE_INVALID = ~0ull;
 constexpr unsigned long long ROUTE_MISS = ~0ull;          // answer of a key that is not in the table
-// mode 0 = probe the table, 1 = extract keys only, 2 = tally from routed answers (variants 0 and 1 only)
+// mode 0 = probe the table, 1 = extract keys only, 2 = tally from routed answers (shapes 0 and 1 only;
+// also the entry of every launch on a wide table)
 cudaError_t launch_tiles_mode(const AnnotParams& p, int variant, int mode, size_t smem, cudaStream_t st);
 cudaError_t tile_kernel_mode_set_smem(size_t bytes);
 // per-owner counts of the valid keys of keys[0..n) (owner = sector >> shard_shift); counts[8] accumulates
@@ -89,14 +90,18 @@ cudaError_t launch_alphabet_scan(const uint8_t* bytes, unsigned long long n, uin
 // errs[0] = k-mers with a byte outside the alphabet, errs[1] = negative role ids,
 // errs[2] = keys that found the overflow table full,
 // counters[0] = distinct keys stored, counters[1] = longest sector chain.
-// cls 32/64: `roles` is unused here, the winning db line of every slot is kept in line_of
-// (atomicMax) and launch_db_finalize writes the roles; cls 128 stores (line, role) itself.
+// Every slot keeps the maximum of (line + 1) << role_bits | role over the lines of its key while
+// the DB streams through: cls 32/64 in best[slot] (8 bytes per primary slot, build-time only),
+// whole-key slots (cls 128, overflow table) in their own value word; launch_db_finalize then writes
+// the plain role of the last line into every slot.
 cudaError_t launch_db_insert(const TableView& tab, const uint8_t* kmers, const int32_t* roles,
                              unsigned long long n, unsigned long long line_base,
-                             const uint8_t* lut, uint32_t* line_of, unsigned long long* counters,
-                             uint32_t* errs, cudaStream_t st);
-cudaError_t launch_db_finalize(const TableView& tab, const uint32_t* line_of,
-                               const int32_t* all_roles, cudaStream_t st);
+                             const uint8_t* lut, unsigned long long* best, uint32_t role_bits,
+                             unsigned long long* counters, uint32_t* errs, cudaStream_t st);
+cudaError_t launch_db_finalize(const TableView& tab, const unsigned long long* best, uint32_t role_bits, cudaStream_t st);
+// synthetic DB lines [first, first + n) for ka_db_load_synthetic (see include/kmeranno.h)
+cudaError_t launch_db_generate(unsigned long long first, unsigned long long n, int K, unsigned long long seed,
+                               uint32_t n_roles, uint8_t* kmers, int32_t* roles, cudaStream_t st);
 
 // ---- build (BuildKmerProcessor.java:138-223) ----
 // table: n_slots (power of two) Slot128 {key, val}; val = role + 1, bit 62 = seen under two

@@ -16,7 +16,7 @@ FLAG_NONE, FLAG_CALLED, FLAG_AMBIGUOUS, FLAG_BELOW_MIN = 0, 1, 2, 3
 
 # every symbol include/kmeranno.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
-    "ka_create", "ka_destroy", "ka_last_error", "ka_set_option", "ka_db_load", "ka_db_get_info",
+    "ka_create", "ka_destroy", "ka_last_error", "ka_set_option", "ka_db_load", "ka_db_load_synthetic", "ka_db_get_info",
     "ka_annotate", "ka_build", "ka_batch_upload", "ka_annotate_resident", "ka_batch_download", "ka_batch_free",
     "ka_host_alloc", "ka_host_free", "ka_get_stats", "ka_probe_roofline", "ka_abi_version",
 ]
@@ -61,6 +61,7 @@ def load_library():
     lib.ka_last_error.restype = C.c_char_p
     lib.ka_set_option.argtypes = [vp, C.c_char_p, C.c_double]
     lib.ka_db_load.argtypes = [vp, u8p, i32p, C.c_uint64, C.c_int]
+    lib.ka_db_load_synthetic.argtypes = [vp, C.c_uint64, C.c_int, C.c_int32, C.c_uint64]
     lib.ka_db_get_info.argtypes = [vp, C.POINTER(DbInfo)]
     lib.ka_annotate.argtypes = [vp, u8p, u64p, C.c_uint64, C.c_int32, i32p, i32p, u8p]
     lib.ka_build.argtypes = [vp, u8p, u64p, C.c_uint64, i32p, i32p, C.c_int, C.c_uint64, u8p, i32p,
@@ -162,6 +163,11 @@ class Engine:
         if kmers.shape[0] != n * K:
             raise KmerAnnoError(-1, f"kmers holds {kmers.shape[0]} bytes, expected n*K = {n * K}")
         self._check(self._lib.ka_db_load(self._h, _ptr(kmers), _ptr(role_ids), n, K))
+
+    def db_load_synthetic(self, n, K, n_roles, seed):
+        """Device-generated DB of n lines (oversized-table configuration); synth.synthetic_db_lines
+        regenerates any line on the host."""
+        self._check(self._lib.ka_db_load_synthetic(self._h, int(n), int(K), int(n_roles), int(seed)))
 
     def db_info(self):
         info = DbInfo()

@@ -68,3 +68,22 @@ class Families:
         n = self.lib.kas_table(self.h, self.seed, K, members_per_role, target, threads,
                                kmers.ctypes.data, roles.ctypes.data)
         return kmers[: n * K], roles[:n]
+
+
+_AA20 = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", dtype=np.uint8)
+
+
+def synthetic_db_lines(index, K, n_roles, seed):
+    """Lines `index` (uint64 array) of the device-generated DB of ka_db_load_synthetic
+    (include/kmeranno.h): (kmers u8[len(index), K], roles i32[len(index)])."""
+    index = np.asarray(index, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        x = np.uint64(seed) + index * np.uint64(0x9E3779B97F4A7C15)
+        for _ in range(2):
+            x ^= x >> np.uint64(32)
+            x *= np.uint64(0xD6E8FEB86659FD93)
+        x ^= x >> np.uint64(32)
+    kmers = np.empty((index.shape[0], K), np.uint8)
+    for j in range(K):
+        kmers[:, j] = _AA20[((x >> np.uint64(5 * j)) & np.uint64(31)) % np.uint64(20)]
+    return kmers, (index % np.uint64(n_roles)).astype(np.int32)

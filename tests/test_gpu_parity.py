@@ -120,6 +120,7 @@ def test_long_sequences_use_big_kernel(ka, oracle):
     lengths = [20000, 300, 7000, 2049, 2048, 64, 0, 12000, 8192, 8193, 2047, 5000]
     seqs, kmers, roles = ragged_case(21, n_seq=len(lengths), K=8, lengths=lengths, db_frac=0.5)
     run_case(ka, oracle, seqs, kmers, roles, 8, min_hits=3)
+    run_case(ka, oracle, seqs, kmers, roles, 8, min_hits=3, options={"wide": 1})
     # the same inputs with a small long_seq so that most sequences take the long path
     run_case(ka, oracle, seqs, kmers, roles, 8, min_hits=3, options={"tile_span": 256, "long_seq": 256})
 
@@ -145,6 +146,11 @@ def test_long_sequences_use_big_kernel(ka, oracle):
     {"filter": 1, "two_phase": 1, "slot_bits": 64},
     {"filter": 1, "two_phase": 1, "slot_bits": 128, "load_factor": 0.9},
     {"filter": 1, "two_phase": 1, "tile_span": 256, "long_seq": 300, "mid_seq": 700},
+    {"wide": 1},
+    {"wide": 1, "slot_bits": 64, "load_factor": 0.9},
+    {"wide": 1, "slot_bits": 32, "variant": 1, "load_factor": 0.9, "tile_span": 256, "long_seq": 300, "mid_seq": 700},
+    {"wide": 1, "slot_bits": 128},      # 128-bit slots have no wide form: the option is ignored
+    {"wide": 1, "filter": 1},           # nor do signatures
     {"filter": 1, "slot_bits": 32, "variant": 1, "load_factor": 0.9},
     {"filter": 1, "slot_bits": 128, "variant": 2, "mid_variant": 0},
 ])
@@ -166,7 +172,7 @@ def test_slot_class_selection(ka, oracle, K, max_role, want_bits):
     assert_same(got, oracle.OracleDb(kmers, roles, K).apply(res, off, 3), f"slot class K={K}")
 
 
-@pytest.mark.parametrize("slot_bits,lf,filt", [(32, 0.9, 0), (64, 0.9, 1), (128, 0.9, 0), (32, 0.4, 1)])
+@pytest.mark.parametrize("slot_bits,lf,filt", [(32, 0.9, 0), (64, 0.9, 1), (128, 0.9, 0), (32, 0.4, 1), (32, 0.9, -2), (64, 0.9, -2)])
 def test_overflow_heavy_table(ka, oracle, slot_bits, lf, filt):
     """Millions of keys at a high load factor: ~13 % of the keys leave their home sector.
     Quotiented slots keep only a remainder, so those keys must live in the overflow table
@@ -178,7 +184,10 @@ def test_overflow_heavy_table(ka, oracle, slot_bits, lf, filt):
     with ka.Engine([0]) as eng:
         eng.set_option("slot_bits", slot_bits)
         eng.set_option("load_factor", lf)
-        eng.set_option("filter", filt)
+        if filt == -2:
+            eng.set_option("wide", 1)         # wide-table kernels on the same table
+        else:
+            eng.set_option("filter", filt)
         eng.db_load(kmers, roles, 8)
         info = eng.db_info()
         got = eng.annotate(res, off, 5)
@@ -267,8 +276,8 @@ def test_multi_device_engine(ka, oracle):
     assert st["sequences"] == off.shape[0] - 1 and st["kernel_launches"] >= 2 * n_dev
 
 
-@pytest.mark.parametrize("slot_bits,lf", [(0, 0.4), (32, 0.9), (64, 0.9)])
-def test_sharded_table_peer_loads(ka, oracle, slot_bits, lf):
+@pytest.mark.parametrize("slot_bits,lf,wide", [(0, 0.4, 0), (32, 0.9, 0), (64, 0.9, 0), (0, 0.4, 1), (64, 0.9, 1)])
+def test_sharded_table_peer_loads(ka, oracle, slot_bits, lf, wide):
     """table_mode=1: the table is split by sector range over the engine's GPUs and probes read
     remote sectors through NVLink peer memory (the config-5 shape, at test size)."""
     n_dev = 0
@@ -287,6 +296,7 @@ def test_sharded_table_peer_loads(ka, oracle, slot_bits, lf):
     res, off, _ = fam.batch(9, 2, n_prot=4500)
     with ka.Engine(list(range(n_dev))) as eng:
         eng.set_option("table_mode", 1)
+        eng.set_option("wide", wide)
         eng.set_option("slot_bits", slot_bits)
         eng.set_option("load_factor", lf)
         eng.db_load(kmers, roles, 8)
@@ -297,8 +307,9 @@ def test_sharded_table_peer_loads(ka, oracle, slot_bits, lf):
     assert_same(got, want, f"sharded table over {n_dev} GPUs slot_bits={slot_bits}")
 
 
-@pytest.mark.parametrize("slot_bits,lf,chunk", [(0, 0.4, 32 << 20), (32, 0.9, 300000), (64, 0.9, 1 << 20)])
-def test_routed_table_nccl_all_to_all(ka, oracle, slot_bits, lf, chunk):
+@pytest.mark.parametrize("slot_bits,lf,chunk,wide", [(0, 0.4, 32 << 20, 0), (32, 0.9, 300000, 0), (64, 0.9, 1 << 20, 0),
+                                                     (0, 0.4, 32 << 20, 1), (32, 0.9, 300000, 1)])
+def test_routed_table_nccl_all_to_all(ka, oracle, slot_bits, lf, chunk, wide):
     """table_mode=2: same sharding, but the keys are routed to the owning GPU with NCCL send/recv
     (all-to-all), probed there and the answers come back in request order."""
     n_dev = 0
@@ -319,6 +330,7 @@ def test_routed_table_nccl_all_to_all(ka, oracle, slot_bits, lf, chunk):
     off = np.concatenate([off, np.full(5000, off[-1], np.uint64)])
     with ka.Engine(list(range(n_dev))) as eng:
         eng.set_option("table_mode", 2)
+        eng.set_option("wide", wide)
         eng.set_option("slot_bits", slot_bits)
         eng.set_option("load_factor", lf)
         eng.set_option("chunk_residues", chunk)
@@ -332,6 +344,81 @@ def test_routed_table_nccl_all_to_all(ka, oracle, slot_bits, lf, chunk):
     assert_same(got, want, f"routed table over {n_dev} GPUs slot_bits={slot_bits}")
     assert_same(again, want, "routed table, second call")
     assert_same(got2, oracle.OracleDb(kmers, roles, 8, threads=8).apply(res, off, 1, threads=8), "routed, min_hits 1")
+
+
+def planted_proteins(rng, kmers, roles, n_prot, K):
+    """Proteins made of DB k-mers of one role (some of two roles) joined by random residues."""
+    by_role = {}
+    for i, r in enumerate(roles):
+        by_role.setdefault(int(r), []).append(i)
+    role_ids = sorted(by_role)
+    seqs = []
+    for p in range(n_prot):
+        r = role_ids[int(rng.integers(len(role_ids)))]
+        picks = [by_role[r][int(j)] for j in rng.integers(0, len(by_role[r]), int(rng.integers(1, 12)))]
+        if p % 7 == 0:                                   # a second role: ambiguous
+            r2 = role_ids[int(rng.integers(len(role_ids)))]
+            picks.append(by_role[r2][0])
+        parts = []
+        for i in picks:
+            parts.append(kmers[i].tobytes())
+            parts.append(random_seq(rng, int(rng.integers(0, 30))))
+        seqs.append(b"".join(parts))
+    return seqs
+
+
+@pytest.mark.parametrize("K,n,n_roles,opts", [(12, 200_000, 300, {}), (12, 200_000, 300, {"wide": 1}),
+                                              (8, 50_000, 40, {"load_factor": 0.9}), (5, 3_000_000, 17, {})])
+def test_synthetic_db_matches_host_lines(ka, oracle, K, n, n_roles, opts):
+    """ka_db_load_synthetic generates the lines on the device; synth.synthetic_db_lines regenerates
+    them on the host for the oracle (K=5: 3e6 draws from 3.2e6 possible k-mers: duplicates, last wins)."""
+    from kmers_anno_b200 import synth
+    seed = 20261018 + K
+    kmers, roles = synth.synthetic_db_lines(np.arange(n, dtype=np.uint64), K, n_roles, seed)
+    rng = np.random.default_rng(K)
+    seqs = planted_proteins(rng, kmers, roles, 1500, K) + [random_seq(rng, 400) for _ in range(200)]
+    res, off = csr(seqs)
+    with ka.Engine([0]) as eng:
+        for k, v in opts.items():
+            eng.set_option(k, v)
+        eng.db_load_synthetic(n, K, n_roles, seed)
+        info = eng.db_info()
+        got = eng.annotate(res, off, 3)
+    db = oracle.OracleDb(kmers.reshape(-1), roles, K, threads=8)
+    assert info["n_keys"] == db.size() and info["n_lines"] == n
+    assert_same(got, db.apply(res, off, 3, threads=8), f"synthetic DB K={K}")
+    if K >= 8:
+        assert set(np.unique(got[2])) >= {1, 2}
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_synthetic_db_sharded(ka, oracle, mode):
+    """The oversized-table path at test size: device-generated lines, sharded wide table."""
+    n_dev = 0
+    for n in (8, 4, 2):
+        try:
+            ka.Engine(list(range(n))).close()
+            n_dev = n
+            break
+        except ka.KmerAnnoError:
+            continue
+    if n_dev < 2:
+        pytest.skip("needs at least 2 GPUs")
+    from kmers_anno_b200 import synth
+    K, n, n_roles, seed = 12, 4_000_000, 3000, 99
+    kmers, roles = synth.synthetic_db_lines(np.arange(n, dtype=np.uint64), K, n_roles, seed)
+    rng = np.random.default_rng(3)
+    seqs = planted_proteins(rng, kmers, roles, 4000, K) + [random_seq(rng, 400) for _ in range(500)]
+    res, off = csr(seqs)
+    with ka.Engine(list(range(n_dev))) as eng:
+        eng.set_option("table_mode", mode)
+        eng.set_option("wide", 1)
+        eng.db_load_synthetic(n, K, n_roles, seed)
+        info = eng.db_info()
+        got = eng.annotate(res, off, 3)
+    db = oracle.OracleDb(kmers.reshape(-1), roles, K, threads=8)
+    assert info["n_keys"] == db.size()
+    assert_same(got, db.apply(res, off, 3, threads=8), f"synthetic sharded DB mode {mode}")
 
 
 def test_error_paths(ka):
