@@ -1096,11 +1096,27 @@ static int db_load_impl(ka_engine* e, const uint8_t* kmers, const int32_t* role_
             e->peers_enabled = true;
         }
     }
+    // communicators first: NCCL sets up its buffers before the table takes most of the HBM
+    if (e->table_mode == 2 && !e->nccl_ready) {
+        if (!g_nccl.load()) return fail(e, KA_ERR_NO_DEVICE, "ka_db_load: table_mode 2 needs libnccl.so.2 (%s)", dlerror() ? dlerror() : "symbols missing");
+        std::vector<ncclComm_t> comms(e->devs.size());
+        std::vector<int> ids;
+        for (Device& d : e->devs) ids.push_back(d.id);
+        auto tn = std::chrono::steady_clock::now();
+        ncclResult_t nr = g_nccl.CommInitAll(comms.data(), (int)ids.size(), ids.data());
+        if (nr != ncclSuccess) return fail(e, KA_ERR_CUDA, "ka_db_load: ncclCommInitAll: %s", g_nccl.GetErrorString(nr));
+        if (getenv("KA_LOAD_TRACE"))
+            fprintf(stderr, "[db load] ncclCommInitAll on %zu devices: %.2f s\n", ids.size(),
+                    std::chrono::duration<double>(std::chrono::steady_clock::now() - tn).count());
+        for (size_t i = 0; i < e->devs.size(); i++) e->devs[i].comm = comms[i];
+        e->nccl_ready = true;
+    }
     if (!choose_geometry(n, K, max_role, e->load_factor, e->slot_bits, n_shards, e->wide != 0, geom))
         return fail(e, KA_ERR_TOO_BIG, "ka_db_load: %llu k-mers (K=%d, max role %d) do not fit %s",
                     (unsigned long long)n, K, max_role, e->slot_bits ? "the forced slot width" : "any slot class of this build");
 
     // 3. build one replica per device
+    auto tb = std::chrono::steady_clock::now();
     std::vector<uint64_t> nk(e->devs.size(), 0);
     std::vector<uint32_t> mp(e->devs.size(), 0);
     int rc = KA_OK;
@@ -1118,6 +1134,10 @@ static int db_load_impl(ka_engine* e, const uint8_t* kmers, const int32_t* role_
         geom.ovf_bbits += 2;  // overflow table was too small for this key set: rebuild 4x larger
     }
     if (rc) return rc;
+    if (getenv("KA_LOAD_TRACE"))
+        fprintf(stderr, "[db load] table build (%llu lines, 2^%u sectors of %d-bit slots%s, %u shard(s)): %.2f s\n",
+                (unsigned long long)n, geom.bbits, geom.cls, geom.wide ? ", wide" : "", n_shards,
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - tb).count());
     if (n_shards > 1) {
         // every device gets the peer pointers of all shards
         std::vector<const uint4*> ps(8, nullptr), po(8, nullptr);
@@ -1130,23 +1150,13 @@ static int db_load_impl(ka_engine* e, const uint8_t* kmers, const int32_t* role_
             cudaMemcpy((void*)d.shard_ovf, po.data(), 64, cudaMemcpyHostToDevice);
         }
     }
-    if (e->table_mode == 2 && !e->nccl_ready) {
-        if (!g_nccl.load()) return fail(e, KA_ERR_NO_DEVICE, "ka_db_load: table_mode 2 needs libnccl.so.2 (%s)", dlerror() ? dlerror() : "symbols missing");
-        std::vector<ncclComm_t> comms(e->devs.size());
-        std::vector<int> ids;
-        for (Device& d : e->devs) ids.push_back(d.id);
-        ncclResult_t nr = g_nccl.CommInitAll(comms.data(), (int)ids.size(), ids.data());
-        if (nr != ncclSuccess) return fail(e, KA_ERR_CUDA, "ka_db_load: ncclCommInitAll: %s", g_nccl.GetErrorString(nr));
-        for (size_t i = 0; i < e->devs.size(); i++) e->devs[i].comm = comms[i];
-        e->nccl_ready = true;
-    }
     e->geom = geom;
     e->info.K = K;
     e->info.n_symbols = nsym;
     e->info.n_lines = n;
     e->info.n_keys = nk[0];
     e->info.n_buckets = 1ull << geom.bbits;
-    e->info.table_bytes = (32ull << geom.bbits) + (geom.cls == 128 ? 0 : (64ull << geom.ovf_bbits));
+    e->info.table_bytes = (32ull << geom.bbits) + (geom.cls == 128 ? 0 : (uint64_t)n_shards * (64ull << geom.ovf_bbits));  // all shards
     e->have_sig = e->devs[0].sig != nullptr;
     e->info.max_probe = mp[0];
     e->info.slot_bits = (uint32_t)geom.cls;
