@@ -162,6 +162,23 @@ int ka_build(ka_engine* e, const uint8_t* residues, const uint64_t* offsets, uin
              const int32_t* n_roles, const int32_t* peg_role, int K, uint64_t cap,
              uint8_t* out_kmers, int32_t* out_roles, uint64_t* n_out, int load_as_db);
 
+/* ---- pairwise k-mer distance (genome/compare/GeneCopyProcessor.java:137-142) --------- */
+
+/* For every query q (sequence query_seq[q] of the CSR batch) and each of its candidates
+ * cand_seq[group_offsets[q] .. group_offsets[q+1]): the ProteinKmers comparison of :137-142,
+ *   A = distinct K-windows of the query (new ProteinKmers(...), :137), B = those of the candidate (:141),
+ *   out_common[m]   = |A ∩ B|                                 (ProteinKmers.similarity)
+ *   out_distance[m] = 1.0 if nothing is shared, else 1.0 - |A ∩ B| / (|A| + |B| - |A ∩ B|)   (:142)
+ * and out_set_size[i] = number of distinct K-windows of EVERY sequence i of the batch (may be NULL).
+ * K is the -K option of `genes` (:70-71, ProteinKmers.setKmerSize :96), 1..12 here; the alphabet is
+ * the distinct bytes of the batch (at most 31).  The caller keeps the reference's selection loop
+ * (closest candidate with distance <= maxDist, later candidates win ties, :139-146).
+ * Queries are split over the engine's devices; no k-mer database needs to be loaded. */
+int ka_kmer_distance(ka_engine* e, const uint8_t* residues, const uint64_t* offsets, uint64_t N, int K,
+                     const uint32_t* query_seq, const uint64_t* group_offsets, uint64_t Q,
+                     const uint32_t* cand_seq, int32_t* out_set_size, int32_t* out_common,
+                     double* out_distance);
+
 /* ---- pinned host memory for zero-staging transfers -------------------------------- */
 void* ka_host_alloc(size_t bytes);
 void ka_host_free(void* p);

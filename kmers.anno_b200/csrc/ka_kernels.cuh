@@ -116,6 +116,38 @@ cudaError_t launch_build_emit(const Slot128* table, unsigned long long n_slots, 
                               unsigned long long cap, uint8_t* out_kmers, int32_t* out_roles,
                               unsigned long long* counter, cudaStream_t st);
 
+// ---- pairwise k-mer distance (GeneCopyProcessor.java:137-142), ka_distance.cu ----
+struct DistParams {
+    const uint8_t* res;                    // residues of the batch; res[0] is absolute offset `base`
+    const unsigned long long* off;         // absolute offsets, n_seq + 1
+    unsigned long long base;
+    uint32_t n_seq;
+    int K;
+    const uint8_t* lut;                    // residue byte -> 5-bit code (every byte of the batch has one)
+    int32_t* set_size;                     // [n_seq] distinct K-windows of every sequence
+    const uint32_t* query_seq;             // [Q] sequence index of every query
+    const unsigned long long* group_off;   // [Q + 1] candidates of query q: cand_seq[group_off[q] .. group_off[q+1])
+    uint32_t q_begin, q_end;               // queries handled by this launch
+    const uint32_t* cand_seq;
+    int32_t* common;                       // [M] |A ∩ B|
+    double* dist;                          // [M]
+    uint32_t smem_cap;                     // entries of the shared-memory hash set (power of two)
+    unsigned long long* scratch_keys;      // hash sets of the sequences too long for shared memory
+    uint32_t* scratch_tags;
+    const unsigned long long* seq_scratch;   // [n_seq] first scratch entry of a sequence's set (set_size_kernel)
+    const unsigned long long* query_scratch; // [Q] first scratch entry of a query's set (common_kernel)
+};
+// hash-set capacity for a sequence with `windows` K-windows: power of two >= 2 * windows, at least 64
+__host__ __device__ inline uint32_t dist_set_cap(uint32_t windows) {
+    uint32_t c = 64;
+    while (c < 2u * windows && c < 0x80000000u) c <<= 1;
+    return c;
+}
+size_t dist_smem_bytes(uint32_t smem_cap);
+cudaError_t dist_set_smem(size_t bytes);
+cudaError_t launch_set_size(const DistParams& p, int sm_count, cudaStream_t st);
+cudaError_t launch_common(const DistParams& p, int sm_count, cudaStream_t st);
+
 cudaError_t launch_random_probe(const uint4* buf, unsigned long long n_slots, int slot_bytes,
                                 unsigned long long n_probes, unsigned long long seed,
                                 unsigned long long* sink, cudaStream_t st);

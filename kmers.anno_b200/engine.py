@@ -17,7 +17,7 @@ FLAG_NONE, FLAG_CALLED, FLAG_AMBIGUOUS, FLAG_BELOW_MIN = 0, 1, 2, 3
 # every symbol include/kmeranno.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
     "ka_create", "ka_destroy", "ka_last_error", "ka_set_option", "ka_db_load", "ka_db_load_synthetic", "ka_db_get_info",
-    "ka_annotate", "ka_build", "ka_batch_upload", "ka_annotate_resident", "ka_batch_download", "ka_batch_free",
+    "ka_annotate", "ka_build", "ka_kmer_distance", "ka_batch_upload", "ka_annotate_resident", "ka_batch_download", "ka_batch_free",
     "ka_host_alloc", "ka_host_free", "ka_get_stats", "ka_probe_roofline", "ka_abi_version",
 ]
 
@@ -66,6 +66,7 @@ def load_library():
     lib.ka_annotate.argtypes = [vp, u8p, u64p, C.c_uint64, C.c_int32, i32p, i32p, u8p]
     lib.ka_build.argtypes = [vp, u8p, u64p, C.c_uint64, i32p, i32p, C.c_int, C.c_uint64, u8p, i32p,
                              C.POINTER(C.c_uint64), C.c_int]
+    lib.ka_kmer_distance.argtypes = [vp, u8p, u64p, C.c_uint64, C.c_int, vp, u64p, C.c_uint64, vp, i32p, i32p, vp]
     lib.ka_batch_upload.argtypes = [vp, C.c_int, u8p, u64p, C.c_uint64, C.POINTER(vp)]
     lib.ka_annotate_resident.argtypes = [vp, vp, C.c_int32]
     lib.ka_batch_download.argtypes = [vp, vp, i32p, i32p, u8p]
@@ -201,6 +202,24 @@ class Engine:
         self._check(self._lib.ka_build(self._h, _ptr(residues), _ptr(offsets), n, _ptr(n_roles), _ptr(peg_role),
                                        K, cap, _ptr(kmers), _ptr(roles), C.byref(found), int(load_as_db)))
         return kmers[: found.value * K], roles[: found.value]
+
+    def kmer_distance(self, residues, offsets, K, query_seq, group_offsets, cand_seq):
+        """ProteinKmers.distance of every query against its candidates (GeneCopyProcessor.java:137-142).
+        Returns (set_size i32[N], common i32[M], distance f64[M])."""
+        residues = np.ascontiguousarray(residues, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        query_seq = np.ascontiguousarray(query_seq, dtype=np.uint32)
+        group_offsets = np.ascontiguousarray(group_offsets, dtype=np.uint64)
+        cand_seq = np.ascontiguousarray(cand_seq, dtype=np.uint32)
+        n, q, m = offsets.shape[0] - 1, query_seq.shape[0], cand_seq.shape[0]
+        if group_offsets.shape[0] != q + 1 or (q and int(group_offsets[-1]) != m):
+            raise KmerAnnoError(-1, "group_offsets must have Q+1 entries ending at len(cand_seq)")
+        size = np.empty(max(n, 1), np.int32)
+        common = np.empty(max(m, 1), np.int32)
+        dist = np.empty(max(m, 1), np.float64)
+        self._check(self._lib.ka_kmer_distance(self._h, _ptr(residues), _ptr(offsets), n, int(K), _ptr(query_seq),
+                                               _ptr(group_offsets), q, _ptr(cand_seq), _ptr(size), _ptr(common), _ptr(dist)))
+        return size[:n], common[:m], dist[:m]
 
     def upload(self, residues, offsets, dev_index=0):
         residues = np.ascontiguousarray(residues, dtype=np.uint8)

@@ -4,4 +4,4 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl refere
 import this package.  The product (kmers.anno_b200/, libkmeranno.so) never does.
 PARITY UNPINNED: see the header of ka_oracle.c.
 """
-from .binding import OracleDb, FastDb, count_probes, lib, LIB_PATH  # noqa: F401
+from .binding import OracleDb, FastDb, count_probes, kmer_distance_pairs, lib, LIB_PATH  # noqa: F401

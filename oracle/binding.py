@@ -38,6 +38,8 @@ def lib():
         L.orc_count_peg_kmers_positions.argtypes = [C.c_char_p, C.c_uint64, C.c_int, vp]
         L.orc_count_peg_kmers_positions.restype = C.c_uint64
         L.orc_count_probes.argtypes = [vp, C.c_uint64, C.c_int]; L.orc_count_probes.restype = C.c_uint64
+        L.orc_kmer_distance_pairs.argtypes = [vp, vp, vp, vp, C.c_uint64, C.c_int, vp, vp, vp, vp]
+        L.orc_kmer_distance_pairs.restype = None
         L.orf_db_load.argtypes = [vp, vp, C.c_uint64, C.c_int]; L.orf_db_load.restype = vp
         L.orf_db_free.argtypes = [vp]; L.orf_db_free.restype = None
         L.orf_db_size.argtypes = [vp]; L.orf_db_size.restype = C.c_uint64
@@ -151,3 +153,18 @@ def build_db(residues, offsets, n_roles, peg_role, K, n_good_roles, distinct=Tru
     L.orc_map_free(h)
     return keys[: n * K], vals[:n], {"buffered": int(stats[0]), "non_unique": int(stats[1]),
                                     "deleted_pass2": int(stats[2]), "remaining": int(stats[3])}
+
+
+def kmer_distance_pairs(residues, offsets, qa, qb, K):
+    """ProteinKmers.distance of the pairs (qa[m], qb[m]) of a CSR batch (GeneCopyProcessor.java:137-142):
+    (size_a i32[M], size_b i32[M], common i32[M], distance f64[M])."""
+    residues = np.ascontiguousarray(residues, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    qa = np.ascontiguousarray(qa, dtype=np.uint32)
+    qb = np.ascontiguousarray(qb, dtype=np.uint32)
+    m = qa.shape[0]
+    sa, sb, co = np.empty(m, np.int32), np.empty(m, np.int32), np.empty(m, np.int32)
+    dist = np.empty(m, np.float64)
+    lib().orc_kmer_distance_pairs(residues.ctypes.data, offsets.ctypes.data, qa.ctypes.data, qb.ctypes.data,
+                                  m, K, sa.ctypes.data, sb.ctypes.data, co.ctypes.data, dist.ctypes.data)
+    return sa, sb, co, dist

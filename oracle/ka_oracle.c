@@ -618,6 +618,53 @@ uint64_t orc_count_peg_kmers_positions(const uint8_t* prot, uint64_t L, int K, u
     return n;
 }
 
+/* ------------------------------------------------------------------------------------
+ * Pairwise k-mer distance: genome/compare/GeneCopyProcessor.java:137-142.
+ *   ProteinKmers kmers = new ProteinKmers(target protein)          (:137)
+ *   ProteinKmers f2Kmers = new ProteinKmers(candidate protein)     (:141)
+ *   double f2Dist = kmers.distance(f2Kmers)                        (:142)
+ * ProteinKmers is not in the repository; recalled (docs/SEMANTICS.md): similarity = number of
+ * k-mers of the other set contained in this one; distance = 1.0 when similarity is 0, else
+ * 1.0 - similarity / ((size() + other.size()) - similarity), all in double.
+ * One pair per call; sizes and similarity are returned for the integer parity checks.
+ * ---------------------------------------------------------------------------------- */
+double orc_kmer_distance(const uint8_t* a, uint64_t la, const uint8_t* b, uint64_t lb, int K,
+                         int32_t* size_a, int32_t* size_b, int32_t* common) {
+    orc_map* sa = orc_map_new(16);
+    orc_map* sb = orc_map_new(16);
+    protein_kmers(sa, a, la, K, 1, 1);
+    protein_kmers(sb, b, lb, K, 1, 1);
+    /* similarity: iterate the other set, count members of this one */
+    int32_t sim = 0;
+    for (uint32_t i = 0; i < sb->n_nodes; i++) {
+        const jnode* nd = &sb->nodes[i];
+        if (jfind(sa, (const uint8_t*)sb->pool + nd->koff, nd->klen, nd->hash) >= 0) sim++;
+    }
+    if (size_a) *size_a = (int32_t)sa->size;
+    if (size_b) *size_b = (int32_t)sb->size;
+    if (common) *common = sim;
+    double ret = 1.0;
+    double similarity = (double)sim;
+    if (similarity > 0) {
+        double uni = (double)((int32_t)sa->size + (int32_t)sb->size) - similarity;
+        ret = 1.0 - similarity / uni;
+    }
+    orc_map_free(sa);
+    orc_map_free(sb);
+    return ret;
+}
+
+/* batch form over a CSR batch: pair m = (qa[m], qb[m]) */
+void orc_kmer_distance_pairs(const uint8_t* residues, const uint64_t* offsets, const uint32_t* qa,
+                             const uint32_t* qb, uint64_t n_pairs, int K, int32_t* size_a,
+                             int32_t* size_b, int32_t* common, double* dist) {
+    for (uint64_t m = 0; m < n_pairs; m++) {
+        const uint64_t a0 = offsets[qa[m]], a1 = offsets[qa[m] + 1], b0 = offsets[qb[m]], b1 = offsets[qb[m] + 1];
+        dist[m] = orc_kmer_distance(residues + a0, a1 - a0, residues + b0, b1 - b0, K,
+                                    size_a ? size_a + m : NULL, size_b ? size_b + m : NULL, common ? common + m : NULL);
+    }
+}
+
 /* window positions P = sum max(0, L_i - K + 1): the metric's unit of work */
 uint64_t orc_count_probes(const uint64_t* offsets, uint64_t N, int K) {
     uint64_t p = 0;

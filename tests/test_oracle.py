@@ -193,3 +193,22 @@ def test_golden_fixtures_regression():
         if flag[i] == 1:
             lines.append(f"{genome_id}\t{fid}\t{ids[role[i]]}\t{hits[i]}\t{fun}")
     assert "\n".join(lines) + "\n" == open(os.path.join(GOLD, "small.verify.tsv")).read()
+
+
+def test_kmer_distance_restatement_against_python_sets():
+    """oracle.kmer_distance_pairs (GeneCopyProcessor.java:137-142, recalled ProteinKmers.distance)
+    against Python sets on the proteins of small.gto."""
+    prots = [p.encode() for _, _, p in load_small_proteins()[1]][:60] + [b"", b"ACD", b"ACDEFGHI"]
+    res, off = csr(prots)
+    rng = np.random.default_rng(4)
+    qa = rng.integers(0, len(prots), 400).astype(np.uint32)
+    qb = rng.integers(0, len(prots), 400).astype(np.uint32)
+    qb[:40] = qa[:40]
+    for K in (2, 8, 10):
+        sa, sb, co, dist = oracle.kmer_distance_pairs(res, off, qa, qb, K)
+        sets = [{p[i:i + K] for i in range(len(p) - K + 1)} for p in prots]
+        for m in range(400):
+            a, b = sets[qa[m]], sets[qb[m]]
+            sim = len(a & b)
+            assert (sa[m], sb[m], co[m]) == (len(a), len(b), sim)
+            assert dist[m] == (1.0 if sim == 0 else 1.0 - sim / ((len(a) + len(b)) - sim))
