@@ -11,10 +11,11 @@
 //   set_size_kernel   one CTA per sequence: the distinct K-windows go into an open-addressed hash set
 //                     (shared memory; an L2-resident global slice for sequences too long for it),
 //                     the number of successful inserts is |set|.
-//   common_kernel     one CTA per query group: the query's set is built once with a 32-bit tag per
-//                     entry; every candidate streams its windows through it, and a hit counts when
-//                     atomicExch(tag, candidate) returns something else — i.e. once per distinct
-//                     shared k-mer and candidate.  The epilogue writes |A ∩ B| and the distance.
+//                     It also marks ONE window of every distinct k-mer (the insert that created the
+//                     entry), so that later passes can count distinct k-mers without a second set.
+//   common_kernel     one CTA per query group: the query's set is built once; every warp then takes
+//                     candidates on its own, streams their marked windows through the set and counts
+//                     the hits = |A ∩ B|; lane 0 writes it and the distance.
 // Integer work in shared memory; the only floating-point operation is the final IEEE double
 // division / subtraction, which equals the Java expression bit for bit.
 #include "ka_kernels.cuh"
@@ -27,7 +28,6 @@ constexpr int DTHREADS = 128;
 
 struct SetRef {
     unsigned long long* keys;   // cap entries, 0 = empty (packed keys are never 0)
-    uint32_t* tags;             // cap entries (common_kernel only)
     uint32_t cap;               // power of two
 };
 
@@ -37,19 +37,30 @@ __device__ __forceinline__ SetRef pick_set(const DistParams& p, unsigned char* s
     s.cap = dist_set_cap(windows);
     if (s.cap <= p.smem_cap) {
         s.keys = reinterpret_cast<unsigned long long*>(smem);
-        s.tags = reinterpret_cast<uint32_t*>(smem + (size_t)p.smem_cap * 8);
     } else {
         s.keys = p.scratch_keys + scratch_first;
-        s.tags = p.scratch_tags + scratch_first;
     }
     return s;
 }
 
-__device__ __forceinline__ unsigned long long window_key(const DistParams& p, const uint8_t* s_lut,
-                                                         const uint8_t* r) {
+// f(w, key) for every K-window w of the W windows starting at residue r0, spread over `nthr`
+// cooperating threads (`me` = this thread's index among them): each thread rolls the 5-bit pack
+// over ONE contiguous run of windows (K - 1 + run byte loads instead of K per window).
+template <typename F>
+__device__ __forceinline__ void for_windows(const DistParams& p, const uint8_t* s_lut, const uint8_t* r0,
+                                            unsigned long long W, uint32_t me, uint32_t nthr, F f) {
+    const unsigned long long run = (W + nthr - 1) / nthr;
+    const unsigned long long w0 = (unsigned long long)me * run;
+    if (w0 >= W) return;
+    const unsigned long long w1 = w0 + run < W ? w0 + run : W;
+    const uint8_t* r = r0 + w0;
     unsigned long long key = 0;
-    for (int j = 0; j < p.K; j++) key = (key << 5) | s_lut[__ldg(r + j)];
-    return key;
+    for (int j = 0; j < p.K - 1; j++) key = (key << 5) | s_lut[__ldg(r + j)];
+    r += p.K - 1;
+    for (unsigned long long w = w0; w < w1; w++, r++) {
+        key = ((key << 5) | s_lut[__ldg(r)]) & p.key_mask;
+        f(w, key);
+    }
 }
 
 // insert: true = the key was not in the set yet
@@ -63,42 +74,37 @@ __device__ __forceinline__ bool set_insert(const SetRef& s, unsigned long long k
     }
 }
 
-// slot of a key, or -1
-__device__ __forceinline__ int set_find(const SetRef& s, unsigned long long key) {
+__device__ __forceinline__ bool set_has(const SetRef& s, unsigned long long key) {
     uint32_t j = (uint32_t)mix64(key) & (s.cap - 1);
     for (;;) {
         const unsigned long long cur = s.keys[j];
-        if (cur == key) return (int)j;
-        if (cur == 0ull) return -1;
+        if (cur == key) return true;
+        if (cur == 0ull) return false;
         j = (j + 1) & (s.cap - 1);
     }
 }
 
-__device__ __forceinline__ int block_sum(int v, int* s_red) {
-    v = __reduce_add_sync(0xffffffffu, v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    int t = 0;
-    for (int w = 0; w < DTHREADS / 32; w++) t += s_red[w];
-    return t;
-}
-
-// fill the set with the windows of sequence `seq`; returns the number of distinct windows (all threads)
+// fill the (cleared) set with the windows of sequence `seq`, the whole CTA cooperating; when
+// `uniq` is given, uniq[window position] = 1 for exactly one window of every distinct k-mer
 __device__ __forceinline__ int build_set(const DistParams& p, const SetRef& s, const uint8_t* s_lut,
-                                         uint32_t seq, bool with_tags, int* s_red) {
+                                         uint32_t seq, uint8_t* uniq) {
     const unsigned long long a = p.off[seq] - p.base, L = p.off[seq + 1] - p.off[seq];
     const unsigned long long W = L >= (unsigned long long)p.K ? L - p.K + 1 : 0;
-    for (uint32_t i = threadIdx.x; i < s.cap; i += DTHREADS) { s.keys[i] = 0ull; if (with_tags) s.tags[i] = 0u; }
+    for (uint32_t i = threadIdx.x; i < s.cap; i += DTHREADS) s.keys[i] = 0ull;
     __syncthreads();
     int mine = 0;
-    for (unsigned long long w = threadIdx.x; w < W; w += DTHREADS)
-        mine += set_insert(s, window_key(p, s_lut, p.res + a + w)) ? 1 : 0;
-    return block_sum(mine, s_red);   // its barriers also publish the inserts
+    for_windows(p, s_lut, p.res + a, W, threadIdx.x, DTHREADS, [&](unsigned long long w, unsigned long long key) {
+        const bool fresh = set_insert(s, key);
+        mine += fresh ? 1 : 0;
+        if (uniq) uniq[a + w] = fresh ? 1 : 0;
+    });
+    return mine;
 }
 
 }  // namespace
 
+// |set| of every sequence, and the first-occurrence marks the pair kernel uses to count every
+// distinct k-mer of a candidate once
 __global__ void __launch_bounds__(DTHREADS) set_size_kernel(DistParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint8_t s_lut[256];
@@ -109,36 +115,46 @@ __global__ void __launch_bounds__(DTHREADS) set_size_kernel(DistParams p) {
         const unsigned long long L = p.off[seq + 1] - p.off[seq];
         const uint32_t W = L >= (unsigned long long)p.K ? (uint32_t)(L - p.K + 1) : 0u;
         const SetRef s = pick_set(p, smem, W, p.seq_scratch[seq]);
-        const int n = build_set(p, s, s_lut, seq, false, s_red);
-        if (threadIdx.x == 0) p.set_size[seq] = n;
+        int n = build_set(p, s, s_lut, seq, p.uniq);
+        n = __reduce_add_sync(0xffffffffu, n);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = n;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < DTHREADS / 32; w++) t += s_red[w];
+            p.set_size[seq] = t;
+        }
         __syncthreads();
     }
 }
 
+// One CTA per query: its set is built once in shared memory; then every WARP takes candidates of
+// the group on its own — a lane rolls over a contiguous run of the candidate's windows and counts
+// the marked (first-occurrence) ones found in the query's set — no barrier per candidate.
 __global__ void __launch_bounds__(DTHREADS) common_kernel(DistParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint8_t s_lut[256];
-    __shared__ int s_red[DTHREADS / 32];
     for (int i = threadIdx.x; i < 256; i += DTHREADS) s_lut[i] = p.lut[i];
     __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (uint32_t q = p.q_begin + blockIdx.x; q < p.q_end; q += gridDim.x) {
         const uint32_t qs = p.query_seq[q];
         const unsigned long long LA = p.off[qs + 1] - p.off[qs];
         const uint32_t WA = LA >= (unsigned long long)p.K ? (uint32_t)(LA - p.K + 1) : 0u;
         const SetRef s = pick_set(p, smem, WA, p.query_scratch[q]);
-        const int size_a = build_set(p, s, s_lut, qs, true, s_red);
-        for (unsigned long long m = p.group_off[q]; m < p.group_off[q + 1]; m++) {
+        build_set(p, s, s_lut, qs, nullptr);
+        __syncthreads();
+        const int size_a = p.set_size[qs];
+        for (unsigned long long m = p.group_off[q] + warp; m < p.group_off[q + 1]; m += DTHREADS / 32) {
             const uint32_t cs = p.cand_seq[m];
             const unsigned long long b = p.off[cs] - p.base, LB = p.off[cs + 1] - p.off[cs];
             const unsigned long long WB = LB >= (unsigned long long)p.K ? LB - p.K + 1 : 0;
-            const uint32_t tag = (uint32_t)(m - p.group_off[q]) + 1u;
             int mine = 0;
-            for (unsigned long long w = threadIdx.x; w < WB; w += DTHREADS) {
-                const int slot = set_find(s, window_key(p, s_lut, p.res + b + w));
-                if (slot >= 0 && atomicExch(s.tags + slot, tag) != tag) mine++;
-            }
-            const int common = block_sum(mine, s_red);
-            if (threadIdx.x == 0) {
+            for_windows(p, s_lut, p.res + b, WB, lane, 32, [&](unsigned long long w, unsigned long long key) {
+                if (p.uniq[b + w] && set_has(s, key)) mine++;
+            });
+            const int common = __reduce_add_sync(0xffffffffu, mine);
+            if (lane == 0) {
                 p.common[m] = common;
                 double d = 1.0;                                   // nothing shared
                 if (common > 0) {
@@ -153,7 +169,7 @@ __global__ void __launch_bounds__(DTHREADS) common_kernel(DistParams p) {
     }
 }
 
-size_t dist_smem_bytes(uint32_t smem_cap) { return (size_t)smem_cap * 12; }
+size_t dist_smem_bytes(uint32_t smem_cap) { return (size_t)smem_cap * 8; }
 
 cudaError_t dist_set_smem(size_t bytes) {
     cudaError_t ce = cudaFuncSetAttribute(set_size_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);

@@ -1440,7 +1440,7 @@ int ka_kmer_distance(ka_engine* e, const uint8_t* residues, const uint64_t* offs
     for (uint64_t m = 0; m < M; m++)
         if (cand_seq[m] >= N) return fail(e, KA_ERR_INVALID, "ka_kmer_distance: candidate %llu names sequence %u of %llu", (unsigned long long)m, cand_seq[m], (unsigned long long)N);
 
-    // hash-set placement: shared memory up to 8192 entries (96 KB), a global slice beyond
+    // hash-set placement: shared memory up to 8192 entries (64 KB), a global slice beyond
     auto windows = [&](uint64_t i) { uint64_t L = offsets[i + 1] - offsets[i]; return (uint32_t)(L >= (uint64_t)K ? L - K + 1 : 0); };
     uint32_t smem_cap = 64;
     for (uint64_t i = 0; i < N; i++) { uint32_t c = dist_set_cap(windows(i)); if (c <= 8192 && c > smem_cap) smem_cap = c; }
@@ -1463,36 +1463,6 @@ int ka_kmer_distance(ka_engine* e, const uint8_t* residues, const uint64_t* offs
         cut[nd] = Q;
         for (size_t i = 1; i < nd; i++)
             cut[i] = std::max<uint64_t>(cut[i - 1], std::lower_bound(work.begin(), work.end(), work[Q] / nd * i) - work.begin());
-    }
-
-    // alphabet of the batch (at most 31 distinct bytes), scanned on the first device
-    uint8_t lut[256];
-    {
-        Device& d = e->devs[0];
-        cudaSetDevice(d.id);
-        cudaStream_t st = d.pipe[0].st;
-        uint32_t* dbm = nullptr; uint8_t* dk = nullptr;
-        uint32_t bitmap[8] = {0};
-        const uint64_t ch = std::min<uint64_t>(256ull << 20, n_res ? n_res : 1);
-        if (cudaMalloc((void**)&dbm, 32) != cudaSuccess || cudaMalloc((void**)&dk, ch) != cudaSuccess) {
-            if (dbm) cudaFree(dbm);
-            return fail(e, KA_ERR_OOM, "ka_kmer_distance: alphabet staging allocation failed");
-        }
-        cudaError_t ce = cudaMemsetAsync(dbm, 0, 32, st);
-        for (uint64_t i = 0; i < n_res && ce == cudaSuccess; i += ch) {
-            uint64_t m = std::min(ch, n_res - i);
-            ce = cudaMemcpyAsync(dk, residues + base + i, m, cudaMemcpyHostToDevice, st);
-            if (ce == cudaSuccess) ce = launch_alphabet_scan(dk, m, dbm, st);
-            if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
-        }
-        if (ce == cudaSuccess) ce = cudaMemcpy(bitmap, dbm, 32, cudaMemcpyDeviceToHost);
-        cudaFree(dbm); cudaFree(dk);
-        if (ce != cudaSuccess) return fail(e, KA_ERR_CUDA, "ka_kmer_distance: alphabet scan: %s", cudaGetErrorString(ce));
-        memset(lut, 0, 256);
-        int nsym = 0;
-        for (int b = 0; b < 256; b++)
-            if (bitmap[b >> 5] & (1u << (b & 31))) { nsym++; if (nsym <= 31) lut[b] = (uint8_t)nsym; }
-        if (nsym > 31) return fail(e, KA_ERR_ALPHABET, "ka_kmer_distance: the proteins use %d distinct residue bytes; at most 31 fit the 5-bit packing", nsym);
     }
 
     auto t0 = std::chrono::steady_clock::now();
@@ -1525,10 +1495,10 @@ int ka_kmer_distance(ka_engine* e, const uint8_t* residues, const uint64_t* offs
         int32_t* d_common = (int32_t*)alloc(M * 4);
         double* d_dist = (double*)alloc(M * 8);
         unsigned long long* d_sk = (unsigned long long*)alloc(n_scratch * 8);
-        uint32_t* d_stg = (uint32_t*)alloc(n_scratch * 4);
+        uint8_t* d_uniq = (uint8_t*)alloc(n_res + 64);
         unsigned long long* d_ss = (unsigned long long*)alloc(N * 8);
         unsigned long long* d_qsc = (unsigned long long*)alloc((Q ? Q : 1) * 8);
-        if (!d_res || !d_off || !d_qs || !d_go || !d_cs || !d_size || !d_common || !d_dist || !d_sk || !d_stg || !d_ss || !d_qsc)
+        if (!d_res || !d_off || !d_qs || !d_go || !d_cs || !d_size || !d_common || !d_dist || !d_sk || !d_uniq || !d_ss || !d_qsc)
             return finish(KA_ERR_OOM, "ka_kmer_distance: device allocation", cudaErrorMemoryAllocation);
         cudaError_t ce = cudaSuccess;
         auto step = [&](cudaError_t c) { if (ce == cudaSuccess) ce = c; };
@@ -1539,15 +1509,34 @@ int ka_kmer_distance(ka_engine* e, const uint8_t* residues, const uint64_t* offs
         if (M) step(cudaMemcpyAsync(d_cs, cand_seq, M * 4, cudaMemcpyHostToDevice, st));
         step(cudaMemcpyAsync(d_ss, seq_scratch.data(), N * 8, cudaMemcpyHostToDevice, st));
         if (Q) step(cudaMemcpyAsync(d_qsc, query_scratch.data(), Q * 8, cudaMemcpyHostToDevice, st));
+        // alphabet of the batch (at most 31 distinct bytes), scanned from the device copy
         uint8_t* d_lut = (uint8_t*)alloc(256);             // not d.lut: that one belongs to the loaded DB
-        if (!d_lut) return finish(KA_ERR_OOM, "ka_kmer_distance: device allocation", cudaErrorMemoryAllocation);
+        uint32_t* d_bm = (uint32_t*)alloc(32);
+        if (!d_lut || !d_bm) return finish(KA_ERR_OOM, "ka_kmer_distance: device allocation", cudaErrorMemoryAllocation);
+        uint32_t bitmap[8] = {0};
+        step(cudaMemsetAsync(d_bm, 0, 32, st));
+        step(launch_alphabet_scan(d_res, n_res, d_bm, st));
+        step(cudaMemcpyAsync(bitmap, d_bm, 32, cudaMemcpyDeviceToHost, st));
+        step(cudaStreamSynchronize(st));
+        if (ce != cudaSuccess) return finish(KA_ERR_CUDA, "ka_kmer_distance: alphabet scan", ce);
+        uint8_t lut[256];
+        memset(lut, 0, 256);
+        int nsym = 0;
+        for (int b = 0; b < 256; b++)
+            if (bitmap[b >> 5] & (1u << (b & 31))) { nsym++; if (nsym <= 31) lut[b] = (uint8_t)nsym; }
+        if (nsym > 31) {
+            for (void* q : owned) cudaFree(q);
+            d.err = KA_ERR_ALPHABET;
+            d.errmsg = "ka_kmer_distance: the proteins use " + std::to_string(nsym) + " distinct residue bytes; at most 31 fit the 5-bit packing";
+            return (int)KA_ERR_ALPHABET;
+        }
         step(cudaMemcpyAsync(d_lut, lut, 256, cudaMemcpyHostToDevice, st));
         d.h2d = n_res + (N + 1) * 8 + Q * 4 + (Q + 1) * 8 + M * 4 + N * 8 + Q * 8;
         step(dist_set_smem(dist_smem_bytes(8192)));
-        dp.res = d_res; dp.off = d_off; dp.base = base; dp.n_seq = (uint32_t)N; dp.K = K; dp.lut = d_lut;
+        dp.res = d_res; dp.off = d_off; dp.base = base; dp.n_seq = (uint32_t)N; dp.K = K; dp.key_mask = (1ull << (5 * K)) - 1; dp.lut = d_lut;
         dp.set_size = d_size; dp.query_seq = d_qs; dp.group_off = d_go; dp.q_begin = (uint32_t)qa; dp.q_end = (uint32_t)qb;
         dp.cand_seq = d_cs; dp.common = d_common; dp.dist = d_dist; dp.smem_cap = smem_cap;
-        dp.scratch_keys = d_sk; dp.scratch_tags = d_stg; dp.seq_scratch = d_ss; dp.query_scratch = d_qsc;
+        dp.scratch_keys = d_sk; dp.uniq = d_uniq; dp.seq_scratch = d_ss; dp.query_scratch = d_qsc;
         step(cudaEventRecord(p.ev_k0, st));
         step(launch_set_size(dp, d.sm_count, st));
         step(launch_common(dp, d.sm_count, st));

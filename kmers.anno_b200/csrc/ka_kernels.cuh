@@ -123,6 +123,7 @@ struct DistParams {
     unsigned long long base;
     uint32_t n_seq;
     int K;
+    unsigned long long key_mask;           // (1 << 5K) - 1
     const uint8_t* lut;                    // residue byte -> 5-bit code (every byte of the batch has one)
     int32_t* set_size;                     // [n_seq] distinct K-windows of every sequence
     const uint32_t* query_seq;             // [Q] sequence index of every query
@@ -133,7 +134,7 @@ struct DistParams {
     double* dist;                          // [M]
     uint32_t smem_cap;                     // entries of the shared-memory hash set (power of two)
     unsigned long long* scratch_keys;      // hash sets of the sequences too long for shared memory
-    uint32_t* scratch_tags;
+    uint8_t* uniq;                         // [residues] 1 = this window is the marked occurrence of its k-mer
     const unsigned long long* seq_scratch;   // [n_seq] first scratch entry of a sequence's set (set_size_kernel)
     const unsigned long long* query_scratch; // [Q] first scratch entry of a query's set (common_kernel)
 };
