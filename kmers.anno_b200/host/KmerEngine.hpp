@@ -45,6 +45,17 @@ public:
     }
     ka_stats stats() { ka_stats s; check(ka_get_stats(h_, &s)); return s; }
 
+    /** ProteinKmers.distance of every query against its candidates (GeneCopyProcessor.java:137-142):
+     *  query q = sequence querySeq[q], candidates cand[groupOff[q] .. groupOff[q+1]). */
+    void kmerDistance(const std::vector<uint8_t>& residues, const std::vector<uint64_t>& offsets, int K,
+                      const std::vector<uint32_t>& querySeq, const std::vector<uint64_t>& groupOff,
+                      const std::vector<uint32_t>& cand, std::vector<int32_t>& common, std::vector<double>& dist) {
+        size_t n = offsets.empty() ? 0 : offsets.size() - 1;
+        common.resize(cand.size()); dist.resize(cand.size());
+        check(ka_kmer_distance(h_, residues.data(), offsets.data(), n, K, querySeq.data(), groupOff.data(),
+                               querySeq.size(), cand.data(), nullptr, common.data(), dist.data()));
+    }
+
 private:
     void check(int rc) { if (rc != KA_OK) throw KmerEngineError(rc, ka_last_error(h_)); }
     ka_engine* h_ = nullptr;

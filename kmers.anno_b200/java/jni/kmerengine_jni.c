@@ -58,3 +58,26 @@ JNIEXPORT void JNICALL Java_org_theseed_proteins_kmers_gpu_KmerEngine_annotate(J
     (*env)->ReleasePrimitiveArrayCritical(env, residues, res, JNI_ABORT);
     if (rc != KA_OK) throw_io(env, rc, ka_last_error(e));
 }
+
+JNIEXPORT void JNICALL Java_org_theseed_proteins_kmers_gpu_KmerEngine_kmerDistance(JNIEnv* env, jclass cls, jlong h,
+        jbyteArray residues, jlongArray offsets, jlong n, jint k, jintArray querySeq, jlongArray groupOff, jlong q,
+        jintArray cand, jintArray common, jdoubleArray dist) {
+    ka_engine* e = (ka_engine*)(intptr_t)h;
+    jbyte* res = (*env)->GetPrimitiveArrayCritical(env, residues, NULL);
+    jlong* off = (*env)->GetPrimitiveArrayCritical(env, offsets, NULL);
+    jint* qs = (*env)->GetPrimitiveArrayCritical(env, querySeq, NULL);
+    jlong* go = (*env)->GetPrimitiveArrayCritical(env, groupOff, NULL);
+    jint* cs = (*env)->GetPrimitiveArrayCritical(env, cand, NULL);
+    jint* co = (*env)->GetPrimitiveArrayCritical(env, common, NULL);
+    jdouble* di = (*env)->GetPrimitiveArrayCritical(env, dist, NULL);
+    int rc = ka_kmer_distance(e, (const uint8_t*)res, (const uint64_t*)off, (uint64_t)n, (int)k, (const uint32_t*)qs,
+                              (const uint64_t*)go, (uint64_t)q, (const uint32_t*)cs, NULL, (int32_t*)co, (double*)di);
+    (*env)->ReleasePrimitiveArrayCritical(env, dist, di, 0);
+    (*env)->ReleasePrimitiveArrayCritical(env, common, co, 0);
+    (*env)->ReleasePrimitiveArrayCritical(env, cand, cs, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, groupOff, go, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, querySeq, qs, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, offsets, off, JNI_ABORT);
+    (*env)->ReleasePrimitiveArrayCritical(env, residues, res, JNI_ABORT);
+    if (rc != KA_OK) throw_io(env, rc, ka_last_error(e));
+}

@@ -96,6 +96,30 @@ public final class KmerEngine implements AutoCloseable {
         return c;
     }
 
+    /**
+     * ProteinKmers.distance of every query protein against its candidates (GeneCopyProcessor.java:137-142).
+     * Query q is proteins.get(querySeq[q]); its candidates are proteins.get(cand[m]) for
+     * groupOff[q] <= m < groupOff[q+1].  Returns one distance per candidate entry; the caller keeps the
+     * selection loop of :139-146.  No k-mer database is needed.
+     */
+    public double[] kmerDistance(List<String> proteins, int kmerSize, int[] querySeq, long[] groupOff, int[] cand)
+            throws IOException {
+        long[] offsets = new long[proteins.size() + 1];
+        int total = 0;
+        for (int i = 0; i < proteins.size(); i++) { offsets[i] = total; total += proteins.get(i).length(); }
+        offsets[proteins.size()] = total;
+        byte[] residues = new byte[total];
+        for (int i = 0; i < proteins.size(); i++) {
+            byte[] p = proteins.get(i).getBytes(StandardCharsets.ISO_8859_1);
+            System.arraycopy(p, 0, residues, (int) offsets[i], p.length);
+        }
+        double[] dist = new double[cand.length];
+        int[] common = new int[cand.length];
+        kmerDistance(this.handle, residues, offsets, proteins.size(), kmerSize, querySeq, groupOff, querySeq.length,
+                cand, common, dist);
+        return dist;
+    }
+
     @Override
     public void close() {
         if (this.handle != 0) { destroy(this.handle); this.handle = 0; }
@@ -107,4 +131,6 @@ public final class KmerEngine implements AutoCloseable {
     private static native void dbLoad(long handle, byte[] kmers, int[] roleIds, long n, int k) throws IOException;  // ka_db_load
     private static native void annotate(long handle, byte[] residues, long[] offsets, long n, int minHits,
             int[] role, int[] hits, byte[] flag) throws IOException;                           // ka_annotate
+    private static native void kmerDistance(long handle, byte[] residues, long[] offsets, long n, int k,
+            int[] querySeq, long[] groupOff, long q, int[] cand, int[] common, double[] dist) throws IOException;  // ka_kmer_distance
 }
