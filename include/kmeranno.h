@@ -91,7 +91,8 @@ const char* ka_last_error(const ka_engine* e);
  *                   token) on any table; 0 (default) = only when the table has more than 2^32 - 16
  *                   slots, e.g. more than ~34 GB of 64-bit slots   (next ka_db_load)
  *   "slot_bits"     force the table slot width (32, 64, 128; 0 = smallest that fits, default)
- *   "variant"       tile kernel shape: 0 = 4 positions x 128 threads (default), 1 = 4 x 256, 2 = 8 x 256
+ *   "variant"       tile kernel shape: 0 = 4 positions x 128 threads (default), 1 = 4 x 256, 2 = 8 x 256,
+ *                   3 = 2 x 128 (48 registers, 10 CTAs/SM)
  *   "chunk_residues" residues per pipelined H2D chunk, default 32 Mi
  *   "l2_persist"    1 = set an L2 persisting access-policy window on the table (default 1)
  */

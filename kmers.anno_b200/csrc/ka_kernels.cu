@@ -726,6 +726,7 @@ static auto with_tile_kernel(int cls, int variant, F f) {
     switch (variant) {                                               \
         case 1: return f(tile_kernel<CLS, 4, 256, 3>, 256);          \
         case 2: return f(tile_kernel<CLS, 8, 256, 2>, 256);          \
+        case 3: return f(tile_kernel<CLS, 2, 128, 10>, 128);         \
         default: return f(tile_kernel<CLS, 4, 128, 6>, 128);         \
     }
     if (cls == 32) { KA_VARIANTS(32) }

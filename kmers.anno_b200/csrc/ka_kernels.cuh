@@ -47,10 +47,10 @@ struct AnnotParams {
 };
 
 // tile kernel shapes (option "variant"): 0 = 4 window positions per thread x 128 threads
-// (7 CTAs/SM, default), 1 = 4 x 256 (default of the mid-sequence launch), 2 = 8 x 256.
+// (7 CTAs/SM, default), 1 = 4 x 256 (default of the mid-sequence launch), 2 = 8 x 256, 3 = 2 x 128.
 // Shapes that were measured and dropped (64-register caps, 512 threads, 2 or 8 positions x 128)
 // are listed in profiles/r01_summary.md.
-constexpr int N_VARIANTS = 3;
+constexpr int N_VARIANTS = 4;
 size_t tile_smem_bytes(uint32_t ext_max, uint32_t* res_bytes_out, bool wide);
 // de-dup token capacity of x window positions: x + x/4 (worst-case load factor 0.8)
 __host__ __device__ inline uint32_t tok_cap(uint32_t x) { return x + (x >> 2); }

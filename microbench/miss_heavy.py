@@ -9,7 +9,9 @@ fam = synth.Families(30000)
 kmers, roles = fam.table(int(1e8), K=8)
 other = synth.Families(30000, seed=777)
 batches = {"c3": fam.batch(0, 60, n_prot=4500)[:2], "unrelated": other.batch(0, 60, n_prot=4500)[:2]}
-for opts in ({}, {"filter": 1}):
+import json
+configs = [json.loads(a) for a in sys.argv[1:]] or [{}, {"filter": 1}]
+for opts in configs:
     eng = ka.Engine([0])
     for k, v in opts.items(): eng.set_option(k, float(v))
     eng.db_load(kmers, roles, 8)

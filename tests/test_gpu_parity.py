@@ -136,6 +136,8 @@ def test_long_sequences_use_big_kernel(ka, oracle):
     {"l2_persist": 0},
     {"variant": 1},
     {"variant": 2},
+    {"variant": 3},
+    {"variant": 3, "filter": 1, "slot_bits": 64},
     {"slot_bits": 32},
     {"slot_bits": 64},
     {"slot_bits": 128},
