@@ -403,11 +403,12 @@ __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
                                 : (WIDE ? (unsigned long long)rem[i] : (((unsigned long long)sec[i] << tab.rem_bits) | (unsigned long long)rem[i]));
                     okmask = 0;
                 } else if (MODE == 2) {
-                    // routed mode, last step: the owning GPUs have answered (role << 32 | token)
+                    // routed mode, last step: the owning GPUs have answered (role << 32 | token); the answer of
+                    // a position sits at the send slot its key was bucketed into (route_slot)
                     unsigned long long ans[C];
 #pragma unroll
                     for (int i = 0; i < C; i++)
-                        if (okmask & (1u << i)) ans[i] = __ldg(p.route_ans + g0a + P0 + i);
+                        if (okmask & (1u << i)) ans[i] = __ldg(p.route_ans + __ldg(p.route_slot + g0a + P0 + i));
 #pragma unroll
                     for (int i = 0; i < C; i++) {
                         role[i] = -1;
@@ -830,7 +831,7 @@ cudaError_t launch_route_count(const unsigned long long* keys, unsigned long lon
 // keys at (range + rank inside the CTA).
 __global__ void __launch_bounds__(256) route_scatter_kernel(const unsigned long long* __restrict__ keys, unsigned long long n,
                                      TableView tab, const unsigned long long* __restrict__ offsets,
-                                     unsigned long long* cursor, unsigned long long* send_keys, uint32_t* send_pos) {
+                                     unsigned long long* cursor, unsigned long long* send_keys, uint32_t* slot_of_pos) {
     constexpr int PER = 16;                       // keys per thread, strided by 256 inside the tile
     __shared__ uint32_t s_cnt[8][8];              // [warp][owner]
     __shared__ unsigned long long s_base[8][8];   // [warp][owner] first output index
@@ -868,7 +869,7 @@ __global__ void __launch_bounds__(256) route_scatter_kernel(const unsigned long 
                 if (own[k] == o) {
                     const unsigned long long w = s_base[warp][o] + done[o] + __popc(b & ((1u << lane) - 1));
                     send_keys[w] = m[k];
-                    send_pos[w] = (uint32_t)i;
+                    slot_of_pos[i] = (uint32_t)w;      // answers come back in send order: position i reads slot w
                 }
                 done[o] += __popc(b);
             }
@@ -879,10 +880,10 @@ __global__ void __launch_bounds__(256) route_scatter_kernel(const unsigned long 
 
 cudaError_t launch_route_scatter(const unsigned long long* keys, unsigned long long n, TableView tab,
                                  const unsigned long long* offsets, unsigned long long* cursor,
-                                 unsigned long long* send_keys, uint32_t* send_pos, cudaStream_t st) {
+                                 unsigned long long* send_keys, uint32_t* slot_of_pos, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     unsigned long long want = (n + 256ull * 16 - 1) / (256ull * 16);
-    route_scatter_kernel<<<(unsigned)(want < 148ull * 8 ? want : 148ull * 8), 256, 0, st>>>(keys, n, tab, offsets, cursor, send_keys, send_pos);
+    route_scatter_kernel<<<(unsigned)(want < 148ull * 8 ? want : 148ull * 8), 256, 0, st>>>(keys, n, tab, offsets, cursor, send_keys, slot_of_pos);
     return cudaGetLastError();
 }
 
@@ -950,21 +951,6 @@ cudaError_t launch_route_lookup(const unsigned long long* keys, unsigned long lo
     if (tab.cls == 32) route_lookup_kernel<32><<<blocks, 256, 0, st>>>(keys, n, tab, ans);
     else if (tab.cls == 64) route_lookup_kernel<64><<<blocks, 256, 0, st>>>(keys, n, tab, ans);
     else return cudaErrorInvalidValue;
-    return cudaGetLastError();
-}
-
-__global__ void route_unpermute_kernel(const unsigned long long* __restrict__ ans_sorted,
-                                       const uint32_t* __restrict__ send_pos, unsigned long long n,
-                                       unsigned long long* ans_by_pos) {
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        ans_by_pos[send_pos[i]] = ans_sorted[i];
-}
-
-cudaError_t launch_route_unpermute(const unsigned long long* ans_sorted, const uint32_t* send_pos,
-                                   unsigned long long n, unsigned long long* ans_by_pos, cudaStream_t st) {
-    if (n == 0) return cudaSuccess;
-    route_unpermute_kernel<<<148 * 8, 256, 0, st>>>(ans_sorted, send_pos, n, ans_by_pos);
     return cudaGetLastError();
 }
 

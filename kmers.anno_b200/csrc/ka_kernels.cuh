@@ -41,9 +41,11 @@ struct AnnotParams {
     uint32_t* dbg;                    // KA_DEBUG builds: [0] OR of the codes of failed bounds checks
     // routed mode (table_mode 2): the tile kernel either only EXTRACTS the mixed key of every window
     // position into route_keys[chunk-relative residue index] (ROUTE_INVALID = no window), or TALLIES
-    // from route_ans[same index] = (role << 32 | de-dup token) answered by the owning GPU.
+    // from route_ans[route_slot[same index]] = (role << 32 | de-dup token) answered by the owning GPU
+    // (route_slot = the send slot the key was bucketed into; answers come back in send order).
     unsigned long long* route_keys;
     const unsigned long long* route_ans;
+    const uint32_t* route_slot;
 };
 
 // tile kernel shapes (option "variant"): 0 = 4 window positions per thread x 128 threads
@@ -70,16 +72,13 @@ cudaError_t tile_kernel_mode_set_smem(size_t bytes);
 // per-owner counts of the valid keys of keys[0..n) (owner = sector >> shard_shift); counts[8] accumulates
 cudaError_t launch_route_count(const unsigned long long* keys, unsigned long long n, TableView tab,
                                unsigned long long* counts, cudaStream_t st);
-// bucket the valid keys by owner: send_keys/send_pos at offsets[o] + running cursor[o]
+// bucket the valid keys by owner: send_keys at offsets[o] + running cursor[o]; slot_of_pos[i] = that index
 cudaError_t launch_route_scatter(const unsigned long long* keys, unsigned long long n, TableView tab,
                                  const unsigned long long* offsets, unsigned long long* cursor,
-                                 unsigned long long* send_keys, uint32_t* send_pos, cudaStream_t st);
+                                 unsigned long long* send_keys, uint32_t* slot_of_pos, cudaStream_t st);
 // owner side: answer every received key from the local shard
 cudaError_t launch_route_lookup(const unsigned long long* keys, unsigned long long n, TableView tab,
                                 unsigned long long* ans, cudaStream_t st);
-// requester side: ans_by_pos[send_pos[i]] = ans_sorted[i]
-cudaError_t launch_route_unpermute(const unsigned long long* ans_sorted, const uint32_t* send_pos,
-                                   unsigned long long n, unsigned long long* ans_by_pos, cudaStream_t st);
 
 cudaError_t launch_plan(const AnnotParams& p, cudaStream_t st);
 cudaError_t launch_tiles(const AnnotParams& p, int variant, size_t smem, cudaStream_t st);
