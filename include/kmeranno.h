@@ -81,7 +81,7 @@ const char* ka_last_error(const ka_engine* e);
  *                   over the engine's 2/4/8 devices, probes load remote sectors through NVLink
  *                   peer memory inside the probe kernel (for tables beyond one GPU); 2 = same sharding,
  *                   but the k-mer keys are ROUTED: NCCL send/recv all-to-all of 8-byte keys to the
- *                   owning GPU, local probe there, 8-byte answers back in request order (sequences
+ *                   owning GPU, local probe there, 8-byte answers back in request order, rounds pipelined (sequences
  *                   longer than mid_seq are rejected in this mode)  (next ka_db_load)
  *   "filter"        per-sector presence signatures kept in L2 (1 on, 0 off (default), -1 = on for
  *                   tables of at least 2^20 sectors)   (next ka_db_load)
