@@ -33,16 +33,53 @@ def case(draw):
     kmers = draw(st.lists(st.sampled_from(windows), min_size=1, max_size=40))
     roles = draw(st.lists(st.integers(0, 5), min_size=len(kmers), max_size=len(kmers)))
     min_hits = draw(st.integers(1, 4))
-    return K, seqs, kmers, roles, min_hits
+    wide = draw(st.integers(0, 1))          # narrow / wide-table kernels
+    return K, seqs, kmers, roles, min_hits, wide
 
 
 @settings(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
 @given(case())
 def test_engine_equals_python_statement(engine, c):
-    K, seqs, kmers, roles, min_hits = c
+    K, seqs, kmers, roles, min_hits, wide = c
     res, off = csr(seqs)
+    engine.set_option("wide", wide)
     engine.db_load(kmers, np.asarray(roles, np.int32), K)
     got = engine.annotate(res, off, min_hits)
     want = py_apply(seqs, kmers, roles, K, min_hits)
     for g, w in zip(got, want):
         assert np.array_equal(g, w), (K, seqs, kmers, roles, min_hits, g.tolist(), w.tolist())
+
+
+@st.composite
+def distance_case(draw):
+    K = draw(st.integers(1, 12))
+    n_sym = draw(st.integers(1, 31))
+    alphabet = draw(st.lists(st.integers(0, 255), min_size=n_sym, max_size=n_sym, unique=True))
+    sym = st.sampled_from(alphabet)
+    motifs = draw(st.lists(st.lists(sym, min_size=K, max_size=K + 8).map(bytes), min_size=1, max_size=5))
+    piece = st.one_of(st.sampled_from(motifs), st.lists(sym, max_size=15).map(bytes))
+    seqs = draw(st.lists(st.lists(piece, max_size=8).map(b"".join), min_size=1, max_size=12))
+    n = len(seqs)
+    groups = draw(st.lists(st.tuples(st.integers(0, n - 1), st.lists(st.integers(0, n - 1), max_size=6)), max_size=8))
+    return K, seqs, groups
+
+
+@settings(max_examples=100, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@given(distance_case())
+def test_distance_equals_python_sets(engine, c):
+    """ka_kmer_distance against Python sets (GeneCopyProcessor.java:137-142, recalled ProteinKmers.distance)."""
+    K, seqs, groups = c
+    res, off = csr(seqs)
+    q = np.asarray([g[0] for g in groups], np.uint32)
+    cs = np.asarray([x for g in groups for x in g[1]], np.uint32)
+    go = np.concatenate([[0], np.cumsum([len(g[1]) for g in groups])]).astype(np.uint64)
+    size, common, dist = engine.kmer_distance(res, off, K, q, go, cs)
+    sets = [{s[i:i + K] for i in range(len(s) - K + 1)} for s in seqs]
+    assert [int(x) for x in size] == [len(t) for t in sets]
+    m = 0
+    for g in groups:
+        for x in g[1]:
+            a, b = sets[g[0]], sets[x]
+            sim = len(a & b)
+            assert common[m] == sim and dist[m] == (1.0 if sim == 0 else 1.0 - sim / ((len(a) + len(b)) - sim)), (K, seqs, groups)
+            m += 1
