@@ -93,7 +93,7 @@ const char* ka_last_error(const ka_engine* e);
  *   "slot_bits"     force the table slot width (32, 64, 128; 0 = smallest that fits, default)
  *   "variant"       tile kernel shape: 0 = 4 positions x 128 threads (default), 1 = 4 x 256, 2 = 8 x 256,
  *                   3 = 2 x 128 (48 registers, 10 CTAs/SM)
- *   "chunk_residues" residues per pipelined H2D chunk, default 32 Mi
+ *   "chunk_residues" residues per pipelined H2D chunk, default 48 Mi (4 chunks in flight per device)
  *   "l2_persist"    1 = set an L2 persisting access-policy window on the table (default 1)
  */
 int ka_set_option(ka_engine* e, const char* name, double value);

@@ -28,7 +28,7 @@ using namespace ka;
 
 namespace {
 
-constexpr int NPIPE = 3;  // chunks in flight per device
+constexpr int NPIPE = 4;  // chunks in flight per device
 
 thread_local std::string g_create_error;
 
@@ -94,7 +94,7 @@ struct ka_engine {
     uint32_t long_seq = 2048;
     uint32_t mid_seq = 8192;
     int mid_variant = 1;
-    uint64_t chunk_residues = 32ull << 20;
+    uint64_t chunk_residues = 48ull << 20;
     int l2_persist = 1;
     int variant = 0;
     int slot_bits = 0;  // 0 = choose automatically

@@ -16,7 +16,7 @@ eng = ka.Engine([0]); eng.db_load(kmers, roles, 8)
 t = time.perf_counter(); b = eng.upload(res, off); dt = time.perf_counter() - t
 print(f"upload (sync cudaMemcpy from pinned) {len(res)/dt/1e9:.1f} GB/s", flush=True)
 eng.annotate_resident(b, 5); eng.annotate_resident(b, 5); print("resident kernel ms", eng.stats()["kernel_ms"], flush=True); b.free()
-for chunk in (4 << 20, 16 << 20, 32 << 20, 64 << 20, 256 << 20):
+for chunk in (16 << 20, 32 << 20, 48 << 20, 64 << 20, 96 << 20):
     eng.set_option("chunk_residues", chunk)
     best = 1e9
     for r in range(4):
