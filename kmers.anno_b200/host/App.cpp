@@ -1,5 +1,5 @@
 // App.cpp — command dispatch, mirror of proteins/kmers/anno/App.java:51-84 for the verbs of the
-// GPU hot path.  `build` and `apply` run on the engine; the reference's other verbs are outside the
+// GPU hot path.  `build`, `apply` and `genes` run on the engine; the reference's other verbs are outside the
 // scope of this engine and are reported as such.
 #include <iostream>
 #include <string>
@@ -7,12 +7,14 @@
 
 #include "ApplyKmerProcessor.hpp"
 #include "BuildKmerProcessor.hpp"
+#include "GeneCopyProcessor.hpp"
 
 using namespace theseed;
 
 static const char* kCommands[][2] = {
     {"build", "build a discriminating-kmer database from annotated genomes (GPU engine)"},
     {"apply", "apply a discriminating-kmer database to genomes (GPU engine)"},
+    {"genes", "copy aliases between close genomes using protein kmer distance (GPU engine)"},
 };
 
 static void showCommands() {
@@ -31,6 +33,11 @@ int main(int argc, char** argv) {
     }
     if (command == "build") {
         BuildKmerProcessor processor;                          // App.java:61
+        if (!processor.parseCommand(newArgs)) return 1;
+        return processor.run();
+    }
+    if (command == "genes") {
+        GeneCopyProcessor processor;                           // App.java:71
         if (!processor.parseCommand(newArgs)) return 1;
         return processor.run();
     }

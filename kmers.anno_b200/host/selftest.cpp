@@ -2,6 +2,8 @@
 // readers and the two reporters, driven by files named on the command line.
 //   kmers-anno-selftest <genome file> <roles.in.use> <VERIFY|APPLY> [calls.tsv]
 // calls.tsv: peg index <TAB> role <TAB> hits (the calls to replay through recordFeature).
+//   kmers-anno-selftest --json in.json out.json     parse and re-serialise a JSON document (JsonDoc.hpp)
+//   kmers-anno-selftest --norm "function text"      print the normalised function (GeneCopyProcessor.hpp)
 #include <fstream>
 #include <iostream>
 #include <map>
@@ -9,10 +11,19 @@
 
 #include "ApplyKmerReporter.hpp"
 #include "Genome.hpp"
+#include "GeneCopyProcessor.hpp"
+#include "JsonDoc.hpp"
 
 using namespace theseed;
 
 int main(int argc, char** argv) {
+    if (argc == 4 && std::string(argv[1]) == "--json") {
+        try {
+            std::ofstream(argv[3], std::ios::binary) << JsonValue::parse(readFile(argv[2])).dump();
+            return 0;
+        } catch (const std::exception& e) { std::cerr << "ERROR: " << e.what() << "\n"; return 1; }
+    }
+    if (argc == 3 && std::string(argv[1]) == "--norm") { std::cout << normalizeFunction(argv[2]) << "\n"; return 0; }
     if (argc < 4) { std::cerr << "usage: kmers-anno-selftest genome roles VERIFY|APPLY [calls.tsv]\n"; return 2; }
     try {
         Genome genome(argv[1]);

@@ -86,3 +86,81 @@ def test_build_verb_then_apply(tmp_path):
     db.write_text(r.stdout)
     _, err = run([str(db), ROLES, str(gdir)])
     assert "Kmer size is 10." in err
+
+
+def test_genes_copies_aliases_of_the_closest_feature(tmp_path):
+    """`genes` end to end (GeneCopyProcessor.java:110-166): the target pegs get the aliases of the
+    closest same-function source peg within maxDist; expectation from the oracle's distances."""
+    import json
+    import numpy as np
+    import oracle
+    from cases import csr
+    rng = np.random.default_rng(12)
+    gid, pegs = load_small()
+    pegs = pegs[:120]
+
+    def mutate(p, rate):
+        a = bytearray(p.encode())
+        for i in range(len(a)):
+            if rng.random() < rate:
+                a[i] = b"ACDEFGHIKLMNPQRSTVWY"[int(rng.integers(20))]
+        return a.decode()
+
+    src_feats, tgt_feats = [], []
+    for i, (fid, fun, prot) in enumerate(pegs):
+        fun = fun if i % 5 else "hypothetical protein"              # a function shared by many pegs
+        f = {"id": fid, "type": "CDS", "function": fun + (" # src note" if i % 3 == 0 else ""), "protein_translation": prot}
+        if i % 4 != 3:
+            f["alias_pairs"] = [["gene_name", f"gen{i}"], ["locus_tag", f"b{i:04d}"], ["gene_name", f"alt{i}"]]
+        src_feats.append(f)
+        rate = [0.0, 0.02, 0.08, 0.5][i % 4]
+        t = {"id": fid.replace(gid, "9.9"), "type": "CDS", "function": fun.upper() if i % 2 else fun,
+             "protein_translation": mutate(prot, rate)}
+        if i % 10 == 0:
+            t["alias_pairs"] = [["locus_tag", f"b{i:04d}"]]         # already has one of the aliases
+        tgt_feats.append(t)
+    src_feats.append({"id": f"fig|{gid}.rna.1", "type": "rna", "function": "tRNA", "alias_pairs": [["gene_name", "rrn"]]})
+    json.dump({"id": gid, "scientific_name": "source", "features": src_feats}, open(tmp_path / "s.gto", "w"))
+    open(tmp_path / "t.gto", "w").write(json.dumps({"id": "9.9", "scientific_name": "target", "features": tgt_feats,
+                                                     "extra": {"keep": [1, 2.5]}}).replace("2.5]", "2.50]"))
+
+    def norm(s):
+        s = s.split(" #")[0]
+        return " ".join("".join(c.lower() if c.isalnum() else " " for c in s).split())
+
+    for K, max_dist in ((8, 0.5), (10, 0.2)):
+        out_file = tmp_path / f"o{K}.gto"
+        r = subprocess.run([CLI, "genes", "-K", str(K), "-m", str(max_dist), str(tmp_path / "s.gto"), str(tmp_path / "t.gto"),
+                            str(out_file)], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out = json.load(open(out_file))
+        assert out["extra"] == {"keep": [1, 2.5]} and "2.50" in open(out_file).read()
+        # expectation: same normalised function, closest within max_dist, later candidate wins ties
+        by_fun = {}
+        for f in src_feats:
+            if ".peg." in f["id"] and f.get("alias_pairs"):
+                by_fun.setdefault(norm(f["function"]), []).append(f)
+        updates = 0
+        for t_in, t_out in zip(tgt_feats, out["features"]):
+            cands = by_fun.get(norm(t_in["function"]), [])
+            want = [list(p) for p in t_in.get("alias_pairs", [])]
+            if cands:
+                seqs = [t_in["protein_translation"].encode()] + [c["protein_translation"].encode() for c in cands]
+                res, off = csr(seqs)
+                _, _, _, dist = oracle.kmer_distance_pairs(res, off, np.zeros(len(cands), np.uint32),
+                                                           np.arange(1, len(cands) + 1, dtype=np.uint32), K)
+                found, fdist = None, max_dist
+                for c, d in zip(cands, dist):
+                    if d <= fdist:
+                        fdist, found = d, c
+                if found is not None:
+                    updates += 1
+                    amap = {}
+                    for ty, al in found["alias_pairs"]:
+                        amap.setdefault(ty, set()).add(al)
+                    for ty in sorted(amap):
+                        for al in sorted(amap[ty]):
+                            if [ty, al] not in want:
+                                want.append([ty, al])
+            assert t_out.get("alias_pairs", []) == want, t_in["id"]
+        assert f"with {updates} updates" in r.stderr and updates > 20

@@ -182,3 +182,52 @@ def test_two_rank_gloo_sharding(tmp_path):
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "SHARDED_OK 2 600" in r.stdout
+
+
+def test_json_document_round_trip(tmp_path):
+    """JsonDoc (the GTO document the `genes` command rewrites): parse + serialise keeps every value,
+    member order and number text."""
+    gid, pegs = load_small()
+    src = tmp_path / "in.json"
+    write_gto(str(src), gid, pegs[:40])
+    doc = json.load(open(src))
+    doc["odd"] = {"esc": "tab\t quote\" back\\ nl\n unié中 \U0001F600 ctl\x01", "nums": [0, -1, 1.5e9, 2.5E-3, 1e+2],
+                  "empty": [{}, [], ""], "null": None, "bools": [True, False]}
+    json.dump(doc, open(src, "w"), indent=2, ensure_ascii=True)      # \uXXXX escapes incl. a surrogate pair
+    st = os.path.join(BIN, "kmers-anno-selftest")
+    out = tmp_path / "out.json"
+    r = subprocess.run([st, "--json", str(src), str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    back = json.load(open(out, encoding="utf-8"))
+    assert back == doc and list(back.keys()) == list(doc.keys())
+    assert "1500000000.0" in open(out, encoding="utf-8").read()      # number text is kept as written
+    bad = tmp_path / "bad.json"
+    bad.write_text('{"a": [1, 2}')
+    r = subprocess.run([st, "--json", str(bad), str(out)], capture_output=True, text=True)
+    assert r.returncode == 1 and "JSON error" in r.stderr
+
+
+def test_genes_cli_validation_and_no_candidates(tmp_path):
+    """`genes` (GeneCopyProcessor.java:88-108): option checks and messages; a source genome without
+    aliases gives no candidates, no engine call, and the target comes back unchanged."""
+    cli = os.path.join(BIN, "kmers-anno")
+    st = os.path.join(BIN, "kmers-anno-selftest")
+    r = subprocess.run([cli, "genes", "-m", "1.5", "a", "b", "c"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Distance must be between 0 and 1." in r.stderr
+    r = subprocess.run([cli, "genes", "-K", "1", "a", "b", "c"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Kmer size must be at least 2." in r.stderr
+    r = subprocess.run([cli, "genes", "a", "b", "c"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Input genome file a not found or unreadable." in r.stderr
+    r = subprocess.run([cli, "genes", "a", "b"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Three arguments are required" in r.stderr
+    gid, pegs = load_small()
+    write_gto(str(tmp_path / "s.gto"), gid, pegs[:30])
+    write_gto(str(tmp_path / "t.gto"), "9.9", [(f.replace(gid, "9.9"), fun, p) for f, fun, p in pegs[:30]])
+    r = subprocess.run([cli, "genes", str(tmp_path / "s.gto"), str(tmp_path / "t.gto"), str(tmp_path / "o.gto")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "0 features with aliases, 0 functions found." in r.stderr and "with 0 updates" in r.stderr
+    assert json.load(open(tmp_path / "o.gto")) == json.load(open(tmp_path / "t.gto"))
+    norm = lambda s: subprocess.run([st, "--norm", s], capture_output=True, text=True).stdout.rstrip("\n")
+    assert norm("DNA polymerase III  alpha subunit (EC 2.7.7.7) # frameshift") == "dna polymerase iii alpha subunit ec 2 7 7 7"
+    assert norm("Hypothetical protein ! truncated") == norm("hypothetical  PROTEIN")
