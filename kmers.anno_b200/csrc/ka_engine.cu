@@ -1511,10 +1511,22 @@ int ka_kmer_distance(ka_engine* e, const uint8_t* residues, const uint64_t* offs
     for (uint64_t m = 0; m < M; m++)
         if (cand_seq[m] >= N) return fail(e, KA_ERR_INVALID, "ka_kmer_distance: candidate %llu names sequence %u of %llu", (unsigned long long)m, cand_seq[m], (unsigned long long)N);
 
-    // hash-set placement: shared memory up to 8192 entries (64 KB), a global slice beyond
+    // hash-set placement: shared memory for the common lengths, a global slice beyond
     auto windows = [&](uint64_t i) { uint64_t L = offsets[i + 1] - offsets[i]; return (uint32_t)(L >= (uint64_t)K ? L - K + 1 : 0); };
+    // shared-memory set size: the smallest power of two that holds the set of 90 % of the sequences
+    // (at most 8192 entries = 64 KB); the long tail uses global slices, the common case keeps
+    // many CTAs per SM
     uint32_t smem_cap = 64;
-    for (uint64_t i = 0; i < N; i++) { uint32_t c = dist_set_cap(windows(i)); if (c <= 8192 && c > smem_cap) smem_cap = c; }
+    {
+        uint64_t by_cap[32] = {0};
+        for (uint64_t i = 0; i < N; i++) { uint32_t c = dist_set_cap(windows(i)); int b = 0; while ((1u << b) < c) b++; by_cap[b]++; }
+        uint64_t seen = 0;
+        for (int b = 6; b <= 13; b++) {
+            seen += by_cap[b];
+            smem_cap = 1u << b;
+            if (seen * 10 >= N * 9) break;
+        }
+    }
     std::vector<unsigned long long> seq_scratch(N, 0), query_scratch(Q ? Q : 1, 0);
     uint64_t need_seq = 0, need_query = 0;
     for (uint64_t i = 0; i < N; i++) { uint32_t c = dist_set_cap(windows(i)); if (c > smem_cap) { seq_scratch[i] = need_seq; need_seq += c; } }
