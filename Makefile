@@ -16,8 +16,10 @@ SELFTEST  := $(PKG)/bin/kmers-anno-selftest
 
 all: $(LIB) $(SYNTH) $(ORACLE) $(CLI) $(SELFTEST)
 
-$(LIB): $(CSRC)/ka_kernels.cu $(CSRC)/ka_distance.cu $(CSRC)/ka_engine.cu $(CSRC)/ka_common.cuh $(CSRC)/ka_kernels.cuh include/kmeranno.h
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/ka_kernels.cu $(CSRC)/ka_distance.cu $(CSRC)/ka_engine.cu -ldl 2> $(PKG)/ptxas.log || (cat $(PKG)/ptxas.log; exit 1)
+CUSRC     := $(CSRC)/ka_kernels.cu $(CSRC)/ka_distance.cu $(CSRC)/ka_engine.cu $(CSRC)/ka_table.cu $(CSRC)/ka_route.cu $(CSRC)/ka_build_api.cu
+
+$(LIB): $(CUSRC) $(CSRC)/ka_common.cuh $(CSRC)/ka_kernels.cuh $(CSRC)/ka_engine_internal.cuh include/kmeranno.h
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(CUSRC) -ldl 2> $(PKG)/ptxas.log || (cat $(PKG)/ptxas.log; exit 1)
 	@grep -E "error|warning|spill|registers" $(PKG)/ptxas.log | grep -v "0 bytes spill" | head -40 || true
 
 $(SYNTH): $(HOST)/ka_synth.cpp

@@ -18,7 +18,7 @@
 //                     the hits = |A ∩ B|; lane 0 writes it and the distance.
 // Integer work in shared memory; the only floating-point operation is the final IEEE double
 // division / subtraction, which equals the Java expression bit for bit.
-#include "ka_kernels.cuh"
+#include "ka_engine_internal.cuh"
 
 namespace ka {
 
@@ -193,3 +193,179 @@ cudaError_t launch_common(const DistParams& p, int sm_count, cudaStream_t st) {
 }
 
 }  // namespace ka
+
+// ======================================================================================
+// C ABI
+// ======================================================================================
+using namespace ka;
+using namespace kai;
+
+extern "C" {
+
+// Pairwise k-mer distance for query groups (GeneCopyProcessor.java:137-142); see include/kmeranno.h.
+int ka_kmer_distance(ka_engine* e, const uint8_t* residues, const uint64_t* offsets, uint64_t N, int K,
+                     const uint32_t* query_seq, const uint64_t* group_offsets, uint64_t Q,
+                     const uint32_t* cand_seq, int32_t* out_set_size, int32_t* out_common, double* out_distance) {
+    if (!e) return KA_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (K < 1 || K > KMAX) return fail(e, KA_ERR_K, "K = %d: this engine packs 5 bits per residue, K must be 1..%d", K, KMAX);
+    if (N == 0) return Q ? fail(e, KA_ERR_INVALID, "ka_kmer_distance: queries over an empty batch") : (int)KA_OK;
+    if (!offsets || (Q && (!query_seq || !group_offsets))) return fail(e, KA_ERR_INVALID, "ka_kmer_distance: NULL argument");
+    if (N > 0xfffffff0ull || Q > 0xfffffff0ull) return fail(e, KA_ERR_TOO_BIG, "ka_kmer_distance: too many sequences or queries");
+    const uint64_t base = offsets[0];
+    for (uint64_t i = 0; i < N; i++) {
+        if (offsets[i + 1] < offsets[i]) return fail(e, KA_ERR_OFFSETS, "ka_kmer_distance: offsets are not monotone");
+        if (offsets[i + 1] - offsets[i] > 0x3fffffffull) return fail(e, KA_ERR_TOO_BIG, "ka_kmer_distance: a sequence exceeds 2^30 residues");
+    }
+    const uint64_t n_res = offsets[N] - base;
+    if (n_res && !residues) return fail(e, KA_ERR_INVALID, "ka_kmer_distance: residues is NULL");
+    const uint64_t M = Q ? group_offsets[Q] : 0;
+    if (Q && group_offsets[0] != 0) return fail(e, KA_ERR_OFFSETS, "ka_kmer_distance: group_offsets must start at 0");
+    for (uint64_t q = 0; q < Q; q++) {
+        if (group_offsets[q + 1] < group_offsets[q]) return fail(e, KA_ERR_OFFSETS, "ka_kmer_distance: group_offsets are not monotone");
+        if (group_offsets[q + 1] - group_offsets[q] > 0xfffffff0ull) return fail(e, KA_ERR_TOO_BIG, "ka_kmer_distance: a query has too many candidates");
+        if (query_seq[q] >= N) return fail(e, KA_ERR_INVALID, "ka_kmer_distance: query %llu names sequence %u of %llu", (unsigned long long)q, query_seq[q], (unsigned long long)N);
+    }
+    if (M && (!cand_seq || !out_common || !out_distance)) return fail(e, KA_ERR_INVALID, "ka_kmer_distance: NULL argument");
+    for (uint64_t m = 0; m < M; m++)
+        if (cand_seq[m] >= N) return fail(e, KA_ERR_INVALID, "ka_kmer_distance: candidate %llu names sequence %u of %llu", (unsigned long long)m, cand_seq[m], (unsigned long long)N);
+
+    // hash-set placement: shared memory for the common lengths, a global slice beyond
+    auto windows = [&](uint64_t i) { uint64_t L = offsets[i + 1] - offsets[i]; return (uint32_t)(L >= (uint64_t)K ? L - K + 1 : 0); };
+    // shared-memory set size: the smallest power of two that holds the set of 90 % of the sequences
+    // (at most 8192 entries = 64 KB); the long tail uses global slices, the common case keeps
+    // many CTAs per SM
+    uint32_t smem_cap = 64;
+    {
+        uint64_t by_cap[32] = {0};
+        for (uint64_t i = 0; i < N; i++) { uint32_t c = dist_set_cap(windows(i)); int b = 0; while ((1u << b) < c) b++; by_cap[b]++; }
+        uint64_t seen = 0;
+        for (int b = 6; b <= 13; b++) {
+            seen += by_cap[b];
+            smem_cap = 1u << b;
+            if (seen * 10 >= N * 9) break;
+        }
+    }
+    std::vector<unsigned long long> seq_scratch(N, 0), query_scratch(Q ? Q : 1, 0);
+    uint64_t need_seq = 0, need_query = 0;
+    for (uint64_t i = 0; i < N; i++) { uint32_t c = dist_set_cap(windows(i)); if (c > smem_cap) { seq_scratch[i] = need_seq; need_seq += c; } }
+    for (uint64_t q = 0; q < Q; q++) { uint32_t c = dist_set_cap(windows(query_seq[q])); if (c > smem_cap) { query_scratch[q] = need_query; need_query += c; } }
+    const uint64_t n_scratch = std::max<uint64_t>(std::max(need_seq, need_query), 1);
+
+    // work-balanced contiguous query ranges, one per device (work = residues streamed)
+    const size_t nd = e->devs.size();
+    std::vector<uint64_t> cut(nd + 1, 0);
+    {
+        std::vector<uint64_t> work(Q + 1, 0);
+        for (uint64_t q = 0; q < Q; q++) {
+            uint64_t w = offsets[query_seq[q] + 1] - offsets[query_seq[q]] + 64;
+            for (uint64_t m = group_offsets[q]; m < group_offsets[q + 1]; m++) w += offsets[cand_seq[m] + 1] - offsets[cand_seq[m]] + 16;
+            work[q + 1] = work[q] + w;
+        }
+        cut[nd] = Q;
+        for (size_t i = 1; i < nd; i++)
+            cut[i] = std::max<uint64_t>(cut[i - 1], std::lower_bound(work.begin(), work.end(), work[Q] / nd * i) - work.begin());
+    }
+
+    auto t0 = std::chrono::steady_clock::now();
+    e->stats = ka_stats{};
+    int rc = for_each_device(e, [&](Device& d, int i) {
+        const uint64_t qa = cut[i], qb = cut[i + 1];
+        d.kernel_ms = d.tile_ms = 0; d.launches = 0; d.h2d = d.d2h = 0; d.probes = 0;
+        if (i != 0 && qa == qb) return (int)KA_OK;          // device 0 always reports the set sizes
+        DCK(d, cudaSetDevice(d.id));
+        cudaStream_t st = d.pipe[0].st;
+        Pipe& p = d.pipe[0];
+        std::vector<void*> owned;
+        auto alloc = [&](size_t bytes) -> void* {
+            void* q = nullptr;
+            if (cudaMalloc(&q, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            owned.push_back(q);
+            return q;
+        };
+        auto finish = [&](int code, const char* what, cudaError_t ce) {
+            for (void* q : owned) cudaFree(q);
+            return code == KA_OK ? (int)KA_OK : dev_fail(d, code, what, ce);
+        };
+        DistParams dp{};
+        uint8_t* d_res = (uint8_t*)alloc(n_res + K + 64);
+        unsigned long long* d_off = (unsigned long long*)alloc((N + 1) * 8);
+        uint32_t* d_qs = (uint32_t*)alloc(Q * 4);
+        unsigned long long* d_go = (unsigned long long*)alloc((Q + 1) * 8);
+        uint32_t* d_cs = (uint32_t*)alloc(M * 4);
+        int32_t* d_size = (int32_t*)alloc(N * 4);
+        int32_t* d_common = (int32_t*)alloc(M * 4);
+        double* d_dist = (double*)alloc(M * 8);
+        unsigned long long* d_sk = (unsigned long long*)alloc(n_scratch * 8);
+        uint8_t* d_uniq = (uint8_t*)alloc(n_res + 64);
+        unsigned long long* d_ss = (unsigned long long*)alloc(N * 8);
+        unsigned long long* d_qsc = (unsigned long long*)alloc((Q ? Q : 1) * 8);
+        if (!d_res || !d_off || !d_qs || !d_go || !d_cs || !d_size || !d_common || !d_dist || !d_sk || !d_uniq || !d_ss || !d_qsc)
+            return finish(KA_ERR_OOM, "ka_kmer_distance: device allocation", cudaErrorMemoryAllocation);
+        cudaError_t ce = cudaSuccess;
+        auto step = [&](cudaError_t c) { if (ce == cudaSuccess) ce = c; };
+        if (n_res) step(cudaMemcpyAsync(d_res, residues + base, n_res, cudaMemcpyHostToDevice, st));
+        step(cudaMemcpyAsync(d_off, offsets, (N + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (Q) step(cudaMemcpyAsync(d_qs, query_seq, Q * 4, cudaMemcpyHostToDevice, st));
+        if (Q) step(cudaMemcpyAsync(d_go, group_offsets, (Q + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (M) step(cudaMemcpyAsync(d_cs, cand_seq, M * 4, cudaMemcpyHostToDevice, st));
+        step(cudaMemcpyAsync(d_ss, seq_scratch.data(), N * 8, cudaMemcpyHostToDevice, st));
+        if (Q) step(cudaMemcpyAsync(d_qsc, query_scratch.data(), Q * 8, cudaMemcpyHostToDevice, st));
+        // alphabet of the batch (at most 31 distinct bytes), scanned from the device copy
+        uint8_t* d_lut = (uint8_t*)alloc(256);             // not d.lut: that one belongs to the loaded DB
+        uint32_t* d_bm = (uint32_t*)alloc(32);
+        if (!d_lut || !d_bm) return finish(KA_ERR_OOM, "ka_kmer_distance: device allocation", cudaErrorMemoryAllocation);
+        uint32_t bitmap[8] = {0};
+        step(cudaMemsetAsync(d_bm, 0, 32, st));
+        step(launch_alphabet_scan(d_res, n_res, d_bm, st));
+        step(cudaMemcpyAsync(bitmap, d_bm, 32, cudaMemcpyDeviceToHost, st));
+        step(cudaStreamSynchronize(st));
+        if (ce != cudaSuccess) return finish(KA_ERR_CUDA, "ka_kmer_distance: alphabet scan", ce);
+        uint8_t lut[256];
+        memset(lut, 0, 256);
+        int nsym = 0;
+        for (int b = 0; b < 256; b++)
+            if (bitmap[b >> 5] & (1u << (b & 31))) { nsym++; if (nsym <= 31) lut[b] = (uint8_t)nsym; }
+        if (nsym > 31) {
+            for (void* q : owned) cudaFree(q);
+            d.err = KA_ERR_ALPHABET;
+            d.errmsg = "ka_kmer_distance: the proteins use " + std::to_string(nsym) + " distinct residue bytes; at most 31 fit the 5-bit packing";
+            return (int)KA_ERR_ALPHABET;
+        }
+        step(cudaMemcpyAsync(d_lut, lut, 256, cudaMemcpyHostToDevice, st));
+        d.h2d = n_res + (N + 1) * 8 + Q * 4 + (Q + 1) * 8 + M * 4 + N * 8 + Q * 8;
+        step(dist_set_smem(dist_smem_bytes(8192)));
+        dp.res = d_res; dp.off = d_off; dp.base = base; dp.n_seq = (uint32_t)N; dp.K = K; dp.key_mask = (1ull << (5 * K)) - 1; dp.lut = d_lut;
+        dp.set_size = d_size; dp.query_seq = d_qs; dp.group_off = d_go; dp.q_begin = (uint32_t)qa; dp.q_end = (uint32_t)qb;
+        dp.cand_seq = d_cs; dp.common = d_common; dp.dist = d_dist; dp.smem_cap = smem_cap;
+        dp.scratch_keys = d_sk; dp.uniq = d_uniq; dp.seq_scratch = d_ss; dp.query_scratch = d_qsc;
+        step(cudaEventRecord(p.ev_k0, st));
+        step(launch_set_size(dp, d.sm_count, st));
+        step(launch_common(dp, d.sm_count, st));
+        step(cudaEventRecord(p.ev_k1, st));
+        d.launches = 2;
+        const uint64_t ma = Q ? group_offsets[qa] : 0, mb = Q ? group_offsets[qb] : 0;
+        if (i == 0 && out_set_size) step(cudaMemcpyAsync(out_set_size, d_size, N * 4, cudaMemcpyDeviceToHost, st));
+        if (mb > ma) {
+            step(cudaMemcpyAsync(out_common + ma, d_common + ma, (mb - ma) * 4, cudaMemcpyDeviceToHost, st));
+            step(cudaMemcpyAsync(out_distance + ma, d_dist + ma, (mb - ma) * 8, cudaMemcpyDeviceToHost, st));
+        }
+        d.d2h = (i == 0 && out_set_size ? N * 4 : 0) + (mb - ma) * 12;
+        step(cudaStreamSynchronize(st));
+        if (ce != cudaSuccess) return finish(KA_ERR_CUDA, "ka_kmer_distance", ce);
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, p.ev_k0, p.ev_k1) == cudaSuccess) d.kernel_ms = ms;
+        return finish(KA_OK, "", cudaSuccess);
+    });
+    if (rc) return rc;
+    ka_stats& s = e->stats;
+    s.sequences = N; s.residues = n_res;
+    for (Device& d : e->devs) {
+        s.kernel_launches += d.launches; s.h2d_bytes += d.h2d; s.d2h_bytes += d.d2h;
+        s.kernel_ms = std::max(s.kernel_ms, d.kernel_ms);
+    }
+    s.wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return KA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,229 @@
+// ka_engine_internal.cuh — types and helpers shared by the engine's translation units
+// (ka_engine.cu: lifetime, options, annotate pipeline; ka_table.cu: table geometry and build;
+// ka_route.cu: NCCL-routed sharded table; ka_build_api.cu: ka_build; ka_distance.cu: ka_kmer_distance).
+// Nothing here is part of the C ABI.
+#pragma once
+#include <algorithm>
+#include <array>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <dlfcn.h>
+#include <nccl.h>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/kmeranno.h"
+#include "ka_kernels.cuh"
+
+
+namespace kai {
+
+using namespace ka;
+
+constexpr int NPIPE = 4;  // chunks in flight per device
+
+struct Pipe {
+    cudaStream_t st = nullptr;
+    uint8_t* res = nullptr; size_t res_cap = 0;
+    unsigned long long* off = nullptr; size_t seq_cap = 0;
+    uint4* first = nullptr; size_t first_cap = 0;
+    int32_t* role = nullptr; int32_t* hits = nullptr; uint8_t* flag = nullptr;
+    uint32_t* ctr = nullptr;  // 16 bytes: [0] big_count, [2..3] token cursor (u64)
+    BigItem* big = nullptr; size_t big_cap = 0;
+    uint4* mid = nullptr; size_t mid_cap = 0;
+    uint32_t* scratch = nullptr; size_t scratch_cap = 0;
+    cudaEvent_t ev_k0 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_k1 = nullptr, done = nullptr;
+    bool busy = false;
+};
+
+struct Device {
+    int id = 0;
+    int sm_count = 148;
+    uint4* table = nullptr;
+    uint4* ovf = nullptr;     // overflow table (cls 32/64)
+    uint16_t* sig = nullptr;  // per-sector presence signatures
+    const uint4** shard_sectors = nullptr;  // sharded mode: device array of peer pointers, one per shard
+    const uint4** shard_ovf = nullptr;
+    // routed mode (table_mode 2)
+    ncclComm_t comm = nullptr;
+    struct RouteLane {   // buffers of one round in flight (two lanes alternate, see annotate_routed_range)
+        unsigned long long *r_keys = nullptr, *r_send = nullptr, *r_recv = nullptr, *r_ans_recv = nullptr,
+                           *r_ans_sorted = nullptr, *r_small = nullptr;  // r_small: 8 counts, 8 offsets, 8 cursors
+        uint32_t* r_pos = nullptr;             // send slot of every residue position
+        size_t r_cap_pos = 0, r_cap_recv = 0;
+        unsigned long long* h_cnt = nullptr;   // pinned: per-owner key counts of the round
+        cudaEvent_t ev_counts = nullptr;
+    } lane[2];
+    cudaEvent_t ev_route0 = nullptr, ev_route1 = nullptr;
+    uint8_t* lut = nullptr;
+    Pipe pipe[NPIPE];
+    size_t smem_set = 0;   // opt-in shared-memory limit once the tile kernels are configured
+    bool route_smem_set = false;
+    // per-call accounting
+    double kernel_ms = 0, tile_ms = 0;
+    uint64_t launches = 0, h2d = 0, d2h = 0, probes = 0;
+    int err = KA_OK;
+    std::string errmsg;
+};
+
+}  // namespace kai
+
+struct ka_batch {
+    int dev_index = 0;
+    uint64_t n_seq = 0, n_res = 0, base = 0, long_res = 0, n_long = 0, n_mid = 0;
+    kai::Pipe p;  // owns device buffers of the resident batch
+};
+
+struct ka_engine {
+    std::vector<kai::Device> devs;
+    std::mutex mu;
+    std::string err;
+    // options
+    double load_factor = 0.4;
+    uint32_t tile_span = 1536;
+    uint32_t long_seq = 2048;
+    uint32_t mid_seq = 8192;
+    int mid_variant = 1;
+    uint64_t chunk_residues = 48ull << 20;
+    int l2_persist = 1;
+    int variant = 0;
+    int slot_bits = 0;  // 0 = choose automatically
+    int filter = 0;     // 1 = per-sector presence signatures in front of the table (measured slower
+                        // in the fused kernel: 40 vs 46 G probes/s, profiles/r01_summary.md), -1 = auto
+    bool have_sig = false;
+    int two_phase = 0;  // with signatures: 1 = two-phase tile kernel (measured slower, kept as an experiment),
+                        // 0 = signature test inside the fused kernel
+    int table_mode = 0; // 0 = table replicated on every device, 1 = sharded by sector range (peer loads)
+    int wide = 0;       // 1 = force the wide-table kernels (64-bit sector indices and tokens) on any table
+    bool peers_enabled = false;
+    bool nccl_ready = false;
+    // db
+    bool have_db = false;
+    ka_db_info info{};
+    ka::TableView geom{};   // geometry of the loaded table (sectors pointer filled per device)
+    uint8_t lut[256];
+    ka_stats stats{};
+};
+
+
+namespace kai {
+
+int fail(ka_engine* e, int code, const char* fmt, ...);
+int dev_fail(Device& d, int code, const char* what, cudaError_t ce);
+
+#define DCK(d, call)                                                         \
+    do {                                                                     \
+        cudaError_t _ce = (call);                                            \
+        if (_ce != cudaSuccess) return dev_fail((d), KA_ERR_CUDA, #call, _ce); \
+    } while (0)
+
+
+template <typename T>
+int ensure(Device& d, T*& ptr, size_t& cap, size_t want, const char* what) {
+    if (want <= cap && ptr) return KA_OK;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr; cap = 0;
+    size_t n = want + want / 8 + 64;
+    cudaError_t ce = cudaMalloc((void**)&ptr, n * sizeof(T));
+    if (ce != cudaSuccess) { ptr = nullptr; return dev_fail(d, KA_ERR_OOM, what, ce); }
+    cap = n;
+    return KA_OK;
+}
+
+
+struct ChunkShape {
+    uint64_t n_res = 0, n_long = 0, long_res = 0, probes = 0, n_mid = 0;
+};
+
+
+int pipe_init(Device& d, Pipe& p);
+void pipe_free(Pipe& p);
+int pipe_reserve(Device& d, Pipe& p, uint64_t n_res, uint64_t n_seq, uint64_t n_tiles,
+                 uint64_t n_long, uint64_t long_res, uint64_t n_mid, bool wide);
+bool scan_offsets(const uint64_t* off, uint64_t cs, uint64_t ce, uint32_t long_seq, uint32_t mid_seq, int K,
+                  ChunkShape& s);
+void fill_params(ka_engine* e, Device& d, Pipe& p, uint64_t base, uint64_t n_res, uint64_t n_seq,
+                 int32_t min_hits, AnnotParams& ap);
+int ensure_tile_smem(Device& d);
+int enqueue_kernels(ka_engine* e, Device& d, Pipe& p, const AnnotParams& ap, uint64_t n_long, uint64_t n_mid);
+int collect_times(Device& d, Pipe& p);
+void set_l2_window(ka_engine* e, Device& d, cudaStream_t st);
+int annotate_range(ka_engine* e, Device& d, const uint8_t* residues, const uint64_t* offsets,
+                   uint64_t s_begin, uint64_t s_end, int32_t min_hits, int32_t* out_role,
+                   int32_t* out_hits, uint8_t* out_flag);
+
+// ---- ka_table.cu ----
+// Source of the DB lines: host arrays, or the synthetic generator (kmers == NULL).
+struct DbSource {
+    const uint8_t* kmers = nullptr;
+    const int32_t* roles = nullptr;
+    uint64_t n = 0;
+    uint64_t seed = 0;        // synthetic only
+    uint32_t n_roles = 0;     // synthetic only
+    uint32_t role_bits = 1;   // bits of the largest role id
+    bool synthetic = false;
+};
+
+int build_table(ka_engine* e, Device& d, const TableView& geom, const DbSource& src, uint64_t* n_keys, uint32_t* max_probe);
+bool choose_geometry(uint64_t n, int K, int32_t max_role, double lf, int force_cls, uint32_t n_shards, bool force_wide, TableView& g);
+// syn_roles > 0: the lines come from the synthetic generator (syn_seed, syn_roles), kmers/role_ids unused
+int db_load_impl(ka_engine* e, const uint8_t* kmers, const int32_t* role_ids, uint64_t n, int K,
+                 uint64_t syn_seed = 0, int32_t syn_roles = 0);
+
+// ---- ka_route.cu ----
+class Barrier {
+public:
+    explicit Barrier(int n) : n_(n) {}
+    void wait() {
+        std::unique_lock<std::mutex> lk(m_);
+        const int gen = gen_;
+        if (++count_ == n_) { count_ = 0; gen_++; cv_.notify_all(); }
+        else cv_.wait(lk, [&] { return gen != gen_; });
+    }
+private:
+    std::mutex m_;
+    std::condition_variable cv_;
+    int n_, count_ = 0, gen_ = 0;
+};
+
+struct RouteShared {
+    Barrier bar;
+    std::vector<std::array<unsigned long long, 8>> counts;   // counts[d][o]: keys device d sends to owner o this round
+    std::vector<size_t> n_chunks;
+    std::atomic<int> abort{0};                                // a device could not size its receive buffers
+    explicit RouteShared(int n) : bar(n), counts(n), n_chunks(n, 0) {}
+};
+
+int route_init_comms(ka_engine* e);      // dlopen libnccl, one communicator per device (idempotent)
+void route_destroy_comm(Device& d);
+int annotate_routed_range(ka_engine* e, Device& d, int idx, RouteShared& sh, const uint8_t* residues,
+                          const uint64_t* offsets, uint64_t s_begin, uint64_t s_end, int32_t min_hits,
+                          int32_t* out_role, int32_t* out_hits, uint8_t* out_flag);
+
+template <typename F>
+int for_each_device(ka_engine* e, F f) {
+    if (e->devs.size() == 1) {
+        int rc = f(e->devs[0], 0);
+        if (rc) e->err = e->devs[0].errmsg;
+        return rc;
+    }
+    std::vector<int> rcs(e->devs.size(), 0);
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < e->devs.size(); i++)
+        th.emplace_back([&, i] { rcs[i] = f(e->devs[i], (int)i); });
+    for (auto& t : th) t.join();
+    for (size_t i = 0; i < e->devs.size(); i++)
+        if (rcs[i]) { e->err = e->devs[i].errmsg; return rcs[i]; }
+    return KA_OK;
+}
+
+
+}  // namespace kai

@@ -1,0 +1,331 @@
+// ka_table.cu — the device table: geometry (slot class, sector count, wide / sharded forms), build
+// from host lines or from the synthetic generator, and the two C-ABI loaders.
+// Replaces ApplyKmerProcessor.java:99-110 (HashMap.put per DB line, last line wins).
+#include "ka_engine_internal.cuh"
+
+using namespace ka;
+using namespace kai;
+
+namespace kai {
+
+// Build the table replica (or shard) of one device from the DB lines.
+int build_table(ka_engine* e, Device& d, const TableView& geom, const DbSource& src, uint64_t* n_keys, uint32_t* max_probe) {
+    const uint8_t* kmers = src.kmers;
+    const int32_t* roles = src.roles;
+    const uint64_t n = src.n;
+    DCK(d, cudaSetDevice(d.id));
+    if (d.table) { cudaFree(d.table); d.table = nullptr; }
+    if (d.ovf) { cudaFree(d.ovf); d.ovf = nullptr; }
+    if (d.sig) { cudaFree(d.sig); d.sig = nullptr; }
+    const int K = geom.K;
+    const size_t n_sectors = (size_t)1 << (geom.n_shards > 1 ? geom.shard_shift : geom.bbits);  // of this device
+    const size_t bytes = n_sectors * 32;
+    const size_t n_slots = n_sectors * (geom.cls == 32 ? 8 : (geom.cls == 64 ? 4 : 2));
+    cudaError_t ce = cudaMalloc((void**)&d.table, bytes);
+    if (ce != cudaSuccess) { d.table = nullptr; return dev_fail(d, KA_ERR_OOM, "table", ce); }
+    const size_t ovf_bytes = geom.cls == 128 ? 0 : ((size_t)64 << geom.ovf_bbits);
+    if (ovf_bytes) {
+        ce = cudaMalloc((void**)&d.ovf, ovf_bytes);
+        if (ce != cudaSuccess) { d.ovf = nullptr; return dev_fail(d, KA_ERR_OOM, "overflow table", ce); }
+    }
+    const bool use_sig = geom.n_shards <= 1 && !geom.wide && (e->filter == 1 || (e->filter < 0 && geom.bbits >= 20));
+    const size_t sig_bytes = use_sig ? (n_sectors * 2 + 4) : 0;
+    if (sig_bytes) {
+        ce = cudaMalloc((void**)&d.sig, sig_bytes);
+        if (ce != cudaSuccess) { d.sig = nullptr; return dev_fail(d, KA_ERR_OOM, "signature array", ce); }
+    }
+    cudaStream_t st = d.pipe[0].st;
+    TableView tab = geom;
+    tab.sectors = d.table;
+    tab.ovf = d.ovf;
+    tab.sig = d.sig;
+    const uint64_t CH = (src.synthetic ? 64ull : 16ull) << 20;  // k-mers per upload / per generator launch
+    uint8_t* dk = nullptr; int32_t* dr = nullptr; unsigned long long* best = nullptr;
+    unsigned long long* dc = nullptr; uint32_t* de = nullptr;
+    uint64_t ch = std::min<uint64_t>(CH, n ? n : 1);
+    const bool packed = geom.cls != 128;
+    // cls 32/64: 8 bytes per primary slot hold the winning (line, role) until db_finalize
+    if ((ce = cudaMalloc((void**)&dk, ch * K)) != cudaSuccess ||
+        (ce = cudaMalloc((void**)&dr, ch * 4)) != cudaSuccess ||
+        (packed && (ce = cudaMalloc((void**)&best, n_slots * 8)) != cudaSuccess) ||
+        (ce = cudaMalloc((void**)&dc, 16)) != cudaSuccess ||
+        (ce = cudaMalloc((void**)&de, 16)) != cudaSuccess) {
+        if (dk) cudaFree(dk);
+        if (dr) cudaFree(dr);
+        if (best) cudaFree(best);
+        if (dc) cudaFree(dc);
+        return dev_fail(d, KA_ERR_OOM, "DB staging", ce);
+    }
+    int rc = KA_OK;
+    auto step = [&](cudaError_t c, const char* what) {
+        if (c != cudaSuccess && rc == KA_OK) rc = dev_fail(d, KA_ERR_CUDA, what, c);
+    };
+    step(cudaMemsetAsync(d.table, 0, bytes, st), "memset table");
+    if (ovf_bytes) step(cudaMemsetAsync(d.ovf, 0, ovf_bytes, st), "memset overflow table");
+    if (sig_bytes) step(cudaMemsetAsync(d.sig, 0, sig_bytes, st), "memset signatures");
+    if (packed) step(cudaMemsetAsync(best, 0, n_slots * 8, st), "memset best");
+    step(cudaMemcpyAsync(d.lut, e->lut, 256, cudaMemcpyHostToDevice, st), "H2D lut");
+    step(cudaMemsetAsync(dc, 0, 16, st), "memset counters");
+    step(cudaMemsetAsync(de, 0, 16, st), "memset errs");
+    for (uint64_t i = 0; i < n && rc == KA_OK; i += ch) {
+        uint64_t m = std::min(ch, n - i);
+        if (!src.synthetic) {
+            step(cudaMemcpyAsync(dk, kmers + i * K, m * K, cudaMemcpyHostToDevice, st), "H2D kmers");
+            step(cudaMemcpyAsync(dr, roles + i, m * 4, cudaMemcpyHostToDevice, st), "H2D roles");
+        } else {
+            step(launch_db_generate(i, m, K, src.seed, src.n_roles, dk, dr, st), "db_generate");
+        }
+        step(launch_db_insert(tab, dk, dr, m, i, d.lut, best, src.role_bits, dc, de, st), "db_insert");
+        step(cudaStreamSynchronize(st), "db_insert sync");
+    }
+    if (rc == KA_OK) step(launch_db_finalize(tab, best, src.role_bits, st), "db_finalize");
+    step(cudaStreamSynchronize(st), "db_finalize sync");
+    unsigned long long hc[2] = {0, 0};
+    uint32_t he[4] = {0, 0, 0, 0};
+    step(cudaMemcpy(hc, dc, 16, cudaMemcpyDeviceToHost), "D2H counters");
+    step(cudaMemcpy(he, de, 16, cudaMemcpyDeviceToHost), "D2H errs");
+    cudaFree(dk); cudaFree(dr); cudaFree(dc); cudaFree(de);
+    if (best) cudaFree(best);
+    if (rc) return rc;
+    if (he[0]) { d.err = KA_ERR_ALPHABET; d.errmsg = "k-mer byte outside the DB alphabet (internal)"; return d.err; }
+    if (he[1]) { d.err = KA_ERR_ROLE; d.errmsg = "negative role id in the DB"; return d.err; }
+    if (he[2]) { d.err = KA_ERR_TOO_BIG; d.errmsg = "overflow table full"; return d.err; }  // caller retries larger
+    *n_keys = hc[0];
+    *max_probe = (uint32_t)hc[1];
+    return KA_OK;
+}
+
+uint32_t ceil_log2(double x) {
+    uint32_t b = 0;
+    while ((double)(1ull << b) < x && b < 62) b++;
+    return b;
+}
+
+// Pick slot class and sector count: the smallest table that holds n keys at the requested
+// load factor with remainder + role fitting the slot (see ka_common.cuh).
+bool choose_geometry(uint64_t n, int K, int32_t max_role, double lf, int force_cls, uint32_t n_shards, bool force_wide, TableView& g) {
+    const uint32_t w = 5u * (uint32_t)K;
+    uint32_t role_bits = 1;
+    while (((uint64_t)max_role + 1) >> role_bits) role_bits++;
+    bool found = false;
+    uint64_t best_bytes = 0;
+    for (int cls : {32, 64, 128}) {
+        if (force_cls && cls != force_cls) continue;
+        if (n_shards > 1 && cls == 128) continue;   // chaining across shards is not supported: quotiented classes only
+        const int S = 256 / cls;
+        uint32_t b = ceil_log2((double)(n ? n : 1) / ((double)S * lf));
+        if (b < 6) b = 6;
+        uint32_t shard_log = 0;
+        while ((1u << shard_log) < n_shards) shard_log++;
+        if (b < 6 + shard_log) b = 6 + shard_log;
+        uint32_t rem_bits = 0;
+        if (cls != 128) {
+            if ((int)(w + role_bits) - cls > (int)b) b = w + role_bits - (uint32_t)cls;
+            if (b > w) b = w;
+            if (b < shard_log) continue;
+            rem_bits = w - b;
+            if (rem_bits + role_bits > (uint32_t)cls) continue;
+        }
+        uint32_t slot_log = cls == 32 ? 3 : (cls == 64 ? 2 : 1);
+        // narrow tables: slot index + 1 must fit the 32-bit de-dup token; beyond that the quotiented
+        // classes switch to the wide kernels (64-bit sector indices, the key is the token)
+        bool wide = force_wide && cls != 128;
+        if (b + slot_log > 31) {
+            if (cls == 128 || b > 40) continue;
+            wide = true;
+        }
+        uint64_t bytes = 32ull << b;
+        if (!found || bytes < best_bytes) {
+            found = true; best_bytes = bytes;
+            g.cls = cls; g.bbits = b; g.rem_bits = rem_bits; g.wbits = w; g.K = K;
+            g.key_mask = (1ull << w) - 1;
+            g.rem_mask = rem_bits ? ((1ull << rem_bits) - 1) : 0;
+            g.sectors = nullptr;
+            g.ovf = nullptr;
+            g.sig = nullptr;
+            g.n_primary_slots = wide ? 0u : (uint32_t)((uint64_t)S << b);
+            g.wide = wide ? 1u : 0u;
+            // expected keys beyond S per sector under Poisson(n / sectors) arrivals
+            double lam = (double)n / (double)(1ull << b), pk = std::exp(-lam), over = 0;
+            for (int k = 1; k < S + 400; k++) {
+                pk *= lam / k;
+                if (k > S) over += (k - S) * pk;
+            }
+            double want = 4.0 * over * (double)(1ull << b) + 4096;
+            g.ovf_bbits = cls == 128 ? 0 : ceil_log2(want / 2.0 / (n_shards ? n_shards : 1));
+            g.n_shards = n_shards;
+            g.shard_shift = b - shard_log;
+            g.my_shard = 0;
+            g.shard_sectors = nullptr;
+            g.shard_ovf = nullptr;
+        }
+    }
+    return found;
+}
+
+}  // namespace kai
+
+extern "C" {
+
+int ka_db_load(ka_engine* e, const uint8_t* kmers, const int32_t* role_ids, uint64_t n, int K) {
+    if (!e) return KA_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (n && (!kmers || !role_ids)) return fail(e, KA_ERR_INVALID, "ka_db_load: NULL input");
+    return db_load_impl(e, kmers, role_ids, n, K);
+}
+
+int ka_db_load_synthetic(ka_engine* e, uint64_t n, int K, int32_t n_roles, uint64_t seed) {
+    if (!e) return KA_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (n == 0 || n_roles < 1) return fail(e, KA_ERR_INVALID, "ka_db_load_synthetic: n and n_roles must be positive");
+    return db_load_impl(e, nullptr, nullptr, n, K, seed, n_roles);
+}
+
+// syn_roles > 0: the lines come from the synthetic generator (syn_seed, syn_roles), kmers/role_ids unused
+}  // extern "C"
+
+namespace kai {
+
+int db_load_impl(ka_engine* e, const uint8_t* kmers, const int32_t* role_ids, uint64_t n, int K,
+                 uint64_t syn_seed, int32_t syn_roles) {
+    if (K < 1 || K > KMAX) return fail(e, KA_ERR_K, "K = %d: this engine packs 5 bits per residue, K must be 1..%d", K, KMAX);
+    e->have_db = false;
+
+    // 1. alphabet: the distinct bytes of the DB, scanned on device 0
+    Device& d0 = e->devs[0];
+    uint32_t bitmap[8] = {0};
+    const bool synthetic = syn_roles > 0;
+    if (synthetic) {
+        for (const char* a = "ACDEFGHIKLMNPQRSTVWY"; *a; a++) bitmap[(uint8_t)*a >> 5] |= 1u << ((uint8_t)*a & 31);
+    } else {
+        cudaSetDevice(d0.id);
+        cudaStream_t st = d0.pipe[0].st;
+        uint32_t* dbm = nullptr; uint8_t* dk = nullptr;
+        const uint64_t CH = 256ull << 20;
+        uint64_t total = n * (uint64_t)K, ch = std::min<uint64_t>(CH, total ? total : 1);
+        if (cudaMalloc((void**)&dbm, 32) != cudaSuccess || cudaMalloc((void**)&dk, ch) != cudaSuccess) {
+            if (dbm) cudaFree(dbm);
+            return fail(e, KA_ERR_OOM, "ka_db_load: alphabet staging allocation failed");
+        }
+        cudaError_t ce = cudaMemsetAsync(dbm, 0, 32, st);
+        for (uint64_t i = 0; i < total && ce == cudaSuccess; i += ch) {
+            uint64_t m = std::min(ch, total - i);
+            ce = cudaMemcpyAsync(dk, kmers + i, m, cudaMemcpyHostToDevice, st);
+            if (ce == cudaSuccess) ce = launch_alphabet_scan(dk, m, dbm, st);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+        }
+        if (ce == cudaSuccess) ce = cudaMemcpy(bitmap, dbm, 32, cudaMemcpyDeviceToHost);
+        cudaFree(dbm); cudaFree(dk);
+        if (ce != cudaSuccess) return fail(e, KA_ERR_CUDA, "ka_db_load: alphabet scan: %s", cudaGetErrorString(ce));
+    }
+    memset(e->lut, 0, 256);
+    int nsym = 0;
+    for (int b = 0; b < 256; b++)
+        if (bitmap[b >> 5] & (1u << (b & 31))) {
+            nsym++;
+            if (nsym <= 31) e->lut[b] = (uint8_t)nsym;  // codes 1..31 in byte order; 0 = absent
+        }
+    if (nsym > 31)
+        return fail(e, KA_ERR_ALPHABET,
+                    "ka_db_load: the DB uses %d distinct residue bytes; at most 31 fit the 5-bit packing", nsym);
+
+    // 2. table geometry (slot class, sector count) from n, K and the largest role id
+    int32_t max_role = synthetic ? syn_roles - 1 : 0;
+    for (uint64_t i = 0; !synthetic && i < n; i++) {
+        if (role_ids[i] < 0) return fail(e, KA_ERR_ROLE, "ka_db_load: negative role id %d at line %llu", role_ids[i], (unsigned long long)i);
+        if (role_ids[i] > max_role) max_role = role_ids[i];
+    }
+    DbSource src;
+    src.kmers = synthetic ? nullptr : kmers; src.roles = role_ids; src.n = n; src.seed = syn_seed; src.n_roles = (uint32_t)syn_roles;
+    src.synthetic = synthetic;
+    while (((uint64_t)max_role + 1) >> src.role_bits) src.role_bits++;
+    {
+        // a slot keeps (line + 1) << role_bits | role in 64 bits while the DB streams in
+        uint32_t line_bits = 1;
+        while (line_bits < 64 && ((n + 1) >> line_bits)) line_bits++;
+        if (line_bits + src.role_bits > 64)
+            return fail(e, KA_ERR_TOO_BIG, "ka_db_load: %llu lines with role ids up to %d exceed the 64-bit (line, role) word",
+                        (unsigned long long)n, max_role);
+    }
+    TableView geom;
+    const uint32_t n_shards = e->table_mode >= 1 ? (uint32_t)e->devs.size() : 1u;
+    if (e->table_mode >= 1) {
+        if (n_shards != 2 && n_shards != 4 && n_shards != 8)
+            return fail(e, KA_ERR_INVALID, "ka_db_load: a sharded table needs an engine on 2, 4 or 8 devices (has %u)", n_shards);
+        if (!e->peers_enabled) {
+            for (Device& a : e->devs) {
+                cudaSetDevice(a.id);
+                for (Device& b : e->devs) {
+                    if (a.id == b.id) continue;
+                    int can = 0;
+                    cudaDeviceCanAccessPeer(&can, a.id, b.id);
+                    if (!can) return fail(e, KA_ERR_NO_DEVICE, "ka_db_load: device %d cannot access device %d's memory (no NVLink/P2P)", a.id, b.id);
+                    cudaError_t pe = cudaDeviceEnablePeerAccess(b.id, 0);
+                    if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled)
+                        return fail(e, KA_ERR_CUDA, "ka_db_load: cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(pe));
+                    cudaGetLastError();
+                }
+            }
+            e->peers_enabled = true;
+        }
+    }
+    // communicators first: NCCL sets up its buffers before the table takes most of the HBM
+    if (e->table_mode == 2) { int nrc = route_init_comms(e); if (nrc) return nrc; }
+    if (!choose_geometry(n, K, max_role, e->load_factor, e->slot_bits, n_shards, e->wide != 0, geom))
+        return fail(e, KA_ERR_TOO_BIG, "ka_db_load: %llu k-mers (K=%d, max role %d) do not fit %s",
+                    (unsigned long long)n, K, max_role, e->slot_bits ? "the forced slot width" : "any slot class of this build");
+
+    // 3. build one replica per device
+    auto tb = std::chrono::steady_clock::now();
+    std::vector<uint64_t> nk(e->devs.size(), 0);
+    std::vector<uint32_t> mp(e->devs.size(), 0);
+    int rc = KA_OK;
+    for (int attempt = 0; attempt < 6; attempt++) {
+        if (!geom.wide && (uint64_t)geom.n_primary_slots + (uint64_t)n_shards * (2ull << geom.ovf_bbits) >= 0xfffffff0ull) {
+            if (geom.cls == 128) return fail(e, KA_ERR_TOO_BIG, "ka_db_load: table exceeds the 32-bit slot index of the 128-bit slot class");
+            geom.wide = 1; geom.n_primary_slots = 0;   // overflow entries pushed the token range past 32 bits
+        }
+        rc = for_each_device(e, [&](Device& d, int i) {
+            TableView g = geom;
+            g.my_shard = n_shards > 1 ? (uint32_t)i : 0u;
+            return build_table(e, d, g, src, &nk[i], &mp[i]);
+        });
+        if (rc != KA_ERR_TOO_BIG) break;
+        geom.ovf_bbits += 2;  // overflow table was too small for this key set: rebuild 4x larger
+    }
+    if (rc) return rc;
+    if (getenv("KA_LOAD_TRACE"))
+        fprintf(stderr, "[db load] table build (%llu lines, 2^%u sectors of %d-bit slots%s, %u shard(s)): %.2f s\n",
+                (unsigned long long)n, geom.bbits, geom.cls, geom.wide ? ", wide" : "", n_shards,
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - tb).count());
+    if (n_shards > 1) {
+        // every device gets the peer pointers of all shards
+        std::vector<const uint4*> ps(8, nullptr), po(8, nullptr);
+        for (size_t i = 0; i < e->devs.size(); i++) { ps[i] = e->devs[i].table; po[i] = e->devs[i].ovf; nk[0] += i ? nk[i] : 0; mp[0] = std::max(mp[0], mp[i]); }
+        for (Device& d : e->devs) {
+            cudaSetDevice(d.id);
+            if (!d.shard_sectors && cudaMalloc((void**)&d.shard_sectors, 64) != cudaSuccess) return fail(e, KA_ERR_OOM, "shard pointer table");
+            if (!d.shard_ovf && cudaMalloc((void**)&d.shard_ovf, 64) != cudaSuccess) return fail(e, KA_ERR_OOM, "shard pointer table");
+            cudaMemcpy((void*)d.shard_sectors, ps.data(), 64, cudaMemcpyHostToDevice);
+            cudaMemcpy((void*)d.shard_ovf, po.data(), 64, cudaMemcpyHostToDevice);
+        }
+    }
+    e->geom = geom;
+    e->info.K = K;
+    e->info.n_symbols = nsym;
+    e->info.n_lines = n;
+    e->info.n_keys = nk[0];
+    e->info.n_buckets = 1ull << geom.bbits;
+    e->info.table_bytes = (32ull << geom.bbits) + (geom.cls == 128 ? 0 : (uint64_t)n_shards * (64ull << geom.ovf_bbits));  // all shards
+    e->have_sig = e->devs[0].sig != nullptr;
+    e->info.max_probe = mp[0];
+    e->info.slot_bits = (uint32_t)geom.cls;
+    e->have_db = true;
+    for (Device& d : e->devs) {
+        cudaSetDevice(d.id);
+        for (int k = 0; k < NPIPE; k++) set_l2_window(e, d, d.pipe[k].st);
+    }
+    return KA_OK;
+}
+
+}  // namespace kai
