@@ -34,7 +34,7 @@ int parseInt(const std::string& opt, const std::string& v) {
 }  // namespace
 
 void ApplyKmerProcessor::usage(std::ostream& os) {
-    os << "apply [--format VERIFY|APPLY] [-m|--min N] [--devices 0,1,..] [--batch N] kmerdb.tbl roles.in.use gtoDir\n"
+    os << "apply [--format VERIFY|APPLY] [-m|--min N] [--devices 0,1,..] [--table-mode 0|1|2] [--batch N] kmerdb.tbl roles.in.use gtoDir\n"
           " kmerdb.tbl     discriminating kmer database\n"
           " roles.in.use   list of roles in use\n"
           " gtoDir         input genome directory\n"
@@ -68,6 +68,10 @@ bool ApplyKmerProcessor::parseCommand(const std::vector<std::string>& args) {
             else if (a == "-m" || a == "--min") minHits_ = parseInt(a, value());
             else if (a == "--batch") batchGenomes_ = parseInt(a, value());
             else if (a == "--threads") loadThreads_ = parseInt(a, value());
+            else if (a == "--table-mode") {
+                tableMode_ = parseInt(a, value());
+                if (tableMode_ < 0 || tableMode_ > 2) throw ParseFailureException("--table-mode must be 0 (replicated), 1 (sharded, peer loads) or 2 (sharded, NCCL routed).");
+            }
             else if (a == "--devices") {
                 devices_.clear();
                 const std::string& v = value();
@@ -191,6 +195,7 @@ void ApplyKmerProcessor::validateParms() {
     kmerSize_ = K;                               // KmerReference.setKmerSize(kmer.length()) (:108)
     log_ << "Kmer size is " << kmerSize_ << ".  (" << roles.size() << " lines parsed, t=" << nowSeconds() << " s)\n";
     engine_ = std::make_unique<KmerEngine>(devices_);   // throws if there is no usable GPU: no CPU fallback
+    if (tableMode_) engine_->setOption("table_mode", tableMode_);   // table beyond one GPU: sharded over --devices
     engine_->loadDb(kmers, roles, K);
     ka_db_info info = engine_->dbInfo();
     log_ << info.n_keys << " distinct kmers for " << roleNames_.size() << " roles loaded on " << devices_.size()

@@ -4,7 +4,7 @@
 // the GPU engine and the reporter calls are replayed in the original peg order.
 //
 //   apply [--format VERIFY|APPLY] [-m|--min N] kmerdb.tbl roles.in.use gtoDir
-// added knobs (ordinary options, as SURVEY §5 asks): --devices 0,1,..  --batch genomes  --threads n
+// added knobs (ordinary options, as SURVEY §5 asks): --devices 0,1,..  --table-mode 0|1|2  --batch genomes  --threads n
 // Genomes of the next batch are parsed by a thread pool while the GPU annotates the current one.
 #pragma once
 #include <iostream>
@@ -49,6 +49,7 @@ private:
     std::vector<int> devices_{0};
     int batchGenomes_ = 64;
     int loadThreads_ = 1;
+    int tableMode_ = 0;                        // 0 replicated table, 1 / 2 sharded over the devices (ka_set_option "table_mode")
     // state
     std::unique_ptr<ApplyKmerReporter> reporter_;
     std::unique_ptr<KmerEngine> engine_;       // replaces Map<String,String> kmerRoleMap (:53)

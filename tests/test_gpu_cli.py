@@ -164,3 +164,19 @@ def test_genes_copies_aliases_of_the_closest_feature(tmp_path):
                                 want.append([ty, al])
             assert t_out.get("alias_pairs", []) == want, t_in["id"]
         assert f"with {updates} updates" in r.stderr and updates > 20
+
+
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_apply_with_a_sharded_table(tmp_path, mode):
+    """`apply --devices 0,1 --table-mode 1|2`: the table sharded over two GPUs gives the same reports."""
+    import kmers_anno_b200 as ka
+    try:
+        ka.Engine([0, 1]).close()
+    except ka.KmerAnnoError:
+        pytest.skip("needs at least 2 GPUs")
+    gid, pegs = load_small()
+    write_gto(str(tmp_path / f"{gid}.gto"), gid, pegs)
+    out, err = run(["--format", "VERIFY", "--devices", "0,1", "--table-mode", mode, DB, ROLES, str(tmp_path)])
+    want = open(os.path.join(GOLD, "small.verify.tsv")).read()
+    assert out == want, [l for l in out.splitlines() if l not in want.splitlines()][:5]
+    assert "loaded on 2" in err
