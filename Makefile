@@ -16,9 +16,9 @@ SELFTEST  := $(PKG)/bin/kmers-anno-selftest
 
 all: $(LIB) $(SYNTH) $(ORACLE) $(CLI) $(SELFTEST)
 
-CUSRC     := $(CSRC)/ka_kernels.cu $(CSRC)/ka_distance.cu $(CSRC)/ka_engine.cu $(CSRC)/ka_table.cu $(CSRC)/ka_route.cu $(CSRC)/ka_build_api.cu
+CUSRC     := $(CSRC)/ka_kernels.cu $(CSRC)/ka_distance.cu $(CSRC)/ka_engine.cu $(CSRC)/ka_table.cu $(CSRC)/ka_route.cu $(CSRC)/ka_build_api.cu $(CSRC)/ka_line.cu
 
-$(LIB): $(CUSRC) $(CSRC)/ka_common.cuh $(CSRC)/ka_kernels.cuh $(CSRC)/ka_engine_internal.cuh include/kmeranno.h
+$(LIB): $(CUSRC) $(CSRC)/ka_common.cuh $(CSRC)/ka_kernels.cuh $(CSRC)/ka_engine_internal.cuh $(CSRC)/ka_line.cuh include/kmeranno.h
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CUSRC) -ldl 2> $(PKG)/ptxas.log || (cat $(PKG)/ptxas.log; exit 1)
 	@grep -E "error|warning|spill|registers" $(PKG)/ptxas.log | grep -v "0 bytes spill" | head -40 || true
 
@@ -36,7 +36,11 @@ $(SELFTEST): $(HOST)/selftest.cpp $(HOST)/Genome.cpp $(wildcard $(HOST)/*.hpp)
 	mkdir -p $(PKG)/bin
 	$(CXX) -O2 -std=c++17 -Wall -Iinclude -o $@ $(HOST)/selftest.cpp $(HOST)/Genome.cpp
 
+# bounds-checking build of the kernels (KA_CHECK): KMERANNO_LIB=kmers.anno_b200/libkmeranno_dbg.so python -m pytest ...
+debuglib: $(CUSRC)
+	$(NVCC) $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -DKA_DEBUG -shared -o $(PKG)/libkmeranno_dbg.so $(CUSRC) -ldl
+
 clean:
 	rm -f $(LIB) $(SYNTH) $(ORACLE) $(CLI) $(SELFTEST) $(PKG)/ptxas.log
 
-.PHONY: all clean
+.PHONY: all clean debuglib

@@ -22,6 +22,7 @@
  * The engine owns all device memory until ka_destroy().  No callbacks.
  * Threading: an engine serialises its entry points internally (one mutex); use one
  * engine per thread for concurrent callers (HashAnnotationProcessor.java:208 style).
+ * ka_pack_residues only reads the alphabet and runs concurrently.
  */
 #ifndef KMERANNO_H
 #define KMERANNO_H
@@ -33,7 +34,7 @@
 extern "C" {
 #endif
 
-#define KA_ABI_VERSION 1
+#define KA_ABI_VERSION 2
 
 typedef struct ka_engine ka_engine;
 typedef struct ka_batch ka_batch;
@@ -71,30 +72,29 @@ void ka_destroy(ka_engine* e);
 /* Last error text of the engine (e == NULL: of the calling thread's last ka_create). */
 const char* ka_last_error(const ka_engine* e);
 
-/* Tunables, set before ka_db_load / ka_annotate.  Unknown name -> KA_ERR_INVALID.
- *   "load_factor"   table load factor in (0,0.9], default 0.4   (next ka_db_load)
- *   "tile_span"     residues of sequence starts per CTA tile, default 1536
- *   "long_seq"      sequences longer than this get a tile of their own (second tile launch), default 2048
- *   "mid_seq"       sequences longer than this use the global-scratch long-sequence kernel, default 8192
- *   "mid_variant"   tile kernel shape of the second launch, default 1
+/* Tunables.  Unknown name or a value out of range -> KA_ERR_INVALID and NOTHING changes.
+ * Table options take effect at the next ka_db_load (the loaded table keeps the geometry it was
+ * built with); tiling options at the next annotate call (a resident batch uploaded under other
+ * tiling options is rejected by ka_annotate_resident: upload it again).
+ *   "load_factor"   table load factor in (0,0.9]; default: 0.65 for the line table, 0.4 for the sector classes
+ *   "slot_bits"     force the table layout: 16 = the 128-byte-line table (16-bit tags + 16-bit roles, spill inside
+ *                   the line, L2-resident presence filter; needs a replicated table, role ids < 65536 and keys of
+ *                   at most 39 bits, e.g. K <= 9 over 20 letters), 32 / 64 / 128 = sector classes with slots of
+ *                   that width; 0 (default) = the line table for large DBs that fit it, else the narrowest sector class
+ *   "filter"        line table only: 1 (default) = probe the L2-resident presence filter first, 0 = always read
+ *                   the table (measurement knob)
  *   "table_mode"    0 = table replicated on every device (default); 1 = table sharded by sector range
  *                   over the engine's 2/4/8 devices, probes load remote sectors through NVLink
  *                   peer memory inside the probe kernel (for tables beyond one GPU); 2 = same sharding,
  *                   but the k-mer keys are ROUTED: NCCL send/recv all-to-all of 8-byte keys to the
- *                   owning GPU, local probe there, 8-byte answers back in request order, rounds pipelined (sequences
- *                   longer than mid_seq are rejected in this mode)  (next ka_db_load)
- *   "filter"        per-sector presence signatures kept in L2 (1 on, 0 off (default), -1 = on for
- *                   tables of at least 2^20 sectors)   (next ka_db_load)
- *   "two_phase"     with "filter": 1 = two-phase tile kernel (signature test and candidate compaction,
- *                   then probes of the survivors only), 0 = test inside the fused kernel (default)
+ *                   owning GPU, local probe there, 8-byte answers back in request order, rounds pipelined
  *   "wide"          1 = use the wide-table kernels (64-bit sector indices, the mixed key as de-dup
- *                   token) on any table; 0 (default) = only when the table has more than 2^32 - 16
- *                   slots, e.g. more than ~34 GB of 64-bit slots   (next ka_db_load)
- *   "slot_bits"     force the table slot width (32, 64, 128; 0 = smallest that fits, default)
- *   "variant"       tile kernel shape: 0 = 4 positions x 128 threads (default), 1 = 4 x 256, 2 = 8 x 256,
- *                   3 = 2 x 128 (48 registers, 10 CTAs/SM)
+ *                   token) on any sector-class table; 0 (default) = only beyond 2^32 - 16 slots
+ *   "tile_span"     residues of sequence starts per CTA tile, default 1536
+ *   "long_seq"      sequences longer than this get a tile of their own (second tile launch), default 1536
+ *   "mid_seq"       sequences longer than this use the global-scratch long-sequence kernel, default 8192
  *   "chunk_residues" residues per pipelined H2D chunk, default 48 Mi (4 chunks in flight per device)
- *   "l2_persist"    1 = set an L2 persisting access-policy window on the table (default 1)
+ *   "l2_persist"    sector classes: 1 = L2 persisting access-policy window on the table (default 1)
  */
 int ka_set_option(ka_engine* e, const char* name, double value);
 
@@ -116,7 +116,10 @@ typedef struct ka_db_info {
     uint64_t n_buckets;      /* 32-byte sectors (8, 4 or 2 slots each)                   */
     uint64_t table_bytes;    /* device bytes of one table replica                        */
     uint32_t max_probe;      /* longest sector chain seen while building                 */
-    uint32_t slot_bits;      /* slot width chosen for this DB: 32, 64 or 128             */
+    uint32_t slot_bits;      /* layout chosen for this DB: 16 (line table), 32, 64 or 128 */
+    uint64_t filter_bytes;   /* line table: device bytes of the presence filter (else 0) */
+    uint64_t n_spilled;      /* line table: keys stored outside their home sector        */
+    uint64_t n_overflow;     /* line table: keys stored in the overflow table            */
 } ka_db_info;
 int ka_db_get_info(ka_engine* e, ka_db_info* out);
 
@@ -132,6 +135,25 @@ int ka_db_get_info(ka_engine* e, ka_db_info* out);
  * Sequences are sharded over the engine's devices; copies are inside the call. */
 int ka_annotate(ka_engine* e, const uint8_t* residues, const uint64_t* offsets, uint64_t N,
                 int32_t min_hits, int32_t* out_role, int32_t* out_hits, uint8_t* out_flag);
+
+/* The same call on the PACKED form of the batch, 0.625 bytes per residue over PCIe instead of 1 and
+ * 32-bit offsets: residue r of the batch occupies bits [5r, 5r+5) of the little-endian byte stream
+ * `codes`; its value is the digit of the residue byte in the DB alphabet (ka_db_get_alphabet: the
+ * distinct bytes of the DB numbered 0.. in byte order) or 31 for a byte that is not in the DB — such a
+ * byte can never be part of a match (String equality, ApplyKmerProcessor.java:130).  offsets[i] is the
+ * residue index of the start of sequence i (N + 1 entries, 32 bits: at most 2^32 - 1 residues per
+ * call).  The stream is what the host writes while it touches the residues anyway (FASTA / GTO
+ * parser, ka_pack_residues); results are identical to ka_annotate on the unpacked batch. */
+int ka_annotate_packed(ka_engine* e, const uint8_t* codes, const uint32_t* offsets, uint64_t N,
+                       int32_t min_hits, int32_t* out_role, int32_t* out_hits, uint8_t* out_flag);
+
+/* code_of_byte[256]: the 5-bit code of every byte value for the loaded DB (digit 0..n_symbols-1, or 31). */
+int ka_db_get_alphabet(ka_engine* e, uint8_t* code_of_byte);
+
+/* Host helper: write the codes of residues[0..n) as residues first_index .. first_index+n-1 of the
+ * stream `codes` (first_index must be a multiple of 8 = a byte boundary of the stream, so that
+ * threads can pack disjoint ranges; only whole bytes of the range are written).  Thread-safe. */
+int ka_pack_residues(ka_engine* e, const uint8_t* residues, uint64_t n, uint64_t first_index, uint8_t* codes);
 
 /* Device-resident variant, used to time the kernels with inputs already in HBM.
  * ka_batch_upload copies a CSR batch to device `dev_index` (index into the engine's device

@@ -37,7 +37,6 @@ struct Slot128 {
 
 struct TableView {
     const uint4* sectors;         // 2^bbits sectors, 2 uint4 each
-    const uint16_t* sig;          // per-sector 16-bit Bloom signature (NULL = no filter), see sig_bits()
     const uint4* ovf;             // overflow table (cls 32/64): 2^ovf_bbits sectors of 2 Slot128
     uint32_t ovf_bbits;
     uint32_t n_primary_slots;     // slots of the primary table (de-dup tokens of overflow entries start here; narrow only)
@@ -93,15 +92,6 @@ __host__ __device__ __forceinline__ void locate(const TableView& t, unsigned lon
         sector = (uint32_t)(m >> t.rem_bits);
         rem = m & t.rem_mask;
     }
-}
-
-// Presence filter: every key sets two of the 16 bits of its HOME sector's signature.  The
-// 2-byte signatures of all sectors (64 MB for 2^25 sectors) stay L2 resident (persisting
-// access-policy window), so a probe whose bits are not both set is answered "absent" without
-// touching HBM — exact, a Bloom signature has no false negatives.
-__host__ __device__ __forceinline__ uint32_t sig_bits(unsigned long long rem) {
-    uint32_t h = ((uint32_t)rem ^ (uint32_t)(rem >> 32)) * 0x9E3779B1u;
-    return (1u << (h >> 28)) | (1u << ((h >> 24) & 15u));
 }
 
 // address of a table sector: local HBM, or the owning GPU's HBM through NVLink peer memory

@@ -46,7 +46,10 @@ int pipe_init(Device& d, Pipe& p) {
 
 void pipe_free(Pipe& p) {
     if (p.res) cudaFree(p.res);
+    if (p.pk) cudaFree(p.pk);
     if (p.off) cudaFree(p.off);
+    if (p.off32_in) cudaFree(p.off32_in);
+    if (p.off32) cudaFree(p.off32);
     if (p.first) cudaFree(p.first);
     if (p.role) cudaFree(p.role);
     if (p.hits) cudaFree(p.hits);
@@ -66,12 +69,17 @@ void pipe_free(Pipe& p) {
 
 // size the per-chunk device buffers
 int pipe_reserve(Device& d, Pipe& p, uint64_t n_res, uint64_t n_seq, uint64_t n_tiles,
-                 uint64_t n_long, uint64_t long_res, uint64_t n_mid, bool wide) {
+                 uint64_t n_long, uint64_t long_res, uint64_t n_mid, bool wide, bool need_bytes, bool need_codes) {
     int rc;
-    if ((rc = ensure(d, p.res, p.res_cap, n_res + 64, "residues"))) return rc;
+    if (need_bytes && (rc = ensure(d, p.res, p.res_cap, n_res + 64, "residues"))) return rc;
+    // 5-bit codes of up to 127 lead residues + the chunk, in groups of 32 residues = 5 words, + over-read slack
+    if (need_codes && (rc = ensure(d, p.pk, p.pk_cap, ((n_res + 127 + 31) / 32) * 5 + 32, "packed residues"))) return rc;
     size_t want_seq = n_seq + 1;
     if (want_seq > p.seq_cap || !p.off) {
         if (p.off) cudaFree(p.off);
+        if (p.off32_in) cudaFree(p.off32_in);
+        if (p.off32) cudaFree(p.off32);
+        p.off32_in = p.off32 = nullptr;
         if (p.role) cudaFree(p.role);
         if (p.hits) cudaFree(p.hits);
         if (p.flag) cudaFree(p.flag);
@@ -79,6 +87,8 @@ int pipe_reserve(Device& d, Pipe& p, uint64_t n_res, uint64_t n_seq, uint64_t n_
         size_t n = want_seq + want_seq / 8 + 64;
         cudaError_t ce;
         if ((ce = cudaMalloc((void**)&p.off, n * 8)) != cudaSuccess ||
+            (ce = cudaMalloc((void**)&p.off32_in, n * 4)) != cudaSuccess ||
+            (ce = cudaMalloc((void**)&p.off32, n * 4)) != cudaSuccess ||
             (ce = cudaMalloc((void**)&p.role, n * 4)) != cudaSuccess ||
             (ce = cudaMalloc((void**)&p.hits, n * 4)) != cudaSuccess ||
             (ce = cudaMalloc((void**)&p.flag, n)) != cudaSuccess)
@@ -94,18 +104,25 @@ int pipe_reserve(Device& d, Pipe& p, uint64_t n_res, uint64_t n_seq, uint64_t n_
 }
 
 // validate offsets of [cs, ce) and collect shape numbers; false = offsets not monotone
-bool scan_offsets(const uint64_t* off, uint64_t cs, uint64_t ce, uint32_t long_seq, uint32_t mid_seq, int K,
-                  ChunkShape& s) {
+template <typename OffT>
+static bool scan_offsets_t(const OffT* off, uint64_t cs, uint64_t ce, uint32_t long_seq, uint32_t mid_seq, int K,
+                           ChunkShape& s) {
     s = ChunkShape();
     for (uint64_t i = cs; i < ce; i++) {
         if (off[i + 1] < off[i]) return false;
-        uint64_t L = off[i + 1] - off[i];
+        uint64_t L = (uint64_t)off[i + 1] - (uint64_t)off[i];
         if (L > mid_seq) { s.n_long++; s.long_res += L; }
         else if (L > long_seq) s.n_mid++;
         if (L >= (uint64_t)K) s.probes += L - K + 1;
     }
-    s.n_res = off[ce] - off[cs];
+    s.n_res = (uint64_t)off[ce] - (uint64_t)off[cs];
     return true;
+}
+
+bool scan_offsets(const BatchIn& in, uint64_t cs, uint64_t ce, uint32_t long_seq, uint32_t mid_seq, int K,
+                  ChunkShape& s) {
+    return in.off64 ? scan_offsets_t(in.off64, cs, ce, long_seq, mid_seq, K, s)
+                    : scan_offsets_t(in.off32, cs, ce, long_seq, mid_seq, K, s);
 }
 
 void fill_params(ka_engine* e, Device& d, Pipe& p, uint64_t base, uint64_t n_res, uint64_t n_seq,
@@ -126,7 +143,6 @@ void fill_params(ka_engine* e, Device& d, Pipe& p, uint64_t base, uint64_t n_res
     ap.tab = e->geom;
     ap.tab.sectors = d.table;
     ap.tab.ovf = d.ovf;
-    ap.tab.sig = d.sig;
     ap.tab.shard_sectors = d.shard_sectors;
     ap.tab.shard_ovf = d.shard_ovf;
     ap.lut = d.lut;
@@ -148,8 +164,8 @@ int ensure_tile_smem(Device& d) {
     DCK(d, cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d.id));
     for (int cls : {32, 64, 128})
         for (int v = 0; v < N_VARIANTS; v++) DCK(d, tile_kernel_set_smem(cls, v, (size_t)optin - 2048));  // minus the static part
-    for (int cls : {32, 64, 128}) DCK(d, tile_kernel_filt_set_smem(cls, (size_t)optin - 2048));
     DCK(d, tile_kernel_mode_set_smem((size_t)optin - 2048));
+    DCK(d, line_tile_set_smem((size_t)optin - 2048));
     d.smem_set = (size_t)optin - 2048;
     return KA_OK;
 }
@@ -164,13 +180,7 @@ int enqueue_kernels(ka_engine* e, Device& d, Pipe& p, const AnnotParams& ap, uin
     DCK(d, cudaEventRecord(p.ev_k0, p.st));
     DCK(d, launch_plan(ap, p.st));
     DCK(d, cudaEventRecord(p.ev_t0, p.st));
-    if (ap.tab.sig && e->two_phase && !wide) {
-        size_t smem_f = tile_smem_bytes_filt(ap.ext_max, nullptr);
-        if (smem_f > d.smem_set) return dev_fail(d, KA_ERR_INVALID, "tile shared memory exceeds the device limit", cudaErrorInvalidValue);
-        DCK(d, launch_tiles_filt(ap, smem_f, p.st));
-    } else {
-        DCK(d, launch_tiles(ap, e->variant, smem, p.st));
-    }
+    DCK(d, launch_tiles(ap, 0, smem, p.st));
     d.launches += 2;
     if (n_mid) {
         // sequences of long_seq < L <= mid_seq: one tile each, same kernel, larger shared-memory shape
@@ -181,10 +191,10 @@ int enqueue_kernels(ka_engine* e, Device& d, Pipe& p, const AnnotParams& ap, uin
         size_t smem_mid = tile_smem_bytes(am.ext_max, &am.res_bytes, wide);
         if (smem_mid > d.smem_set) return dev_fail(d, KA_ERR_INVALID, "mid tile shared memory exceeds the device limit", cudaErrorInvalidValue);
         {
-            cudaError_t ce = launch_tiles(am, e->mid_variant, smem_mid, p.st);
+            cudaError_t ce = launch_tiles(am, 1, smem_mid, p.st);
             if (ce != cudaSuccess) {
                 char buf[256];
-                snprintf(buf, sizeof buf, "mid tile launch (tiles %u, smem %zu, variant %d, cls %d)", am.n_tiles, smem_mid, e->mid_variant, am.tab.cls);
+                snprintf(buf, sizeof buf, "mid tile launch (tiles %u, smem %zu, cls %d)", am.n_tiles, smem_mid, am.tab.cls);
                 return dev_fail(d, KA_ERR_CUDA, buf, ce);
             }
         }
@@ -221,7 +231,16 @@ int collect_times(Device& d, Pipe& p) {
 }
 
 void set_l2_window(ka_engine* e, Device& d, cudaStream_t st) {
-    if (!e->l2_persist || !d.table) return;
+    // The line table keeps its filter in L2 through cache hints on the loads themselves (evict_last on
+    // the filter words, evict_first on the table lines); a persisting carve-out measured slower
+    // (microbench/filter_probe.cu: 93 -> 86 G probes/s), so no window is set for it.
+    if (!e->l2_persist || !d.table || e->line) {
+        cudaStreamAttrValue v;
+        memset(&v, 0, sizeof v);
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v);
+        cudaGetLastError();
+        return;
+    }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, d.id) != cudaSuccess) return;
     if (prop.persistingL2CacheMaxSize <= 0 || prop.accessPolicyMaxWindowSize <= 0) return;
@@ -229,12 +248,10 @@ void set_l2_window(ka_engine* e, Device& d, cudaStream_t st) {
     cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist);
     cudaStreamAttrValue v;
     memset(&v, 0, sizeof v);
-    // with the presence filter the signatures are the hot, reusable data: pin them; otherwise
     // pin as much of the table as the persisting carve-out holds
-    const bool sig = d.sig != nullptr;
-    size_t span = sig ? ((size_t)2 << e->geom.bbits) : (size_t)e->info.table_bytes;
+    size_t span = (size_t)e->info.table_bytes;
     size_t win = std::min<size_t>(span, (size_t)prop.accessPolicyMaxWindowSize);
-    v.accessPolicyWindow.base_ptr = sig ? (void*)d.sig : (void*)d.table;
+    v.accessPolicyWindow.base_ptr = (void*)d.table;
     v.accessPolicyWindow.num_bytes = win;
     v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)persist / (double)win);
     v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
@@ -243,26 +260,102 @@ void set_l2_window(ka_engine* e, Device& d, cudaStream_t st) {
     cudaGetLastError();  // the window is an optimisation; never fail the call on it
 }
 
-// Annotate sequences [s_begin, s_end) of the host batch on device d.
-int annotate_range(ka_engine* e, Device& d, const uint8_t* residues, const uint64_t* offsets,
-                   uint64_t s_begin, uint64_t s_end, int32_t min_hits, int32_t* out_role,
-                   int32_t* out_hits, uint8_t* out_flag) {
+// ---- line table (slot class 16): parameters and launches of one chunk ----
+void fill_line_params(ka_engine* e, Device& d, Pipe& p, uint64_t n_res, uint64_t n_seq, int32_t min_hits, LineParams& lp) {
+    lp.pk = p.pk;
+    lp.off = p.off32;
+    lp.n_seq = (uint32_t)n_seq;
+    lp.n_tiles = (uint32_t)(n_res / e->tile_span + 1);
+    lp.tile_span = e->tile_span;
+    lp.long_seq = e->long_seq;
+    lp.mid_seq = std::max(e->mid_seq, e->long_seq);
+    lp.ext_max = e->tile_span + e->long_seq;
+    line_tile_smem_bytes(lp.ext_max, &lp.stage_bytes);
+    lp.first = p.first;
+    lp.mid_desc = p.mid;
+    lp.mid_count = p.ctr + 1;
+    lp.big_count = p.ctr;
+    lp.tok_cursor = reinterpret_cast<unsigned long long*>(p.ctr + 2);
+    lp.big_list = p.big;
+    lp.scratch = p.scratch;
+    lp.tab = e->lgeom;
+    lp.tab.lines = d.table;
+    lp.tab.ovf = d.ovf;
+    lp.tab.filt = e->filter ? d.filt : nullptr;
+    lp.min_hits = min_hits;
+    lp.out_role = p.role;
+    lp.out_hits = p.hits;
+    lp.out_flag = p.flag;
+    lp.dbg = p.ctr + 4;
+}
+
+// plan + tiles (+ single-sequence tiles, + long sequences) of the line table on the pipe's stream
+int enqueue_line_kernels(ka_engine* e, Device& d, Pipe& p, const LineParams& lp, bool off_is_64, uint64_t origin,
+                         uint64_t n_long, uint64_t n_mid) {
+    const size_t smem = line_tile_smem_bytes(lp.ext_max, nullptr);
+    { int rc = ensure_tile_smem(d); if (rc) return rc; }
+    if (smem > d.smem_set) return dev_fail(d, KA_ERR_INVALID, "tile shared memory exceeds the device limit", cudaErrorInvalidValue);
+    DCK(d, cudaMemsetAsync(p.ctr, 0, 16, p.st));
+    DCK(d, cudaEventRecord(p.ev_k0, p.st));
+    DCK(d, launch_line_plan(lp, off_is_64 ? p.off : nullptr, p.off32_in, origin, p.st));
+    DCK(d, cudaEventRecord(p.ev_t0, p.st));
+    DCK(d, launch_line_tiles(lp, smem, p.st));
+    d.launches += 2;
+    if (n_mid) {
+        LineParams lm = lp;
+        lm.first = p.mid;
+        lm.n_tiles = (uint32_t)n_mid;
+        lm.ext_max = lp.mid_seq;
+        const size_t smem_mid = line_tile_smem_bytes(lm.ext_max, &lm.stage_bytes);
+        if (smem_mid > d.smem_set) return dev_fail(d, KA_ERR_INVALID, "mid tile shared memory exceeds the device limit", cudaErrorInvalidValue);
+        DCK(d, launch_line_tiles(lm, smem_mid, p.st));
+        d.launches += 1;
+    }
+    DCK(d, cudaEventRecord(p.ev_t1, p.st));
+    if (n_long) {
+        int grid = (int)std::min<uint64_t>(n_long, (uint64_t)d.sm_count * 4);
+        DCK(d, launch_line_big(lp, grid, p.st));
+        d.launches += 1;
+    }
+    DCK(d, cudaEventRecord(p.ev_k1, p.st));
+    return KA_OK;
+}
+
+template <typename OffT>
+static uint64_t chunk_end(const OffT* off, uint64_t cs, uint64_t s_end, uint64_t chunk_residues) {
+    const uint64_t lim = (uint64_t)off[cs] + chunk_residues;
+    // last sequence boundary at or below the limit (at least one sequence per chunk)
+    uint64_t lo = cs + 1, hi = s_end + 1;
+    while (lo < hi) {
+        const uint64_t mid = lo + ((hi - lo) >> 1);
+        if ((uint64_t)off[mid] <= lim) lo = mid + 1; else hi = mid;
+    }
+    return lo - 1;
+}
+
+// Annotate sequences [s_begin, s_end) of the host batch on device d.  Four combinations:
+//   line table   + packed input : H2D codes                 -> line kernels        (fast path)
+//   line table   + byte input   : H2D bytes -> pack kernel  -> line kernels
+//   sector table + byte input   : H2D bytes                 -> sector kernels
+//   sector table + packed input : H2D codes -> unpack kernel -> sector kernels
+int annotate_range(ka_engine* e, Device& d, const BatchIn& in, uint64_t s_begin, uint64_t s_end, int32_t min_hits,
+                   int32_t* out_role, int32_t* out_hits, uint8_t* out_flag) {
     DCK(d, cudaSetDevice(d.id));
     d.kernel_ms = d.tile_ms = 0; d.launches = 0; d.h2d = d.d2h = 0; d.probes = 0;
+    const bool line = e->line, packed = in.packed();
     int slot = 0;
     uint64_t cs = s_begin;
     while (cs < s_end) {
         // chunk = as many whole sequences as fit in chunk_residues (at least one)
-        uint64_t lim = offsets[cs] + e->chunk_residues;
-        uint64_t ce = std::upper_bound(offsets + cs + 1, offsets + s_end + 1, lim) - offsets - 1;
+        uint64_t ce = in.off64 ? chunk_end(in.off64, cs, s_end, e->chunk_residues) : chunk_end(in.off32, cs, s_end, e->chunk_residues);
         if (ce <= cs) ce = cs + 1;
         if (ce - cs > 0xfffffff0ull) ce = cs + 0xfffffff0ull;
         ChunkShape sh;
-        if (!scan_offsets(offsets, cs, ce, e->long_seq, e->mid_seq, e->info.K, sh)) {
+        if (!scan_offsets(in, cs, ce, e->long_seq, e->mid_seq, e->info.K, sh)) {
             d.err = KA_ERR_OFFSETS; d.errmsg = "offsets are not monotone";
             return d.err;
         }
-        if (sh.n_res > 0x7fffffffull) {
+        if (sh.n_res > 0x7fffff00ull) {
             d.err = KA_ERR_TOO_BIG; d.errmsg = "a single sequence exceeds 2^31 residues";
             return d.err;
         }
@@ -274,18 +367,41 @@ int annotate_range(ka_engine* e, Device& d, const uint8_t* residues, const uint6
             if (rc) return rc;
             p.busy = false;
         }
-        uint64_t n = ce - cs;
-        uint64_t n_tiles = sh.n_res / e->tile_span + 1;
-        int rc = pipe_reserve(d, p, sh.n_res, n, n_tiles, sh.n_long, sh.long_res, sh.n_mid, e->geom.wide != 0);
+        const uint64_t n = ce - cs;
+        const uint64_t n_tiles = sh.n_res / e->tile_span + 1;
+        int rc = pipe_reserve(d, p, sh.n_res, n, n_tiles, sh.n_long, sh.long_res, sh.n_mid, e->geom.wide != 0,
+                              !packed || !line, packed || line);
         if (rc) return rc;
-        if (sh.n_res)
-            DCK(d, cudaMemcpyAsync(p.res, residues + offsets[cs], sh.n_res, cudaMemcpyHostToDevice, p.st));
-        DCK(d, cudaMemcpyAsync(p.off, offsets + cs, (n + 1) * 8, cudaMemcpyHostToDevice, p.st));
-        d.h2d += sh.n_res + (n + 1) * 8;
-        AnnotParams ap;
-        fill_params(e, d, p, offsets[cs], sh.n_res, n, min_hits, ap);
-        if (!out_flag) ap.out_flag = p.flag;  // kernel always writes flags; host may skip them
-        rc = enqueue_kernels(e, d, p, ap, sh.n_long, sh.n_mid);
+        const uint64_t r_begin = in.off(cs), r_end = in.off(ce);
+        const uint64_t origin = r_begin & ~127ull;          // chunk-relative residue 0 (5 * 128 bits = 80 bytes: byte aligned)
+        const uint32_t lead = (uint32_t)(r_begin - origin);
+        if (packed) {
+            const uint64_t byte0 = origin * 5 / 8, byte1 = (r_end * 5 + 7) / 8;
+            if (byte1 > byte0)
+                DCK(d, cudaMemcpyAsync(p.pk, in.codes + byte0, byte1 - byte0, cudaMemcpyHostToDevice, p.st));
+            DCK(d, cudaMemcpyAsync(p.off32_in, in.off32 + cs, (n + 1) * 4, cudaMemcpyHostToDevice, p.st));
+            d.h2d += (byte1 - byte0) + (n + 1) * 4;
+        } else {
+            if (sh.n_res)
+                DCK(d, cudaMemcpyAsync(p.res, in.residues + r_begin, sh.n_res, cudaMemcpyHostToDevice, p.st));
+            DCK(d, cudaMemcpyAsync(p.off, in.off64 + cs, (n + 1) * 8, cudaMemcpyHostToDevice, p.st));
+            d.h2d += sh.n_res + (n + 1) * 8;
+        }
+        if (line) {
+            if (!packed) { DCK(d, launch_pack(p.res, lead, sh.n_res, d.lut5, p.pk, p.st)); d.launches += 1; }
+            LineParams lp;
+            fill_line_params(e, d, p, sh.n_res, n, min_hits, lp);
+            rc = enqueue_line_kernels(e, d, p, lp, !packed, origin, sh.n_long, sh.n_mid);
+        } else {
+            if (packed) {
+                DCK(d, launch_unpack(p.pk, lead, sh.n_res, d.inv32, p.res, p.st));
+                DCK(d, launch_widen_offsets(p.off32_in, n + 1, p.off, p.st));
+                d.launches += 2;
+            }
+            AnnotParams ap;
+            fill_params(e, d, p, r_begin, sh.n_res, n, min_hits, ap);
+            rc = enqueue_kernels(e, d, p, ap, sh.n_long, sh.n_mid);
+        }
         if (rc) return rc;
         DCK(d, cudaMemcpyAsync(out_role + cs, p.role, n * 4, cudaMemcpyDeviceToHost, p.st));
         DCK(d, cudaMemcpyAsync(out_hits + cs, p.hits, n * 4, cudaMemcpyDeviceToHost, p.st));
@@ -359,7 +475,8 @@ int ka_create(const int* device_ids, int n_devices, ka_engine** out) {
         d.sm_count = prop.multiProcessorCount;
         int rc = KA_OK;
         for (int k = 0; k < NPIPE && rc == KA_OK; k++) rc = pipe_init(d, d.pipe[k]);
-        if (rc == KA_OK && cudaMalloc((void**)&d.lut, 256) != cudaSuccess) rc = KA_ERR_OOM;
+        if (rc == KA_OK && (cudaMalloc((void**)&d.lut, 256) != cudaSuccess || cudaMalloc((void**)&d.lut5, 256) != cudaSuccess ||
+                            cudaMalloc((void**)&d.inv32, 32) != cudaSuccess)) rc = KA_ERR_OOM;
         if (rc) {
             std::string m = d.errmsg.empty() ? "device allocation failed" : d.errmsg;
             e->devs.resize(i + 1);
@@ -378,7 +495,9 @@ void ka_destroy(ka_engine* e) {
         for (int k = 0; k < NPIPE; k++) pipe_free(d.pipe[k]);
         if (d.table) cudaFree(d.table);
         if (d.ovf) cudaFree(d.ovf);
-        if (d.sig) cudaFree(d.sig);
+        if (d.filt) cudaFree(d.filt);
+        if (d.lut5) cudaFree(d.lut5);
+        if (d.inv32) cudaFree(d.inv32);
         route_destroy_comm(d);
         for (auto& ln : d.lane) {
             for (void* q : {(void*)ln.r_keys, (void*)ln.r_send, (void*)ln.r_recv, (void*)ln.r_ans_recv, (void*)ln.r_ans_sorted,
@@ -400,50 +519,51 @@ const char* ka_last_error(const ka_engine* e) { return e ? e->err.c_str() : g_cr
 int ka_set_option(ka_engine* e, const char* name, double v) {
     if (!e || !name) return KA_ERR_INVALID;
     std::lock_guard<std::mutex> lk(e->mu);
-    std::string n(name);
+    const std::string n(name);
+    // every value is validated into a copy; the engine changes only when the whole call succeeds
+    double load_factor = e->load_factor;
+    uint32_t tile_span = e->tile_span, long_seq = e->long_seq, mid_seq = e->mid_seq;
+    uint64_t chunk_residues = e->chunk_residues;
+    int l2_persist = e->l2_persist, table_mode = e->table_mode, wide = e->wide, filter = e->filter, slot_bits = e->slot_bits;
     if (n == "load_factor") {
         if (!(v > 0.0 && v <= 0.9)) return fail(e, KA_ERR_INVALID, "load_factor must be in (0, 0.9]");
-        e->load_factor = v;
+        load_factor = v;
     } else if (n == "tile_span") {
-        if (v < 256 || v > 65536) return fail(e, KA_ERR_INVALID, "tile_span must be in [256, 65536]");
-        e->tile_span = (uint32_t)v & ~15u;
-        if (e->long_seq < e->tile_span) e->long_seq = e->tile_span;
+        if (!(v >= 256 && v <= 65536)) return fail(e, KA_ERR_INVALID, "tile_span must be in [256, 65536]");
+        tile_span = (uint32_t)v & ~15u;
+        if (long_seq < tile_span) long_seq = tile_span;
     } else if (n == "long_seq") {
-        if (v < 256 || v > (1 << 20)) return fail(e, KA_ERR_INVALID, "long_seq must be in [256, 2^20]");
-        e->long_seq = (uint32_t)v;
-        if (e->long_seq < e->tile_span) e->long_seq = e->tile_span;
+        if (!(v >= 256 && v <= (1 << 20))) return fail(e, KA_ERR_INVALID, "long_seq must be in [256, 2^20]");
+        long_seq = (uint32_t)v;
+        if (long_seq < tile_span) long_seq = tile_span;
     } else if (n == "mid_seq") {
-        if (v < 256 || v > 49152) return fail(e, KA_ERR_INVALID, "mid_seq must be in [256, 49152]");
-        e->mid_seq = (uint32_t)v;
-    } else if (n == "mid_variant") {
-        if (v < 0 || v >= N_VARIANTS) return fail(e, KA_ERR_INVALID, "mid_variant must be 0..%d", N_VARIANTS - 1);
-        e->mid_variant = (int)v;
+        if (!(v >= 256 && v <= 49152)) return fail(e, KA_ERR_INVALID, "mid_seq must be in [256, 49152]");
+        mid_seq = (uint32_t)v;
     } else if (n == "chunk_residues") {
-        if (v < 4096 || v > (double)(1ull << 30)) return fail(e, KA_ERR_INVALID, "chunk_residues must be in [4096, 2^30]");
-        e->chunk_residues = (uint64_t)v;
+        if (!(v >= 4096 && v <= (double)(1ull << 30))) return fail(e, KA_ERR_INVALID, "chunk_residues must be in [4096, 2^30]");
+        chunk_residues = (uint64_t)v;
     } else if (n == "l2_persist") {
-        e->l2_persist = v != 0;
-    } else if (n == "two_phase") {
-        e->two_phase = v != 0;
+        l2_persist = v != 0;
     } else if (n == "table_mode") {
         if (v != 0 && v != 1 && v != 2) return fail(e, KA_ERR_INVALID, "table_mode must be 0 (replicated), 1 (sharded, peer loads) or 2 (sharded, routed)");
-        e->table_mode = (int)v;
+        table_mode = (int)v;
     } else if (n == "wide") {
-        e->wide = v != 0;
+        wide = v != 0;
     } else if (n == "filter") {
-        e->filter = v < 0 ? -1 : (v != 0);
+        filter = v != 0;
     } else if (n == "slot_bits") {
-        if (v != 0 && v != 32 && v != 64 && v != 128) return fail(e, KA_ERR_INVALID, "slot_bits must be 0, 32, 64 or 128");
-        e->slot_bits = (int)v;
-    } else if (n == "variant") {
-        if (v < 0 || v >= N_VARIANTS) return fail(e, KA_ERR_INVALID, "variant must be 0..%d", N_VARIANTS - 1);
-        e->variant = (int)v;
+        if (v != 0 && v != 16 && v != 32 && v != 64 && v != 128) return fail(e, KA_ERR_INVALID, "slot_bits must be 0, 16, 32, 64 or 128");
+        slot_bits = (int)v;
     } else {
         return fail(e, KA_ERR_INVALID, "unknown option '%s'", name);
     }
-    if (tile_smem_bytes(e->tile_span + e->long_seq, nullptr, e->wide != 0) > 225 * 1024 ||
-        tile_smem_bytes(std::max(e->mid_seq, e->long_seq), nullptr, e->wide != 0) > 225 * 1024)
+    const uint32_t mid_eff = std::max(mid_seq, long_seq);
+    if (tile_smem_bytes(tile_span + long_seq, nullptr, true) > 225 * 1024 || tile_smem_bytes(mid_eff, nullptr, true) > 225 * 1024 ||
+        line_tile_smem_bytes(tile_span + long_seq, nullptr) > 225 * 1024 || line_tile_smem_bytes(mid_eff, nullptr) > 225 * 1024)
         return fail(e, KA_ERR_INVALID, "tile_span + long_seq (or mid_seq) needs more than 227 KB of shared memory");
+    e->load_factor = load_factor; e->tile_span = tile_span; e->long_seq = long_seq; e->mid_seq = mid_seq;
+    e->chunk_residues = chunk_residues; e->l2_persist = l2_persist; e->table_mode = table_mode; e->wide = wide;
+    e->filter = filter; e->slot_bits = slot_bits;
     return KA_OK;
 }
 
@@ -455,40 +575,42 @@ int ka_db_get_info(ka_engine* e, ka_db_info* out) {
     return KA_OK;
 }
 
-int ka_annotate(ka_engine* e, const uint8_t* residues, const uint64_t* offsets, uint64_t N,
-                int32_t min_hits, int32_t* out_role, int32_t* out_hits, uint8_t* out_flag) {
-    if (!e) return KA_ERR_INVALID;
+static int annotate_impl(ka_engine* e, const BatchIn& in, uint64_t N, int32_t min_hits, int32_t* out_role,
+                         int32_t* out_hits, uint8_t* out_flag, const char* who) {
     std::lock_guard<std::mutex> lk(e->mu);
-    if (!e->have_db) return fail(e, KA_ERR_NO_DB, "ka_annotate: no k-mer database loaded");
-    if (min_hits < 1) return fail(e, KA_ERR_INVALID, "ka_annotate: min_hits must be positive");  // ApplyKmerProcessor.java:91-92
-    if (N && (!offsets || !out_role || !out_hits)) return fail(e, KA_ERR_INVALID, "ka_annotate: NULL argument");
-    if (N && offsets[N] > offsets[0] && !residues) return fail(e, KA_ERR_INVALID, "ka_annotate: residues is NULL");
+    if (!e->have_db) return fail(e, KA_ERR_NO_DB, "%s: no k-mer database loaded", who);
+    if (min_hits < 1) return fail(e, KA_ERR_INVALID, "%s: min_hits must be positive", who);  // ApplyKmerProcessor.java:91-92
+    if (N && ((!in.off64 && !in.off32) || !out_role || !out_hits)) return fail(e, KA_ERR_INVALID, "%s: NULL argument", who);
+    if (N && in.off(N) > in.off(0) && !in.residues && !in.codes) return fail(e, KA_ERR_INVALID, "%s: residues is NULL", who);
     auto t0 = std::chrono::steady_clock::now();
     e->stats = ka_stats{};
     if (N == 0) return KA_OK;
-    if (offsets[N] < offsets[0]) return fail(e, KA_ERR_OFFSETS, "ka_annotate: offsets are not monotone");
+    if (in.off(N) < in.off(0)) return fail(e, KA_ERR_OFFSETS, "%s: offsets are not monotone", who);
 
     // residue-balanced contiguous ranges, one per device
     size_t nd = e->devs.size();
     std::vector<uint64_t> cut(nd + 1, 0);
     cut[nd] = N;
-    uint64_t total = offsets[N] - offsets[0];
+    uint64_t total = in.off(N) - in.off(0);
     for (size_t i = 1; i < nd; i++) {
-        uint64_t target = offsets[0] + total / nd * i;
-        uint64_t c = std::lower_bound(offsets, offsets + N + 1, target) - offsets;
-        cut[i] = std::min<uint64_t>(std::max<uint64_t>(c, cut[i - 1]), N);
+        const uint64_t target = in.off(0) + total / nd * i;
+        uint64_t lo = 0, hi = N + 1;                         // first index with off >= target
+        while (lo < hi) { const uint64_t mid = lo + ((hi - lo) >> 1); if (in.off(mid) < target) lo = mid + 1; else hi = mid; }
+        cut[i] = std::min<uint64_t>(std::max<uint64_t>(lo, cut[i - 1]), N);
     }
     int rc;
-    if (e->table_mode == 2) {
+    if (e->db_table_mode == 2) {
+        if (in.packed()) return fail(e, KA_ERR_INVALID, "%s: the routed table (table_mode 2) takes byte residues (ka_annotate)", who);
+        if (!e->nccl_ready || e->geom.n_shards <= 1) return fail(e, KA_ERR_INVALID, "%s: the loaded table is not a routed table", who);
         // routed sharded table: every device must walk every round, even with an empty range
         RouteShared shared((int)nd);
         rc = for_each_device(e, [&](Device& d, int i) {
-            return annotate_routed_range(e, d, i, shared, residues, offsets, cut[i], cut[i + 1], min_hits, out_role, out_hits, out_flag);
+            return annotate_routed_range(e, d, i, shared, in.residues, in.off64, cut[i], cut[i + 1], min_hits, out_role, out_hits, out_flag);
         });
     } else {
         rc = for_each_device(e, [&](Device& d, int i) {
             if (cut[i] == cut[i + 1]) { d.kernel_ms = d.tile_ms = 0; d.launches = d.h2d = d.d2h = d.probes = 0; return (int)KA_OK; }
-            return annotate_range(e, d, residues, offsets, cut[i], cut[i + 1], min_hits, out_role, out_hits, out_flag);
+            return annotate_range(e, d, in, cut[i], cut[i + 1], min_hits, out_role, out_hits, out_flag);
         });
     }
     if (rc) {
@@ -510,6 +632,58 @@ int ka_annotate(ka_engine* e, const uint8_t* residues, const uint64_t* offsets, 
     return KA_OK;
 }
 
+int ka_annotate(ka_engine* e, const uint8_t* residues, const uint64_t* offsets, uint64_t N,
+                int32_t min_hits, int32_t* out_role, int32_t* out_hits, uint8_t* out_flag) {
+    if (!e) return KA_ERR_INVALID;
+    BatchIn in;
+    in.residues = residues; in.off64 = offsets;
+    return annotate_impl(e, in, N, min_hits, out_role, out_hits, out_flag, "ka_annotate");
+}
+
+int ka_annotate_packed(ka_engine* e, const uint8_t* codes, const uint32_t* offsets, uint64_t N,
+                       int32_t min_hits, int32_t* out_role, int32_t* out_hits, uint8_t* out_flag) {
+    if (!e) return KA_ERR_INVALID;
+    BatchIn in;
+    in.codes = codes; in.off32 = offsets;
+    return annotate_impl(e, in, N, min_hits, out_role, out_hits, out_flag, "ka_annotate_packed");
+}
+
+int ka_db_get_alphabet(ka_engine* e, uint8_t* code_of_byte) {
+    if (!e || !code_of_byte) return KA_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(e->mu);
+    if (!e->have_db) return fail(e, KA_ERR_NO_DB, "ka_db_get_alphabet: no k-mer database loaded");
+    memcpy(code_of_byte, e->lut5, 256);
+    return KA_OK;
+}
+
+// 8 residues -> 40 bits -> 5 bytes; the tail (n % 8 residues) is written bit by bit into zeroed bytes
+int ka_pack_residues(ka_engine* e, const uint8_t* residues, uint64_t n, uint64_t first_index, uint8_t* codes) {
+    if (!e || (n && (!residues || !codes))) return KA_ERR_INVALID;
+    uint8_t lut[256];
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        if (!e->have_db) return fail(e, KA_ERR_NO_DB, "ka_pack_residues: no k-mer database loaded");
+        if (first_index % 8) return fail(e, KA_ERR_INVALID, "ka_pack_residues: first_index must be a multiple of 8 (byte boundary of the stream)");
+        memcpy(lut, e->lut5, 256);
+    }
+    uint8_t* o = codes + first_index / 8 * 5;
+    uint64_t i = 0;
+    for (; i + 8 <= n; i += 8, o += 5) {
+        const uint8_t* r = residues + i;
+        const uint64_t v = (uint64_t)lut[r[0]] | (uint64_t)lut[r[1]] << 5 | (uint64_t)lut[r[2]] << 10 | (uint64_t)lut[r[3]] << 15 |
+                           (uint64_t)lut[r[4]] << 20 | (uint64_t)lut[r[5]] << 25 | (uint64_t)lut[r[6]] << 30 | (uint64_t)lut[r[7]] << 35;
+        o[0] = (uint8_t)v; o[1] = (uint8_t)(v >> 8); o[2] = (uint8_t)(v >> 16); o[3] = (uint8_t)(v >> 24); o[4] = (uint8_t)(v >> 32);
+    }
+    if (i < n) {
+        uint64_t v = 0;
+        const uint64_t rest = n - i;
+        for (uint64_t k = 0; k < rest; k++) v |= (uint64_t)lut[residues[i + k]] << (5 * k);
+        const uint64_t nbytes = (rest * 5 + 7) / 8;
+        for (uint64_t k = 0; k < nbytes; k++) o[k] = (uint8_t)(v >> (8 * k));
+    }
+    return KA_OK;
+}
+
 int ka_batch_upload(ka_engine* e, int dev_index, const uint8_t* residues, const uint64_t* offsets,
                     uint64_t N, ka_batch** out) {
     if (!e || !out) return KA_ERR_INVALID;
@@ -517,21 +691,33 @@ int ka_batch_upload(ka_engine* e, int dev_index, const uint8_t* residues, const 
     std::lock_guard<std::mutex> lk(e->mu);
     if (!e->have_db) return fail(e, KA_ERR_NO_DB, "ka_batch_upload: load the k-mer database first");
     if (dev_index < 0 || dev_index >= (int)e->devs.size()) return fail(e, KA_ERR_INVALID, "ka_batch_upload: bad device index");
-    if (e->table_mode == 2) return fail(e, KA_ERR_INVALID, "ka_batch_upload: resident batches are not available with the routed table (table_mode 2)");
+    if (e->db_table_mode == 2) return fail(e, KA_ERR_INVALID, "ka_batch_upload: resident batches are not available with the routed table (table_mode 2)");
     if (N == 0 || !offsets) return fail(e, KA_ERR_INVALID, "ka_batch_upload: empty batch");
     if (N > 0xfffffff0ull) return fail(e, KA_ERR_TOO_BIG, "ka_batch_upload: too many sequences");
     Device& d = e->devs[dev_index];
     cudaSetDevice(d.id);
+    BatchIn in;
+    in.residues = residues; in.off64 = offsets;
     ChunkShape sh;
-    if (!scan_offsets(offsets, 0, N, e->long_seq, e->mid_seq, e->info.K, sh)) return fail(e, KA_ERR_OFFSETS, "ka_batch_upload: offsets are not monotone");
+    if (!scan_offsets(in, 0, N, e->long_seq, e->mid_seq, e->info.K, sh)) return fail(e, KA_ERR_OFFSETS, "ka_batch_upload: offsets are not monotone");
+    if (e->line && sh.n_res > 0x7fffff00ull) return fail(e, KA_ERR_TOO_BIG, "ka_batch_upload: more than 2^31 residues in one resident batch");
     ka_batch* b = new ka_batch();
     b->dev_index = dev_index; b->n_seq = N; b->n_res = sh.n_res; b->base = offsets[0];
     b->long_res = sh.long_res; b->n_long = sh.n_long; b->n_mid = sh.n_mid;
+    b->origin = offsets[0] & ~127ull;
+    b->tile_span = e->tile_span; b->long_seq = e->long_seq; b->mid_seq = e->mid_seq; b->db_serial = e->db_serial;
     int rc = pipe_init(d, b->p);
-    if (rc == KA_OK) rc = pipe_reserve(d, b->p, sh.n_res, N, sh.n_res / e->tile_span + 1, sh.n_long, sh.long_res, sh.n_mid, e->geom.wide != 0);
+    if (rc == KA_OK) rc = pipe_reserve(d, b->p, sh.n_res, N, sh.n_res / e->tile_span + 1, sh.n_long, sh.long_res, sh.n_mid, e->geom.wide != 0,
+                                       true, e->line);
     cudaError_t ce = cudaSuccess;
     if (rc == KA_OK && sh.n_res) ce = cudaMemcpy(b->p.res, residues + offsets[0], sh.n_res, cudaMemcpyHostToDevice);
     if (rc == KA_OK && ce == cudaSuccess) ce = cudaMemcpy(b->p.off, offsets, (N + 1) * 8, cudaMemcpyHostToDevice);
+    if (rc == KA_OK && ce == cudaSuccess && e->line) {
+        // the resident form of a batch for the line table is the 5-bit stream (what ka_annotate_packed ships)
+        ce = launch_pack(b->p.res, (uint32_t)(offsets[0] - b->origin), sh.n_res, d.lut5, b->p.pk, b->p.st);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(b->p.st);
+        if (ce == cudaSuccess) { cudaFree(b->p.res); b->p.res = nullptr; b->p.res_cap = 0; }
+    }
     if (rc || ce != cudaSuccess) {
         std::string m = rc ? d.errmsg : std::string(cudaGetErrorString(ce));
         pipe_free(b->p);
@@ -550,13 +736,24 @@ int ka_annotate_resident(ka_engine* e, ka_batch* b, int32_t min_hits) {
     std::lock_guard<std::mutex> lk(e->mu);
     if (!e->have_db) return fail(e, KA_ERR_NO_DB, "ka_annotate_resident: no k-mer database loaded");
     if (min_hits < 1) return fail(e, KA_ERR_INVALID, "ka_annotate_resident: min_hits must be positive");
+    if (b->db_serial != e->db_serial)
+        return fail(e, KA_ERR_INVALID, "ka_annotate_resident: the k-mer database was reloaded after this batch was uploaded; upload it again");
+    if (b->tile_span != e->tile_span || b->long_seq != e->long_seq || b->mid_seq != e->mid_seq)
+        return fail(e, KA_ERR_INVALID, "ka_annotate_resident: tile_span / long_seq / mid_seq changed after this batch was uploaded; upload it again");
     Device& d = e->devs[b->dev_index];
     cudaSetDevice(d.id);
     auto t0 = std::chrono::steady_clock::now();
     d.kernel_ms = d.tile_ms = 0; d.launches = 0;
-    AnnotParams ap;
-    fill_params(e, d, b->p, b->base, b->n_res, b->n_seq, min_hits, ap);
-    int rc = enqueue_kernels(e, d, b->p, ap, b->n_long, b->n_mid);
+    int rc;
+    if (e->line) {
+        LineParams lp;
+        fill_line_params(e, d, b->p, b->n_res, b->n_seq, min_hits, lp);
+        rc = enqueue_line_kernels(e, d, b->p, lp, true, b->origin, b->n_long, b->n_mid);
+    } else {
+        AnnotParams ap;
+        fill_params(e, d, b->p, b->base, b->n_res, b->n_seq, min_hits, ap);
+        rc = enqueue_kernels(e, d, b->p, ap, b->n_long, b->n_mid);
+    }
     if (rc == KA_OK) {
         cudaError_t ce = cudaStreamSynchronize(b->p.st);
         if (ce != cudaSuccess) rc = dev_fail(d, KA_ERR_CUDA, "annotate kernels", ce);

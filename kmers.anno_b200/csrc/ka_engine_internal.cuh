@@ -23,6 +23,7 @@
 
 #include "../../include/kmeranno.h"
 #include "ka_kernels.cuh"
+#include "ka_line.cuh"
 
 
 namespace kai {
@@ -33,8 +34,11 @@ constexpr int NPIPE = 4;  // chunks in flight per device
 
 struct Pipe {
     cudaStream_t st = nullptr;
-    uint8_t* res = nullptr; size_t res_cap = 0;
-    unsigned long long* off = nullptr; size_t seq_cap = 0;
+    uint8_t* res = nullptr; size_t res_cap = 0;          // residue bytes of the chunk
+    uint32_t* pk = nullptr; size_t pk_cap = 0;           // 5-bit codes of the chunk (words), ka_line.cuh
+    unsigned long long* off = nullptr; size_t seq_cap = 0;   // absolute 64-bit offsets
+    uint32_t* off32_in = nullptr;                        // absolute 32-bit offsets as given to ka_annotate_packed
+    uint32_t* off32 = nullptr;                           // chunk-relative offsets written by line_plan_kernel
     uint4* first = nullptr; size_t first_cap = 0;
     int32_t* role = nullptr; int32_t* hits = nullptr; uint8_t* flag = nullptr;
     uint32_t* ctr = nullptr;  // 16 bytes: [0] big_count, [2..3] token cursor (u64)
@@ -50,7 +54,9 @@ struct Device {
     int sm_count = 148;
     uint4* table = nullptr;
     uint4* ovf = nullptr;     // overflow table (cls 32/64)
-    uint16_t* sig = nullptr;  // per-sector presence signatures
+    uint32_t* filt = nullptr; // presence filter of the line table: one word per sector
+    uint8_t* lut5 = nullptr;  // 256-byte residue -> radix digit table (31 = not in the DB alphabet)
+    uint8_t* inv32 = nullptr; // 32-byte digit -> residue byte table (entry 31 = a byte outside the alphabet)
     const uint4** shard_sectors = nullptr;  // sharded mode: device array of peer pointers, one per shard
     const uint4** shard_ovf = nullptr;
     // routed mode (table_mode 2)
@@ -80,6 +86,9 @@ struct Device {
 struct ka_batch {
     int dev_index = 0;
     uint64_t n_seq = 0, n_res = 0, base = 0, long_res = 0, n_long = 0, n_mid = 0;
+    uint64_t origin = 0;                       // line table: absolute residue index of chunk-relative residue 0
+    uint32_t tile_span = 0, long_seq = 0, mid_seq = 0;   // tiling options the batch was scanned with
+    uint64_t db_serial = 0;                    // the DB load this batch was prepared for
     kai::Pipe p;  // owns device buffers of the resident batch
 };
 
@@ -88,29 +97,30 @@ struct ka_engine {
     std::mutex mu;
     std::string err;
     // options
-    double load_factor = 0.4;
+    double load_factor = 0;     // 0 = default of the chosen layout (0.4 sector classes, 0.65 line table)
     uint32_t tile_span = 1536;
-    uint32_t long_seq = 2048;
+    uint32_t long_seq = 1536;
     uint32_t mid_seq = 8192;
-    int mid_variant = 1;
     uint64_t chunk_residues = 48ull << 20;
     int l2_persist = 1;
-    int variant = 0;
-    int slot_bits = 0;  // 0 = choose automatically
-    int filter = 0;     // 1 = per-sector presence signatures in front of the table (measured slower
-                        // in the fused kernel: 40 vs 46 G probes/s, profiles/r01_summary.md), -1 = auto
-    bool have_sig = false;
-    int two_phase = 0;  // with signatures: 1 = two-phase tile kernel (measured slower, kept as an experiment),
-                        // 0 = signature test inside the fused kernel
-    int table_mode = 0; // 0 = table replicated on every device, 1 = sharded by sector range (peer loads)
-    int wide = 0;       // 1 = force the wide-table kernels (64-bit sector indices and tokens) on any table
+    int slot_bits = 0;  // 0 = choose automatically; 16 = the 128-byte-line table (ka_line.cuh)
+    int filter = 1;     // line table: 1 = L2-resident presence filter in front of it (measurement knob)
+    int table_mode = 0; // next ka_db_load: 0 = replicated, 1 = sharded by sector range (peer loads), 2 = sharded + NCCL routing
+    int wide = 0;       // next ka_db_load: 1 = force the wide-table kernels (64-bit sector indices and tokens)
+    // state of the LOADED database (options above only take effect at the next ka_db_load)
+    int db_table_mode = 0;
+    bool line = false;          // the loaded table is a line table (slot class 16)
+    ka::LineTable lgeom{};      // its geometry (pointers filled per device)
+    uint64_t db_serial = 0;     // bumped by every successful load
     bool peers_enabled = false;
     bool nccl_ready = false;
     // db
     bool have_db = false;
     ka_db_info info{};
     ka::TableView geom{};   // geometry of the loaded table (sectors pointer filled per device)
-    uint8_t lut[256];
+    uint8_t lut[256];           // residue byte -> 5-bit field 1..31 (0 = absent): sector classes 32/64/128
+    uint8_t lut5[256];          // residue byte -> radix digit 0..n-1 (31 = absent): line table and packed streams
+    uint8_t inv32[32];          // digit -> residue byte; inv32[31] = some byte outside the alphabet
     ka_stats stats{};
 };
 
@@ -140,6 +150,14 @@ int ensure(Device& d, T*& ptr, size_t& cap, size_t want, const char* what) {
 }
 
 
+// A host batch in one of the two input forms of the ABI.
+struct BatchIn {
+    const uint8_t* residues = nullptr; const uint64_t* off64 = nullptr;   // ka_annotate: bytes + absolute 64-bit offsets
+    const uint8_t* codes = nullptr; const uint32_t* off32 = nullptr;      // ka_annotate_packed: 5-bit stream + 32-bit offsets
+    uint64_t off(uint64_t i) const { return off64 ? off64[i] : (uint64_t)off32[i]; }
+    bool packed() const { return codes != nullptr; }
+};
+
 struct ChunkShape {
     uint64_t n_res = 0, n_long = 0, long_res = 0, probes = 0, n_mid = 0;
 };
@@ -148,8 +166,8 @@ struct ChunkShape {
 int pipe_init(Device& d, Pipe& p);
 void pipe_free(Pipe& p);
 int pipe_reserve(Device& d, Pipe& p, uint64_t n_res, uint64_t n_seq, uint64_t n_tiles,
-                 uint64_t n_long, uint64_t long_res, uint64_t n_mid, bool wide);
-bool scan_offsets(const uint64_t* off, uint64_t cs, uint64_t ce, uint32_t long_seq, uint32_t mid_seq, int K,
+                 uint64_t n_long, uint64_t long_res, uint64_t n_mid, bool wide, bool need_bytes, bool need_codes);
+bool scan_offsets(const BatchIn& in, uint64_t cs, uint64_t ce, uint32_t long_seq, uint32_t mid_seq, int K,
                   ChunkShape& s);
 void fill_params(ka_engine* e, Device& d, Pipe& p, uint64_t base, uint64_t n_res, uint64_t n_seq,
                  int32_t min_hits, AnnotParams& ap);
@@ -157,9 +175,11 @@ int ensure_tile_smem(Device& d);
 int enqueue_kernels(ka_engine* e, Device& d, Pipe& p, const AnnotParams& ap, uint64_t n_long, uint64_t n_mid);
 int collect_times(Device& d, Pipe& p);
 void set_l2_window(ka_engine* e, Device& d, cudaStream_t st);
-int annotate_range(ka_engine* e, Device& d, const uint8_t* residues, const uint64_t* offsets,
-                   uint64_t s_begin, uint64_t s_end, int32_t min_hits, int32_t* out_role,
-                   int32_t* out_hits, uint8_t* out_flag);
+int annotate_range(ka_engine* e, Device& d, const BatchIn& in, uint64_t s_begin, uint64_t s_end, int32_t min_hits,
+                   int32_t* out_role, int32_t* out_hits, uint8_t* out_flag);
+void fill_line_params(ka_engine* e, Device& d, Pipe& p, uint64_t n_res, uint64_t n_seq, int32_t min_hits, LineParams& lp);
+int enqueue_line_kernels(ka_engine* e, Device& d, Pipe& p, const LineParams& lp, bool off_is_64, uint64_t origin,
+                         uint64_t n_long, uint64_t n_mid);
 
 // ---- ka_table.cu ----
 // Source of the DB lines: host arrays, or the synthetic generator (kmers == NULL).
@@ -174,6 +194,9 @@ struct DbSource {
 };
 
 int build_table(ka_engine* e, Device& d, const TableView& geom, const DbSource& src, uint64_t* n_keys, uint32_t* max_probe);
+// line table (slot class 16): geometry for n keys of K digits over `nsym` symbols; false = not representable
+bool choose_line_geometry(uint64_t n, int K, int nsym, double lf, bool forced, LineTable& g);
+int build_line_table(ka_engine* e, Device& d, const LineTable& geom, const DbSource& src, uint64_t* counts3);
 bool choose_geometry(uint64_t n, int K, int32_t max_role, double lf, int force_cls, uint32_t n_shards, bool force_wide, TableView& g);
 // syn_roles > 0: the lines come from the synthetic generator (syn_seed, syn_roles), kmers/role_ids unused
 int db_load_impl(ka_engine* e, const uint8_t* kmers, const int32_t* role_ids, uint64_t n, int K,

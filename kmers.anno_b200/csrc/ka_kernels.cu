@@ -68,19 +68,6 @@ __device__ __forceinline__ void probe_batch(const TableView& tab,
                                             const typename rem_type<CLS>::type (&rem)[C],
                                             uint32_t (&sec)[C], unsigned okmask, int (&role)[C]) {
     constexpr int S = slots_per_sector<CLS>();
-    if (tab.sig) {
-        // stage 0: L2-resident signatures; only probes whose two bits are set go to HBM
-        uint32_t sg[C];
-#pragma unroll
-        for (int i = 0; i < C; i++)
-            if (okmask & (1u << i)) sg[i] = __ldg(tab.sig + sec[i]);
-#pragma unroll
-        for (int i = 0; i < C; i++)
-            if (okmask & (1u << i)) {
-                const uint32_t need = sig_bits(rem[i]);
-                if ((sg[i] & need) != need) okmask &= ~(1u << i);
-            }
-    }
     uint4 a[C], b[C];
 #pragma unroll
     for (int i = 0; i < C; i++)
@@ -466,268 +453,11 @@ __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
     }
 }
 
-// ------------------------------------------------------------------------------------
-// two-phase tile kernel for tables with presence signatures (option "filter")
-// ------------------------------------------------------------------------------------
-// Same tiles, staging, token set and epilogue as tile_kernel; the per-pass body is split:
-//   phase A  every thread rolls the key over up to FA consecutive positions, reads the 16-bit
-//            signature of each home sector (L2 resident) and keeps the positions whose two
-//            bits are set; survivors are compacted into a shared-memory candidate list;
-//   phase B  the candidates (true hits + ~10 % false positives, ~40 % of the positions on the
-//            synthetic proteomes) are spread evenly over the threads, FB sector loads in
-//            flight each; match, de-dup token, tally.
-// Most absent k-mers never reach HBM, and the signature latency of a whole super-pass
-// overlaps instead of preceding every DRAM round.
-constexpr int FILT_THREADS = 128, FA = 8, FB = 4, FILT_CAND = FILT_THREADS * FA;
-
-size_t tile_smem_bytes_filt(uint32_t ext_max, uint32_t* res_bytes_out) {
-    return tile_smem_bytes(ext_max, res_bytes_out, false) + 8 + (size_t)FILT_CAND * (4 + 8 + 1) + 16;
-}
-
-template <int CLS>
-__global__ void __launch_bounds__(FILT_THREADS, 5) tile_kernel_filt(AnnotParams p) {
-    constexpr int THREADS = FILT_THREADS;
-    constexpr int S = slots_per_sector<CLS>();
-    typedef typename rem_type<CLS>::type rem_t;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t s_bar;
-    __shared__ uint32_t s_ncand[2];   // candidate counters, ping-pong per super-pass
-
-    uint8_t* s_res = smem_raw;
-    uint8_t* s_lut = s_res + p.res_bytes;
-    uint32_t* s_off = (uint32_t*)(s_lut + 256);
-    int* s_cnt = (int*)(s_off + MAX_TILE_SEQ + 4);
-    int* s_min = s_cnt + MAX_TILE_SEQ;
-    int* s_max = s_min + MAX_TILE_SEQ;
-    uint32_t* s_tok = (uint32_t*)(s_max + MAX_TILE_SEQ);
-    unsigned long long* c_rem64 = (unsigned long long*)(s_tok + ((tok_cap(p.ext_max) + 4 * MAX_TILE_SEQ + 8 + 1) & ~1u));
-    uint32_t* c_sec = (uint32_t*)(c_rem64 + FILT_CAND);
-    uint8_t* c_seq = (uint8_t*)(c_sec + FILT_CAND);
-
-    const uint32_t tid = threadIdx.x;
-    const uint32_t lane = tid & 31;
-    const uint4 desc = p.first[blockIdx.x];
-    uint8_t lut_byte[2];
-    lut_byte[0] = p.lut[tid]; lut_byte[1] = p.lut[tid + 128];
-    const uint32_t s0 = desc.x, s1 = desc.x + desc.y;
-    if (desc.y == 0) return;
-    s_lut[tid] = lut_byte[0]; s_lut[tid + 128] = lut_byte[1];
-    if (tid == 0) { mbar_init(&s_bar, 1); s_ncand[0] = 0; s_ncand[1] = 0; }
-    uint32_t flip = 0;
-    __syncthreads();
-
-    const TableView tab = p.tab;
-    const int K = tab.K;
-    uint32_t parity = 0;
-
-    for (uint32_t sb = s0; sb < s1; sb += MAX_TILE_SEQ) {
-        const uint32_t ns = min((uint32_t)MAX_TILE_SEQ, s1 - sb);
-        const unsigned long long g0 = (sb == s0) ? desc.z : p.off[sb] - p.base;
-        const unsigned long long g1 = (sb + ns == s1) ? desc.w : p.off[sb + ns] - p.base;
-        const unsigned long long g0a = g0 & ~15ull;
-        const uint32_t lead = (uint32_t)(g0 - g0a);
-        const uint32_t ext = (uint32_t)(g1 - g0a);
-        const uint32_t nbytes = (ext + 15u) & ~15u;
-        if (tid == 0 && nbytes) {
-            mbar_expect_tx(&s_bar, nbytes);
-            bulk_g2s(s_res, p.res + g0a, nbytes, &s_bar);
-        }
-        for (uint32_t i = tid; i <= ns; i += THREADS)
-            s_off[i] = (uint32_t)(p.off[sb + i] - p.base - g0a);
-        for (uint32_t i = tid; i < ns; i += THREADS) { s_cnt[i] = 0; s_min[i] = 0x7fffffff; s_max[i] = -1; }
-        {
-            const uint32_t ntok = tok_cap(ext - lead) + 4u * ns + 4u;
-            const uint4 z = make_uint4(0, 0, 0, 0);
-            for (uint32_t i = tid * 4; i < ntok; i += THREADS * 4) *reinterpret_cast<uint4*>(s_tok + i) = z;
-        }
-        __syncthreads();
-        if (nbytes) { mbar_wait(&s_bar, parity); parity ^= 1; }
-
-        for (uint32_t pb = lead; pb < ext; pb += THREADS * FA) {
-            // ---------------- phase A: keys + signature test ----------------
-            const uint32_t pend = min(ext, pb + THREADS * FA);
-            const uint32_t run = (pend - pb + THREADS - 1) / THREADS;   // positions per thread, <= FA
-            const uint32_t P0 = pb + tid * run;
-            uint32_t sec[FA];
-            rem_t rem[FA];
-            uint32_t seqlo = 0, seqhi = 0;
-            unsigned ok = 0;
-            if (P0 < pend) {
-                int lo = 0, hi = (int)ns + 1;
-                while (lo < hi) {
-                    int mid = (lo + hi) >> 1;
-                    if (s_off[mid] <= P0) lo = mid + 1; else hi = mid;
-                }
-                int si = lo - 1;
-                uint32_t nb = s_off[si + 1];
-                const uint8_t* r = s_res + P0;
-                unsigned long long key = 0;
-                int vr = 0;
-                for (int j = 0; j < K - 1; j++) {
-                    uint32_t c = s_lut[r[j]];
-                    key = (key << 5) | c;
-                    vr = c ? vr + 1 : 0;
-                }
-                r += K - 1;
-#pragma unroll
-                for (int i = 0; i < FA; i++) {
-                    const uint32_t pos = P0 + i;
-                    if (i < (int)run && pos < pend) {
-                        uint32_t c = s_lut[r[i]];
-                        key = (key << 5) | c;
-                        vr = c ? vr + 1 : 0;
-                        while (pos >= nb) { si++; nb = s_off[si + 1]; }
-                        if (pos + K <= nb && vr >= K) {
-                            ok |= 1u << i;
-                            if (i < 4) seqlo |= (uint32_t)si << (8 * (i & 3));
-                            else seqhi |= (uint32_t)si << (8 * (i & 3));
-                            unsigned long long rm;
-                            locate(tab, key & tab.key_mask, sec[i], rm);
-                            rem[i] = (rem_t)rm;
-                        }
-                    }
-                }
-            }
-            uint32_t sg[FA];
-#pragma unroll
-            for (int i = 0; i < FA; i++)
-                if (ok & (1u << i)) sg[i] = __ldg(tab.sig + sec[i]);
-#pragma unroll
-            for (int i = 0; i < FA; i++)
-                if (ok & (1u << i)) {
-                    const uint32_t need = sig_bits(rem[i]);
-                    if ((sg[i] & need) != need) ok &= ~(1u << i);
-                }
-            // compact the survivors of the warp into the candidate list
-            {
-                const uint32_t n = __popc(ok);
-                uint32_t incl = n;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-                    if ((int)lane >= d) incl += v;
-                }
-                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-                uint32_t base = 0;
-                if (lane == 31 && total) base = atomicAdd(&s_ncand[flip], total);
-                base = __shfl_sync(0xffffffffu, base, 31);
-                uint32_t w = base + incl - n;
-#pragma unroll
-                for (int i = 0; i < FA; i++)
-                    if (ok & (1u << i)) {
-                        c_sec[w] = sec[i];
-                        c_rem64[w] = (unsigned long long)rem[i];
-                        c_seq[w] = (uint8_t)(((i < 4 ? seqlo : seqhi) >> (8 * (i & 3))) & 0xffu);
-                        w++;
-                    }
-            }
-            __syncthreads();
-            const uint32_t ncand = s_ncand[flip];
-            if (tid == 0) s_ncand[flip ^ 1] = 0;   // nobody appends to the other counter before the next barrier
-
-            // ---------------- phase B: probe the candidates ----------------
-            for (uint32_t cb = 0; cb < ncand; cb += THREADS * FB) {
-                uint32_t bsec[FB];
-                rem_t brem[FB];
-                uint4 a[FB], b[FB];
-                unsigned live = 0;
-#pragma unroll
-                for (int i = 0; i < FB; i++) {
-                    const uint32_t c = cb + i * THREADS + tid;
-                    if (c < ncand) {
-                        live |= 1u << i;
-                        bsec[i] = c_sec[c];
-                        brem[i] = (rem_t)c_rem64[c];
-                        load_sector(sector_ptr(tab, bsec[i]), a[i], b[i]);
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < FB; i++) {
-                    int role = -1, q = -1;
-                    uint32_t tok = 0;
-                    if (live & (1u << i)) {
-                        uint32_t j = 0;
-                        bool full;
-                        role = match_sector<CLS>(tab, a[i], b[i], brem[i], j, full);
-                        if (role >= 0) tok = bsec[i] * S + j + 1;
-                        else if (full) {
-                            if (CLS == 128) {
-                                // whole keys: follow the chain
-                                uint32_t sx = bsec[i];
-                                const uint32_t sec_mask = (1u << tab.bbits) - 1;
-                                for (;;) {
-                                    sx = (sx + 1) & sec_mask;
-                                    uint4 xa, xb;
-                                    load_sector(sector_ptr(tab, sx), xa, xb);
-                                    bool f2;
-                                    role = match_sector<CLS>(tab, xa, xb, brem[i], j, f2);
-                                    if (role >= 0) { tok = sx * S + j + 1; break; }
-                                    if (!f2) break;
-                                }
-                            } else {
-                                role = ovf_lookup(tab, ((unsigned long long)bsec[i] << tab.rem_bits) | brem[i], tok);
-                            }
-                        }
-                        if (role >= 0) {
-                            q = c_seq[cb + i * THREADS + tid];
-                            const uint32_t sa = s_off[q], sbb = s_off[q + 1];
-                            if (!token_insert(s_tok + tok_cap(sa - lead) + 4u * (uint32_t)q, tok_cap(sbb - sa) + 4u, tok)) q = -1;
-                        }
-                    }
-                    // candidates of neighbouring lanes mostly belong to the same sequence: one lane
-                    // per sequence and round updates the shared tallies
-                    if (__any_sync(0xffffffffu, q >= 0)) {
-                        const unsigned grp = __match_any_sync(0xffffffffu, q);
-                        const int gmin = __reduce_min_sync(grp, q >= 0 ? role : 0x7fffffff);
-                        const int gmax = __reduce_max_sync(grp, q >= 0 ? role : -1);
-                        if (q >= 0 && lane == (uint32_t)(__ffs(grp) - 1)) {
-                            atomicAdd(&s_cnt[q], __popc(grp));
-                            atomicMin(&s_min[q], gmin);
-                            atomicMax(&s_max[q], gmax);
-                        }
-                    }
-                }
-            }
-            __syncthreads();
-            flip ^= 1;
-        }
-        __syncthreads();
-        for (uint32_t i = tid; i < ns; i += THREADS)
-            emit_call(p, sb + i, s_cnt[i], s_min[i], s_max[i]);
-        __syncthreads();
-    }
-}
-
-cudaError_t tile_kernel_filt_set_smem(int cls, size_t bytes) {
-    cudaError_t ce;
-    if (cls == 32) {
-        ce = cudaFuncSetAttribute(tile_kernel_filt<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(tile_kernel_filt<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    } else if (cls == 64) {
-        ce = cudaFuncSetAttribute(tile_kernel_filt<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(tile_kernel_filt<64>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    } else {
-        ce = cudaFuncSetAttribute(tile_kernel_filt<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(tile_kernel_filt<128>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    }
-    return ce;
-}
-
-cudaError_t launch_tiles_filt(const AnnotParams& p, size_t smem, cudaStream_t st) {
-    if (p.n_tiles == 0) return cudaSuccess;
-    if (p.tab.cls == 32) tile_kernel_filt<32><<<p.n_tiles, FILT_THREADS, smem, st>>>(p);
-    else if (p.tab.cls == 64) tile_kernel_filt<64><<<p.n_tiles, FILT_THREADS, smem, st>>>(p);
-    else tile_kernel_filt<128><<<p.n_tiles, FILT_THREADS, smem, st>>>(p);
-    return cudaGetLastError();
-}
-
 template <typename F>
 static auto with_tile_kernel(int cls, int variant, F f) {
 #define KA_VARIANTS(CLS)                                             \
     switch (variant) {                                               \
         case 1: return f(tile_kernel<CLS, 4, 256, 3>, 256);          \
-        case 2: return f(tile_kernel<CLS, 8, 256, 2>, 256);          \
-        case 3: return f(tile_kernel<CLS, 2, 128, 10>, 128);         \
         default: return f(tile_kernel<CLS, 4, 128, 6>, 128);         \
     }
     if (cls == 32) { KA_VARIANTS(32) }
@@ -1151,11 +881,6 @@ __global__ void db_insert_kernel(TableView tab, const uint8_t* __restrict__ kmer
             sec &= (1ull << tab.shard_shift) - 1;
         }
         const unsigned long long mine = ((line_base + i + 1) << role_bits) | (unsigned long long)(uint32_t)roles[i];
-        if (tab.sig) {
-            uint32_t* word = reinterpret_cast<uint32_t*>(const_cast<uint16_t*>(tab.sig)) + (sec >> 1);
-            const uint32_t bits = sig_bits(rem) << ((sec & 1u) * 16);
-            if ((*reinterpret_cast<volatile uint32_t*>(word) & bits) != bits) atomicOr(word, bits);
-        }
         uint32_t chain = 1;
         bool done = false;
         if (CLS == 128) {

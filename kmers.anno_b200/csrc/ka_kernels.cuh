@@ -48,20 +48,14 @@ struct AnnotParams {
     const uint32_t* route_slot;
 };
 
-// tile kernel shapes (option "variant"): 0 = 4 window positions per thread x 128 threads
-// (7 CTAs/SM, default), 1 = 4 x 256 (default of the mid-sequence launch), 2 = 8 x 256, 3 = 2 x 128.
-// Shapes that were measured and dropped (64-register caps, 512 threads, 2 or 8 positions x 128)
-// are listed in profiles/r01_summary.md.
-constexpr int N_VARIANTS = 4;
+// tile kernel shapes: 0 = 4 window positions per thread x 128 threads (7 CTAs/SM, the residue tiles),
+// 1 = 4 x 256 (the single-sequence tiles of the second launch).  Shapes that were measured and
+// dropped (8 x 256, 2 x 128, 64-register caps, 512 threads) are listed in profiles/r01_summary.md.
+constexpr int N_VARIANTS = 2;
 size_t tile_smem_bytes(uint32_t ext_max, uint32_t* res_bytes_out, bool wide);
 // de-dup token capacity of x window positions: x + x/4 (worst-case load factor 0.8)
 __host__ __device__ inline uint32_t tok_cap(uint32_t x) { return x + (x >> 2); }
 cudaError_t tile_kernel_set_smem(int cls, int variant, size_t bytes);
-
-// two-phase tile kernel used when the table has presence signatures (tab.sig != NULL)
-size_t tile_smem_bytes_filt(uint32_t ext_max, uint32_t* res_bytes_out);
-cudaError_t tile_kernel_filt_set_smem(int cls, size_t bytes);
-cudaError_t launch_tiles_filt(const AnnotParams& p, size_t smem, cudaStream_t st);
 
 constexpr unsigned long long ROUTE_INVALID = ~0ull;
 constexpr unsigned long long ROUTE_MISS = ~0ull;          // answer of a key that is not in the table

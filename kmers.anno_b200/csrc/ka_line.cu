@@ -1,0 +1,728 @@
+// ka_line.cu — kernels of the 128-byte-line table (slot class 16) and of the packed residue stream
+// (layout and rationale: ka_line.cuh).  Same reference semantics as ka_kernels.cu:
+// ApplyKmerProcessor.java:122-148 (distinct K-windows of a peg :123, kmerRoleMap.get :130,
+// unanimous-role tally :131-144, thresholded call :146-147) and :99-110 (HashMap.put, last line wins).
+//
+//   line_plan_kernel    chunk-relative 32-bit offsets, one descriptor per residue tile, lists of the
+//                       sequences that get a tile of their own (mid) or the long-sequence kernel (big)
+//   line_tile_kernel    one CTA per tile: the tile's 5-bit codes are staged with one TMA bulk copy;
+//                       every warp owns a quarter of the tile's window positions.  Phase A: a lane
+//                       rolls the radix-n key over a run of <= A consecutive positions, mixes it and
+//                       issues the filter loads (L2) of the whole run; survivors are compacted
+//                       into the warp's shared-memory queue.  Phase B: whenever the queue holds a
+//                       full warp of survivors, every lane pops one, loads its home sector (the
+//                       only HBM access of the probe), matches the eight tags SIMD-in-register and
+//                       on a hit de-duplicates (token set) and tallies (warp match + redux).
+//   line_big_kernel     sequences beyond the shared-memory tile sizes
+//   line_insert/finalize, pack/unpack: table build and stream conversion
+#include "ka_line.cuh"
+#include "ka_common.cuh"
+#include "ka_kernels.cuh"
+#include <type_traits>
+
+#ifdef KA_DEBUG
+#define KA_CHECK(cond, code) do { if (!(cond)) atomicOr(p.dbg, (code)); } while (0)
+#else
+#define KA_CHECK(cond, code) do { } while (0)
+#endif
+
+namespace ka {
+
+namespace {
+
+__device__ __forceinline__ unsigned long long policy_evict_first() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ unsigned long long policy_evict_last() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// one table sector: a single 256-bit load, no L1 allocation, evict-first in L2 (a line is used once)
+__device__ __forceinline__ void load_line_sector(const uint4* p, unsigned long long pol, uint4& a, uint4& b) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p), "l"(pol));
+}
+__device__ __forceinline__ uint32_t load_filter_word(const uint32_t* p, unsigned long long pol) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
+// 0x8000 in every 16-bit half of x that is zero (exact: no carries between the halves)
+__device__ __forceinline__ uint32_t zero_halves(uint32_t x) {
+    const uint32_t t = (x & 0x7FFF7FFFu) + 0x7FFF7FFFu;
+    return ~(t | x | 0x7FFF7FFFu);
+}
+
+// compare the eight tags of a sector (a) with `tagdup` (the tag in both halves); role or -1
+__device__ __forceinline__ int match16(const uint4& a, const uint4& b, uint32_t tagdup, uint32_t& j) {
+    constexpr uint32_t M = TAG_CMP | (TAG_CMP << 16);
+    const uint32_t z0 = zero_halves((a.x ^ tagdup) & M), z1 = zero_halves((a.y ^ tagdup) & M);
+    const uint32_t z2 = zero_halves((a.z ^ tagdup) & M), z3 = zero_halves((a.w ^ tagdup) & M);
+    if ((z0 | z1 | z2 | z3) == 0u) return -1;
+    uint32_t z, r, base;
+    if (z0) { z = z0; r = b.x; base = 0; }
+    else if (z1) { z = z1; r = b.y; base = 2; }
+    else if (z2) { z = z2; r = b.z; base = 4; }
+    else { z = z3; r = b.w; base = 6; }
+    const uint32_t hi = (z & 0x8000u) ? 0u : 1u;
+    j = base + hi;
+    return (int)((r >> (16u * hi)) & 0xFFFFu);
+}
+
+// flag bits of a home sector: bit a-1 = keys of this home live in sector home^a, bit 3 = in the overflow table
+__device__ __forceinline__ uint32_t sector_flags(const uint4& a) {
+    return ((a.x >> 12) & 1u) | ((a.x >> 27) & 2u) | ((a.y >> 10) & 4u) | ((a.y >> 25) & 8u);
+}
+
+__device__ __forceinline__ int line_ovf_lookup(const LineTable& t, uint32_t sector, uint32_t tag, uint32_t& tok) {
+    const unsigned long long k = line_ovf_key(sector, tag);
+    const uint32_t mask = (1u << t.ovf_bbits) - 1u;
+    uint32_t s = t.ovf_bbits ? (uint32_t)(mix64(k) >> (64 - t.ovf_bbits)) : 0u;
+    for (;;) {
+        uint4 a, b;
+        load_sector(t.ovf + 2 * (size_t)s, a, b);
+        const unsigned long long k0 = u64_of(a.x, a.y), k1 = u64_of(b.x, b.y);
+        if (k0 == k) { tok = t.n_lines * 32u + 2u * s + 1u; return (int)a.z; }
+        if (k1 == k) { tok = t.n_lines * 32u + 2u * s + 2u; return (int)b.z; }
+        if (k1 == 0) return -1;
+        s = (s + 1) & mask;
+    }
+}
+
+// Full lookup of (sector, tag) given its already loaded home sector; role or -1, tok = de-dup token.
+__device__ __forceinline__ int line_resolve(const LineTable& t, unsigned long long pol, uint32_t sector, uint32_t tag,
+                                            const uint4& a, const uint4& b, uint32_t& tok) {
+    const uint32_t tagdup = tag | (tag << 16);
+    uint32_t j = 0;
+    int role = match16(a, b, tagdup, j);
+    if (role >= 0) { tok = sector * 8u + j + 1u; return role; }
+    const uint32_t flags = sector_flags(a);
+    if (flags == 0u) return -1;
+    const uint32_t line0 = sector & ~3u, home = sector & 3u;
+#pragma unroll
+    for (uint32_t alt = 1; alt < 4; alt++) {
+        if (flags & (1u << (alt - 1))) {
+            const uint32_t s2 = line0 | (home ^ alt);
+            uint4 xa, xb;
+            load_line_sector(t.lines + 2 * (size_t)s2, pol, xa, xb);    // L2 hit: the line was just fetched
+            role = match16(xa, xb, tagdup, j);
+            if (role >= 0) { tok = s2 * 8u + j + 1u; return role; }
+        }
+    }
+    if (flags & 8u) return line_ovf_lookup(t, sector, tag, tok);
+    return -1;
+}
+
+__device__ __forceinline__ bool line_token_insert(uint32_t* region, uint32_t n, uint32_t token) {
+    uint32_t j = (uint32_t)(((unsigned long long)(token * 0x9E3779B1u) * n) >> 32);
+    for (;;) {
+        const uint32_t old = atomicCAS(region + j, 0u, token);
+        if (old == 0u) return true;
+        if (old == token) return false;
+        j = (j + 1 == n) ? 0 : j + 1;
+    }
+}
+
+__device__ __forceinline__ void line_emit(const LineParams& p, uint32_t seq, int cnt, int rmin, int rmax) {
+    int role = -1, hits = 0;
+    uint8_t flag = 0;                                   // KA_FLAG_NONE
+    if (cnt > 0) {
+        if (rmin != rmax) { flag = 2; }                 // badPeg: two roles hit (ApplyKmerProcessor.java:140-143)
+        else if (cnt >= p.min_hits) { role = rmin; hits = cnt; flag = 1; }  // :146
+        else { hits = cnt; flag = 3; }
+    }
+    p.out_role[seq] = role;
+    p.out_hits[seq] = hits;
+    if (p.out_flag) p.out_flag[seq] = flag;
+}
+
+// 5-bit code number I (compile time) of a 128-bit window held in four registers
+template <int I>
+__device__ __forceinline__ uint32_t window_code(const uint32_t (&v)[4]) {
+    constexpr int bit = 5 * I, q = bit >> 5, sh = bit & 31;
+    static_assert(q < 4, "code outside the window");
+    if (sh <= 27) return (v[q] >> sh) & 31u;
+    else return __funnelshift_r(v[q], v[q < 3 ? q + 1 : 3], sh) & 31u;
+}
+template <int I>
+__device__ __forceinline__ uint32_t window_code64(uint32_t u0, uint32_t u1) {
+    constexpr int bit = 5 * I, sh = bit & 31;
+    static_assert(bit + 5 <= 64, "code outside the window");
+    if (bit + 5 <= 32) return (u0 >> sh) & 31u;
+    else if (bit >= 32) return (u1 >> sh) & 31u;
+    else return __funnelshift_r(u0, u1, sh) & 31u;
+}
+
+// code of residue g of a packed stream in global memory
+__device__ __forceinline__ uint32_t global_code(const uint32_t* pk, unsigned long long g) {
+    const unsigned long long bit = 5ull * g;
+    const uint32_t* w = pk + (bit >> 5);
+    const uint32_t sh = (uint32_t)bit & 31u;
+    const uint32_t lo = __ldg(w), hi = sh > 27 ? __ldg(w + 1) : 0u;
+    return __funnelshift_r(lo, hi, sh) & 31u;
+}
+
+template <typename OffT>
+__device__ __forceinline__ uint32_t first_seq_at(const OffT* off, uint32_t n_seq, unsigned long long target) {
+    uint32_t lo = 0, hi = n_seq;
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if ((unsigned long long)off[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------
+template <typename OffT>
+__global__ void line_plan_kernel(LineParams p, const OffT* __restrict__ off, unsigned long long origin) {
+    const unsigned long long gid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long base = off[0];
+    if (gid < p.n_tiles) {
+        const uint32_t s0 = first_seq_at(off, p.n_seq, base + gid * (unsigned long long)p.tile_span);
+        uint32_t s1 = first_seq_at(off, p.n_seq, base + (gid + 1) * (unsigned long long)p.tile_span);
+        // only the last sequence starting in a tile can be a long one (long_seq >= tile_span)
+        if (s1 > s0 && (unsigned long long)off[s1] - (unsigned long long)off[s1 - 1] > p.long_seq) s1--;
+        uint4 d;
+        d.x = s0; d.y = s1 - s0;
+        d.z = (uint32_t)((unsigned long long)off[s0] - origin);
+        d.w = (uint32_t)((unsigned long long)off[s1] - origin);
+        p.first[gid] = d;
+    }
+    if (gid <= p.n_seq) p.off[gid] = (uint32_t)((unsigned long long)off[gid] - origin);
+    if (gid < p.n_seq) {
+        const unsigned long long L = (unsigned long long)off[gid + 1] - (unsigned long long)off[gid];
+        if (L > p.mid_seq) {
+            const uint32_t idx = atomicAdd(p.big_count, 1u);
+            const unsigned long long tb = atomicAdd(p.tok_cursor, 2ull * L);
+            BigItem it; it.seq = (uint32_t)gid; it.pad = 0; it.tok_base = tb;
+            reinterpret_cast<BigItem*>(p.big_list)[idx] = it;
+        } else if (L > p.long_seq) {
+            const uint32_t idx = atomicAdd(p.mid_count, 1u);
+            uint4 d;
+            d.x = (uint32_t)gid; d.y = 1;
+            d.z = (uint32_t)((unsigned long long)off[gid] - origin);
+            d.w = (uint32_t)((unsigned long long)off[gid + 1] - origin);
+            p.mid_desc[idx] = d;
+        }
+    }
+}
+
+cudaError_t launch_line_plan(const LineParams& p, const unsigned long long* off64, const uint32_t* off32,
+                             unsigned long long origin, cudaStream_t st) {
+    unsigned long long n = (unsigned long long)p.n_seq + 1;
+    if (p.n_tiles > n) n = p.n_tiles;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    if (off64) line_plan_kernel<unsigned long long><<<blocks, 256, 0, st>>>(p, off64, origin);
+    else line_plan_kernel<uint32_t><<<blocks, 256, 0, st>>>(p, off32, origin);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------
+// tile kernel
+// ------------------------------------------------------------------------------------
+constexpr int LT_THREADS = 128, LT_WARPS = LT_THREADS / 32;
+constexpr int LT_A = 8;        // window positions per lane and pass
+constexpr int LT_PB = 1;       // sector loads in flight per lane in phase B
+constexpr int LT_QCAP = 32 * LT_A + 32 * LT_PB;
+
+// dynamic shared memory (bytes):
+//   [0, stage_bytes)                      packed stage (TMA destination, 16-byte aligned) + 32 bytes of over-read slack
+//   [+4*(LINE_MAX_SEQ+4))                 s_off: sequence starts relative to the tile's first residue
+//   [+3*4*LINE_MAX_SEQ)                   s_cnt, s_min, s_max
+//   [+4*(tok_cap(ext_max)+4*LINE_MAX_SEQ+8))  token set, region of sequence q at tok_cap(start) + 4q
+//   [+8*LT_WARPS*LT_QCAP)                 survivor queues
+size_t line_tile_smem_bytes(uint32_t ext_max, uint32_t* stage_bytes_out) {
+    const uint32_t stage = (((ext_max * 5u + 7u) >> 3) + 16u + 16u + 32u + 15u) & ~15u;   // lead alignment, rounding, over-read
+    if (stage_bytes_out) *stage_bytes_out = stage;
+    size_t tok = ((size_t)tok_cap(ext_max) + 4 * LINE_MAX_SEQ + 8 + 1) & ~(size_t)1;
+    return (size_t)stage + 4 * (LINE_MAX_SEQ + 4) + 3 * 4 * LINE_MAX_SEQ + 4 * tok + 8 * (size_t)LT_WARPS * LT_QCAP;
+}
+
+__global__ void __launch_bounds__(LT_THREADS, 8) line_tile_kernel(LineParams p) {
+    constexpr int A = LT_A, PB = LT_PB;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t s_bar;
+
+    uint32_t* s_pk = reinterpret_cast<uint32_t*>(smem_raw);
+    uint32_t* s_off = reinterpret_cast<uint32_t*>(smem_raw + p.stage_bytes);
+    int* s_cnt = reinterpret_cast<int*>(s_off + LINE_MAX_SEQ + 4);
+    int* s_min = s_cnt + LINE_MAX_SEQ;
+    int* s_max = s_min + LINE_MAX_SEQ;
+    uint32_t* s_tok = reinterpret_cast<uint32_t*>(s_max + LINE_MAX_SEQ);
+    const uint32_t tok_words = (tok_cap(p.ext_max) + 4u * LINE_MAX_SEQ + 8u + 1u) & ~1u;
+    uint2* s_q = reinterpret_cast<uint2*>(s_tok + tok_words) + (threadIdx.x >> 5) * LT_QCAP;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint4 desc = p.first[blockIdx.x];
+    const uint32_t s0 = desc.x, s1 = desc.x + desc.y;
+    if (desc.y == 0) return;
+    if (tid == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+
+    const LineTable tab = p.tab;
+    const int K = tab.K;
+    const uint32_t radix = tab.radix;
+    const unsigned long long pow_k1 = tab.pow_k1;
+    const unsigned long long pol_first = policy_evict_first(), pol_last = policy_evict_last();
+    uint32_t parity = 0;
+
+    for (uint32_t sb = s0; sb < s1; sb += LINE_MAX_SEQ) {
+        const uint32_t ns = min((uint32_t)LINE_MAX_SEQ, s1 - sb);
+        const uint32_t g0 = (sb == s0) ? desc.z : p.off[sb];
+        const uint32_t g1 = (sb + ns == s1) ? desc.w : p.off[sb + ns];
+        const uint32_t ext = g1 - g0;                                   // window positions of the sub-batch
+        const unsigned long long bit_g0 = 5ull * g0;
+        const unsigned long long bt = (bit_g0 >> 3) & ~15ull;           // 16-byte aligned start of the copy
+        const uint32_t leadbits = (uint32_t)(bit_g0 - 8ull * bt);       // stage bit of tile position 0
+        const uint32_t nbytes = (uint32_t)((((5ull * g1 + 7ull) >> 3) - bt + 15ull) & ~15ull);
+        KA_CHECK(nbytes + 32u <= p.stage_bytes, 1u);
+        KA_CHECK(tok_cap(ext) + 4u * ns + 8u <= tok_cap(p.ext_max) + 4u * LINE_MAX_SEQ + 8u, 2u);
+
+        if (tid == 0 && nbytes) {
+            mbar_expect_tx(&s_bar, nbytes);
+            bulk_g2s(s_pk, reinterpret_cast<const unsigned char*>(p.pk) + bt, nbytes, &s_bar);
+        }
+        for (uint32_t i = tid; i <= ns; i += LT_THREADS) s_off[i] = p.off[sb + i] - g0;
+        for (uint32_t i = tid; i < ns; i += LT_THREADS) { s_cnt[i] = 0; s_min[i] = 0x7fffffff; s_max[i] = -1; }
+        {
+            const uint32_t ntok = tok_cap(ext) + 4u * ns + 4u;
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            for (uint32_t i = tid * 4; i < ntok; i += LT_THREADS * 4) *reinterpret_cast<uint4*>(s_tok + i) = z;
+        }
+        __syncthreads();
+        if (nbytes) { mbar_wait(&s_bar, parity); parity ^= 1; }
+
+        // this warp's quarter of the positions
+        const uint32_t wq = (ext + LT_WARPS - 1) / LT_WARPS;
+        const uint32_t wbeg = min(ext, warp * wq), wend = min(ext, wbeg + wq);
+        uint32_t qn = 0;                                                // queue fill (warp-uniform)
+
+        // ---- phase B: every lane takes one queued survivor (live lanes only), probes, tallies ----
+        auto pop = [&](uint32_t first, bool live) {
+            uint2 e = make_uint2(0, 0);
+            uint4 a = make_uint4(0, 0, 0, 0), b = a;
+            if (live) {
+                e = s_q[first + lane];
+                load_line_sector(tab.lines + 2 * (size_t)e.x, pol_first, a, b);
+            }
+            int role = -1, q = -1;
+            if (live) {
+                uint32_t tok = 0;
+                role = line_resolve(tab, pol_first, e.x, e.y & 0xFFFFu, a, b, tok);
+                if (role >= 0) {
+                    q = (int)(e.y >> 16);
+                    const uint32_t sa = s_off[q], se = s_off[q + 1];
+                    KA_CHECK(q < (int)ns && se >= sa, 8u);
+                    if (!line_token_insert(s_tok + tok_cap(sa) + 4u * (uint32_t)q, tok_cap(se - sa) + 4u, tok)) q = -1;
+                }
+            }
+            // survivors of neighbouring positions mostly belong to one sequence: one lane per
+            // sequence updates the shared tallies
+            if (__any_sync(0xffffffffu, q >= 0)) {
+                const unsigned grp = __match_any_sync(0xffffffffu, q);
+                const int gmin = __reduce_min_sync(grp, q >= 0 ? role : 0x7fffffff);
+                const int gmax = __reduce_max_sync(grp, q >= 0 ? role : -1);
+                if (q >= 0 && lane == (uint32_t)(__ffs(grp) - 1)) {
+                    atomicAdd(&s_cnt[q], __popc(grp));
+                    atomicMin(&s_min[q], gmin);
+                    atomicMax(&s_max[q], gmax);
+                }
+            }
+        };
+
+        for (uint32_t pb = wbeg; pb < wend; pb += 32 * A) {
+            // ---- phase A: keys + filter for a run of <= A positions per lane ----
+            const uint32_t pend = min(wend, pb + 32 * A);
+            const uint32_t run = (pend - pb + 31) >> 5;                 // <= A
+            const uint32_t P0 = pb + lane * run;
+            const uint32_t nrun = P0 < pend ? min(run, pend - P0) : 0u;
+            uint32_t sec[A], tg[A], fw[A];
+            unsigned okm = 0;
+            if (nrun) {
+                // sequence containing P0: last i with s_off[i] <= P0 (P0 < ext = s_off[ns])
+                int lo = 0, hi = (int)ns + 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_off[mid] <= P0) lo = mid + 1; else hi = mid;
+                }
+                uint32_t si = (uint32_t)(lo - 1);
+                KA_CHECK(si < ns, 32u);
+                uint32_t nb = s_off[si + 1];
+
+                // warm-up: the K-1 codes in front of the run's first window end
+                const uint32_t bit0 = leadbits + 5u * P0;
+                uint32_t u0, u1;
+                {
+                    const uint32_t* w = s_pk + (bit0 >> 5);
+                    const uint32_t sh = bit0 & 31u, w0 = w[0], w1 = w[1], w2 = w[2];
+                    u0 = __funnelshift_r(w0, w1, sh);
+                    u1 = __funnelshift_r(w1, w2, sh);
+                }
+                unsigned long long key = 0;
+                int okc = 0;                                            // consecutive codes inside the alphabet
+                {
+                    uint32_t t0 = u0, t1 = u1;
+                    for (int j = 0; j < K - 1; j++) {
+                        const uint32_t c = t0 & 31u;
+                        t0 = __funnelshift_r(t0, t1, 5);
+                        t1 >>= 5;
+                        key = key * radix + c;
+                        okc = (c == CODE_INVALID) ? 0 : okc + 1;
+                    }
+                }
+                uint32_t v[4];
+                {
+                    const uint32_t bit1 = bit0 + 5u * (uint32_t)(K - 1);
+                    const uint32_t* w = s_pk + (bit1 >> 5);
+                    const uint32_t sh = bit1 & 31u, w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+                    v[0] = __funnelshift_r(w0, w1, sh);
+                    v[1] = __funnelshift_r(w1, w2, sh);
+                    v[2] = __funnelshift_r(w2, w3, sh);
+                    v[3] = w3 >> sh;
+                }
+                auto step = [&](auto I_) {
+                    constexpr int I = decltype(I_)::value;
+                    if (I < (int)nrun) {
+                        const uint32_t pos = P0 + I;
+                        const uint32_t c = window_code<I>(v);
+                        if (I > 0) key -= (unsigned long long)window_code64<(I > 0 ? I - 1 : 0)>(u0, u1) * pow_k1;
+                        key = key * radix + c;
+                        okc = (c == CODE_INVALID) ? 0 : okc + 1;
+                        while (pos >= nb) { si++; KA_CHECK(si < ns, 4u); nb = s_off[si + 1]; }
+                        if (pos + (uint32_t)K <= nb && okc >= K) {
+                            uint32_t tag;
+                            line_locate(tab, key, sec[I], tag);
+                            tg[I] = tag | (si << 16);
+                            okm |= 1u << I;
+                            if (tab.filt) fw[I] = load_filter_word(tab.filt + sec[I], pol_last);
+                        }
+                    }
+                };
+                step(std::integral_constant<int, 0>()); step(std::integral_constant<int, 1>());
+                step(std::integral_constant<int, 2>()); step(std::integral_constant<int, 3>());
+                step(std::integral_constant<int, 4>()); step(std::integral_constant<int, 5>());
+                step(std::integral_constant<int, 6>()); step(std::integral_constant<int, 7>());
+                static_assert(A == 8, "unrolled for 8 positions per lane");
+                if (tab.filt) {
+#pragma unroll
+                    for (int i = 0; i < A; i++)
+                        if (okm & (1u << i)) {
+                            const uint32_t need = line_filter_bits(tg[i] & 0xFFFFu);
+                            if ((fw[i] & need) != need) okm &= ~(1u << i);
+                        }
+                }
+            }
+            // compact the survivors of the warp into its queue
+#pragma unroll
+            for (int i = 0; i < A; i++) {
+                const bool ok = (okm >> i) & 1u;
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                if (ok) s_q[qn + __popc(m & ((1u << lane) - 1u))] = make_uint2(sec[i], tg[i]);
+                qn += __popc(m);
+            }
+            __syncwarp();
+            while (qn >= 32u * PB) {
+                qn -= 32u;
+                pop(qn, true);
+            }
+            __syncwarp();
+        }
+        while (qn > 0) {                                                // drain
+            const uint32_t take = min(qn, 32u);
+            qn -= take;
+            pop(qn, lane < take);
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < ns; i += LT_THREADS) line_emit(p, sb + i, s_cnt[i], s_min[i], s_max[i]);
+        __syncthreads();
+    }
+}
+
+cudaError_t line_tile_set_smem(size_t bytes) {
+    cudaError_t ce = cudaFuncSetAttribute(line_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (ce != cudaSuccess) return ce;
+    return cudaFuncSetAttribute(line_tile_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
+cudaError_t launch_line_tiles(const LineParams& p, size_t smem, cudaStream_t st) {
+    if (p.n_tiles == 0) return cudaSuccess;
+    line_tile_kernel<<<p.n_tiles, LT_THREADS, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------
+// long sequences: one CTA per sequence, codes read from global memory, token set in global scratch
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) line_big_kernel(LineParams p) {
+    constexpr int THREADS = 256;
+    __shared__ int sh_cnt, sh_min, sh_max;
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t nbig = *p.big_count;
+    const LineTable tab = p.tab;
+    const int K = tab.K;
+    const unsigned long long pol_first = policy_evict_first(), pol_last = policy_evict_last();
+    const BigItem* list = reinterpret_cast<const BigItem*>(p.big_list);
+
+    for (uint32_t bi = blockIdx.x; bi < nbig; bi += gridDim.x) {
+        const BigItem it = list[bi];
+        const uint32_t a0 = p.off[it.seq], L = p.off[it.seq + 1] - a0;
+        const uint32_t W = L - (uint32_t)K + 1;                       // L > mid_seq >= K
+        uint32_t* region = p.scratch + it.tok_base;
+        const uint32_t nreg = 2u * L;
+        for (uint32_t i = tid; i < nreg; i += THREADS) region[i] = 0;
+        if (tid == 0) { sh_cnt = 0; sh_min = 0x7fffffff; sh_max = -1; }
+        __syncthreads();
+        int cnt = 0, mn = 0x7fffffff, mx = -1;
+        for (uint32_t pos = tid; pos < W; pos += THREADS) {
+            unsigned long long key = 0;
+            bool ok = true;
+            for (int j = 0; j < K; j++) {
+                const uint32_t c = global_code(p.pk, (unsigned long long)a0 + pos + j);
+                ok &= (c != CODE_INVALID);
+                key = key * tab.radix + c;
+            }
+            if (!ok) continue;
+            uint32_t sector, tag;
+            line_locate(tab, key, sector, tag);
+            if (tab.filt) {
+                const uint32_t need = line_filter_bits(tag);
+                if ((load_filter_word(tab.filt + sector, pol_last) & need) != need) continue;
+            }
+            uint4 a, b;
+            load_line_sector(tab.lines + 2 * (size_t)sector, pol_first, a, b);
+            uint32_t tok = 0;
+            const int role = line_resolve(tab, pol_first, sector, tag, a, b, tok);
+            if (role >= 0 && line_token_insert(region, nreg, tok)) {
+                cnt++;
+                mn = min(mn, role);
+                mx = max(mx, role);
+            }
+        }
+        const int tot = __reduce_add_sync(0xffffffffu, cnt);
+        const int gmin = __reduce_min_sync(0xffffffffu, mn);
+        const int gmax = __reduce_max_sync(0xffffffffu, mx);
+        if (lane == 0 && tot > 0) {
+            atomicAdd(&sh_cnt, tot);
+            atomicMin(&sh_min, gmin);
+            atomicMax(&sh_max, gmax);
+        }
+        __syncthreads();
+        if (tid == 0) line_emit(p, it.seq, sh_cnt, sh_min, sh_max);
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_line_big(const LineParams& p, int grid, cudaStream_t st) {
+    line_big_kernel<<<grid, 256, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------
+// stream conversion
+// ------------------------------------------------------------------------------------
+// one thread per 32 residues = 160 bits = 5 words
+__global__ void __launch_bounds__(256) pack_kernel(const uint8_t* __restrict__ bytes, uint32_t lead, unsigned long long n,
+                                                   const uint8_t* __restrict__ lut5, uint32_t* __restrict__ out,
+                                                   unsigned long long n_groups) {
+    __shared__ uint8_t s_lut[256];
+    s_lut[threadIdx.x] = lut5[threadIdx.x];
+    __syncthreads();
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_groups; t += stride) {
+        unsigned long long acc = 0;
+        int nb = 0;
+        uint32_t* o = out + 5 * t;
+#pragma unroll
+        for (int k = 0; k < 32; k++) {
+            const unsigned long long g = 32ull * t + k;              // chunk-relative residue
+            uint32_t c = CODE_INVALID;
+            if (g >= lead && g - lead < n) c = s_lut[bytes[g - lead]];
+            acc |= (unsigned long long)c << nb;
+            nb += 5;
+            if (nb >= 32) { *o++ = (uint32_t)acc; acc >>= 32; nb -= 32; }
+        }
+    }
+}
+
+cudaError_t launch_pack(const uint8_t* bytes, uint32_t lead, unsigned long long n, const uint8_t* lut5,
+                        uint32_t* out_words, cudaStream_t st) {
+    const unsigned long long groups = (lead + n + 31) / 32;
+    if (groups == 0) return cudaSuccess;
+    const unsigned long long want = (groups + 255) / 256;
+    pack_kernel<<<(unsigned)(want < 148ull * 32 ? want : 148ull * 32), 256, 0, st>>>(bytes, lead, n, lut5, out_words, groups);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) unpack_kernel(const uint32_t* __restrict__ words, uint32_t lead, unsigned long long n,
+                                                     const uint8_t* __restrict__ inv32, uint8_t* __restrict__ out) {
+    __shared__ uint8_t s_inv[32];
+    if (threadIdx.x < 32) s_inv[threadIdx.x] = inv32[threadIdx.x];
+    __syncthreads();
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride)
+        out[j] = s_inv[global_code(words, (unsigned long long)lead + j)];
+}
+
+cudaError_t launch_unpack(const uint32_t* words, uint32_t lead, unsigned long long n, const uint8_t* inv32,
+                          uint8_t* out, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const unsigned long long want = (n + 255) / 256;
+    unpack_kernel<<<(unsigned)(want < 148ull * 32 ? want : 148ull * 32), 256, 0, st>>>(words, lead, n, inv32, out);
+    return cudaGetLastError();
+}
+
+__global__ void widen_offsets_kernel(const uint32_t* __restrict__ off32, unsigned long long n, unsigned long long* __restrict__ off64) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) off64[i] = off32[i];
+}
+
+cudaError_t launch_widen_offsets(const uint32_t* off32, unsigned long long n, unsigned long long* off64, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const unsigned long long want = (n + 255) / 256;
+    widen_offsets_kernel<<<(unsigned)(want < 148ull * 8 ? want : 148ull * 8), 256, 0, st>>>(off32, n, off64);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------
+// table build
+// ------------------------------------------------------------------------------------
+// HashMap.put for every DB line (ApplyKmerProcessor.java:106).  A key scans its home sector, then the
+// sectors home^1, home^2, home^3 of the same line, always in this order and slots are never freed, so
+// a duplicate of a stored key reaches the stored copy before any empty slot: one slot per distinct key.
+__global__ void __launch_bounds__(256) line_insert_kernel(LineTable t, const uint8_t* __restrict__ kmers,
+                                                          const int32_t* __restrict__ roles, unsigned long long n,
+                                                          unsigned long long line_base, const uint8_t* __restrict__ lut5,
+                                                          unsigned long long* best, uint32_t role_bits,
+                                                          unsigned long long* counters, uint32_t* errs) {
+    __shared__ uint8_t s_lut[256];
+    s_lut[threadIdx.x] = lut5[threadIdx.x];
+    __syncthreads();
+    const int K = t.K;
+    uint32_t* words = reinterpret_cast<uint32_t*>(const_cast<uint4*>(t.lines));
+    uint32_t* filt = const_cast<uint32_t*>(t.filt);
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint8_t* km = kmers + i * (unsigned long long)K;
+        unsigned long long key = 0;
+        bool bad = false;
+        for (int j = 0; j < K; j++) {
+            const uint32_t c = s_lut[km[j]];
+            bad |= (c == CODE_INVALID);
+            key = key * t.radix + c;
+        }
+        if (bad) { atomicAdd(&errs[0], 1u); continue; }
+        if (roles[i] < 0) { atomicAdd(&errs[1], 1u); continue; }
+        uint32_t sector, tag;
+        line_locate(t, key, sector, tag);
+        const unsigned long long mine = ((line_base + i + 1) << role_bits) | (unsigned long long)(uint32_t)roles[i];
+        if (filt) {
+            const uint32_t bits = line_filter_bits(tag);
+            if ((*reinterpret_cast<volatile uint32_t*>(filt + sector) & bits) != bits) atomicOr(filt + sector, bits);
+        }
+        const uint32_t line0 = sector & ~3u, home = sector & 3u;
+        bool done = false;
+        for (uint32_t alt = 0; alt < 4 && !done; alt++) {
+            const uint32_t s = line0 | (home ^ alt);
+            for (uint32_t j = 0; j < 8 && !done; j++) {
+                uint32_t* w = words + (size_t)s * 8 + (j >> 1);
+                const uint32_t sh = 16u * (j & 1u);
+                for (;;) {
+                    const uint32_t cur = *reinterpret_cast<volatile uint32_t*>(w);
+                    const uint32_t half = (cur >> sh) & 0xFFFFu;
+                    if (half == 0u) {
+                        if (atomicCAS(w, cur, cur | (tag << sh)) != cur) continue;   // the word changed: look again
+                        atomicAdd(&counters[0], 1ull);
+                        if (alt) atomicAdd(&counters[1], 1ull);
+                        done = true;
+                    } else if (((half ^ tag) & TAG_CMP) == 0u) {
+                        done = true;                                                  // the key is already stored here
+                    }
+                    break;
+                }
+                if (done) {
+                    atomicMax(&best[(size_t)s * 8 + j], mine);
+                    if (alt) {   // tell lookups that sector home^alt holds keys of this home: flag of slot alt-1
+                        uint32_t* fwd = words + (size_t)sector * 8 + ((alt - 1) >> 1);
+                        const uint32_t fb = TAG_FLAG << (16u * ((alt - 1) & 1u));
+                        if ((*reinterpret_cast<volatile uint32_t*>(fwd) & fb) == 0u) atomicOr(fwd, fb);
+                    }
+                }
+            }
+        }
+        if (!done) {
+            // the whole line is full: (sector, rem) + 1 goes to the overflow table, flag of slot 3
+            uint32_t* fwd = words + (size_t)sector * 8 + 1;
+            if ((*reinterpret_cast<volatile uint32_t*>(fwd) & (TAG_FLAG << 16)) == 0u) atomicOr(fwd, TAG_FLAG << 16);
+            const unsigned long long k = line_ovf_key(sector, tag);
+            const uint32_t omask = (1u << t.ovf_bbits) - 1u;
+            uint32_t os = t.ovf_bbits ? (uint32_t)(mix64(k) >> (64 - t.ovf_bbits)) : 0u;
+            Slot128* ovf = reinterpret_cast<Slot128*>(const_cast<uint4*>(t.ovf));
+            for (uint32_t chain = 0; !done && chain <= omask; chain++) {
+                Slot128* sl = ovf + 2 * (size_t)os;
+                for (int h = 0; h < 2 && !done; h++) {
+                    const unsigned long long old = atomicCAS(&sl[h].key, 0ull, k);
+                    if (old == 0ull || old == k) {
+                        if (old == 0ull) { atomicAdd(&counters[0], 1ull); atomicAdd(&counters[2], 1ull); }
+                        atomicMax(&sl[h].val, mine);
+                        done = true;
+                    }
+                }
+                os = (os + 1) & omask;
+            }
+            if (!done) atomicAdd(&errs[2], 1u);
+        }
+    }
+}
+
+cudaError_t launch_line_insert(const LineTable& t, const uint8_t* kmers, const int32_t* roles, unsigned long long n,
+                               unsigned long long line_base, const uint8_t* lut5, unsigned long long* best,
+                               uint32_t role_bits, unsigned long long* counters, uint32_t* errs, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const unsigned long long want = (n + 255) / 256;
+    line_insert_kernel<<<(unsigned)(want < 148ull * 32 ? want : 148ull * 32), 256, 0, st>>>(t, kmers, roles, n, line_base, lut5, best,
+                                                                                         role_bits, counters, errs);
+    return cudaGetLastError();
+}
+
+// role of the winning DB line into the role half of every occupied slot; one thread per pair of slots
+__global__ void __launch_bounds__(256) line_finalize_kernel(LineTable t, const unsigned long long* __restrict__ best, uint32_t role_bits) {
+    const unsigned long long role_mask = (1ull << role_bits) - 1;
+    uint32_t* words = reinterpret_cast<uint32_t*>(const_cast<uint4*>(t.lines));
+    const unsigned long long n_pairs = (unsigned long long)t.n_lines * 16;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long pr = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; pr < n_pairs; pr += stride) {
+        const unsigned long long sector = pr >> 2, wj = pr & 3;
+        const uint32_t tags = words[sector * 8 + wj];
+        if (tags == 0u) continue;
+        uint32_t r = 0;
+        if (tags & 0xFFFFu) r |= (uint32_t)(best[sector * 8 + 2 * wj] & role_mask);
+        if (tags >> 16) r |= (uint32_t)(best[sector * 8 + 2 * wj + 1] & role_mask) << 16;
+        words[sector * 8 + 4 + wj] = r;
+    }
+}
+
+__global__ void line_finalize_ovf_kernel(Slot128* slots, unsigned long long n_slots, uint32_t role_bits) {
+    const unsigned long long role_mask = (1ull << role_bits) - 1;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long s = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += stride)
+        if (slots[s].key) slots[s].val &= role_mask;
+}
+
+cudaError_t launch_line_finalize(const LineTable& t, const unsigned long long* best, uint32_t role_bits, cudaStream_t st) {
+    line_finalize_kernel<<<148 * 16, 256, 0, st>>>(t, best, role_bits);
+    if (t.ovf)
+        line_finalize_ovf_kernel<<<148 * 4, 256, 0, st>>>(reinterpret_cast<Slot128*>(const_cast<uint4*>(t.ovf)),
+                                                          2ull << t.ovf_bbits, role_bits);
+    return cudaGetLastError();
+}
+
+}  // namespace ka

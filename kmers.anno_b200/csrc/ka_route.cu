@@ -120,6 +120,8 @@ int annotate_routed_range(ka_engine* e, Device& d, int idx, RouteShared& sh, con
     cudaSetDevice(d.id);
     d.kernel_ms = d.tile_ms = 0; d.launches = 0; d.h2d = d.d2h = 0; d.probes = 0;
     d.err = KA_OK; d.errmsg.clear();
+    BatchIn bin;
+    bin.residues = residues; bin.off64 = offsets;
     std::vector<std::pair<uint64_t, uint64_t>> chunks;
     for (uint64_t cs = s_begin; cs < s_end;) {
         uint64_t lim = offsets[cs] + e->chunk_residues;
@@ -169,13 +171,13 @@ int annotate_routed_range(ka_engine* e, Device& d, int idx, RouteShared& sh, con
         if (route_reserve(d, ln, 64, 64) != KA_OK) R.has = false;     // counters, pinned counts, event
         if (R.has) {
             R.cs = chunks[r].first; R.ce = chunks[r].second; R.n = R.ce - R.cs;
-            if (!scan_offsets(offsets, R.cs, R.ce, e->long_seq, e->mid_seq, e->info.K, R.shp)) { d.err = KA_ERR_OFFSETS; d.errmsg = "offsets are not monotone"; R.has = false; }
+            if (!scan_offsets(bin, R.cs, R.ce, e->long_seq, e->mid_seq, e->info.K, R.shp)) { d.err = KA_ERR_OFFSETS; d.errmsg = "offsets are not monotone"; R.has = false; }
             else if (R.shp.n_long) { d.err = KA_ERR_TOO_BIG; d.errmsg = "routed table mode: a sequence is longer than mid_seq (raise the mid_seq option)"; R.has = false; }
             else if (R.shp.n_res > 0x7fffffffull) { d.err = KA_ERR_TOO_BIG; d.errmsg = "chunk exceeds 2^31 residues"; R.has = false; }
         }
         if (R.has) {
             d.probes += R.shp.probes;
-            if (pipe_reserve(d, p, R.shp.n_res, R.n, R.shp.n_res / e->tile_span + 1, 0, 0, R.shp.n_mid, e->geom.wide != 0) ||
+            if (pipe_reserve(d, p, R.shp.n_res, R.n, R.shp.n_res / e->tile_span + 1, 0, 0, R.shp.n_mid, e->geom.wide != 0, true, false) ||
                 route_reserve(d, ln, R.shp.n_res + 64, 0)) R.has = false;
         }
         if (ln.h_cnt) memset(ln.h_cnt, 0, 64);
@@ -256,7 +258,7 @@ int annotate_routed_range(ka_engine* e, Device& d, int idx, RouteShared& sh, con
             if (recv_cnt[idx]) cuda_ok(cudaMemcpyAsync(ln.r_recv + recv_off[idx], ln.r_send + send_off[idx], recv_cnt[idx] * 8, cudaMemcpyDeviceToDevice, st), "self keys");
             // the owner answers from its local shard
             TableView tab = e->geom;
-            tab.sectors = d.table; tab.ovf = d.ovf; tab.sig = nullptr; tab.my_shard = (uint32_t)idx;
+            tab.sectors = d.table; tab.ovf = d.ovf; tab.my_shard = (uint32_t)idx;
             mark(5);
             cuda_ok(launch_route_lookup(ln.r_recv, total_recv, tab, ln.r_ans_recv, st), "route lookup");
             mark(6);

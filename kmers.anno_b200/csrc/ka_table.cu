@@ -16,7 +16,7 @@ int build_table(ka_engine* e, Device& d, const TableView& geom, const DbSource& 
     DCK(d, cudaSetDevice(d.id));
     if (d.table) { cudaFree(d.table); d.table = nullptr; }
     if (d.ovf) { cudaFree(d.ovf); d.ovf = nullptr; }
-    if (d.sig) { cudaFree(d.sig); d.sig = nullptr; }
+    if (d.filt) { cudaFree(d.filt); d.filt = nullptr; }
     const int K = geom.K;
     const size_t n_sectors = (size_t)1 << (geom.n_shards > 1 ? geom.shard_shift : geom.bbits);  // of this device
     const size_t bytes = n_sectors * 32;
@@ -28,17 +28,10 @@ int build_table(ka_engine* e, Device& d, const TableView& geom, const DbSource& 
         ce = cudaMalloc((void**)&d.ovf, ovf_bytes);
         if (ce != cudaSuccess) { d.ovf = nullptr; return dev_fail(d, KA_ERR_OOM, "overflow table", ce); }
     }
-    const bool use_sig = geom.n_shards <= 1 && !geom.wide && (e->filter == 1 || (e->filter < 0 && geom.bbits >= 20));
-    const size_t sig_bytes = use_sig ? (n_sectors * 2 + 4) : 0;
-    if (sig_bytes) {
-        ce = cudaMalloc((void**)&d.sig, sig_bytes);
-        if (ce != cudaSuccess) { d.sig = nullptr; return dev_fail(d, KA_ERR_OOM, "signature array", ce); }
-    }
     cudaStream_t st = d.pipe[0].st;
     TableView tab = geom;
     tab.sectors = d.table;
     tab.ovf = d.ovf;
-    tab.sig = d.sig;
     const uint64_t CH = (src.synthetic ? 64ull : 16ull) << 20;  // k-mers per upload / per generator launch
     uint8_t* dk = nullptr; int32_t* dr = nullptr; unsigned long long* best = nullptr;
     unsigned long long* dc = nullptr; uint32_t* de = nullptr;
@@ -62,9 +55,10 @@ int build_table(ka_engine* e, Device& d, const TableView& geom, const DbSource& 
     };
     step(cudaMemsetAsync(d.table, 0, bytes, st), "memset table");
     if (ovf_bytes) step(cudaMemsetAsync(d.ovf, 0, ovf_bytes, st), "memset overflow table");
-    if (sig_bytes) step(cudaMemsetAsync(d.sig, 0, sig_bytes, st), "memset signatures");
     if (packed) step(cudaMemsetAsync(best, 0, n_slots * 8, st), "memset best");
     step(cudaMemcpyAsync(d.lut, e->lut, 256, cudaMemcpyHostToDevice, st), "H2D lut");
+    step(cudaMemcpyAsync(d.lut5, e->lut5, 256, cudaMemcpyHostToDevice, st), "H2D lut5");
+    step(cudaMemcpyAsync(d.inv32, e->inv32, 32, cudaMemcpyHostToDevice, st), "H2D inv32");
     step(cudaMemsetAsync(dc, 0, 16, st), "memset counters");
     step(cudaMemsetAsync(de, 0, 16, st), "memset errs");
     for (uint64_t i = 0; i < n && rc == KA_OK; i += ch) {
@@ -142,7 +136,6 @@ bool choose_geometry(uint64_t n, int K, int32_t max_role, double lf, int force_c
             g.rem_mask = rem_bits ? ((1ull << rem_bits) - 1) : 0;
             g.sectors = nullptr;
             g.ovf = nullptr;
-            g.sig = nullptr;
             g.n_primary_slots = wide ? 0u : (uint32_t)((uint64_t)S << b);
             g.wide = wide ? 1u : 0u;
             // expected keys beyond S per sector under Poisson(n / sectors) arrivals
@@ -161,6 +154,135 @@ bool choose_geometry(uint64_t n, int K, int32_t max_role, double lf, int force_c
         }
     }
     return found;
+}
+
+
+// ---- line table (slot class 16, ka_line.cuh) ----------------------------------------------------
+static uint32_t bit_length(unsigned long long x) {
+    uint32_t b = 0;
+    while (x) { b++; x >>= 1; }
+    return b;
+}
+
+// B = c * 2^s lines (c in 8..15) for n keys at load factor lf; the 11 remainder bits of a tag need
+// s >= w - 16.  `forced` (option slot_bits = 16) accepts a table that is larger than the keys need.
+bool choose_line_geometry(uint64_t n, int K, int nsym, double lf, bool forced, LineTable& g) {
+    if (nsym < 2 || nsym > 31 || K < 1 || K > KMAX) return false;
+    unsigned long long pw = 1;
+    for (int i = 0; i < K; i++) pw *= (unsigned long long)nsym;           // nsym^K <= 31^12 < 2^60
+    const uint32_t w = bit_length(pw - 1);
+    if (w < 5) return false;
+    const double want = std::max(8.0, std::ceil((double)(n ? n : 1) / (32.0 * lf)));
+    uint64_t best = 0;
+    uint32_t bc = 0, bs = 0;
+    for (uint32_t s = 0; s <= 24; s++)
+        for (uint32_t c = 8; c < 16; c++) {
+            const uint64_t B = (uint64_t)c << s;
+            if ((double)B >= want && (!best || B < best)) { best = B; bc = c; bs = s; }
+        }
+    if (!best) return false;                                               // more than 15 * 2^24 lines
+    const uint32_t s_min = w > 16 ? w - 16 : 0;
+    if (bs < s_min) {
+        // the keys would need a padded table: accepted up to 2x (no larger than the 32-bit sector class at its
+        // default load factor), or whenever the layout is forced
+        if (!forced && (bs + 1 < s_min)) return false;
+        bs = s_min; bc = 8;
+    }
+    uint32_t u = 12;
+    if (w < bs + 2 + 12) {
+        // short keys: power-of-two table, the top 3 bits choose the part
+        u = 3;
+        if (bc != 8) { bc = 8; bs += 1; }                                  // round up to the next power of two
+        if (w < bs + 5) bs = w - 5;                                        // the table already exceeds the key space
+    }
+    if (((uint64_t)bc << bs) >= (1ull << 27)) return false;                // 32-bit slot tokens
+    g = LineTable{};
+    g.c = bc; g.s = bs; g.u = u;
+    g.n_lines = bc << bs;
+    g.inv_c = (65536u + bc - 1) / bc;
+    g.wbits = w; g.wl = w / 2; g.wh = w - w / 2;
+    g.low_bits = w - u - bs;
+    g.rem0_bits = g.low_bits - 2;
+    if (g.rem0_bits + (u - 3) > TAG_REM_BITS) return false;
+    g.radix = (uint32_t)nsym;
+    g.pow_k1 = pw / (unsigned long long)nsym;
+    g.K = K;
+    // expected keys beyond 32 per line under Poisson(n / lines) arrivals -> overflow table size
+    const double lam = (double)n / (double)g.n_lines;
+    double pk = std::exp(-lam), over = 0;
+    for (int k = 1; k < 32 + 400; k++) {
+        pk *= lam / k;
+        if (k > 32) over += (k - 32) * pk;
+    }
+    const double want_ovf = 4.0 * over * (double)g.n_lines + 4096;
+    g.ovf_bbits = ceil_log2(want_ovf / 2.0);
+    return true;
+}
+
+// Build the line table of one device (replicated on every device of the engine).
+// counts3: [0] distinct keys, [1] keys outside their home sector, [2] keys in the overflow table.
+int build_line_table(ka_engine* e, Device& d, const LineTable& geom, const DbSource& src, uint64_t* counts3) {
+    DCK(d, cudaSetDevice(d.id));
+    if (d.table) { cudaFree(d.table); d.table = nullptr; }
+    if (d.ovf) { cudaFree(d.ovf); d.ovf = nullptr; }
+    if (d.filt) { cudaFree(d.filt); d.filt = nullptr; }
+    const int K = geom.K;
+    const size_t bytes = (size_t)geom.n_lines * 128, n_slots = (size_t)geom.n_lines * 32;
+    const size_t ovf_bytes = (size_t)64 << geom.ovf_bbits, filt_bytes = (size_t)geom.n_lines * 16;
+    cudaError_t ce;
+    if ((ce = cudaMalloc((void**)&d.table, bytes)) != cudaSuccess) { d.table = nullptr; return dev_fail(d, KA_ERR_OOM, "table", ce); }
+    if ((ce = cudaMalloc((void**)&d.ovf, ovf_bytes)) != cudaSuccess) { d.ovf = nullptr; return dev_fail(d, KA_ERR_OOM, "overflow table", ce); }
+    if ((ce = cudaMalloc((void**)&d.filt, filt_bytes)) != cudaSuccess) { d.filt = nullptr; return dev_fail(d, KA_ERR_OOM, "presence filter", ce); }
+    cudaStream_t st = d.pipe[0].st;
+    LineTable tab = geom;
+    tab.lines = d.table; tab.ovf = d.ovf; tab.filt = d.filt;
+    const uint64_t n = src.n, CH = (src.synthetic ? 64ull : 16ull) << 20;
+    const uint64_t ch = std::min<uint64_t>(CH, n ? n : 1);
+    uint8_t* dk = nullptr; int32_t* dr = nullptr; unsigned long long* best = nullptr;
+    unsigned long long* dc = nullptr; uint32_t* de = nullptr;
+    if ((ce = cudaMalloc((void**)&dk, ch * K)) != cudaSuccess || (ce = cudaMalloc((void**)&dr, ch * 4)) != cudaSuccess ||
+        (ce = cudaMalloc((void**)&best, n_slots * 8)) != cudaSuccess || (ce = cudaMalloc((void**)&dc, 32)) != cudaSuccess ||
+        (ce = cudaMalloc((void**)&de, 16)) != cudaSuccess) {
+        for (void* q : {(void*)dk, (void*)dr, (void*)best, (void*)dc}) if (q) cudaFree(q);
+        return dev_fail(d, KA_ERR_OOM, "DB staging", ce);
+    }
+    int rc = KA_OK;
+    auto step = [&](cudaError_t c, const char* what) {
+        if (c != cudaSuccess && rc == KA_OK) rc = dev_fail(d, KA_ERR_CUDA, what, c);
+    };
+    step(cudaMemsetAsync(d.table, 0, bytes, st), "memset table");
+    step(cudaMemsetAsync(d.ovf, 0, ovf_bytes, st), "memset overflow table");
+    step(cudaMemsetAsync(d.filt, 0, filt_bytes, st), "memset filter");
+    step(cudaMemsetAsync(best, 0, n_slots * 8, st), "memset best");
+    step(cudaMemcpyAsync(d.lut, e->lut, 256, cudaMemcpyHostToDevice, st), "H2D lut");
+    step(cudaMemcpyAsync(d.lut5, e->lut5, 256, cudaMemcpyHostToDevice, st), "H2D lut5");
+    step(cudaMemcpyAsync(d.inv32, e->inv32, 32, cudaMemcpyHostToDevice, st), "H2D inv32");
+    step(cudaMemsetAsync(dc, 0, 32, st), "memset counters");
+    step(cudaMemsetAsync(de, 0, 16, st), "memset errs");
+    for (uint64_t i = 0; i < n && rc == KA_OK; i += ch) {
+        const uint64_t m = std::min(ch, n - i);
+        if (!src.synthetic) {
+            step(cudaMemcpyAsync(dk, src.kmers + i * K, m * K, cudaMemcpyHostToDevice, st), "H2D kmers");
+            step(cudaMemcpyAsync(dr, src.roles + i, m * 4, cudaMemcpyHostToDevice, st), "H2D roles");
+        } else {
+            step(launch_db_generate(i, m, K, src.seed, src.n_roles, dk, dr, st), "db_generate");
+        }
+        step(launch_line_insert(tab, dk, dr, m, i, d.lut5, best, src.role_bits, dc, de, st), "line_insert");
+        step(cudaStreamSynchronize(st), "line_insert sync");
+    }
+    if (rc == KA_OK) step(launch_line_finalize(tab, best, src.role_bits, st), "line_finalize");
+    step(cudaStreamSynchronize(st), "line_finalize sync");
+    unsigned long long hc[4] = {0, 0, 0, 0};
+    uint32_t he[4] = {0, 0, 0, 0};
+    step(cudaMemcpy(hc, dc, 32, cudaMemcpyDeviceToHost), "D2H counters");
+    step(cudaMemcpy(he, de, 16, cudaMemcpyDeviceToHost), "D2H errs");
+    cudaFree(dk); cudaFree(dr); cudaFree(dc); cudaFree(de); cudaFree(best);
+    if (rc) return rc;
+    if (he[0]) { d.err = KA_ERR_ALPHABET; d.errmsg = "k-mer byte outside the DB alphabet (internal)"; return d.err; }
+    if (he[1]) { d.err = KA_ERR_ROLE; d.errmsg = "negative role id in the DB"; return d.err; }
+    if (he[2]) { d.err = KA_ERR_TOO_BIG; d.errmsg = "overflow table full"; return d.err; }  // caller retries larger
+    counts3[0] = hc[0]; counts3[1] = hc[1]; counts3[2] = hc[2];
+    return KA_OK;
 }
 
 }  // namespace kai
@@ -228,6 +350,17 @@ int db_load_impl(ka_engine* e, const uint8_t* kmers, const int32_t* role_ids, ui
     if (nsym > 31)
         return fail(e, KA_ERR_ALPHABET,
                     "ka_db_load: the DB uses %d distinct residue bytes; at most 31 fit the 5-bit packing", nsym);
+    // radix digits 0..nsym-1 in byte order (line table, packed streams); 31 = byte not in the alphabet
+    memset(e->lut5, (int)CODE_INVALID, 256);
+    memset(e->inv32, 0, 32);
+    {
+        int outside = -1;
+        for (int b = 0; b < 256; b++) {
+            if (e->lut[b]) { e->lut5[b] = (uint8_t)(e->lut[b] - 1); e->inv32[e->lut[b] - 1] = (uint8_t)b; }
+            else if (outside < 0) outside = b;
+        }
+        for (int c = nsym; c < 32; c++) e->inv32[c] = (uint8_t)outside;     // nsym <= 31 < 256: such a byte exists
+    }
 
     // 2. table geometry (slot class, sector count) from n, K and the largest role id
     int32_t max_role = synthetic ? syn_roles - 1 : 0;
@@ -246,6 +379,54 @@ int db_load_impl(ka_engine* e, const uint8_t* kmers, const int32_t* role_ids, ui
         if (line_bits + src.role_bits > 64)
             return fail(e, KA_ERR_TOO_BIG, "ka_db_load: %llu lines with role ids up to %d exceed the 64-bit (line, role) word",
                         (unsigned long long)n, max_role);
+    }
+    // line table (slot class 16): replicated narrow tables with 16-bit role ids; chosen automatically for
+    // large DBs whose keys fill its 11 remainder bits without padding, or forced by slot_bits = 16
+    if (e->slot_bits == 16 || (e->slot_bits == 0 && e->table_mode == 0 && !e->wide && max_role <= 0xFFFF && n >= (1ull << 20))) {
+        LineTable lg;
+        const bool forced = e->slot_bits == 16;
+        if (forced && (e->table_mode != 0 || e->wide || max_role > 0xFFFF))
+            return fail(e, KA_ERR_INVALID, "ka_db_load: slot_bits = 16 needs a replicated narrow table and role ids below 65536");
+        if (choose_line_geometry(n, K, nsym, e->load_factor > 0 ? std::min(e->load_factor, 0.8) : 0.65, forced, lg)) {
+            std::vector<std::array<uint64_t, 3>> cnt(e->devs.size());
+            auto tb = std::chrono::steady_clock::now();
+            int rc = KA_OK;
+            for (int attempt = 0; attempt < 6; attempt++) {
+                rc = for_each_device(e, [&](Device& d, int i) { return build_line_table(e, d, lg, src, cnt[i].data()); });
+                if (rc != KA_ERR_TOO_BIG) break;
+                lg.ovf_bbits += 2;
+            }
+            if (rc) return rc;
+            if (getenv("KA_LOAD_TRACE"))
+                fprintf(stderr, "[db load] line table (%llu lines of DB, %u x 2^%u table lines, %llu spilled, %llu overflowed): %.2f s\n",
+                        (unsigned long long)n, lg.c, lg.s, (unsigned long long)cnt[0][1], (unsigned long long)cnt[0][2],
+                        std::chrono::duration<double>(std::chrono::steady_clock::now() - tb).count());
+            e->lgeom = lg;
+            e->geom = TableView{};
+            e->geom.K = K;
+            e->line = true;
+            e->db_table_mode = 0;
+            e->info = ka_db_info{};
+            e->info.K = K;
+            e->info.n_symbols = nsym;
+            e->info.n_lines = n;
+            e->info.n_keys = cnt[0][0];
+            e->info.n_buckets = (uint64_t)lg.n_lines * 4;
+            e->info.table_bytes = (uint64_t)lg.n_lines * 128 + ((uint64_t)64 << lg.ovf_bbits);
+            e->info.max_probe = cnt[0][2] ? 3 : (cnt[0][1] ? 2 : 1);
+            e->info.slot_bits = 16;
+            e->info.filter_bytes = (uint64_t)lg.n_lines * 16;
+            e->info.n_spilled = cnt[0][1];
+            e->info.n_overflow = cnt[0][2];
+            e->have_db = true;
+            e->db_serial++;
+            for (Device& d : e->devs) {
+                cudaSetDevice(d.id);
+                for (int k = 0; k < NPIPE; k++) set_l2_window(e, d, d.pipe[k].st);
+            }
+            return KA_OK;
+        }
+        if (forced) return fail(e, KA_ERR_TOO_BIG, "ka_db_load: %llu k-mers (K=%d, %d symbols) do not fit the 16-bit line table", (unsigned long long)n, K, nsym);
     }
     TableView geom;
     const uint32_t n_shards = e->table_mode >= 1 ? (uint32_t)e->devs.size() : 1u;
@@ -271,7 +452,7 @@ int db_load_impl(ka_engine* e, const uint8_t* kmers, const int32_t* role_ids, ui
     }
     // communicators first: NCCL sets up its buffers before the table takes most of the HBM
     if (e->table_mode == 2) { int nrc = route_init_comms(e); if (nrc) return nrc; }
-    if (!choose_geometry(n, K, max_role, e->load_factor, e->slot_bits, n_shards, e->wide != 0, geom))
+    if (!choose_geometry(n, K, max_role, e->load_factor > 0 ? e->load_factor : 0.4, e->slot_bits == 16 ? 0 : e->slot_bits, n_shards, e->wide != 0, geom))
         return fail(e, KA_ERR_TOO_BIG, "ka_db_load: %llu k-mers (K=%d, max role %d) do not fit %s",
                     (unsigned long long)n, K, max_role, e->slot_bits ? "the forced slot width" : "any slot class of this build");
 
@@ -311,13 +492,16 @@ int db_load_impl(ka_engine* e, const uint8_t* kmers, const int32_t* role_ids, ui
         }
     }
     e->geom = geom;
+    e->line = false;
+    e->db_table_mode = e->table_mode;
+    e->db_serial++;
+    e->info = ka_db_info{};
     e->info.K = K;
     e->info.n_symbols = nsym;
     e->info.n_lines = n;
     e->info.n_keys = nk[0];
     e->info.n_buckets = 1ull << geom.bbits;
     e->info.table_bytes = (32ull << geom.bbits) + (geom.cls == 128 ? 0 : (uint64_t)n_shards * (64ull << geom.ovf_bbits));  // all shards
-    e->have_sig = e->devs[0].sig != nullptr;
     e->info.max_probe = mp[0];
     e->info.slot_bits = (uint32_t)geom.cls;
     e->have_db = true;

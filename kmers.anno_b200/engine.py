@@ -10,14 +10,15 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkmeranno.so")
+# KMERANNO_LIB selects another build of the same library (e.g. the bounds-checking `make debuglib`)
+LIB_PATH = os.environ.get("KMERANNO_LIB") or os.path.join(_HERE, "libkmeranno.so")
 
 FLAG_NONE, FLAG_CALLED, FLAG_AMBIGUOUS, FLAG_BELOW_MIN = 0, 1, 2, 3
 
 # every symbol include/kmeranno.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
     "ka_create", "ka_destroy", "ka_last_error", "ka_set_option", "ka_db_load", "ka_db_load_synthetic", "ka_db_get_info",
-    "ka_annotate", "ka_build", "ka_kmer_distance", "ka_batch_upload", "ka_annotate_resident", "ka_batch_download", "ka_batch_free",
+    "ka_annotate", "ka_annotate_packed", "ka_db_get_alphabet", "ka_pack_residues", "ka_build", "ka_kmer_distance", "ka_batch_upload", "ka_annotate_resident", "ka_batch_download", "ka_batch_free",
     "ka_host_alloc", "ka_host_free", "ka_get_stats", "ka_probe_roofline", "ka_abi_version",
 ]
 
@@ -31,7 +32,8 @@ class KmerAnnoError(RuntimeError):
 class DbInfo(C.Structure):
     _fields_ = [("K", C.c_int32), ("n_symbols", C.c_int32), ("n_lines", C.c_uint64),
                 ("n_keys", C.c_uint64), ("n_buckets", C.c_uint64), ("table_bytes", C.c_uint64),
-                ("max_probe", C.c_uint32), ("slot_bits", C.c_uint32)]
+                ("max_probe", C.c_uint32), ("slot_bits", C.c_uint32), ("filter_bytes", C.c_uint64),
+                ("n_spilled", C.c_uint64), ("n_overflow", C.c_uint64)]
 
 
 class Stats(C.Structure):
@@ -64,6 +66,9 @@ def load_library():
     lib.ka_db_load_synthetic.argtypes = [vp, C.c_uint64, C.c_int, C.c_int32, C.c_uint64]
     lib.ka_db_get_info.argtypes = [vp, C.POINTER(DbInfo)]
     lib.ka_annotate.argtypes = [vp, u8p, u64p, C.c_uint64, C.c_int32, i32p, i32p, u8p]
+    lib.ka_annotate_packed.argtypes = [vp, u8p, vp, C.c_uint64, C.c_int32, i32p, i32p, u8p]
+    lib.ka_db_get_alphabet.argtypes = [vp, u8p]
+    lib.ka_pack_residues.argtypes = [vp, u8p, C.c_uint64, C.c_uint64, u8p]
     lib.ka_build.argtypes = [vp, u8p, u64p, C.c_uint64, i32p, i32p, C.c_int, C.c_uint64, u8p, i32p,
                              C.POINTER(C.c_uint64), C.c_int]
     lib.ka_kmer_distance.argtypes = [vp, u8p, u64p, C.c_uint64, C.c_int, vp, u64p, C.c_uint64, vp, i32p, i32p, vp]
@@ -185,6 +190,55 @@ class Engine:
         role, hits, flag = out
         self._check(self._lib.ka_annotate(self._h, _ptr(residues), _ptr(offsets), n, int(min_hits),
                                           _ptr(role), _ptr(hits), _ptr(flag)))
+        return role, hits, flag
+
+    def alphabet(self):
+        """code_of_byte[256] of the loaded DB: digit 0..n-1 in byte order, 31 = byte not in the DB."""
+        lut = np.empty(256, np.uint8)
+        self._check(self._lib.ka_db_get_alphabet(self._h, _ptr(lut)))
+        return lut
+
+    def pack(self, residues, offsets, alloc=None, threads=None):
+        """The packed form of a CSR batch for annotate_packed: (codes u8 stream, offsets u32).  The
+        stream is indexed like `residues` (residue r at bits [5r, 5r+5)); ka_pack_residues on
+        8-aligned slices, one per thread."""
+        residues = np.ascontiguousarray(residues, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        total = int(offsets[-1]) if offsets.shape[0] else 0
+        if total >= 1 << 32:
+            raise KmerAnnoError(-10, "annotate_packed takes at most 2^32 - 1 residues per call")
+        alloc = alloc or (lambda shape, dtype: np.empty(shape, dtype))
+        codes = alloc((total * 5 + 7) // 8 + 16, np.uint8)
+        off32 = alloc(offsets.shape[0], np.uint32)
+        off32[:] = offsets
+        threads = threads or min(os.cpu_count() or 1, 32)
+        step = max(1 << 20, -(-total // threads) + 7 & ~7)
+        cuts = list(range(0, total, step)) + [total]
+
+        def work(i):
+            a, b = cuts[i], cuts[i + 1]
+            rc = self._lib.ka_pack_residues(self._h, residues.ctypes.data + a, b - a, a, _ptr(codes))
+            if rc != 0:
+                raise KmerAnnoError(rc, (self._lib.ka_last_error(self._h) or b"").decode())
+
+        if len(cuts) > 2:
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(threads) as ex:
+                list(ex.map(work, range(len(cuts) - 1)))
+        elif total:
+            work(0)
+        return codes, off32
+
+    def annotate_packed(self, codes, offsets32, min_hits=5, out=None):
+        """codes: 5-bit stream (see pack), offsets32 uint32[N+1] (host).  Returns (role, hits, flag)."""
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        offsets32 = np.ascontiguousarray(offsets32, dtype=np.uint32)
+        n = max(offsets32.shape[0] - 1, 0)
+        if out is None:
+            out = (np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n, np.uint8))
+        role, hits, flag = out
+        self._check(self._lib.ka_annotate_packed(self._h, _ptr(codes), _ptr(offsets32), n, int(min_hits),
+                                                 _ptr(role), _ptr(hits), _ptr(flag)))
         return role, hits, flag
 
     def build(self, residues, offsets, n_roles, peg_role, K, load_as_db=False):

@@ -34,20 +34,38 @@ def case(draw):
     roles = draw(st.lists(st.integers(0, 5), min_size=len(kmers), max_size=len(kmers)))
     min_hits = draw(st.integers(1, 4))
     wide = draw(st.integers(0, 1))          # narrow / wide-table kernels
-    return K, seqs, kmers, roles, min_hits, wide
+    layout = draw(st.sampled_from([0, 16, 16, 32, 64]))   # 16 = the 128-byte-line table, when the keys fit it
+    packed = draw(st.booleans())            # ka_annotate_packed (5-bit stream) instead of ka_annotate
+    return K, seqs, kmers, roles, min_hits, wide, layout, packed
 
 
 @settings(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
 @given(case())
 def test_engine_equals_python_statement(engine, c):
-    K, seqs, kmers, roles, min_hits, wide = c
+    import kmers_anno_b200 as ka
+    K, seqs, kmers, roles, min_hits, wide, layout, packed = c
     res, off = csr(seqs)
+    if layout == 16:
+        wide = 0
     engine.set_option("wide", wide)
-    engine.db_load(kmers, np.asarray(roles, np.int32), K)
-    got = engine.annotate(res, off, min_hits)
+    engine.set_option("slot_bits", layout)
+    try:
+        engine.db_load(kmers, np.asarray(roles, np.int32), K)
+    except ka.KmerAnnoError as err:
+        # keys of more than 39 bits (or a one-letter alphabet) do not fit the line table: loud error, then the default layout
+        assert layout == 16 and err.code == -10, err
+        engine.set_option("slot_bits", 0)
+        engine.db_load(kmers, np.asarray(roles, np.int32), K)
+    else:
+        assert layout == 0 or engine.db_info()["slot_bits"] == layout
+    if packed:
+        codes, off32 = engine.pack(res, off, threads=1)
+        got = engine.annotate_packed(codes, off32, min_hits)
+    else:
+        got = engine.annotate(res, off, min_hits)
     want = py_apply(seqs, kmers, roles, K, min_hits)
     for g, w in zip(got, want):
-        assert np.array_equal(g, w), (K, seqs, kmers, roles, min_hits, g.tolist(), w.tolist())
+        assert np.array_equal(g, w), (K, seqs, kmers, roles, min_hits, layout, packed, g.tolist(), w.tolist())
 
 
 @st.composite

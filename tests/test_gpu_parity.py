@@ -127,34 +127,30 @@ def test_long_sequences_use_big_kernel(ka, oracle):
 
 @pytest.mark.parametrize("opts", [
     {"tile_span": 256, "long_seq": 1024},
-    {"tile_span": 4096, "long_seq": 8192, "mid_seq": 8192, "variant": 1},
+    {"tile_span": 4096, "long_seq": 8192, "mid_seq": 8192},
     {"tile_span": 512, "long_seq": 512, "mid_seq": 600},
     {"mid_seq": 2048},
+    {"long_seq": 2048},
     {"chunk_residues": 4096},
     {"load_factor": 0.9},
     {"load_factor": 0.05},
     {"l2_persist": 0},
-    {"variant": 1},
-    {"variant": 2},
-    {"variant": 3},
-    {"variant": 3, "filter": 1, "slot_bits": 64},
     {"slot_bits": 32},
     {"slot_bits": 64},
     {"slot_bits": 128},
-    {"slot_bits": 64, "variant": 2, "load_factor": 0.9},
-    {"slot_bits": 32, "variant": 1, "load_factor": 0.9},
-    {"filter": 1},
-    {"filter": 1, "two_phase": 1},
-    {"filter": 1, "two_phase": 1, "slot_bits": 64},
-    {"filter": 1, "two_phase": 1, "slot_bits": 128, "load_factor": 0.9},
-    {"filter": 1, "two_phase": 1, "tile_span": 256, "long_seq": 300, "mid_seq": 700},
+    {"slot_bits": 64, "load_factor": 0.9},
+    {"slot_bits": 32, "load_factor": 0.9},
     {"wide": 1},
     {"wide": 1, "slot_bits": 64, "load_factor": 0.9},
-    {"wide": 1, "slot_bits": 32, "variant": 1, "load_factor": 0.9, "tile_span": 256, "long_seq": 300, "mid_seq": 700},
+    {"wide": 1, "slot_bits": 32, "load_factor": 0.9, "tile_span": 256, "long_seq": 300, "mid_seq": 700},
     {"wide": 1, "slot_bits": 128},      # 128-bit slots have no wide form: the option is ignored
-    {"wide": 1, "filter": 1},           # nor do signatures
-    {"filter": 1, "slot_bits": 32, "variant": 1, "load_factor": 0.9},
-    {"filter": 1, "slot_bits": 128, "variant": 2, "mid_variant": 0},
+    # the 128-byte-line table (16-bit tags and roles, spill inside the line, presence filter)
+    {"slot_bits": 16},
+    {"slot_bits": 16, "filter": 0},
+    {"slot_bits": 16, "tile_span": 256, "long_seq": 300, "mid_seq": 700},
+    {"slot_bits": 16, "tile_span": 4096, "long_seq": 8192, "mid_seq": 8192},
+    {"slot_bits": 16, "chunk_residues": 4096},
+    {"slot_bits": 16, "load_factor": 0.8, "filter": 0},
 ])
 def test_options_do_not_change_results(ka, oracle, opts):
     seqs, kmers, roles = ragged_case(33, n_seq=500, K=8, max_len=900)
@@ -174,7 +170,7 @@ def test_slot_class_selection(ka, oracle, K, max_role, want_bits):
     assert_same(got, oracle.OracleDb(kmers, roles, K).apply(res, off, 3), f"slot class K={K}")
 
 
-@pytest.mark.parametrize("slot_bits,lf,filt", [(32, 0.9, 0), (64, 0.9, 1), (128, 0.9, 0), (32, 0.4, 1), (32, 0.9, -2), (64, 0.9, -2)])
+@pytest.mark.parametrize("slot_bits,lf,filt", [(32, 0.9, 0), (64, 0.9, 0), (128, 0.9, 0), (32, 0.4, 0), (32, 0.9, -2), (64, 0.9, -2)])
 def test_overflow_heavy_table(ka, oracle, slot_bits, lf, filt):
     """Millions of keys at a high load factor: ~13 % of the keys leave their home sector.
     Quotiented slots keep only a remainder, so those keys must live in the overflow table
@@ -188,8 +184,6 @@ def test_overflow_heavy_table(ka, oracle, slot_bits, lf, filt):
         eng.set_option("load_factor", lf)
         if filt == -2:
             eng.set_option("wide", 1)         # wide-table kernels on the same table
-        else:
-            eng.set_option("filter", filt)
         eng.db_load(kmers, roles, 8)
         info = eng.db_info()
         got = eng.annotate(res, off, 5)

@@ -26,7 +26,7 @@ def test_abi_library_exports_every_declared_symbol():
     for name in declared:
         assert getattr(lib, name) is not None
     lib.ka_abi_version.restype = ctypes.c_int
-    assert lib.ka_abi_version() == 1      # no compute call: fine without a GPU
+    assert lib.ka_abi_version() == 2      # no compute call: fine without a GPU
 
 
 def test_no_gpu_means_error_not_fallback():
