@@ -76,11 +76,12 @@ const char* ka_last_error(const ka_engine* e);
  * Table options take effect at the next ka_db_load (the loaded table keeps the geometry it was
  * built with); tiling options at the next annotate call (a resident batch uploaded under other
  * tiling options is rejected by ka_annotate_resident: upload it again).
- *   "load_factor"   table load factor in (0,0.9]; default: 0.65 for the line table, 0.4 for the sector classes
- *   "slot_bits"     force the table layout: 16 = the 128-byte-line table (16-bit tags + 16-bit roles, spill inside
- *                   the line, L2-resident presence filter; needs a replicated table, role ids < 65536 and keys of
- *                   at most 39 bits, e.g. K <= 9 over 20 letters), 32 / 64 / 128 = sector classes with slots of
- *                   that width; 0 (default) = the line table for large DBs that fit it, else the narrowest sector class
+ *   "load_factor"   table load factor in (0,0.9]; default: 0.68 for the line table, 0.4 for the sector classes
+ *   "slot_bits"     force the table layout: 32 / 64 / 128 = sector classes with slots of that width; 16 = the
+ *                   128-byte-line table (16-bit tags + 16-bit roles, spill inside the line, L2-resident
+ *                   presence filter: half the DRAM traffic per probe, but a slower kernel — measured, not the
+ *                   default; needs a replicated table, role ids < 65536 and 2 <= K <= 10 with key halves of at
+ *                   most 25 bits); 0 (default) = the narrowest sector class that holds the DB
  *   "filter"        line table only: 1 (default) = probe the L2-resident presence filter first, 0 = always read
  *                   the table (measurement knob)
  *   "table_mode"    0 = table replicated on every device (default); 1 = table sharded by sector range
@@ -91,7 +92,7 @@ const char* ka_last_error(const ka_engine* e);
  *   "wide"          1 = use the wide-table kernels (64-bit sector indices, the mixed key as de-dup
  *                   token) on any sector-class table; 0 (default) = only beyond 2^32 - 16 slots
  *   "tile_span"     residues of sequence starts per CTA tile, default 1536
- *   "long_seq"      sequences longer than this get a tile of their own (second tile launch), default 1536
+ *   "long_seq"      sequences longer than this get a tile of their own (second tile launch), default 2048
  *   "mid_seq"       sequences longer than this use the global-scratch long-sequence kernel, default 8192
  *   "chunk_residues" residues per pipelined H2D chunk, default 48 Mi (4 chunks in flight per device)
  *   "l2_persist"    sector classes: 1 = L2 persisting access-policy window on the table (default 1)

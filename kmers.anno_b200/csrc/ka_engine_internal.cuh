@@ -97,9 +97,9 @@ struct ka_engine {
     std::mutex mu;
     std::string err;
     // options
-    double load_factor = 0;     // 0 = default of the chosen layout (0.4 sector classes, 0.65 line table)
+    double load_factor = 0;     // 0 = default of the chosen layout (0.4 sector classes, 0.68 line table)
     uint32_t tile_span = 1536;
-    uint32_t long_seq = 1536;
+    uint32_t long_seq = 2048;
     uint32_t mid_seq = 8192;
     uint64_t chunk_residues = 48ull << 20;
     int l2_persist = 1;

@@ -76,7 +76,7 @@ __device__ __forceinline__ int match16(const uint4& a, const uint4& b, uint32_t 
 
 // flag bits of a home sector: bit a-1 = keys of this home live in sector home^a, bit 3 = in the overflow table
 __device__ __forceinline__ uint32_t sector_flags(const uint4& a) {
-    return ((a.x >> 12) & 1u) | ((a.x >> 27) & 2u) | ((a.y >> 10) & 4u) | ((a.y >> 25) & 8u);
+    return ((a.x >> 14) & 1u) | ((a.x >> 29) & 2u) | ((a.y >> 12) & 4u) | ((a.y >> 27) & 8u);
 }
 
 __device__ __forceinline__ int line_ovf_lookup(const LineTable& t, uint32_t sector, uint32_t tag, uint32_t& tok) {
@@ -141,21 +141,21 @@ __device__ __forceinline__ void line_emit(const LineParams& p, uint32_t seq, int
     if (p.out_flag) p.out_flag[seq] = flag;
 }
 
-// 5-bit code number I (compile time) of a 128-bit window held in four registers
+// 5-bit code number I (compile time) of a 64-bit window held in two registers
 template <int I>
-__device__ __forceinline__ uint32_t window_code(const uint32_t (&v)[4]) {
-    constexpr int bit = 5 * I, q = bit >> 5, sh = bit & 31;
-    static_assert(q < 4, "code outside the window");
-    if (sh <= 27) return (v[q] >> sh) & 31u;
-    else return __funnelshift_r(v[q], v[q < 3 ? q + 1 : 3], sh) & 31u;
-}
-template <int I>
-__device__ __forceinline__ uint32_t window_code64(uint32_t u0, uint32_t u1) {
+__device__ __forceinline__ uint32_t window_code(uint32_t u0, uint32_t u1) {
     constexpr int bit = 5 * I, sh = bit & 31;
     static_assert(bit + 5 <= 64, "code outside the window");
     if (bit + 5 <= 32) return (u0 >> sh) & 31u;
     else if (bit >= 32) return (u1 >> sh) & 31u;
     else return __funnelshift_r(u0, u1, sh) & 31u;
+}
+// the 64 stream bits starting at stage bit `bit`
+__device__ __forceinline__ void load_window(const uint32_t* s_pk, uint32_t bit, uint32_t& u0, uint32_t& u1) {
+    const uint32_t* w = s_pk + (bit >> 5);
+    const uint32_t sh = bit & 31u, w0 = w[0], w1 = w[1], w2 = w[2];
+    u0 = __funnelshift_r(w0, w1, sh);
+    u1 = __funnelshift_r(w1, w2, sh);
 }
 
 // code of residue g of a packed stream in global memory
@@ -231,35 +231,48 @@ cudaError_t launch_line_plan(const LineParams& p, const unsigned long long* off6
 // ------------------------------------------------------------------------------------
 constexpr int LT_THREADS = 128, LT_WARPS = LT_THREADS / 32;
 constexpr int LT_A = 8;        // window positions per lane and pass
-constexpr int LT_PB = 1;       // sector loads in flight per lane in phase B
+#ifndef KA_LT_PB
+#define KA_LT_PB 2
+#endif
+constexpr int LT_PB = KA_LT_PB; // sector loads in flight per lane in phase B
 constexpr int LT_QCAP = 32 * LT_A + 32 * LT_PB;
+constexpr int LT_Q2CAP = 32 + 4 * 32;     // second-stage queue: < 32 left over + at most 4 entries per lane of one sector round
 
-// dynamic shared memory (bytes):
-//   [0, stage_bytes)                      packed stage (TMA destination, 16-byte aligned) + 32 bytes of over-read slack
-//   [+4*(LINE_MAX_SEQ+4))                 s_off: sequence starts relative to the tile's first residue
+// dynamic shared memory (bytes), fixed-size parts first so that their addresses are compile-time constants:
+//   [0, 4*(LINE_MAX_SEQ+4))               s_off: sequence starts relative to the tile's first residue
 //   [+3*4*LINE_MAX_SEQ)                   s_cnt, s_min, s_max
+//   [+8*LT_WARPS*(LT_QCAP+LT_Q2CAP))      survivor queues and second-stage queues, one pair per warp
+//   [+stage_bytes)                        packed stage (TMA destination, 16-byte aligned) + over-read slack
 //   [+4*(tok_cap(ext_max)+4*LINE_MAX_SEQ+8))  token set, region of sequence q at tok_cap(start) + 4q
-//   [+8*LT_WARPS*LT_QCAP)                 survivor queues
+constexpr uint32_t LT_OFF_CNT = 4 * (LINE_MAX_SEQ + 4);
+constexpr uint32_t LT_OFF_Q = LT_OFF_CNT + 3 * 4 * LINE_MAX_SEQ;
+constexpr uint32_t LT_OFF_Q2 = LT_OFF_Q + 8 * LT_WARPS * LT_QCAP;
+constexpr uint32_t LT_OFF_PK = LT_OFF_Q2 + 8 * LT_WARPS * LT_Q2CAP;
+static_assert(LT_OFF_PK % 16 == 0 && LT_OFF_Q % 8 == 0, "alignment of the shared-memory parts");
+
 size_t line_tile_smem_bytes(uint32_t ext_max, uint32_t* stage_bytes_out) {
     const uint32_t stage = (((ext_max * 5u + 7u) >> 3) + 16u + 16u + 32u + 15u) & ~15u;   // lead alignment, rounding, over-read
     if (stage_bytes_out) *stage_bytes_out = stage;
-    size_t tok = ((size_t)tok_cap(ext_max) + 4 * LINE_MAX_SEQ + 8 + 1) & ~(size_t)1;
-    return (size_t)stage + 4 * (LINE_MAX_SEQ + 4) + 3 * 4 * LINE_MAX_SEQ + 4 * tok + 8 * (size_t)LT_WARPS * LT_QCAP;
+    return (size_t)LT_OFF_PK + stage + 4 * ((size_t)tok_cap(ext_max) + 4 * LINE_MAX_SEQ + 8);
 }
 
-__global__ void __launch_bounds__(LT_THREADS, 8) line_tile_kernel(LineParams p) {
+#ifndef KA_LT_MINB
+#define KA_LT_MINB 6
+#endif
+template <bool FILTER>
+__global__ void __launch_bounds__(LT_THREADS, KA_LT_MINB) line_tile_kernel(LineParams p) {
     constexpr int A = LT_A, PB = LT_PB;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t s_bar;
 
-    uint32_t* s_pk = reinterpret_cast<uint32_t*>(smem_raw);
-    uint32_t* s_off = reinterpret_cast<uint32_t*>(smem_raw + p.stage_bytes);
-    int* s_cnt = reinterpret_cast<int*>(s_off + LINE_MAX_SEQ + 4);
-    int* s_min = s_cnt + LINE_MAX_SEQ;
-    int* s_max = s_min + LINE_MAX_SEQ;
-    uint32_t* s_tok = reinterpret_cast<uint32_t*>(s_max + LINE_MAX_SEQ);
-    const uint32_t tok_words = (tok_cap(p.ext_max) + 4u * LINE_MAX_SEQ + 8u + 1u) & ~1u;
-    uint2* s_q = reinterpret_cast<uint2*>(s_tok + tok_words) + (threadIdx.x >> 5) * LT_QCAP;
+    uint32_t* const s_off = reinterpret_cast<uint32_t*>(smem_raw);
+    int* const s_cnt = reinterpret_cast<int*>(smem_raw + LT_OFF_CNT);
+    int* const s_min = s_cnt + LINE_MAX_SEQ;
+    int* const s_max = s_min + LINE_MAX_SEQ;
+    uint2* const s_q = reinterpret_cast<uint2*>(smem_raw + LT_OFF_Q) + (threadIdx.x >> 5) * LT_QCAP;
+    uint2* const s_q2 = reinterpret_cast<uint2*>(smem_raw + LT_OFF_Q2) + (threadIdx.x >> 5) * LT_Q2CAP;
+    uint32_t* const s_pk = reinterpret_cast<uint32_t*>(smem_raw + LT_OFF_PK);
+    uint32_t* const s_tok = reinterpret_cast<uint32_t*>(smem_raw + LT_OFF_PK + p.stage_bytes);
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint4 desc = p.first[blockIdx.x];
@@ -270,8 +283,7 @@ __global__ void __launch_bounds__(LT_THREADS, 8) line_tile_kernel(LineParams p) 
 
     const LineTable tab = p.tab;
     const int K = tab.K;
-    const uint32_t radix = tab.radix;
-    const unsigned long long pow_k1 = tab.pow_k1;
+    const uint32_t radix = tab.radix, Kh = tab.Kh, pw_h = tab.pw_h, pw_l = tab.pw_l;
     const unsigned long long pol_first = policy_evict_first(), pol_last = policy_evict_last();
     uint32_t parity = 0;
 
@@ -306,27 +318,19 @@ __global__ void __launch_bounds__(LT_THREADS, 8) line_tile_kernel(LineParams p) 
         const uint32_t wbeg = min(ext, warp * wq), wend = min(ext, wbeg + wq);
         uint32_t qn = 0;                                                // queue fill (warp-uniform)
 
-        // ---- phase B: every lane takes one queued survivor (live lanes only), probes, tallies ----
-        auto pop = [&](uint32_t first, bool live) {
-            uint2 e = make_uint2(0, 0);
-            uint4 a = make_uint4(0, 0, 0, 0), b = a;
-            if (live) {
-                e = s_q[first + lane];
-                load_line_sector(tab.lines + 2 * (size_t)e.x, pol_first, a, b);
+        uint32_t q2n = 0;                                               // second-stage queue fill (warp-uniform)
+
+        // ---- phase B ----
+        // a hit: de-duplicate against the sequence's token set, then one lane per sequence updates the
+        // shared tallies (survivors of neighbouring positions mostly belong to one sequence)
+        auto hit = [&](int role, uint32_t tok, uint32_t si) {
+            int q = -1;
+            if (role >= 0) {
+                q = (int)si;
+                const uint32_t sa = s_off[q], se = s_off[q + 1];
+                KA_CHECK(q < (int)ns && se >= sa, 8u);
+                if (!line_token_insert(s_tok + tok_cap(sa) + 4u * (uint32_t)q, tok_cap(se - sa) + 4u, tok)) q = -1;
             }
-            int role = -1, q = -1;
-            if (live) {
-                uint32_t tok = 0;
-                role = line_resolve(tab, pol_first, e.x, e.y & 0xFFFFu, a, b, tok);
-                if (role >= 0) {
-                    q = (int)(e.y >> 16);
-                    const uint32_t sa = s_off[q], se = s_off[q + 1];
-                    KA_CHECK(q < (int)ns && se >= sa, 8u);
-                    if (!line_token_insert(s_tok + tok_cap(sa) + 4u * (uint32_t)q, tok_cap(se - sa) + 4u, tok)) q = -1;
-                }
-            }
-            // survivors of neighbouring positions mostly belong to one sequence: one lane per
-            // sequence updates the shared tallies
             if (__any_sync(0xffffffffu, q >= 0)) {
                 const unsigned grp = __match_any_sync(0xffffffffu, q);
                 const int gmin = __reduce_min_sync(grp, q >= 0 ? role : 0x7fffffff);
@@ -338,6 +342,82 @@ __global__ void __launch_bounds__(LT_THREADS, 8) line_tile_kernel(LineParams p) 
                 }
             }
         };
+        // second stage (a key outside its home sector): entries (sector of the same line, tag | seq << 16), or
+        // (home sector, tag | seq << 16 | 1 << 31) for the overflow table; popped a full warp at a time
+        auto second = [&](uint32_t first, uint32_t count) {
+            int role = -1;
+            uint32_t tok = 0, si = 0;
+            if (lane < count) {
+                const uint2 e = s_q2[first + lane];
+                si = (e.y >> 16) & 63u;
+                if (e.y >> 31) {
+                    role = line_ovf_lookup(tab, e.x, e.y & 0xFFFFu, tok);
+                } else {
+                    uint4 a, b;
+                    load_line_sector(tab.lines + 2 * (size_t)e.x, pol_first, a, b);   // L2 hit: the line was just fetched
+                    uint32_t j = 0;
+                    const uint32_t tag = e.y & 0xFFFFu;
+                    role = match16(a, b, tag | (tag << 16), j);
+                    tok = e.x * 8u + j + 1u;
+                }
+            }
+            hit(role, tok, si);
+        };
+        // first stage: the home sector is loaded; a miss in a sector whose flags name other places queues them
+        auto consume = [&](const uint2& e, const uint4& a, const uint4& b, bool live) {
+            int role = -1;
+            uint32_t tok = 0, flags = 0;
+            if (live) {
+                uint32_t j = 0;
+                const uint32_t tag = e.y & 0xFFFFu;
+                role = match16(a, b, tag | (tag << 16), j);
+                tok = e.x * 8u + j + 1u;
+                if (role < 0) flags = sector_flags(a);
+            }
+            if (__any_sync(0xffffffffu, flags != 0u)) {
+                const uint32_t mine = __popc(flags);
+                uint32_t incl = mine;
+#pragma unroll
+                for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, dlt);
+                    if ((int)lane >= dlt) incl += up;
+                }
+                uint2* w = s_q2 + q2n + (incl - mine);
+                const uint32_t line0 = e.x & ~3u, home = e.x & 3u;
+#pragma unroll
+                for (uint32_t alt = 1; alt < 4; alt++)
+                    if (flags & (1u << (alt - 1))) *w++ = make_uint2(line0 | (home ^ alt), e.y & 0x3FFFFFu);
+                if (flags & 8u) *w++ = make_uint2(e.x, (e.y & 0x3FFFFFu) | 0x80000000u);
+                q2n += __shfl_sync(0xffffffffu, incl, 31);
+                __syncwarp();
+            }
+            hit(role, tok, e.y >> 16);
+            while (q2n >= 32u) {
+                q2n -= 32u;
+                second(q2n, 32u);
+            }
+        };
+
+        // PB survivors per lane with all their sector loads in flight before the first use
+        auto pop = [&](uint32_t first, uint32_t count) {
+            uint2 e[PB];
+            uint4 sa[PB], sb2[PB];
+#pragma unroll
+            for (int k = 0; k < PB; k++) {
+                e[k] = make_uint2(0, 0);
+                sa[k] = make_uint4(0, 0, 0, 0); sb2[k] = sa[k];
+                if (lane + 32u * k < count) {
+                    const uint2 kq = s_q[first + lane + 32u * k];       // (H | seq << 26, Lo)
+                    uint32_t tag;
+                    line_locate(tab, kq.x & 0x3FFFFFFu, kq.y, e[k].x, tag);
+                    e[k].y = tag | ((kq.x >> 26) << 16);
+                    load_line_sector(tab.lines + 2 * (size_t)e[k].x, pol_first, sa[k], sb2[k]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < PB; k++)
+                if (32u * k < count) consume(e[k], sa[k], sb2[k], lane + 32u * k < count);
+        };
 
         for (uint32_t pb = wbeg; pb < wend; pb += 32 * A) {
             // ---- phase A: keys + filter for a run of <= A positions per lane ----
@@ -345,7 +425,7 @@ __global__ void __launch_bounds__(LT_THREADS, 8) line_tile_kernel(LineParams p) 
             const uint32_t run = (pend - pb + 31) >> 5;                 // <= A
             const uint32_t P0 = pb + lane * run;
             const uint32_t nrun = P0 < pend ? min(run, pend - P0) : 0u;
-            uint32_t sec[A], tg[A], fw[A];
+            uint32_t qh[A], ql[A], fw[A];
             unsigned okm = 0;
             if (nrun) {
                 // sequence containing P0: last i with s_off[i] <= P0 (P0 < ext = s_off[ns])
@@ -358,52 +438,49 @@ __global__ void __launch_bounds__(LT_THREADS, 8) line_tile_kernel(LineParams p) 
                 KA_CHECK(si < ns, 32u);
                 uint32_t nb = s_off[si + 1];
 
-                // warm-up: the K-1 codes in front of the run's first window end
+                // Three 64-bit code windows: u at the run's first position (warm-up codes and the digit
+                // leaving H), m at +Kh-1 (the digit moving from Lo to H), v at +K-1 (the digit entering Lo);
+                // code I of each window then sits at a compile-time bit position.
                 const uint32_t bit0 = leadbits + 5u * P0;
-                uint32_t u0, u1;
-                {
-                    const uint32_t* w = s_pk + (bit0 >> 5);
-                    const uint32_t sh = bit0 & 31u, w0 = w[0], w1 = w[1], w2 = w[2];
-                    u0 = __funnelshift_r(w0, w1, sh);
-                    u1 = __funnelshift_r(w1, w2, sh);
-                }
-                unsigned long long key = 0;
+                uint32_t u0, u1, m0, m1, v0, v1;
+                load_window(s_pk, bit0, u0, u1);
+                load_window(s_pk, bit0 + 5u * (Kh - 1u), m0, m1);
+                load_window(s_pk, bit0 + 5u * (uint32_t)(K - 1), v0, v1);
+                // warm-up over the K-1 codes in front of the first window end: H complete, Lo short of one digit
+                uint32_t H = 0, Lo = 0;
                 int okc = 0;                                            // consecutive codes inside the alphabet
                 {
                     uint32_t t0 = u0, t1 = u1;
-                    for (int j = 0; j < K - 1; j++) {
+                    for (uint32_t j = 0; j + 1 < (uint32_t)K; j++) {
                         const uint32_t c = t0 & 31u;
                         t0 = __funnelshift_r(t0, t1, 5);
                         t1 >>= 5;
-                        key = key * radix + c;
+                        if (j < Kh) H = H * radix + c; else Lo = Lo * radix + c;
                         okc = (c == CODE_INVALID) ? 0 : okc + 1;
                     }
-                }
-                uint32_t v[4];
-                {
-                    const uint32_t bit1 = bit0 + 5u * (uint32_t)(K - 1);
-                    const uint32_t* w = s_pk + (bit1 >> 5);
-                    const uint32_t sh = bit1 & 31u, w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
-                    v[0] = __funnelshift_r(w0, w1, sh);
-                    v[1] = __funnelshift_r(w1, w2, sh);
-                    v[2] = __funnelshift_r(w2, w3, sh);
-                    v[3] = w3 >> sh;
                 }
                 auto step = [&](auto I_) {
                     constexpr int I = decltype(I_)::value;
                     if (I < (int)nrun) {
                         const uint32_t pos = P0 + I;
-                        const uint32_t c = window_code<I>(v);
-                        if (I > 0) key -= (unsigned long long)window_code64<(I > 0 ? I - 1 : 0)>(u0, u1) * pow_k1;
-                        key = key * radix + c;
-                        okc = (c == CODE_INVALID) ? 0 : okc + 1;
-                        while (pos >= nb) { si++; KA_CHECK(si < ns, 4u); nb = s_off[si + 1]; }
+                        const uint32_t cnew = window_code<I>(v0, v1);
+                        if (I > 0) {
+                            const uint32_t cmid = window_code<I>(m0, m1);
+                            H = (H - window_code<(I > 0 ? I - 1 : 0)>(u0, u1) * pw_h) * radix + cmid;
+                            Lo = (Lo - cmid * pw_l) * radix + cnew;
+                        } else {
+                            Lo = Lo * radix + cnew;
+                        }
+                        okc = (cnew == CODE_INVALID) ? 0 : okc + 1;
+                        if (pos >= nb) {                                // rare: the run crosses into the next sequence(s)
+                            do { si++; KA_CHECK(si < ns, 4u); nb = s_off[si + 1]; } while (pos >= nb);
+                        }
                         if (pos + (uint32_t)K <= nb && okc >= K) {
-                            uint32_t tag;
-                            line_locate(tab, key, sec[I], tag);
-                            tg[I] = tag | (si << 16);
+                            qh[I] = H | (si << 26);                     // H < 31^5 < 2^25, si < 64
+                            ql[I] = Lo;
                             okm |= 1u << I;
-                            if (tab.filt) fw[I] = load_filter_word(tab.filt + sec[I], pol_last);
+                            if (FILTER)
+                                fw[I] = load_filter_word(tab.filt + line_filter_word(line_filter_hash(H, Lo), tab.n_filt), pol_last);
                         }
                     }
                 };
@@ -412,35 +489,40 @@ __global__ void __launch_bounds__(LT_THREADS, 8) line_tile_kernel(LineParams p) 
                 step(std::integral_constant<int, 4>()); step(std::integral_constant<int, 5>());
                 step(std::integral_constant<int, 6>()); step(std::integral_constant<int, 7>());
                 static_assert(A == 8, "unrolled for 8 positions per lane");
-                if (tab.filt) {
+                if (FILTER) {
 #pragma unroll
                     for (int i = 0; i < A; i++)
                         if (okm & (1u << i)) {
-                            const uint32_t need = line_filter_bits(tg[i] & 0xFFFFu);
+                            const uint32_t need = line_filter_bits(line_filter_hash(qh[i] & 0x3FFFFFFu, ql[i]));
                             if ((fw[i] & need) != need) okm &= ~(1u << i);
                         }
                 }
             }
-            // compact the survivors of the warp into its queue
+            // compact the survivors of the warp into its queue: one warp scan of the per-lane counts, then
+            // every lane writes its own survivors back to back
+            {
+                const uint32_t mine = __popc(okm);
+                uint32_t incl = mine;
 #pragma unroll
-            for (int i = 0; i < A; i++) {
-                const bool ok = (okm >> i) & 1u;
-                const unsigned m = __ballot_sync(0xffffffffu, ok);
-                if (ok) s_q[qn + __popc(m & ((1u << lane) - 1u))] = make_uint2(sec[i], tg[i]);
-                qn += __popc(m);
+                for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, dlt);
+                    if ((int)lane >= dlt) incl += up;
+                }
+                uint2* w = s_q + qn + (incl - mine);
+#pragma unroll
+                for (int i = 0; i < A; i++)
+                    if ((okm >> i) & 1u) *w++ = make_uint2(qh[i], ql[i]);
+                qn += __shfl_sync(0xffffffffu, incl, 31);
             }
             __syncwarp();
             while (qn >= 32u * PB) {
-                qn -= 32u;
-                pop(qn, true);
+                qn -= 32u * PB;
+                pop(qn, 32u * PB);
             }
             __syncwarp();
         }
-        while (qn > 0) {                                                // drain
-            const uint32_t take = min(qn, 32u);
-            qn -= take;
-            pop(qn, lane < take);
-        }
+        if (qn > 0) pop(0, qn);                                         // drain (qn < 32 * PB)
+        if (q2n > 0) second(0, q2n);                                    // (q2n < 32)
         __syncthreads();
         for (uint32_t i = tid; i < ns; i += LT_THREADS) line_emit(p, sb + i, s_cnt[i], s_min[i], s_max[i]);
         __syncthreads();
@@ -448,14 +530,17 @@ __global__ void __launch_bounds__(LT_THREADS, 8) line_tile_kernel(LineParams p) 
 }
 
 cudaError_t line_tile_set_smem(size_t bytes) {
-    cudaError_t ce = cudaFuncSetAttribute(line_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (ce != cudaSuccess) return ce;
-    return cudaFuncSetAttribute(line_tile_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaError_t ce = cudaFuncSetAttribute(line_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(line_tile_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(line_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(line_tile_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    return ce;
 }
 
 cudaError_t launch_line_tiles(const LineParams& p, size_t smem, cudaStream_t st) {
     if (p.n_tiles == 0) return cudaSuccess;
-    line_tile_kernel<<<p.n_tiles, LT_THREADS, smem, st>>>(p);
+    if (p.tab.filt) line_tile_kernel<true><<<p.n_tiles, LT_THREADS, smem, st>>>(p);
+    else line_tile_kernel<false><<<p.n_tiles, LT_THREADS, smem, st>>>(p);
     return cudaGetLastError();
 }
 
@@ -483,20 +568,20 @@ __global__ void __launch_bounds__(256) line_big_kernel(LineParams p) {
         __syncthreads();
         int cnt = 0, mn = 0x7fffffff, mx = -1;
         for (uint32_t pos = tid; pos < W; pos += THREADS) {
-            unsigned long long key = 0;
+            uint32_t H = 0, Lo = 0;
             bool ok = true;
             for (int j = 0; j < K; j++) {
                 const uint32_t c = global_code(p.pk, (unsigned long long)a0 + pos + j);
                 ok &= (c != CODE_INVALID);
-                key = key * tab.radix + c;
+                if ((uint32_t)j < tab.Kh) H = H * tab.radix + c; else Lo = Lo * tab.radix + c;
             }
             if (!ok) continue;
-            uint32_t sector, tag;
-            line_locate(tab, key, sector, tag);
             if (tab.filt) {
-                const uint32_t need = line_filter_bits(tag);
-                if ((load_filter_word(tab.filt + sector, pol_last) & need) != need) continue;
+                const uint32_t fh = line_filter_hash(H, Lo), need = line_filter_bits(fh);
+                if ((load_filter_word(tab.filt + line_filter_word(fh, tab.n_filt), pol_last) & need) != need) continue;
             }
+            uint32_t sector, tag;
+            line_locate(tab, H, Lo, sector, tag);
             uint4 a, b;
             load_line_sector(tab.lines + 2 * (size_t)sector, pol_first, a, b);
             uint32_t tok = 0;
@@ -612,21 +697,22 @@ __global__ void __launch_bounds__(256) line_insert_kernel(LineTable t, const uin
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint8_t* km = kmers + i * (unsigned long long)K;
-        unsigned long long key = 0;
+        uint32_t H = 0, Lo = 0;
         bool bad = false;
         for (int j = 0; j < K; j++) {
             const uint32_t c = s_lut[km[j]];
             bad |= (c == CODE_INVALID);
-            key = key * t.radix + c;
+            if ((uint32_t)j < t.Kh) H = H * t.radix + c; else Lo = Lo * t.radix + c;
         }
         if (bad) { atomicAdd(&errs[0], 1u); continue; }
         if (roles[i] < 0) { atomicAdd(&errs[1], 1u); continue; }
         uint32_t sector, tag;
-        line_locate(t, key, sector, tag);
+        line_locate(t, H, Lo, sector, tag);
         const unsigned long long mine = ((line_base + i + 1) << role_bits) | (unsigned long long)(uint32_t)roles[i];
         if (filt) {
-            const uint32_t bits = line_filter_bits(tag);
-            if ((*reinterpret_cast<volatile uint32_t*>(filt + sector) & bits) != bits) atomicOr(filt + sector, bits);
+            const uint32_t fh = line_filter_hash(H, Lo), bits = line_filter_bits(fh);
+            uint32_t* fword = filt + line_filter_word(fh, t.n_filt);
+            if ((*reinterpret_cast<volatile uint32_t*>(fword) & bits) != bits) atomicOr(fword, bits);
         }
         const uint32_t line0 = sector & ~3u, home = sector & 3u;
         bool done = false;

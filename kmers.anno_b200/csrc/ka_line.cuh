@@ -5,28 +5,33 @@
 // small L2-resident filter can answer without touching HBM (microbench/filter_probe.cu: 54 -> 93 G
 // probes/s memory-side at a 35 % pass rate).
 //
-//   keys    radix-n integers: the n distinct bytes of the DB get digits 0..n-1 in byte order,
-//           key = sum d_j * n^(K-1-j) < n^K, w = bit length of n^K - 1 (35 bits for 20^8 instead of
-//           the 40 of 5-bit fields).  A 4-round Feistel network on the two halves of the w bits
-//           (32-bit multiplies) is the bijective mixer m = mix(key).
-//   lines   B = c * 2^s lines of 128 bytes, c in 8..15 (so the load factor is controllable to ~10 %
-//           with power-of-two-cheap indexing): the top u bits U of m choose the c-way part
+//   keys    radix-n digits: the n distinct bytes of the DB get digits 0..n-1 in byte order.  A k-mer is
+//           the PAIR (H, Lo) of the radix-n values of its first Kh = K/2 and last Kl = K - Kh digits,
+//           bh and bl bits wide (18 + 18 = 36 bits for 20^8 instead of the 40 of 5-bit fields); all
+//           arithmetic stays in 32 bits.  A 3-round Feistel network on the two halves (one 32-bit
+//           multiply per round) is the bijective mixer (L, R) = mix(H, Lo).
+//   lines   B = c * 2^s lines of 128 bytes, c in 8..15 (load factor controllable to ~10 % with
+//           power-of-two-cheap indexing): the top u bits U of L choose the c-way part
 //           hi = (U * c) >> u — and idx = ((U * c) mod 2^u) / c tells which of the <= 2^(u-3)
-//           values of U with the same hi it was —, the next s bits the line inside the part, the
-//           next 2 bits the HOME SECTOR of the line, the rest (rem0) stays.  (hi, idx) is a
-//           bijection of U, so (line, home, rem = idx : rem0) identifies the key: quotienting.
+//           values of U with the same hi it was —, the other la bits of L and the low a bits of R
+//           the line inside the part (la + a = s), the next 2 bits of R the HOME SECTOR of the line,
+//           and rem = idx : (R >> a) stays (<= 14 bits).  (hi, idx) is a bijection of U, so
+//           (line, rem) identifies the key: quotienting.
 //   sector  32 bytes = 8 slots: words 0-3 hold eight 16-bit TAGS, words 4-7 eight 16-bit ROLES.
-//           tag = 1 valid | 2 home | 1 flag | 1 spare | 11 rem.  A lookup loads the home sector
-//           (one 256-bit load = the DRAM fetch of the whole line), compares all eight tags with three
-//           SIMD-in-register operations per word, and reads the role of the matching slot.
-//   spill   a key whose home sector is full lives in another sector of the SAME line (its tag
+//           tag = 1 valid | 1 flag | 14 rem.  A lookup loads the home sector (one 256-bit load =
+//           the DRAM fetch of the whole line), compares all eight tags with three SIMD-in-register
+//           operations per word, and reads the role of the matching slot.
+//   spill   a key whose home sector is full lives in another sector of the SAME line (its rem
 //           keeps the home bits); the flag bits of slots 0,1,2 of the home sector say which of the
 //           sectors home^1, home^2, home^3 hold such keys, so the second-stage loads are L2 hits
 //           on the line that was just fetched.  A key whose whole line is full goes to the small
 //           overflow table (flag bit of slot 3) under (sector index : rem) + 1.
-//   filter  one 32-bit word per sector, two bits per key (of its HOME sector): no false negatives.
-//           B*16 bytes (77 MB for 1e8 8-mers at load factor 0.65) — L2 resident next to a table
-//           whose lines are read with an evict-first hint.
+//   filter  a Bloom filter of n_filt 32-bit words (one per table sector: B*16 bytes, 75 MB for 1e8
+//           8-mers), two bits per key in ONE word chosen by a cheap hash of the raw halves
+//           (two multiplies and a xor — no mixer, no table geometry), so the ~65 % of the windows
+//           that are absent cost a few instructions and one L2 access; only the survivors pay
+//           the mixer, the line arithmetic and the HBM access.  No false negatives; L2 resident
+//           next to a table whose lines are read with an evict-first hint.
 //   stream  residues travel and are staged as 5-bit codes (digit 0..n-1, 31 = byte not in the DB
 //           alphabet): residue r of the batch occupies bits [5r, 5r+5) of a little-endian byte
 //           stream — 0.625 bytes per residue over PCIe instead of 1.
@@ -38,55 +43,58 @@ namespace ka {
 
 constexpr uint32_t CODE_INVALID = 31u;      // 5-bit code of a byte that is not in the DB alphabet
 constexpr uint32_t TAG_VALID = 0x8000u;
-constexpr uint32_t TAG_FLAG = 0x1000u;      // per-slot flag bit, ignored by the compare
-constexpr uint32_t TAG_CMP = 0xEFFFu;
-constexpr uint32_t TAG_REM_BITS = 11;
+constexpr uint32_t TAG_FLAG = 0x4000u;      // per-slot flag bit, ignored by the compare
+constexpr uint32_t TAG_CMP = 0xBFFFu;
+constexpr uint32_t TAG_REM_BITS = 14;
 constexpr int LINE_MAX_SEQ = 64;            // sequences per tile sub-batch of the line kernels
+constexpr int LINE_KMAX = 10;               // the three 64-bit code windows of a lane hold K + 7 <= 17 codes... (Kh <= 5)
 
 struct LineTable {
     const uint4* lines;          // n_lines * 8 uint4
-    const uint32_t* filt;        // one word per sector (n_lines * 4), NULL = no filter
+    const uint32_t* filt;        // Bloom filter words, NULL = no filter
+    uint32_t n_filt;             // number of filter words (n_lines * 4)
     const uint4* ovf;            // overflow table: 2^ovf_bbits sectors of 2 {key + 1, role} entries
     uint32_t ovf_bbits;
     uint32_t n_lines;            // c << s
     uint32_t c, s, u, inv_c;     // inv_c = ceil(65536 / c)
-    uint32_t wbits, wl, wh;      // key bits and their Feistel halves (wl low, wh high)
-    uint32_t low_bits;           // w - u - s: 2 home bits + rem0
-    uint32_t rem0_bits;
+    uint32_t bh, bl;             // bits of the two key halves
+    uint32_t la, a, r;           // la = bh - u bits of L and a = s - la bits of R index the line; r = bl - a bits of R stay
     uint32_t radix;              // number of DB symbols
-    unsigned long long pow_k1;   // radix^(K-1)
+    uint32_t Kh, Kl;             // digits of the two halves
+    uint32_t pw_h, pw_l;         // radix^(Kh-1), radix^(Kl-1)
     int K;
 };
 
-__host__ __device__ __forceinline__ unsigned long long line_mix(unsigned long long key, uint32_t wl, uint32_t wh) {
-    uint32_t L = (uint32_t)(key >> wl), R = (uint32_t)key & ((1u << wl) - 1u);   // wl <= 30
-    // (x * C) >> (32 - bits) through a 64-bit shift: well defined for bits == 0
-    L ^= (uint32_t)((unsigned long long)(R * 0x9E3779B1u) >> (32 - wh));
-    R ^= (uint32_t)((unsigned long long)(L * 0x85EBCA6Bu) >> (32 - wl));
-    L ^= (uint32_t)((unsigned long long)(R * 0xC2B2AE35u) >> (32 - wh));
-    R ^= (uint32_t)((unsigned long long)(L * 0x27D4EB2Fu) >> (32 - wl));
-    return ((unsigned long long)L << wl) | R;
+// 3-round Feistel network on (bh, bl)-bit halves: a bijection whatever the round functions are
+__host__ __device__ __forceinline__ void line_mix(uint32_t& L, uint32_t& R, uint32_t bh, uint32_t bl) {
+    L ^= (R * 0x9E3779B1u) >> (32u - bh);       // 3 <= bh, bl <= 30
+    R ^= (L * 0x85EBCA6Bu) >> (32u - bl);
+    L ^= (R * 0xC2B2AE35u) >> (32u - bh);
 }
 
-// key -> (global sector index of the home sector, 16-bit tag)
-__host__ __device__ __forceinline__ void line_locate(const LineTable& t, unsigned long long key,
+// key halves -> (global sector index of the home sector, 16-bit tag)
+__host__ __device__ __forceinline__ void line_locate(const LineTable& t, uint32_t H, uint32_t Lo,
                                                      uint32_t& sector, uint32_t& tag) {
-    const unsigned long long m = line_mix(key, t.wl, t.wh);
-    const uint32_t U = (uint32_t)(m >> (t.wbits - t.u));
-    const uint32_t x = U * t.c;
-    const uint32_t hi = x >> t.u, frac = x & ((1u << t.u) - 1u);
-    const uint32_t idx = (frac * t.inv_c) >> 16;                 // frac / c, exact for frac < 4096, c < 16
-    const uint32_t low = (uint32_t)m & ((1u << t.low_bits) - 1u);
-    const uint32_t line = (hi << t.s) | ((uint32_t)(m >> t.low_bits) & ((1u << t.s) - 1u));
-    const uint32_t home = low & 3u;
-    tag = TAG_VALID | (home << 13) | (idx << t.rem0_bits) | (low >> 2);
-    sector = line * 4u + home;
+    uint32_t L = H, R = Lo;
+    line_mix(L, R, t.bh, t.bl);
+    const uint32_t x = (L >> t.la) * t.c;
+    const uint32_t hi = x >> t.u;
+    const uint32_t idx = ((x & ((1u << t.u) - 1u)) * t.inv_c) >> 16;   // (x mod 2^u) / c, exact for u <= 12, c < 16
+    const uint32_t line = (hi << t.s) | ((L & ((1u << t.la) - 1u)) << t.a) | (R & ((1u << t.a) - 1u));
+    const uint32_t rest = R >> t.a;                                     // r bits: home in the low two
+    sector = line * 4u + (rest & 3u);
+    tag = TAG_VALID | (idx << t.r) | rest;
 }
 
-// the two filter bits of a key inside the word of its home sector
-__host__ __device__ __forceinline__ uint32_t line_filter_bits(uint32_t tag) {
-    const uint32_t h = (tag & ((1u << TAG_REM_BITS) - 1u)) * 0x9E3779B1u;
-    return (1u << (h >> 27)) | (1u << ((h >> 22) & 31u));
+// filter hash of the raw key halves: word = top bits scaled to n_filt, the two bits from the low bits
+__host__ __device__ __forceinline__ uint32_t line_filter_hash(uint32_t H, uint32_t Lo) {
+    return (H * 0x9E3779B1u) ^ (Lo * 0x85EBCA6Bu);
+}
+__host__ __device__ __forceinline__ uint32_t line_filter_word(uint32_t fh, uint32_t n_filt) {
+    return (uint32_t)(((unsigned long long)fh * n_filt) >> 32);
+}
+__host__ __device__ __forceinline__ uint32_t line_filter_bits(uint32_t fh) {
+    return (1u << (fh & 31u)) | (1u << ((fh >> 5) & 31u));
 }
 
 // key under which a (sector, tag) pair lives in the overflow table; never 0

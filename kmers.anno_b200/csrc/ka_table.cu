@@ -164,48 +164,53 @@ static uint32_t bit_length(unsigned long long x) {
     return b;
 }
 
-// B = c * 2^s lines (c in 8..15) for n keys at load factor lf; the 11 remainder bits of a tag need
-// s >= w - 16.  `forced` (option slot_bits = 16) accepts a table that is larger than the keys need.
+// B = c * 2^s lines (c in 8..15) for n keys at load factor lf (ka_line.cuh).  The 14 remainder bits
+// of a tag need s >= bh + bl - 17, the line index needs s >= bh - u.  `forced` (option slot_bits = 16)
+// accepts a table that is larger than the keys need.
 bool choose_line_geometry(uint64_t n, int K, int nsym, double lf, bool forced, LineTable& g) {
-    if (nsym < 2 || nsym > 31 || K < 1 || K > KMAX) return false;
-    unsigned long long pw = 1;
-    for (int i = 0; i < K; i++) pw *= (unsigned long long)nsym;           // nsym^K <= 31^12 < 2^60
-    const uint32_t w = bit_length(pw - 1);
-    if (w < 5) return false;
-    const double want = std::max(8.0, std::ceil((double)(n ? n : 1) / (32.0 * lf)));
+    if (nsym < 2 || nsym > 31 || K < 2 || K > LINE_KMAX) return false;
+    const uint32_t Kh = (uint32_t)K / 2, Kl = (uint32_t)K - Kh;
+    unsigned long long ph = 1, pl = 1;
+    for (uint32_t i = 0; i < Kh; i++) ph *= (unsigned long long)nsym;
+    for (uint32_t i = 0; i < Kl; i++) pl *= (unsigned long long)nsym;
+    const uint32_t bh = bit_length(ph - 1), bl = bit_length(pl - 1);
+    if (bh < 3 || bl < 3 || bh > 25 || bl > 30) return false;                // (the survivor queue packs H in 26 bits)
+    const uint32_t w = bh + bl;
+    const uint32_t u = bh >= 12 ? 12 : 3;                                  // short high halves: power-of-two tables only
+    const uint32_t la = bh - u;
+    const uint32_t s_min = std::max<uint32_t>(la, w > 17 ? w - 17 : 0), s_max = w - u - 2;
+    if (s_min > s_max || s_min > 23) return false;
+    // (a DB holds at most nsym^K distinct keys however many lines it has)
+    const double n_keys = std::min((double)(n ? n : 1), (double)ph * (double)pl);
+    const double want = std::max(8.0, std::ceil(n_keys / (32.0 * lf)));
     uint64_t best = 0;
     uint32_t bc = 0, bs = 0;
-    for (uint32_t s = 0; s <= 24; s++)
+    for (uint32_t s = 0; s <= std::min<uint32_t>(s_max, 23); s++)
         for (uint32_t c = 8; c < 16; c++) {
+            if (u == 3 && c != 8) continue;
             const uint64_t B = (uint64_t)c << s;
             if ((double)B >= want && (!best || B < best)) { best = B; bc = c; bs = s; }
         }
-    if (!best) return false;                                               // more than 15 * 2^24 lines
-    const uint32_t s_min = w > 16 ? w - 16 : 0;
+    if (!best) return false;                                               // more lines than the layout can index
     if (bs < s_min) {
         // the keys would need a padded table: accepted up to 2x (no larger than the 32-bit sector class at its
         // default load factor), or whenever the layout is forced
         if (!forced && (bs + 1 < s_min)) return false;
         bs = s_min; bc = 8;
     }
-    uint32_t u = 12;
-    if (w < bs + 2 + 12) {
-        // short keys: power-of-two table, the top 3 bits choose the part
-        u = 3;
-        if (bc != 8) { bc = 8; bs += 1; }                                  // round up to the next power of two
-        if (w < bs + 5) bs = w - 5;                                        // the table already exceeds the key space
-    }
     if (((uint64_t)bc << bs) >= (1ull << 27)) return false;                // 32-bit slot tokens
     g = LineTable{};
     g.c = bc; g.s = bs; g.u = u;
     g.n_lines = bc << bs;
+    g.n_filt = g.n_lines * 4;
     g.inv_c = (65536u + bc - 1) / bc;
-    g.wbits = w; g.wl = w / 2; g.wh = w - w / 2;
-    g.low_bits = w - u - bs;
-    g.rem0_bits = g.low_bits - 2;
-    if (g.rem0_bits + (u - 3) > TAG_REM_BITS) return false;
+    g.bh = bh; g.bl = bl;
+    g.la = la; g.a = bs - la; g.r = bl - g.a;
+    if (g.r < 2 || (u - 3) + g.r > TAG_REM_BITS) return false;
     g.radix = (uint32_t)nsym;
-    g.pow_k1 = pw / (unsigned long long)nsym;
+    g.Kh = Kh; g.Kl = Kl;
+    g.pw_h = (uint32_t)(ph / (unsigned long long)nsym);
+    g.pw_l = (uint32_t)(pl / (unsigned long long)nsym);
     g.K = K;
     // expected keys beyond 32 per line under Poisson(n / lines) arrivals -> overflow table size
     const double lam = (double)n / (double)g.n_lines;
@@ -380,14 +385,15 @@ int db_load_impl(ka_engine* e, const uint8_t* kmers, const int32_t* role_ids, ui
             return fail(e, KA_ERR_TOO_BIG, "ka_db_load: %llu lines with role ids up to %d exceed the 64-bit (line, role) word",
                         (unsigned long long)n, max_role);
     }
-    // line table (slot class 16): replicated narrow tables with 16-bit role ids; chosen automatically for
-    // large DBs whose keys fill its 11 remainder bits without padding, or forced by slot_bits = 16
-    if (e->slot_bits == 16 || (e->slot_bits == 0 && e->table_mode == 0 && !e->wide && max_role <= 0xFFFF && n >= (1ull << 20))) {
+    // line table (slot class 16): option slot_bits = 16 only.  It halves the DRAM traffic per probe (51 B against
+    // 95 B, profiles/r02_summary.md) but its queue-based kernel reaches 38 G probes/s against 52 for the sector
+    // kernel on the C3 batch, so it is never chosen automatically.
+    if (e->slot_bits == 16) {
         LineTable lg;
         const bool forced = e->slot_bits == 16;
         if (forced && (e->table_mode != 0 || e->wide || max_role > 0xFFFF))
             return fail(e, KA_ERR_INVALID, "ka_db_load: slot_bits = 16 needs a replicated narrow table and role ids below 65536");
-        if (choose_line_geometry(n, K, nsym, e->load_factor > 0 ? std::min(e->load_factor, 0.8) : 0.65, forced, lg)) {
+        if (choose_line_geometry(n, K, nsym, e->load_factor > 0 ? std::min(e->load_factor, 0.8) : 0.68, forced, lg)) {
             std::vector<std::array<uint64_t, 3>> cnt(e->devs.size());
             auto tb = std::chrono::steady_clock::now();
             int rc = KA_OK;

@@ -18,9 +18,7 @@ def world():
     eng = ka.Engine([0])
     eng.db_load(kmers, roles, 8)
     info = eng.db_info()
-    # the full-size table takes the 128-byte-line layout: 9 * 2^19 lines = 604 MB + a 75 MB presence filter
-    assert info["n_keys"] == int(1e8) and info["slot_bits"] == 16 and info["n_buckets"] == 4 * 9 * 2**19
-    assert info["n_overflow"] < info["n_spilled"] < info["n_keys"] // 20
+    assert info["n_keys"] == int(1e8) and info["slot_bits"] == 32
     base = eng.annotate(res, off, 5)
     yield {"ka": ka, "eng": eng, "kmers": kmers, "roles": roles, "res": res, "off": off, "true": true_role,
            "base": base, "fam": fam}
@@ -107,16 +105,18 @@ def test_resident_path_equals_host_path(world):
 
 
 def test_layouts_and_input_forms_agree(world):
-    """The same batch through the 32-bit sector table, and through ka_annotate_packed on both tables."""
+    """The same batch through ka_annotate_packed, and through the 128-byte-line table (slot_bits = 16: 9 * 2^19
+    lines = 604 MB + a 75 MB presence filter) with and without its filter, in both input forms."""
     ka, eng = world["ka"], world["eng"]
     codes, off32 = eng.pack(world["res"], world["off"])
     assert same(eng.annotate_packed(codes, off32, 5), world["base"])
-    eng.set_option("filter", 0)
-    assert same(eng.annotate(world["res"], world["off"], 5), world["base"])
-    eng.set_option("filter", 1)
-    with ka.Engine([0]) as e32:
-        e32.set_option("slot_bits", 32)
-        e32.db_load(world["kmers"], world["roles"], 8)
-        assert e32.db_info()["slot_bits"] == 32
-        assert same(e32.annotate(world["res"], world["off"], 5), world["base"])
-        assert same(e32.annotate_packed(codes, off32, 5), world["base"])
+    with ka.Engine([0]) as e16:
+        e16.set_option("slot_bits", 16)
+        e16.db_load(world["kmers"], world["roles"], 8)
+        info = e16.db_info()
+        assert info["slot_bits"] == 16 and info["n_keys"] == int(1e8) and info["n_buckets"] == 4 * 9 * 2**19
+        assert info["n_overflow"] < info["n_spilled"] < info["n_keys"] // 20
+        assert same(e16.annotate(world["res"], world["off"], 5), world["base"])
+        assert same(e16.annotate_packed(codes, off32, 5), world["base"])
+        e16.set_option("filter", 0)
+        assert same(e16.annotate_packed(codes, off32, 5), world["base"])

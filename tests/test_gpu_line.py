@@ -54,7 +54,7 @@ def run_line(ka, oracle, seqs, kmers, roles, K, min_hits=3, options=None, form="
     return got, info
 
 
-@pytest.mark.parametrize("K", [1, 2, 5, 7, 8])
+@pytest.mark.parametrize("K", [2, 3, 5, 7, 8, 9])
 @pytest.mark.parametrize("form", ["bytes", "packed", "resident"])
 def test_line_table_ragged(ka, oracle, K, form):
     seqs, kmers, roles = ragged_case(200 + K, n_seq=400, K=K)
@@ -68,7 +68,10 @@ def test_line_table_rejects_what_it_cannot_hold(ka):
     with ka.Engine([0]) as eng:
         eng.set_option("slot_bits", 16)
         with pytest.raises(ka.KmerAnnoError) as ei:
-            eng.db_load(kmers, roles, 12)                      # 20^12 needs 52 key bits
+            eng.db_load(kmers, roles, 12)                      # 20^12: halves of 26 + 26 bits
+        assert ei.value.code == -10
+        with pytest.raises(ka.KmerAnnoError) as ei:
+            eng.db_load([b"A", b"C"], np.asarray([1, 2], np.int32), 1)     # K = 1 has no two halves
         assert ei.value.code == -10
         seqs, kmers, roles = ragged_case(3, n_seq=50, K=8)
         big = roles.copy(); big[0] = 70000
@@ -95,22 +98,23 @@ def test_line_table_duplicates_last_line_and_odd_bytes(ka, oracle):
 
 
 def test_line_table_spill_and_overflow(ka, oracle):
-    """6-mers at load factor 0.8: ~20 % of the sectors spill into their line, ~9 % of the lines
+    """7-mers at load factor 0.8: ~20 % of the sectors spill into their line, ~9 % of the lines
     overflow into the overflow table; every distinct key must survive and resolve exactly."""
     from kmers_anno_b200 import synth
     fam = synth.Families(2000)
-    kmers, roles = fam.table(3_000_000, K=6)
-    res, off, _ = fam.batch(5, 2, n_prot=3000, K=6)
-    want = oracle.OracleDb(kmers, roles, 6, threads=8).apply(res, off, 5, threads=8)
+    K = 7
+    kmers, roles = fam.table(3_000_000, K=K)
+    res, off, _ = fam.batch(5, 2, n_prot=3000, K=K)
+    want = oracle.OracleDb(kmers, roles, K, threads=8).apply(res, off, 5, threads=8)
     for filt in (1, 0):
         with ka.Engine([0]) as eng:
             eng.set_option("slot_bits", 16)
             eng.set_option("load_factor", 0.8)
             eng.set_option("filter", filt)
-            eng.db_load(kmers, roles, 6)
+            eng.db_load(kmers, roles, K)
             info = eng.db_info()
             got = eng.annotate(res, off, 5)
-        assert info["n_keys"] == oracle.OracleDb(kmers, roles, 6, threads=8).size()
+        assert info["n_keys"] == oracle.OracleDb(kmers, roles, K, threads=8).size()
         assert info["n_spilled"] > info["n_keys"] // 50 and info["n_overflow"] > 1000, info
         assert_same(got, want, f"spill / overflow heavy line table, filter={filt}")
 
@@ -172,7 +176,7 @@ def test_options_are_validated_atomically(ka):
         eng.set_option("long_seq", 4096)
         with pytest.raises(ka.KmerAnnoError):
             eng.annotate_resident(b, 3)
-        eng.set_option("long_seq", 1536)
+        eng.set_option("long_seq", 2048)
         eng.annotate_resident(b, 3)
         assert_same(eng.download(b), base, "resident after restoring the tiling options")
         eng.db_load(kmers, roles, 8)
