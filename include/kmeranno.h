@@ -84,6 +84,8 @@ const char* ka_last_error(const ka_engine* e);
  *                   most 25 bits); 0 (default) = the narrowest sector class that holds the DB
  *   "filter"        line table only: 1 (default) = probe the L2-resident presence filter first, 0 = always read
  *                   the table (measurement knob)
+ *   "resident_packed" 1 (default) = ka_batch_upload keeps the batch as the 5-bit stream where the tile kernels can stage
+ *                   it (what ka_annotate_packed ships), 0 = as residue bytes (measurement knob)
  *   "table_mode"    0 = table replicated on every device (default); 1 = table sharded by sector range
  *                   over the engine's 2/4/8 devices, probes load remote sectors through NVLink
  *                   peer memory inside the probe kernel (for tables beyond one GPU); 2 = same sharding,
@@ -94,7 +96,7 @@ const char* ka_last_error(const ka_engine* e);
  *   "tile_span"     residues of sequence starts per CTA tile, default 1536
  *   "long_seq"      sequences longer than this get a tile of their own (second tile launch), default 2048
  *   "mid_seq"       sequences longer than this use the global-scratch long-sequence kernel, default 8192
- *   "chunk_residues" residues per pipelined H2D chunk, default 48 Mi (4 chunks in flight per device)
+ *   "chunk_residues" residues per pipelined H2D chunk, default 64 Mi (4 chunks in flight per device)
  *   "l2_persist"    sector classes: 1 = L2 persisting access-policy window on the table (default 1)
  */
 int ka_set_option(ka_engine* e, const char* name, double value);

@@ -127,6 +127,8 @@ bool scan_offsets(const BatchIn& in, uint64_t cs, uint64_t ce, uint32_t long_seq
 
 void fill_params(ka_engine* e, Device& d, Pipe& p, uint64_t base, uint64_t n_res, uint64_t n_seq,
                  int32_t min_hits, AnnotParams& ap) {
+    ap.pk = nullptr;
+    ap.pk_lead = 0;
     ap.res = p.res;
     ap.off = p.off;
     ap.base = base;
@@ -393,13 +395,17 @@ int annotate_range(ka_engine* e, Device& d, const BatchIn& in, uint64_t s_begin,
             fill_line_params(e, d, p, sh.n_res, n, min_hits, lp);
             rc = enqueue_line_kernels(e, d, p, lp, !packed, origin, sh.n_long, sh.n_mid);
         } else {
+            // packed input: the narrow probe kernels stage the code stream themselves; the wide / sharded forms and
+            // the long-sequence kernel read residue bytes, so those chunks are expanded first
+            const bool stage_packed = packed && !e->geom.wide && e->geom.n_shards <= 1;
             if (packed) {
-                DCK(d, launch_unpack(p.pk, lead, sh.n_res, d.inv32, p.res, p.st));
+                if (!stage_packed || sh.n_long) { DCK(d, launch_unpack(p.pk, lead, sh.n_res, d.inv32, p.res, p.st)); d.launches += 1; }
                 DCK(d, launch_widen_offsets(p.off32_in, n + 1, p.off, p.st));
-                d.launches += 2;
+                d.launches += 1;
             }
             AnnotParams ap;
             fill_params(e, d, p, r_begin, sh.n_res, n, min_hits, ap);
+            if (stage_packed) { ap.pk = p.pk; ap.pk_lead = lead; }
             rc = enqueue_kernels(e, d, p, ap, sh.n_long, sh.n_mid);
         }
         if (rc) return rc;
@@ -525,6 +531,7 @@ int ka_set_option(ka_engine* e, const char* name, double v) {
     uint32_t tile_span = e->tile_span, long_seq = e->long_seq, mid_seq = e->mid_seq;
     uint64_t chunk_residues = e->chunk_residues;
     int l2_persist = e->l2_persist, table_mode = e->table_mode, wide = e->wide, filter = e->filter, slot_bits = e->slot_bits;
+    int resident_packed = e->resident_packed;
     if (n == "load_factor") {
         if (!(v > 0.0 && v <= 0.9)) return fail(e, KA_ERR_INVALID, "load_factor must be in (0, 0.9]");
         load_factor = v;
@@ -551,6 +558,8 @@ int ka_set_option(ka_engine* e, const char* name, double v) {
         wide = v != 0;
     } else if (n == "filter") {
         filter = v != 0;
+    } else if (n == "resident_packed") {
+        resident_packed = v != 0;
     } else if (n == "slot_bits") {
         if (v != 0 && v != 16 && v != 32 && v != 64 && v != 128) return fail(e, KA_ERR_INVALID, "slot_bits must be 0, 16, 32, 64 or 128");
         slot_bits = (int)v;
@@ -563,7 +572,7 @@ int ka_set_option(ka_engine* e, const char* name, double v) {
         return fail(e, KA_ERR_INVALID, "tile_span + long_seq (or mid_seq) needs more than 227 KB of shared memory");
     e->load_factor = load_factor; e->tile_span = tile_span; e->long_seq = long_seq; e->mid_seq = mid_seq;
     e->chunk_residues = chunk_residues; e->l2_persist = l2_persist; e->table_mode = table_mode; e->wide = wide;
-    e->filter = filter; e->slot_bits = slot_bits;
+    e->filter = filter; e->slot_bits = slot_bits; e->resident_packed = resident_packed;
     return KA_OK;
 }
 
@@ -707,16 +716,18 @@ int ka_batch_upload(ka_engine* e, int dev_index, const uint8_t* residues, const 
     b->origin = offsets[0] & ~127ull;
     b->tile_span = e->tile_span; b->long_seq = e->long_seq; b->mid_seq = e->mid_seq; b->db_serial = e->db_serial;
     int rc = pipe_init(d, b->p);
+    // resident form: the 5-bit stream wherever the tile kernels can stage it (line table; narrow unsharded sector tables)
+    const bool keep_codes = e->line || (!e->geom.wide && e->geom.n_shards <= 1 && e->resident_packed);
     if (rc == KA_OK) rc = pipe_reserve(d, b->p, sh.n_res, N, sh.n_res / e->tile_span + 1, sh.n_long, sh.long_res, sh.n_mid, e->geom.wide != 0,
-                                       true, e->line);
+                                       true, keep_codes);
     cudaError_t ce = cudaSuccess;
     if (rc == KA_OK && sh.n_res) ce = cudaMemcpy(b->p.res, residues + offsets[0], sh.n_res, cudaMemcpyHostToDevice);
     if (rc == KA_OK && ce == cudaSuccess) ce = cudaMemcpy(b->p.off, offsets, (N + 1) * 8, cudaMemcpyHostToDevice);
-    if (rc == KA_OK && ce == cudaSuccess && e->line) {
-        // the resident form of a batch for the line table is the 5-bit stream (what ka_annotate_packed ships)
+    if (rc == KA_OK && ce == cudaSuccess && keep_codes) {
+        // (what ka_annotate_packed ships; the long-sequence kernel of the sector tables still reads bytes)
         ce = launch_pack(b->p.res, (uint32_t)(offsets[0] - b->origin), sh.n_res, d.lut5, b->p.pk, b->p.st);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(b->p.st);
-        if (ce == cudaSuccess) { cudaFree(b->p.res); b->p.res = nullptr; b->p.res_cap = 0; }
+        if (ce == cudaSuccess && (e->line || sh.n_long == 0)) { cudaFree(b->p.res); b->p.res = nullptr; b->p.res_cap = 0; }
     }
     if (rc || ce != cudaSuccess) {
         std::string m = rc ? d.errmsg : std::string(cudaGetErrorString(ce));
@@ -752,6 +763,7 @@ int ka_annotate_resident(ka_engine* e, ka_batch* b, int32_t min_hits) {
     } else {
         AnnotParams ap;
         fill_params(e, d, b->p, b->base, b->n_res, b->n_seq, min_hits, ap);
+        if (b->p.pk) { ap.pk = b->p.pk; ap.pk_lead = (uint32_t)(b->base - b->origin); }
         rc = enqueue_kernels(e, d, b->p, ap, b->n_long, b->n_mid);
     }
     if (rc == KA_OK) {

@@ -101,10 +101,11 @@ struct ka_engine {
     uint32_t tile_span = 1536;
     uint32_t long_seq = 2048;
     uint32_t mid_seq = 8192;
-    uint64_t chunk_residues = 48ull << 20;
+    uint64_t chunk_residues = 64ull << 20;
     int l2_persist = 1;
     int slot_bits = 0;  // 0 = choose automatically; 16 = the 128-byte-line table (ka_line.cuh)
     int filter = 1;     // line table: 1 = L2-resident presence filter in front of it (measurement knob)
+    int resident_packed = 1;  // resident batches of narrow sector tables are kept as the 5-bit stream (measurement knob)
     int table_mode = 0; // next ka_db_load: 0 = replicated, 1 = sharded by sector range (peer loads), 2 = sharded + NCCL routing
     int wide = 0;       // next ka_db_load: 1 = force the wide-table kernels (64-bit sector indices and tokens)
     // state of the LOADED database (options above only take effect at the next ka_db_load)

@@ -250,15 +250,19 @@ cudaError_t launch_plan(const AnnotParams& p, cudaStream_t st) {
 //                                        [tok_cap(a)+4q, +tok_cap(L)+4), never full (hits <= L-K+1)
 // (tokens are 8 bytes each for wide tables)
 size_t tile_smem_bytes(uint32_t ext_max, uint32_t* res_bytes_out, bool wide) {
-    uint32_t res_bytes = (ext_max + 16 + 32 + 15) & ~15u;  // lead slack + K-1 over-read
+    uint32_t res_bytes = (ext_max + 16 + 32 + 32 + 15) & ~15u;  // lead slack + K-1 over-read + in-place unpack slack
     if (res_bytes_out) *res_bytes_out = res_bytes;
     return (size_t)res_bytes + 256 + 4 * (MAX_TILE_SEQ + 4) + 3 * 4 * MAX_TILE_SEQ +
            (wide ? 8 : 4) * ((size_t)tok_cap(ext_max) + 4 * MAX_TILE_SEQ + 8);
 }
 
-template <int CLS, int C, int THREADS, int MINB, int MODE = 0, bool WIDE = false>
+// PACKED: the chunk's residues are the 5-bit code stream of ka_annotate_packed (p.pk); the tile's slice of it is
+// bulk-copied to the END of the residue stage and expanded in place to one code byte per residue, so the
+// rest of the kernel is unchanged (the LUT then maps digit d to field code d + 1, and 31 to 0).
+template <int CLS, int C, int THREADS, int MINB, int MODE = 0, bool WIDE = false, bool PACKED = false>
 __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
     static_assert(!WIDE || CLS != 128, "wide tables are quotiented");
+    static_assert(!PACKED || (MODE == 0 && !WIDE), "packed staging: plain probe kernels only");
     typedef typename std::conditional<WIDE, unsigned long long, uint32_t>::type tok_t;
     typedef typename std::conditional<WIDE, unsigned long long, typename rem_type<CLS>::type>::type rem_t;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -278,7 +282,10 @@ __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
     const uint4 desc = p.first[blockIdx.x];
     uint8_t lut_byte[(256 + THREADS - 1) / THREADS];
 #pragma unroll
-    for (int i = 0; i < (256 + THREADS - 1) / THREADS; i++) lut_byte[i] = p.lut[(tid + i * THREADS) & 255];
+    for (int i = 0; i < (256 + THREADS - 1) / THREADS; i++) {
+        const uint32_t b = (tid + i * THREADS) & 255;
+        lut_byte[i] = PACKED ? (uint8_t)(b < 31 ? b + 1 : 0) : p.lut[b];
+    }
     const uint32_t s0 = desc.x, s1 = desc.x + desc.y;
     if (desc.y == 0) return;
 
@@ -297,17 +304,24 @@ __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
         // the common case (one sub-batch) needs no further global load to know its residue range
         const unsigned long long g0 = (sb == s0) ? desc.z : p.off[sb] - p.base;
         const unsigned long long g1 = (sb + ns == s1) ? desc.w : p.off[sb + ns] - p.base;
-        const unsigned long long g0a = g0 & ~15ull;
+        const unsigned long long g0a = PACKED ? g0 : (g0 & ~15ull);
         const uint32_t lead = (uint32_t)(g0 - g0a);
         const uint32_t ext = (uint32_t)(g1 - g0a);           // stage-relative end of the residues
-        const uint32_t nbytes = (ext + 15u) & ~15u;
-        KA_CHECK(nbytes + 32 <= p.res_bytes, 1u);                               // residue stage holds the tile
+        // packed form: bytes [bt, bt + nbytes) of the chunk's code stream hold the tile; they land at pk_dst
+        const unsigned long long pbit0 = 5ull * (g0 + p.pk_lead);
+        const unsigned long long bt = (pbit0 >> 3) & ~15ull;
+        const uint32_t leadbits = (uint32_t)(pbit0 - 8ull * bt);
+        const uint32_t nbytes = PACKED ? (uint32_t)((((5ull * (g1 + p.pk_lead) + 7ull) >> 3) - bt + 15ull) & ~15ull) : ((ext + 15u) & ~15u);
+        const uint32_t pk_dst = PACKED ? ((p.res_bytes - nbytes - 16u) & ~15u) : 0u;
+        KA_CHECK((PACKED ? ext + 64u : nbytes + 32u) <= p.res_bytes, 1u);        // residue stage holds the tile
+        KA_CHECK(!PACKED || 3u * ((ext + 7u) >> 3) <= pk_dst + 24u, 64u);        // in-place expansion never overtakes the unread codes
         KA_CHECK(tok_cap(ext - lead) + 4u * ns + 8u <= tok_cap(p.ext_max) + 4u * MAX_TILE_SEQ + 8u, 2u);  // token set too
 
         // stage the residues of sequences [sb, sb+ns) with one bulk copy
         if (tid == 0 && nbytes) {
             mbar_expect_tx(&s_bar, nbytes);
-            bulk_g2s(s_res, p.res + g0a, nbytes, &s_bar);
+            if (PACKED) bulk_g2s(s_res + pk_dst, reinterpret_cast<const unsigned char*>(p.pk) + bt, nbytes, &s_bar);
+            else bulk_g2s(s_res, p.res + g0a, nbytes, &s_bar);
         }
         for (uint32_t i = tid; i <= ns; i += THREADS)
             s_off[i] = (uint32_t)(p.off[sb + i] - p.base - g0a);
@@ -322,6 +336,27 @@ __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
         }
         __syncthreads();
         if (nbytes) { mbar_wait(&s_bar, parity); parity ^= 1; }
+        if (PACKED) {
+            // 8 residues = 40 bits per thread and round: read, barrier, write one byte per code.  Round r writes
+            // below 8 (r+1) THREADS, the codes still unread start at pk_dst + 5 (r+1) THREADS: disjoint (check 64).
+            const uint32_t n_groups = (ext + 7u) >> 3;
+            const uint32_t* pw = reinterpret_cast<const uint32_t*>(s_res + pk_dst);
+            for (uint32_t g8 = 0; g8 < n_groups; g8 += THREADS) {
+                const uint32_t g = g8 + tid;
+                uint32_t lo = 0, hi = 0;
+                if (g < n_groups) {
+                    const uint32_t bit = leadbits + 40u * g;
+                    const uint32_t* w = pw + (bit >> 5);
+                    const uint32_t sh = bit & 31u, w0 = w[0], w1 = w[1], w2 = w[2];
+                    const uint32_t u0 = __funnelshift_r(w0, w1, sh), u1 = __funnelshift_r(w1, w2, sh);
+                    lo = (u0 & 31u) | ((u0 >> 5) & 31u) << 8 | ((u0 >> 10) & 31u) << 16 | ((u0 >> 15) & 31u) << 24;
+                    hi = ((u0 >> 20) & 31u) | ((u0 >> 25) & 31u) << 8 | (__funnelshift_r(u0, u1, 30) & 31u) << 16 | ((u1 >> 3) & 31u) << 24;
+                }
+                __syncthreads();
+                if (g < n_groups) *reinterpret_cast<uint2*>(s_res + 8u * g) = make_uint2(lo, hi);
+            }
+            __syncthreads();
+        }
 
         // passes of up to THREADS*C positions, spread evenly over the threads
         for (uint32_t pb = lead; pb < ext; pb += THREADS * C) {
@@ -454,11 +489,17 @@ __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
 }
 
 template <typename F>
-static auto with_tile_kernel(int cls, int variant, F f) {
-#define KA_VARIANTS(CLS)                                             \
-    switch (variant) {                                               \
-        case 1: return f(tile_kernel<CLS, 4, 256, 3>, 256);          \
-        default: return f(tile_kernel<CLS, 4, 128, 6>, 128);         \
+static auto with_tile_kernel(int cls, int variant, bool packed, F f) {
+#define KA_VARIANTS(CLS)                                                                  \
+    if (packed) {                                                                         \
+        switch (variant) {                                                                \
+            case 1: return f(tile_kernel<CLS, 4, 256, 3, 0, false, true>, 256);           \
+            default: return f(tile_kernel<CLS, 4, 128, 7, 0, false, true>, 128);          \
+        }                                                                                 \
+    }                                                                                     \
+    switch (variant) {                                                                    \
+        case 1: return f(tile_kernel<CLS, 4, 256, 3>, 256);                               \
+        default: return f(tile_kernel<CLS, 4, 128, 6>, 128);                              \
     }
     if (cls == 32) { KA_VARIANTS(32) }
     if (cls == 64) { KA_VARIANTS(64) }
@@ -467,18 +508,23 @@ static auto with_tile_kernel(int cls, int variant, F f) {
 }
 
 cudaError_t tile_kernel_set_smem(int cls, int variant, size_t bytes) {
-    return with_tile_kernel(cls, variant, [&](auto kern, int) {
-        cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        if (ce != cudaSuccess) return ce;
-        // ask for the largest shared-memory carve-out so that as many CTAs as the registers allow fit
-        return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    });
+    cudaError_t ce = cudaSuccess;
+    for (bool packed : {false, true}) {
+        if (ce != cudaSuccess) break;
+        ce = with_tile_kernel(cls, variant, packed, [&](auto kern, int) {
+            cudaError_t c2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+            if (c2 != cudaSuccess) return c2;
+            // ask for the largest shared-memory carve-out so that as many CTAs as the registers allow fit
+            return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        });
+    }
+    return ce;
 }
 
 cudaError_t launch_tiles(const AnnotParams& p, int variant, size_t smem, cudaStream_t st) {
     if (p.n_tiles == 0) return cudaSuccess;
     if (p.tab.wide) return launch_tiles_mode(p, variant, 0, smem, st);
-    return with_tile_kernel(p.tab.cls, variant, [&](auto kern, int threads) {
+    return with_tile_kernel(p.tab.cls, variant, p.pk != nullptr, [&](auto kern, int threads) {
         kern<<<p.n_tiles, threads, smem, st>>>(p);
         return cudaGetLastError();
     });

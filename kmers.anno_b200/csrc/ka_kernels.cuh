@@ -15,6 +15,8 @@ struct BigItem {
 };
 
 struct AnnotParams {
+    const uint32_t* pk;               // non-NULL: the chunk's residues as the 5-bit code stream (ka_line.cuh); the tile
+    uint32_t pk_lead;                 //   kernels stage from it: residue `base` + g sits at bits [5 (g + pk_lead), +5)
     const uint8_t* res;               // residues of the chunk; res[0] is absolute offset `base`
     const unsigned long long* off;    // absolute offsets, n_seq + 1
     unsigned long long base;

@@ -35,19 +35,22 @@ NcclApi g_nccl;
 
 int route_init_comms(ka_engine* e) {
     if (e->nccl_ready) return KA_OK;
-    // NCCL writes its log (with NCCL_DEBUG set, at least the version banner) to STDOUT, which belongs
-    // to the caller's report (ApplyKmerProcessor.java:94): send it to stderr unless the user chose a file
-    setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
     if (!g_nccl.load()) return fail(e, KA_ERR_NO_DEVICE, "ka_db_load: table_mode 2 needs libnccl.so.2 (%s)", dlerror() ? dlerror() : "symbols missing");
     std::vector<ncclComm_t> comms(e->devs.size());
     std::vector<int> ids;
     for (Device& d : e->devs) ids.push_back(d.id);
     auto tn = std::chrono::steady_clock::now();
-    // (NCCL_DEBUG_FILE does not move the version banner of every NCCL build: point fd 1 at stderr
-    // for the duration of the initialisation; nothing else writes during a DB load)
-    fflush(stdout);
-    const int saved_stdout = dup(1);
-    if (saved_stdout >= 0) dup2(2, 1);
+    // NCCL writes its log (with NCCL_DEBUG set, at least the version banner) to STDOUT, which belongs to the
+    // caller's report (ApplyKmerProcessor.java:94).  The library itself touches neither the environment nor
+    // the process's file descriptors; a single-threaded host that wants the banner on stderr (the CLI, bench.py)
+    // sets NCCL_DEBUG_FILE itself and opts into the descriptor swap with KA_NCCL_STDOUT_TO_STDERR=1.
+    const char* swap = getenv("KA_NCCL_STDOUT_TO_STDERR");
+    int saved_stdout = -1;
+    if (swap && swap[0] == '1') {
+        fflush(stdout);
+        saved_stdout = dup(1);
+        if (saved_stdout >= 0) dup2(2, 1);
+    }
     ncclResult_t nr = g_nccl.CommInitAll(comms.data(), (int)ids.size(), ids.data());
     if (saved_stdout >= 0) { fflush(stdout); dup2(saved_stdout, 1); close(saved_stdout); }
     if (nr != ncclSuccess) return fail(e, KA_ERR_CUDA, "ka_db_load: ncclCommInitAll: %s", g_nccl.GetErrorString(nr));

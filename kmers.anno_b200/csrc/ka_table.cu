@@ -317,6 +317,7 @@ int db_load_impl(ka_engine* e, const uint8_t* kmers, const int32_t* role_ids, ui
                  uint64_t syn_seed, int32_t syn_roles) {
     if (K < 1 || K > KMAX) return fail(e, KA_ERR_K, "K = %d: this engine packs 5 bits per residue, K must be 1..%d", K, KMAX);
     e->have_db = false;
+    for (Device& d : e->devs) { cudaSetDevice(d.id); cudaGetLastError(); }   // a stale error of an earlier call is not this call's
 
     // 1. alphabet: the distinct bytes of the DB, scanned on device 0
     Device& d0 = e->devs[0];

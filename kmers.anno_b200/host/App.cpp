@@ -2,6 +2,7 @@
 // GPU hot path.  `build`, `apply` and `genes` run on the engine; the reference's other verbs are outside the
 // scope of this engine and are reported as such.
 #include <iostream>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -24,6 +25,10 @@ static void showCommands() {
 
 int main(int argc, char** argv) {
     if (argc < 2) { showCommands(); return 1; }
+    // stdout carries the report (ApplyKmerProcessor.java:94): NCCL's start-up lines (--table-mode 2) go to stderr.
+    // Done here, in the still single-threaded host, not inside the library.
+    setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
+    setenv("KA_NCCL_STDOUT_TO_STDERR", "1", 0);
     std::string command = argv[1];
     std::vector<std::string> newArgs(argv + 2, argv + argc);   // App.java:54-55
     if (command == "apply") {

@@ -87,3 +87,49 @@ def synthetic_db_lines(index, K, n_roles, seed):
     for j in range(K):
         kmers[:, j] = _AA20[((x >> np.uint64(5 * j)) & np.uint64(31)) % np.uint64(20)]
     return kmers, (index % np.uint64(n_roles)).astype(np.int32)
+
+
+def planted_batch(n_keys, n_prot, K, n_roles, seed, alloc=None, rng_seed=5, min_hits=5):
+    """Queries for a device-generated DB (ka_db_load_synthetic) that is too large to regenerate on the host:
+    PLANTED proteins made of DB k-mers of one role (every 7th protein: plus one k-mer of a second role) joined
+    by random residues, so that the expected call of every protein is known by construction, up to chance
+    hits of the random windows.  Returns (residues u8, offsets u64, expected role i32, expected hits i32,
+    ambiguous bool, probes)."""
+    alloc = alloc or (lambda shape, dtype: np.empty(shape, dtype))
+    rng = np.random.default_rng(rng_seed)
+    h = rng.integers(1, 12, n_prot)                      # planted k-mers per protein
+    role = rng.integers(0, n_roles, n_prot)
+    ambiguous = (np.arange(n_prot) % 7) == 0
+    n_seg = h + ambiguous                                # + one k-mer of another role
+    seg_prot = np.repeat(np.arange(n_prot), n_seg)
+    seg_first = np.concatenate([[0], np.cumsum(n_seg)])[:-1]
+    is_extra = np.zeros(seg_prot.shape[0], bool)
+    is_extra[(seg_first + n_seg - 1)[ambiguous]] = True
+    seg_role = role[seg_prot].copy()
+    seg_role[is_extra] = (seg_role[is_extra] + 1 + rng.integers(0, n_roles - 1, int(is_extra.sum()))) % n_roles
+    lines_per_role = n_keys // n_roles
+    seg_line = (seg_role + n_roles * rng.integers(0, lines_per_role, seg_prot.shape[0])).astype(np.uint64)
+    seg_kmers, seg_roles_chk = synthetic_db_lines(seg_line, K, n_roles, seed)
+    assert np.array_equal(seg_roles_chk, seg_role.astype(np.int32))
+    spacer = rng.integers(0, 60, seg_prot.shape[0])
+    seg_start = np.concatenate([[0], np.cumsum(K + spacer)])
+    total = int(seg_start[-1])
+    res = alloc(total, np.uint8)
+    res[:] = _AA20[rng.integers(0, 20, total)]
+    pos = (seg_start[:-1, None] + np.arange(K)[None, :]).reshape(-1)
+    res[pos] = seg_kmers.reshape(-1)
+    off = alloc(n_prot + 1, np.uint64)
+    off[:] = np.concatenate([[0], seg_start[1:][np.cumsum(n_seg) - 1]])
+    # expectation: distinct planted k-mers of the protein's role (duplicate picks count once)
+    key = np.zeros(seg_prot.shape[0], np.uint64)
+    for j in range(K):
+        key = key * np.uint64(32) + seg_kmers[:, j].astype(np.uint64)
+    order = np.lexsort((key, seg_prot))
+    sp, sk = seg_prot[order], key[order]
+    first = np.ones(sp.shape[0], bool)
+    first[1:] = (sp[1:] != sp[:-1]) | (sk[1:] != sk[:-1])
+    distinct = np.bincount(sp[first], minlength=n_prot)
+    exp_hits = np.where(ambiguous, 0, distinct).astype(np.int32)
+    exp_role = np.where(ambiguous | (distinct < min_hits), -1, role).astype(np.int32)
+    probes = int(np.maximum((off[1:] - off[:-1]).astype(np.int64) - K + 1, 0).sum())
+    return res, off, exp_role, exp_hits, ambiguous, probes

@@ -16,11 +16,13 @@ eng = ka.Engine([0]); eng.db_load(kmers, roles, 8)
 t = time.perf_counter(); b = eng.upload(res, off); dt = time.perf_counter() - t
 print(f"upload (sync cudaMemcpy from pinned) {len(res)/dt/1e9:.1f} GB/s", flush=True)
 eng.annotate_resident(b, 5); eng.annotate_resident(b, 5); print("resident kernel ms", eng.stats()["kernel_ms"], flush=True); b.free()
-for chunk in (16 << 20, 32 << 20, 48 << 20, 64 << 20, 96 << 20):
+codes, off32 = eng.pack(res, off, alloc=pinned_array)
+for chunk in (16 << 20, 32 << 20, 48 << 20, 64 << 20, 96 << 20, 128 << 20, 256 << 20):
     eng.set_option("chunk_residues", chunk)
-    best = 1e9
-    for r in range(4):
-        t = time.perf_counter(); eng.annotate(res, off, 5, out=out); dt = (time.perf_counter() - t) * 1e3
-        if r: best = min(best, dt)
-    st = eng.stats()
-    print(f"chunk {chunk>>20:4d} Mi: e2e {best:.2f} ms  ({n/best/1e3:.1f} M seq/s)  kernel_sum {st['kernel_ms']:.2f} ms  wall_inside {st['wall_ms']:.2f}", flush=True)
+    for name, call in (("bytes ", lambda: eng.annotate(res, off, 5, out=out)), ("packed", lambda: eng.annotate_packed(codes, off32, 5, out=out))):
+        best = 1e9
+        for r in range(4):
+            t = time.perf_counter(); call(); dt = (time.perf_counter() - t) * 1e3
+            if r: best = min(best, dt)
+        st = eng.stats()
+        print(f"chunk {chunk>>20:4d} Mi {name}: e2e {best:.2f} ms  ({n/best/1e3:.1f} M seq/s)  kernel_sum {st['kernel_ms']:.2f} ms  tile_sum {st['tile_kernel_ms']:.2f}  launches {st['kernel_launches']}  wall_inside {st['wall_ms']:.2f}", flush=True)
