@@ -30,7 +30,7 @@ $(ORACLE): oracle/ka_oracle.c oracle/ka_oracle_fast.c
 
 $(CLI): $(wildcard $(HOST)/*.cpp) $(wildcard $(HOST)/*.hpp) $(LIB)
 	mkdir -p $(PKG)/bin
-	$(CXX) -O2 -std=c++17 -Wall -Iinclude -o $@ $(HOST)/App.cpp $(HOST)/ApplyKmerProcessor.cpp $(HOST)/BuildKmerProcessor.cpp $(HOST)/GeneCopyProcessor.cpp $(HOST)/Genome.cpp -L$(PKG) -lkmeranno -Wl,-rpath,'$$ORIGIN/..' -pthread
+	$(CXX) -O2 -std=c++17 -Wall -Iinclude -o $@ $(HOST)/App.cpp $(HOST)/ApplyKmerProcessor.cpp $(HOST)/BuildKmerProcessor.cpp $(HOST)/GeneCopyProcessor.cpp $(HOST)/Genome.cpp $(HOST)/PackedBatch.cpp -L$(PKG) -lkmeranno -Wl,-rpath,'$$ORIGIN/..' -pthread
 
 $(SELFTEST): $(HOST)/selftest.cpp $(HOST)/Genome.cpp $(wildcard $(HOST)/*.hpp)
 	mkdir -p $(PKG)/bin

@@ -202,74 +202,61 @@ void ApplyKmerProcessor::validateParms() {
          << " device(s), " << info.table_bytes / (1024 * 1024) << " MiB table, " << info.slot_bits << "-bit slots.  (t=" << nowSeconds() << " s)\n";
 }
 
-void ApplyKmerProcessor::flushBatch(std::vector<std::unique_ptr<Genome>>& genomes) {
-    if (genomes.empty()) return;
-    // CSR of every peg of the batch, genome by genome, peg order preserved (:122)
-    std::vector<uint8_t> residues;
-    std::vector<uint64_t> offsets{0};
-    std::vector<std::vector<const Feature*>> pegs(genomes.size());
-    for (size_t g = 0; g < genomes.size(); g++) {
-        pegs[g] = genomes[g]->getPegs();
-        for (const Feature* f : pegs[g]) {
-            const std::string& prot = f->getProteinTranslation();
-            residues.insert(residues.end(), prot.begin(), prot.end());
-            offsets.push_back(residues.size());
-        }
-    }
-    std::vector<int32_t> role, hits;
-    std::vector<uint8_t> flag;
-    engine_->annotate(residues, offsets, minHits_, role, hits, flag);   // the peg loop :122-148 for the whole batch
-    size_t s = 0;
-    for (size_t g = 0; g < genomes.size(); g++) {
-        log_ << "Processing genome " << genomes[g]->toString() << ".\n";   // :119
-        reporter_->openGenome(*genomes[g]);                               // :120
-        for (const Feature* f : pegs[g]) {
-            if (flag[s] == KA_FLAG_CALLED)                                // :146
-                reporter_->recordFeature(*f, roleNames_[(size_t)role[s]], hits[s]);  // :147
-            s++;
+void ApplyKmerProcessor::flushBatch(PackedBatch& batch) {
+    if (batch.numGenomes() == 0) return;
+    batch.annotate(minHits_);                                             // the peg loop :122-148 for the whole batch
+    const int32_t* role = batch.role();
+    const int32_t* hits = batch.hits();
+    const uint8_t* flag = batch.flag();
+    for (size_t g = 0; g < batch.numGenomes(); g++) {
+        const PackedGenome& genome = batch.genome(g);
+        log_ << "Processing genome " << genome.toString() << ".\n";       // :119
+        reporter_->openGenome(genome.id);                                 // :120
+        const size_t s0 = genome.firstPeg;
+        for (size_t k = 0; k < genome.pegs.size(); k++) {
+            const size_t s = s0 + k;
+            if (flag[s] == KA_FLAG_CALLED) {                              // :146
+                const size_t r = (size_t)role[s];
+                reporter_->recordCall(genome.pegId(k), genome.pegFunction(k), roleNames_[r], roleColumn_[r], hits[s]);  // :147
+            }
         }
         reporter_->closeGenome();                                         // :150
     }
-    genomes.clear();
+    proteinsDone_ += batch.numPegs();
+    residuesDone_ += batch.numResidues();
 }
 
 void ApplyKmerProcessor::runCommand() {
     GenomeDirectory genomes(inDir_);                                      // :116
     log_ << genomes.size() << " genomes found in input directory.\n";     // :117
     const std::vector<std::string>& files = genomes.files();
-    // Ingest pipeline: the genomes of batch i+1 are parsed by `loadThreads_` threads while the
-    // GPU annotates batch i; reports are still written in directory order (:118).
-    auto loadBatch = [&](size_t b0) {
-        size_t n = std::min(files.size() - b0, (size_t)batchGenomes_);
-        std::vector<std::unique_ptr<Genome>> out(n);
-        std::vector<std::string> errors(n);
-        std::atomic<size_t> next{0};
-        auto work = [&] {
-            for (size_t i = next++; i < n; i = next++) {
-                try { out[i] = std::make_unique<Genome>(files[b0 + i]); }
-                catch (const std::exception& e) { errors[i] = e.what(); }
-            }
-        };
-        size_t nt = std::min<size_t>(std::max(1, loadThreads_), n);
-        std::vector<std::thread> th;
-        for (size_t t = 1; t < nt; t++) th.emplace_back(work);
-        work();
-        for (auto& t : th) t.join();
-        for (size_t i = 0; i < n; i++)
-            if (!out[i]) throw IOException("Error loading " + files[b0 + i] + ": " + errors[i]);
-        return out;
+    const double t0 = nowSeconds();
+    // report column of every dense role id, once (ApplyKmerReporter.getRoleIdx, :92-95)
+    roleColumn_.resize(roleNames_.size());
+    for (size_t r = 0; r < roleNames_.size(); r++) roleColumn_[r] = reporter_->getRoleIdx(roleNames_[r]);
+    // Ingest pipeline: two pinned batches alternate — the genomes of batch i+1 are parsed and packed by
+    // `loadThreads_` threads while the GPU annotates batch i; reports are written in directory order (:118).
+    PackedBatch bufs[2] = {PackedBatch(*engine_), PackedBatch(*engine_)};
+    auto loadBatch = [&](int which, size_t b0) {
+        const size_t n = std::min(files.size() - b0, (size_t)batchGenomes_);
+        bufs[which].load(files.data() + b0, n, loadThreads_);
     };
-    std::future<std::vector<std::unique_ptr<Genome>>> pending;
-    if (!files.empty()) pending = std::async(std::launch::async, loadBatch, (size_t)0);
+    std::future<void> pending;
+    if (!files.empty()) pending = std::async(std::launch::async, loadBatch, 0, (size_t)0);
+    int cur = 0;
     for (size_t b0 = 0; b0 < files.size(); b0 += (size_t)batchGenomes_) {
-        std::vector<std::unique_ptr<Genome>> batch = pending.get();
-        size_t nextStart = b0 + (size_t)batchGenomes_;
-        if (nextStart < files.size()) pending = std::async(std::launch::async, loadBatch, nextStart);
-        flushBatch(batch);
+        pending.get();
+        const size_t nextStart = b0 + (size_t)batchGenomes_;
+        if (nextStart < files.size()) pending = std::async(std::launch::async, loadBatch, cur ^ 1, nextStart);
+        flushBatch(bufs[cur]);
+        cur ^= 1;
     }
     reporter_->closeReport();                                             // :153
     reporter_->close();                                                   // :154
-    log_ << "All done.  (t=" << nowSeconds() << " s)\n";
+    const double dt = nowSeconds() - t0;
+    log_ << "All done.  (t=" << nowSeconds() << " s)  " << proteinsDone_ << " proteins (" << residuesDone_ << " residues) of "
+         << files.size() << " genomes, files to report in " << dt << " s = " << (dt > 0 ? proteinsDone_ / dt / 1e6 : 0.0)
+         << " M proteins/s with " << loadThreads_ << " ingest threads.\n";
 }
 
 int ApplyKmerProcessor::run() {

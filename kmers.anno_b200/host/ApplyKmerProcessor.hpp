@@ -5,7 +5,8 @@
 //
 //   apply [--format VERIFY|APPLY] [-m|--min N] kmerdb.tbl roles.in.use gtoDir
 // added knobs (ordinary options, as SURVEY §5 asks): --devices 0,1,..  --table-mode 0|1|2  --batch genomes  --threads n
-// Genomes of the next batch are parsed by a thread pool while the GPU annotates the current one.
+// Genomes of the next batch are parsed and packed into pinned memory by a thread pool (PackedBatch) while the
+// GPU annotates the current one.
 #pragma once
 #include <iostream>
 #include <memory>
@@ -16,6 +17,7 @@
 #include "ApplyKmerReporter.hpp"
 #include "Genome.hpp"
 #include "KmerEngine.hpp"
+#include "PackedBatch.hpp"
 
 namespace theseed {
 
@@ -38,7 +40,7 @@ public:
     static void usage(std::ostream& os);
 
 private:
-    void flushBatch(std::vector<std::unique_ptr<Genome>>& genomes);
+    void flushBatch(PackedBatch& batch);
 
     std::ostream& out_;
     std::ostream& log_;
@@ -54,6 +56,8 @@ private:
     std::unique_ptr<ApplyKmerReporter> reporter_;
     std::unique_ptr<KmerEngine> engine_;       // replaces Map<String,String> kmerRoleMap (:53)
     std::vector<std::string> roleNames_;       // dense role id -> role string
+    std::vector<int> roleColumn_;              // dense role id -> report column (getRoleIdx), 0 = not in roles.in.use
+    uint64_t proteinsDone_ = 0, residuesDone_ = 0;
     int kmerSize_ = 0;
 };
 

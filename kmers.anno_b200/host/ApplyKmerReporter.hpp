@@ -7,6 +7,7 @@
 #include <memory>
 #include <ostream>
 #include <string>
+#include <string_view>
 #include <unordered_map>
 #include <vector>
 
@@ -32,7 +33,11 @@ public:
         }
         openReport();
     }
-    virtual void openGenome(const Genome& genome) = 0;                                   // :66
+    virtual void openGenome(const Genome& genome) { openGenome(genome.getId()); }        // :66
+    virtual void openGenome(const std::string& genomeId) = 0;
+    /** recordFeature (:75) without a Feature object: the ingest pipeline keeps peg ids and functions as views
+     *  into the genome file, and knows the report column of every role id (getRoleIdx, computed once). */
+    virtual void recordCall(std::string_view pegId, std::string_view function, const std::string& role, int roleIdx, int count) = 0;
     virtual void recordFeature(const Feature& feat, const std::string& role, int count) = 0;  // :75
     virtual void closeGenome() = 0;                                                      // :80
     virtual void closeReport() = 0;                                                      // :85
@@ -59,35 +64,51 @@ class DefaultApplyKmerReporter : public ApplyKmerReporter {
 public:
     using ApplyKmerReporter::ApplyKmerReporter;
     void openReport() override { roleCounts_.assign((size_t)getNumRoles(), 0); }          // :33-35
-    void openGenome(const Genome& genome) override {                                      // :38-41
-        genomeId_ = genome.getId();
+    using ApplyKmerReporter::openGenome;
+    void openGenome(const std::string& genomeId) override {                               // :38-41
+        genomeId_ = genomeId;
         std::fill(roleCounts_.begin(), roleCounts_.end(), 0);
     }
     void recordFeature(const Feature&, const std::string& role, int) override {           // :44-48
         int idx = getRoleIdx(role);
         if (idx > 0) roleCounts_[(size_t)idx - 1]++;
     }
+    void recordCall(std::string_view, std::string_view, const std::string&, int roleIdx, int) override {
+        if (roleIdx > 0) roleCounts_[(size_t)roleIdx - 1]++;
+    }
     void closeGenome() override {                                                         // :51-55
-        std::string line = genomeId_ + "\t";
+        line_.assign(genomeId_);
+        line_ += '\t';
+        char buf[16];
         for (size_t i = 0; i < roleCounts_.size(); i++) {
-            if (i) line += '\t';
-            line += std::to_string(roleCounts_[i]);
+            if (i) line_ += '\t';
+            int v = roleCounts_[i], n = 0;
+            if (v < 10) { line_ += (char)('0' + v); continue; }
+            while (v) { buf[n++] = (char)('0' + v % 10); v /= 10; }
+            while (n) line_ += buf[--n];
         }
-        println(line);
+        println(line_);
     }
     void closeReport() override {}
 private:
     std::vector<int> roleCounts_;
-    std::string genomeId_;
+    std::string genomeId_, line_;
 };
 
 class VerifyApplyKmerReporter : public ApplyKmerReporter {
 public:
     using ApplyKmerReporter::ApplyKmerReporter;
     void openReport() override { println("genome_id\tpeg_id\trole\thits\tfunction"); }    // :33-35
-    void openGenome(const Genome& genome) override { genomeId_ = genome.getId(); }        // :38-40
+    using ApplyKmerReporter::openGenome;
+    void openGenome(const std::string& genomeId) override { genomeId_ = genomeId; }       // :38-40
     void recordFeature(const Feature& feat, const std::string& role, int count) override {  // :43-45
         println(genomeId_ + "\t" + feat.getId() + "\t" + role + "\t" + std::to_string(count) + "\t" + feat.getFunction());
+    }
+    void recordCall(std::string_view pegId, std::string_view function, const std::string& role, int, int count) override {
+        std::string line = genomeId_;
+        line += '\t'; line.append(pegId); line += '\t'; line += role; line += '\t'; line += std::to_string(count);
+        line += '\t'; line.append(function);
+        println(line);
     }
     void closeGenome() override {}
     void closeReport() override {}

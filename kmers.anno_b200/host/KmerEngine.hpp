@@ -43,6 +43,15 @@ public:
         role.resize(n); hits.resize(n); flag.resize(n);
         check(ka_annotate(h_, residues.data(), offsets.data(), n, minHits, role.data(), hits.data(), flag.data()));
     }
+    /** The same on the packed form of the batch (ka_annotate_packed): caller-owned, ideally pinned, buffers. */
+    void annotatePacked(const uint8_t* codes, const uint32_t* offsets, size_t n, int minHits,
+                        int32_t* role, int32_t* hits, uint8_t* flag) {
+        check(ka_annotate_packed(h_, codes, offsets, n, minHits, role, hits, flag));
+    }
+    /** 5-bit codes of residues[0..n) into the stream at residue index `first` (a multiple of 8); thread-safe. */
+    void packResidues(const uint8_t* residues, uint64_t n, uint64_t first, uint8_t* codes) {
+        check(ka_pack_residues(h_, residues, n, first, codes));
+    }
     ka_stats stats() { ka_stats s; check(ka_get_stats(h_, &s)); return s; }
 
     /** ProteinKmers.distance of every query against its candidates (GeneCopyProcessor.java:137-142):

@@ -1,6 +1,8 @@
 package org.theseed.proteins.kmers.gpu;
 
 import java.io.IOException;
+import java.nio.ByteBuffer;
+import java.nio.ByteOrder;
 import java.nio.charset.StandardCharsets;
 import java.util.ArrayList;
 import java.util.HashMap;
@@ -13,9 +15,14 @@ import java.util.Map;
  * and runs its peg loop (:122-148) for a whole batch of proteins on the GPU(s).
  *
  * NOT COMPILED IN THIS REPOSITORY: the authoring image has no JDK (SURVEY.md fact 4).  The
- * ctypes binding kmers.anno_b200/engine.py and the C++ class host/KmerEngine.hpp exercise the
- * same C entry points one for one.  Java 21 is the reference's target (pom.xml:14-15), where
- * java.lang.foreign is still a preview API, hence JNI.
+ * ctypes binding kmers.anno_b200/engine.py and the C++ classes host/KmerEngine.hpp and
+ * host/PackedBatch.* exercise the same C entry points one for one; the JNI shim is
+ * syntax-checked against a stub jni.h (tests/test_host.py).  Java 21 is the reference's target
+ * (pom.xml:14-15), where java.lang.foreign is still a preview API, hence JNI.
+ *
+ * All bulk data crosses in direct ByteBuffers over PINNED host memory ({@link #allocPinned}):
+ * the Java side writes the batch once, in the engine's packed input form (5-bit residue codes +
+ * 32-bit offsets, 0.625 bytes per residue over PCIe), while it touches the protein strings anyway.
  */
 public final class KmerEngine implements AutoCloseable {
 
@@ -37,6 +44,9 @@ public final class KmerEngine implements AutoCloseable {
     private final List<String> roleNames = new ArrayList<>();
     private final Map<String, Integer> roleIds = new HashMap<>();
     private int kmerSize;
+    private byte[] codeOfByte;                 // ka_db_get_alphabet: 0..n-1 for the DB's residues, 31 otherwise
+    // pinned buffers of the current batch, grown on demand
+    private ByteBuffer codes, offsets, role, hits, flag;
 
     public KmerEngine(int[] devices) throws IOException {
         this.handle = create(devices);
@@ -51,17 +61,24 @@ public final class KmerEngine implements AutoCloseable {
     public void loadDb(List<String> kmers, List<String> roles) throws IOException {
         if (kmers.isEmpty()) throw new IOException("Empty kmer database.");
         this.kmerSize = kmers.get(kmers.size() - 1).length();          // :108
-        byte[] packed = new byte[kmers.size() * this.kmerSize];
-        int[] ids = new int[kmers.size()];
-        for (int i = 0; i < ids.length; i++) {
-            byte[] k = kmers.get(i).getBytes(StandardCharsets.ISO_8859_1);
-            if (k.length != this.kmerSize)
-                throw new IOException("Kmer database mixes kmer lengths at line " + (i + 1) + ".");
-            System.arraycopy(k, 0, packed, i * this.kmerSize, this.kmerSize);
-            final String role = roles.get(i);
-            ids[i] = this.roleIds.computeIfAbsent(role, r -> { this.roleNames.add(r); return this.roleNames.size() - 1; });
+        final int n = kmers.size();
+        ByteBuffer km = allocPinned((long) n * this.kmerSize);
+        ByteBuffer ids = allocPinned((long) n * 4).order(ByteOrder.LITTLE_ENDIAN);
+        try {
+            for (int i = 0; i < n; i++) {
+                byte[] k = kmers.get(i).getBytes(StandardCharsets.ISO_8859_1);
+                if (k.length != this.kmerSize)
+                    throw new IOException("Kmer database mixes kmer lengths at line " + (i + 1) + ".");
+                km.put(k);
+                final String r = roles.get(i);
+                ids.putInt(this.roleIds.computeIfAbsent(r, x -> { this.roleNames.add(x); return this.roleNames.size() - 1; }));
+            }
+            dbLoad(this.handle, km, ids, n, this.kmerSize);
+            this.codeOfByte = alphabet(this.handle);
+        } finally {
+            freePinned(km);
+            freePinned(ids);
         }
-        dbLoad(this.handle, packed, ids, ids.length, this.kmerSize);
     }
 
     /** @return the role string of a dense id returned in {@link Calls#role} */
@@ -74,63 +91,85 @@ public final class KmerEngine implements AutoCloseable {
     }
 
     /**
-     * Annotate a batch of proteins (the peg loop :122-148).  The caller replays
-     * reporter.recordFeature(feat, getRole(role[i]), hits[i]) for every i with flag[i] == CALLED,
-     * in the original peg order.
+     * Annotate a batch of proteins (the peg loop :122-148).  The proteins are written once, as 5-bit
+     * codes, into the pinned stream (residue r of the batch at bits [5r, 5r+5), little endian).  The
+     * caller replays reporter.recordFeature(feat, getRole(role[i]), hits[i]) for every i with
+     * flag[i] == CALLED, in the original peg order.
      */
     public Calls annotate(List<String> proteins, int minHits) throws IOException {
-        long[] offsets = new long[proteins.size() + 1];
-        int total = 0;
-        for (int i = 0; i < proteins.size(); i++) { offsets[i] = total; total += proteins.get(i).length(); }
-        offsets[proteins.size()] = total;
-        byte[] residues = new byte[total];
-        for (int i = 0; i < proteins.size(); i++) {
-            byte[] p = proteins.get(i).getBytes(StandardCharsets.ISO_8859_1);
-            System.arraycopy(p, 0, residues, (int) offsets[i], p.length);
+        final int n = proteins.size();
+        long total = 0;
+        for (String p : proteins) total += p.length();
+        if (total >= (1L << 32)) throw new IOException("More than 2^32 residues in one batch.");
+        reserve(total, n);
+        long acc = 0;          // bits not yet written
+        int nbits = 0;
+        long r = 0;
+        this.codes.clear();
+        this.offsets.clear();
+        for (String p : proteins) {
+            this.offsets.putInt((int) r);
+            for (int i = 0; i < p.length(); i++) {
+                final char ch = p.charAt(i);
+                final long c = ch < 256 ? (this.codeOfByte[ch] & 31) : 31;   // a char outside Latin-1 is in no kmer
+                acc |= c << nbits;
+                nbits += 5;
+                if (nbits >= 40) { putBits40(acc); acc >>>= 40; nbits -= 40; }
+            }
+            r += p.length();
         }
+        this.offsets.putInt((int) r);
+        for (; nbits > 0; nbits -= 8, acc >>>= 8) this.codes.put((byte) acc);
+        annotatePacked(this.handle, this.codes, (total * 5 + 7) / 8, this.offsets, n, minHits, this.role, this.hits, this.flag);
         Calls c = new Calls();
-        c.role = new int[proteins.size()];
-        c.hits = new int[proteins.size()];
-        c.flag = new byte[proteins.size()];
-        annotate(this.handle, residues, offsets, proteins.size(), minHits, c.role, c.hits, c.flag);
+        c.role = new int[n];
+        c.hits = new int[n];
+        c.flag = new byte[n];
+        this.role.clear(); this.role.asIntBuffer().get(c.role, 0, n);
+        this.hits.clear(); this.hits.asIntBuffer().get(c.hits, 0, n);
+        this.flag.clear(); this.flag.get(c.flag, 0, n);
         return c;
     }
 
-    /**
-     * ProteinKmers.distance of every query protein against its candidates (GeneCopyProcessor.java:137-142).
-     * Query q is proteins.get(querySeq[q]); its candidates are proteins.get(cand[m]) for
-     * groupOff[q] <= m < groupOff[q+1].  Returns one distance per candidate entry; the caller keeps the
-     * selection loop of :139-146.  No k-mer database is needed.
-     */
-    public double[] kmerDistance(List<String> proteins, int kmerSize, int[] querySeq, long[] groupOff, int[] cand)
-            throws IOException {
-        long[] offsets = new long[proteins.size() + 1];
-        int total = 0;
-        for (int i = 0; i < proteins.size(); i++) { offsets[i] = total; total += proteins.get(i).length(); }
-        offsets[proteins.size()] = total;
-        byte[] residues = new byte[total];
-        for (int i = 0; i < proteins.size(); i++) {
-            byte[] p = proteins.get(i).getBytes(StandardCharsets.ISO_8859_1);
-            System.arraycopy(p, 0, residues, (int) offsets[i], p.length);
+    private void putBits40(long v) {
+        this.codes.put((byte) v).put((byte) (v >>> 8)).put((byte) (v >>> 16)).put((byte) (v >>> 24)).put((byte) (v >>> 32));
+    }
+
+    private void reserve(long residues, int n) throws IOException {
+        final long needCodes = (residues * 5 + 7) / 8 + 64;
+        if (this.codes == null || this.codes.capacity() < needCodes) {
+            freePinned(this.codes);
+            this.codes = allocPinned(needCodes + needCodes / 4);
         }
-        double[] dist = new double[cand.length];
-        int[] common = new int[cand.length];
-        kmerDistance(this.handle, residues, offsets, proteins.size(), kmerSize, querySeq, groupOff, querySeq.length,
-                cand, common, dist);
-        return dist;
+        if (this.offsets == null || this.offsets.capacity() < 4L * (n + 1)) {
+            freePinned(this.offsets); freePinned(this.role); freePinned(this.hits); freePinned(this.flag);
+            final long cap = n + 1 + n / 4;
+            this.offsets = allocPinned(4 * cap).order(ByteOrder.LITTLE_ENDIAN);
+            this.role = allocPinned(4 * cap).order(ByteOrder.LITTLE_ENDIAN);
+            this.hits = allocPinned(4 * cap).order(ByteOrder.LITTLE_ENDIAN);
+            this.flag = allocPinned(cap);
+        }
     }
 
     @Override
     public void close() {
+        freePinned(this.codes); freePinned(this.offsets); freePinned(this.role); freePinned(this.hits); freePinned(this.flag);
+        this.codes = this.offsets = this.role = this.hits = this.flag = null;
         if (this.handle != 0) { destroy(this.handle); this.handle = 0; }
     }
 
     // ---- native methods: each maps to one C-ABI entry point; a non-zero code becomes an IOException
     private static native long create(int[] devices) throws IOException;                     // ka_create
     private static native void destroy(long handle);                                          // ka_destroy
-    private static native void dbLoad(long handle, byte[] kmers, int[] roleIds, long n, int k) throws IOException;  // ka_db_load
-    private static native void annotate(long handle, byte[] residues, long[] offsets, long n, int minHits,
-            int[] role, int[] hits, byte[] flag) throws IOException;                           // ka_annotate
-    private static native void kmerDistance(long handle, byte[] residues, long[] offsets, long n, int k,
-            int[] querySeq, long[] groupOff, long q, int[] cand, int[] common, double[] dist) throws IOException;  // ka_kmer_distance
+    public static native ByteBuffer allocPinned(long bytes) throws IOException;               // ka_host_alloc
+    public static native void freePinned(ByteBuffer buffer);                                  // ka_host_free (null is fine)
+    private static native void dbLoad(long handle, ByteBuffer kmers, ByteBuffer roleIds, long n, int k) throws IOException;  // ka_db_load
+    private static native byte[] alphabet(long handle) throws IOException;                    // ka_db_get_alphabet
+    private static native void annotatePacked(long handle, ByteBuffer codes, long codeBytes, ByteBuffer offsets, long n,
+            int minHits, ByteBuffer role, ByteBuffer hits, ByteBuffer flag) throws IOException;       // ka_annotate_packed
+    public static native void annotate(long handle, ByteBuffer residues, long residueBytes, ByteBuffer offsets, long n,
+            int minHits, ByteBuffer role, ByteBuffer hits, ByteBuffer flag) throws IOException;       // ka_annotate
+    public static native void kmerDistance(long handle, ByteBuffer residues, long residueBytes, ByteBuffer offsets, long n, int k,
+            ByteBuffer querySeq, ByteBuffer groupOff, long q, ByteBuffer cand, long m, ByteBuffer common, ByteBuffer dist)
+            throws IOException;                                                                // ka_kmer_distance
 }

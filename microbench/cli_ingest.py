@@ -31,14 +31,16 @@ for g in range(n_genomes):
 print(f"wrote {n_genomes} FASTA files ({total/1e6:.0f} M aa) and a {len(roles)}-line kmerdb.tbl in {time.time()-t:.1f}s", flush=True)
 cli = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "kmers.anno_b200", "bin", "kmers-anno")
 outs = []
+batch = sys.argv[3] if len(sys.argv) > 3 else "100"
 for threads in (1, 4, 16):
     t = time.time()
-    r = subprocess.run([cli, "apply", "--threads", str(threads), "--batch", "64", os.path.join(root, "kmerdb.tbl"),
+    r = subprocess.run([cli, "apply", "--threads", str(threads), "--batch", batch, os.path.join(root, "kmerdb.tbl"),
                         os.path.join(root, "roles.in.use"), gdir], capture_output=True)
     dt = time.time() - t
     assert r.returncode == 0, r.stderr[-500:]
     outs.append(r.stdout)
     marks = [l for l in r.stderr.decode().splitlines() if "t=" in l]
-    print("   ", " | ".join(m[-40:] for m in marks))
+    print("   ", " | ".join(m[-40:] for m in marks[:-1]))
+    print("   ", marks[-1])
     print(f"--threads {threads:2d}: {dt:.2f} s wall for the whole command ({n_genomes*4500/dt/1e3:.0f} k proteins/s incl. DB load), report {len(r.stdout)} bytes", flush=True)
 print("reports identical:", all(o == outs[0] for o in outs))

@@ -29,6 +29,36 @@ def test_abi_library_exports_every_declared_symbol():
     assert lib.ka_abi_version() == 2      # no compute call: fine without a GPU
 
 
+def test_jni_shim_compiles_against_a_stub_jni_header():
+    """No JDK in this image: the JNI shim is at least syntax- and type-checked (gcc -fsyntax-only -Wall -Werror)
+    against tests/stub_jni/jni.h, and every ka_* function it calls is a declared entry point."""
+    src = os.path.join(ROOT, "kmers.anno_b200", "java", "jni", "kmerengine_jni.c")
+    r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "tests", "stub_jni"),
+                        "-I", os.path.join(ROOT, "include"), src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    from kmers_anno_b200.engine import ABI_SYMBOLS
+    used = set(re.findall(r"\b(ka_[a-z_]+)\s*\(", open(src).read()))
+    assert used and used <= set(ABI_SYMBOLS), used - set(ABI_SYMBOLS)
+    # the Java class declares one native method per shim function
+    java = open(os.path.join(ROOT, "kmers.anno_b200", "java", "org", "theseed", "proteins", "kmers", "gpu", "KmerEngine.java")).read()
+    natives = set(re.findall(r"native\s+[\w\[\]]+\s+(\w+)\(", java))
+    shims = set(re.findall(r"Java_org_theseed_proteins_kmers_gpu_KmerEngine_(\w+)\(", open(src).read()))
+    assert natives == shims, natives ^ shims
+
+
+def test_mixed_kmer_lengths_are_rejected_before_any_gpu_work(tmp_path):
+    """HashMap<String,String> takes k-mers of any length (ApplyKmerProcessor.java:106); one packed table has one K:
+    the C++ `apply` refuses such a DB loudly while parsing it (documented deviation, docs/SEMANTICS.md #2)."""
+    db = tmp_path / "kmerdb.tbl"
+    db.write_text("ACDEFGHI\tRoleA\nACDEFGHIK\tRoleB\n")
+    roles = tmp_path / "roles.in.use"
+    roles.write_text("RoleA\tsome role\nRoleB\tother role\n")
+    gdir = tmp_path / "genomes"
+    gdir.mkdir()
+    r = subprocess.run([os.path.join(BIN, "kmers-anno"), "apply", str(db), str(roles), str(gdir)], capture_output=True, text=True)
+    assert r.returncode == 1 and "mixed k-mer lengths (8 and 9)" in r.stderr and r.stdout == ""
+
+
 def test_no_gpu_means_error_not_fallback():
     from conftest import has_gpu
     if has_gpu():
