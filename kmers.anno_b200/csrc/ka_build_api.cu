@@ -17,12 +17,14 @@ int ka_build(ka_engine* e, const uint8_t* residues, const uint64_t* offsets, uin
     if (!offsets || !n_roles || !peg_role || (cap && (!out_kmers || !out_roles))) return fail(e, KA_ERR_INVALID, "ka_build: NULL argument");
     if (N > 0xfffffff0ull) return fail(e, KA_ERR_TOO_BIG, "ka_build: too many pegs");
     uint64_t windows = 0;
+    int32_t max_role = 0;
     for (uint64_t i = 0; i < N; i++) {
         if (offsets[i + 1] < offsets[i]) return fail(e, KA_ERR_OFFSETS, "ka_build: offsets are not monotone");
         uint64_t L = offsets[i + 1] - offsets[i];
         if (n_roles[i] == 1) {
             if (peg_role[i] < 0) return fail(e, KA_ERR_ROLE, "ka_build: negative role id at peg %llu", (unsigned long long)i);
             if (L >= (uint64_t)K) windows += L - K + 1;
+            max_role = std::max(max_role, peg_role[i]);
         }
     }
     Device& d = e->devs[0];
@@ -85,13 +87,29 @@ int ka_build(ka_engine* e, const uint8_t* residues, const uint64_t* offsets, uin
     }
     if ((ce = cudaMemcpyAsync(d_lut, lut, 256, cudaMemcpyHostToDevice, st)) != cudaSuccess) return bail("H2D lut", ce);
     if ((ce = cudaMemcpyAsync(d_inv, inv, 32, cudaMemcpyHostToDevice, st)) != cudaSuccess) return bail("H2D inv", ce);
+    cudaEventRecord(d.pipe[0].ev_k0, st);
     if ((ce = launch_build_pass(1, d_res, d_off, (uint32_t)N, d_nr, d_pr, K, d_lut, d_tab, n_slots, st)) != cudaSuccess) return bail("build pass 1", ce);
     if ((ce = launch_build_pass(2, d_res, d_off, (uint32_t)N, d_nr, d_pr, K, d_lut, d_tab, n_slots, st)) != cudaSuccess) return bail("build pass 2", ce);
     if ((ce = launch_build_emit(d_tab, n_slots, K, d_inv, cap, d_ok, d_or, d_cnt, st)) != cudaSuccess) return bail("build emit", ce);
+    cudaEventRecord(d.pipe[0].ev_k1, st);
     unsigned long long found = 0;
     if ((ce = cudaMemcpyAsync(&found, d_cnt, 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return bail("D2H count", ce);
     if ((ce = cudaStreamSynchronize(st)) != cudaSuccess) return bail("build kernels", ce);
     *n_out = found;
+    {
+        // ka_get_stats after ka_build: device time of the two passes + emit, window positions inserted or probed
+        float ms = 0;
+        cudaEventElapsedTime(&ms, d.pipe[0].ev_k0, d.pipe[0].ev_k1);
+        e->stats = ka_stats{};
+        e->stats.sequences = N; e->stats.residues = n_res; e->stats.kernel_ms = ms; e->stats.kernel_launches = 3;
+        uint64_t w_all = 0;
+        for (uint64_t i = 0; i < N; i++) {
+            const uint64_t L = offsets[i + 1] - offsets[i];
+            if (n_roles[i] <= 1 && L >= (uint64_t)K) w_all += L - K + 1;
+        }
+        e->stats.probes = w_all;
+        e->stats.h2d_bytes = n_res + (N + 1) * 8 + N * 8;
+    }
     if (found > cap) {
         cleanup();
         return fail(e, KA_ERR_TOO_BIG, "ka_build: %llu k-mers found, output capacity is %llu", found, (unsigned long long)cap);
@@ -100,9 +118,11 @@ int ka_build(ka_engine* e, const uint8_t* residues, const uint64_t* offsets, uin
         if ((ce = cudaMemcpy(out_kmers, d_ok, found * K, cudaMemcpyDeviceToHost)) != cudaSuccess) return bail("D2H kmers", ce);
         if ((ce = cudaMemcpy(out_roles, d_or, found * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) return bail("D2H roles", ce);
     }
+    // load_as_db: the table is built from the k-mers where they are, in HBM (no kmerdb.tbl, no host round trip)
+    int rc = KA_OK;
+    if (load_as_db && found) rc = db_load_impl(e, d_ok, d_or, found, K, 0, 0, true, max_role);
     cleanup();
-    if (load_as_db && found) return db_load_impl(e, out_kmers, out_roles, found, K);
-    return KA_OK;
+    return rc;
 }
 
 }  // extern "C"

@@ -199,9 +199,11 @@ int build_table(ka_engine* e, Device& d, const TableView& geom, const DbSource& 
 bool choose_line_geometry(uint64_t n, int K, int nsym, double lf, bool forced, LineTable& g);
 int build_line_table(ka_engine* e, Device& d, const LineTable& geom, const DbSource& src, uint64_t* counts3);
 bool choose_geometry(uint64_t n, int K, int32_t max_role, double lf, int force_cls, uint32_t n_shards, bool force_wide, TableView& g);
-// syn_roles > 0: the lines come from the synthetic generator (syn_seed, syn_roles), kmers/role_ids unused
+// syn_roles > 0: the lines come from the synthetic generator (syn_seed, syn_roles), kmers/role_ids unused.
+// on_device: kmers / role_ids are DEVICE pointers (the output of ka_build, never copied to the host) and
+// max_role_hint bounds the role ids.
 int db_load_impl(ka_engine* e, const uint8_t* kmers, const int32_t* role_ids, uint64_t n, int K,
-                 uint64_t syn_seed = 0, int32_t syn_roles = 0);
+                 uint64_t syn_seed = 0, int32_t syn_roles = 0, bool on_device = false, int32_t max_role_hint = 0);
 
 // ---- ka_route.cu ----
 class Barrier {

@@ -64,8 +64,8 @@ int build_table(ka_engine* e, Device& d, const TableView& geom, const DbSource& 
     for (uint64_t i = 0; i < n && rc == KA_OK; i += ch) {
         uint64_t m = std::min(ch, n - i);
         if (!src.synthetic) {
-            step(cudaMemcpyAsync(dk, kmers + i * K, m * K, cudaMemcpyHostToDevice, st), "H2D kmers");
-            step(cudaMemcpyAsync(dr, roles + i, m * 4, cudaMemcpyHostToDevice, st), "H2D roles");
+            step(cudaMemcpyAsync(dk, kmers + i * K, m * K, cudaMemcpyDefault, st), "copy kmers");
+            step(cudaMemcpyAsync(dr, roles + i, m * 4, cudaMemcpyDefault, st), "copy roles");
         } else {
             step(launch_db_generate(i, m, K, src.seed, src.n_roles, dk, dr, st), "db_generate");
         }
@@ -267,8 +267,8 @@ int build_line_table(ka_engine* e, Device& d, const LineTable& geom, const DbSou
     for (uint64_t i = 0; i < n && rc == KA_OK; i += ch) {
         const uint64_t m = std::min(ch, n - i);
         if (!src.synthetic) {
-            step(cudaMemcpyAsync(dk, src.kmers + i * K, m * K, cudaMemcpyHostToDevice, st), "H2D kmers");
-            step(cudaMemcpyAsync(dr, src.roles + i, m * 4, cudaMemcpyHostToDevice, st), "H2D roles");
+            step(cudaMemcpyAsync(dk, src.kmers + i * K, m * K, cudaMemcpyDefault, st), "copy kmers");
+            step(cudaMemcpyAsync(dr, src.roles + i, m * 4, cudaMemcpyDefault, st), "copy roles");
         } else {
             step(launch_db_generate(i, m, K, src.seed, src.n_roles, dk, dr, st), "db_generate");
         }
@@ -314,7 +314,7 @@ int ka_db_load_synthetic(ka_engine* e, uint64_t n, int K, int32_t n_roles, uint6
 namespace kai {
 
 int db_load_impl(ka_engine* e, const uint8_t* kmers, const int32_t* role_ids, uint64_t n, int K,
-                 uint64_t syn_seed, int32_t syn_roles) {
+                 uint64_t syn_seed, int32_t syn_roles, bool on_device, int32_t max_role_hint) {
     if (K < 1 || K > KMAX) return fail(e, KA_ERR_K, "K = %d: this engine packs 5 bits per residue, K must be 1..%d", K, KMAX);
     e->have_db = false;
     for (Device& d : e->devs) { cudaSetDevice(d.id); cudaGetLastError(); }   // a stale error of an earlier call is not this call's
@@ -338,7 +338,7 @@ int db_load_impl(ka_engine* e, const uint8_t* kmers, const int32_t* role_ids, ui
         cudaError_t ce = cudaMemsetAsync(dbm, 0, 32, st);
         for (uint64_t i = 0; i < total && ce == cudaSuccess; i += ch) {
             uint64_t m = std::min(ch, total - i);
-            ce = cudaMemcpyAsync(dk, kmers + i, m, cudaMemcpyHostToDevice, st);
+            ce = cudaMemcpyAsync(dk, kmers + i, m, cudaMemcpyDefault, st);   // host lines, or the device-resident output of ka_build
             if (ce == cudaSuccess) ce = launch_alphabet_scan(dk, m, dbm, st);
             if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
         }
@@ -369,8 +369,8 @@ int db_load_impl(ka_engine* e, const uint8_t* kmers, const int32_t* role_ids, ui
     }
 
     // 2. table geometry (slot class, sector count) from n, K and the largest role id
-    int32_t max_role = synthetic ? syn_roles - 1 : 0;
-    for (uint64_t i = 0; !synthetic && i < n; i++) {
+    int32_t max_role = synthetic ? syn_roles - 1 : (on_device ? max_role_hint : 0);
+    for (uint64_t i = 0; !synthetic && !on_device && i < n; i++) {
         if (role_ids[i] < 0) return fail(e, KA_ERR_ROLE, "ka_db_load: negative role id %d at line %llu", role_ids[i], (unsigned long long)i);
         if (role_ids[i] > max_role) max_role = role_ids[i];
     }

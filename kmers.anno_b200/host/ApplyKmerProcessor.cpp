@@ -41,7 +41,7 @@ void ApplyKmerProcessor::usage(std::ostream& os) {
           " --format       reporting format (default APPLY)\n"
           " -m (--min)     minimum number of hits required to call a role (default 5)\n"
           " --devices      CUDA devices to shard the sequences over (default 0)\n"
-          " --batch        genomes per GPU batch (default 64)\n"
+          " --batch        genomes per GPU batch (default 32)\n"
           " --threads      genome-parsing threads (default: hardware threads)\n";
 }
 
@@ -49,7 +49,7 @@ void ApplyKmerProcessor::setDefaults() {
     outputType_ = ApplyKmerReporter::Type::APPLY;  // :78
     minHits_ = 5;                                  // :79
     devices_ = {0};
-    batchGenomes_ = 64;
+    batchGenomes_ = 32;
     loadThreads_ = (int)std::max(1u, std::thread::hardware_concurrency());
 }
 
@@ -230,27 +230,55 @@ void ApplyKmerProcessor::runCommand() {
     GenomeDirectory genomes(inDir_);                                      // :116
     log_ << genomes.size() << " genomes found in input directory.\n";     // :117
     const std::vector<std::string>& files = genomes.files();
-    const double t0 = nowSeconds();
     // report column of every dense role id, once (ApplyKmerReporter.getRoleIdx, :92-95)
     roleColumn_.resize(roleNames_.size());
     for (size_t r = 0; r < roleNames_.size(); r++) roleColumn_[r] = reporter_->getRoleIdx(roleNames_[r]);
     // Ingest pipeline: two pinned batches alternate — the genomes of batch i+1 are parsed and packed by
     // `loadThreads_` threads while the GPU annotates batch i; reports are written in directory order (:118).
     PackedBatch bufs[2] = {PackedBatch(*engine_), PackedBatch(*engine_)};
+    {
+        // pinned buffers sized once from the file sizes (a file holds at least one byte per residue and ~40 per peg)
+        uint64_t worst = 0;
+        for (size_t b0 = 0; b0 < files.size(); b0 += (size_t)batchGenomes_) {
+            uint64_t bytes = 0;
+            for (size_t i = b0; i < std::min(files.size(), b0 + (size_t)batchGenomes_); i++) {
+                struct stat st;
+                if (stat(files[i].c_str(), &st) == 0) bytes += (uint64_t)st.st_size;
+            }
+            worst = std::max(worst, bytes);
+        }
+        const double tr = nowSeconds();
+        if (worst < 0xf0000000ull)
+            for (PackedBatch& b : bufs) b.reserve(worst, (size_t)(worst / 40 + 1024));
+        log_ << "Two pinned ingest buffers for batches of up to " << worst / (1024 * 1024) << " MiB of genome files reserved in "
+             << nowSeconds() - tr << " s.\n";
+    }
+    const double t0 = nowSeconds();
+    const bool trace = getenv("KA_CLI_TRACE") != nullptr;
+    double tLoad = 0, tFlush = 0, tWait = 0;
     auto loadBatch = [&](int which, size_t b0) {
         const size_t n = std::min(files.size() - b0, (size_t)batchGenomes_);
+        const double t = nowSeconds();
         bufs[which].load(files.data() + b0, n, loadThreads_);
+        tLoad += nowSeconds() - t;
+        if (trace) log_ << "[ingest] batch at " << b0 << ": parse " << bufs[which].parseSeconds << " s, pack " << bufs[which].packSeconds << " s\n";
     };
     std::future<void> pending;
     if (!files.empty()) pending = std::async(std::launch::async, loadBatch, 0, (size_t)0);
     int cur = 0;
     for (size_t b0 = 0; b0 < files.size(); b0 += (size_t)batchGenomes_) {
+        double t = nowSeconds();
         pending.get();
+        tWait += nowSeconds() - t;
         const size_t nextStart = b0 + (size_t)batchGenomes_;
         if (nextStart < files.size()) pending = std::async(std::launch::async, loadBatch, cur ^ 1, nextStart);
+        t = nowSeconds();
         flushBatch(bufs[cur]);
+        tFlush += nowSeconds() - t;
         cur ^= 1;
     }
+    if (trace) log_ << "[ingest] load (parse + pack, worker threads) " << tLoad << " s, main thread waited for it " << tWait
+                    << " s, annotate + report " << tFlush << " s\n";
     reporter_->closeReport();                                             // :153
     reporter_->close();                                                   // :154
     const double dt = nowSeconds() - t0;

@@ -49,7 +49,7 @@ private:
     int minHits_ = 5;
     std::string kmerDbFile_, goodRoleFile_, inDir_;
     std::vector<int> devices_{0};
-    int batchGenomes_ = 64;
+    int batchGenomes_ = 32;
     int loadThreads_ = 1;
     int tableMode_ = 0;                        // 0 replicated table, 1 / 2 sharded over the devices (ka_set_option "table_mode")
     // state

@@ -105,7 +105,7 @@ Genome::Genome(const std::string& path) {
     size_t slash = path.find_last_of('/');
     std::string base = slash == std::string::npos ? path : path.substr(slash + 1);
     if (endsWith(base, ".gto")) loadGto(text);
-    else loadFasta(text, base.substr(0, base.find_last_of('.')));
+    else { fromFasta_ = true; loadFasta(text, base.substr(0, base.find_last_of('.'))); }
 }
 
 void Genome::loadGto(const std::string& text) {
@@ -178,8 +178,8 @@ std::vector<const Feature*> Genome::getPegs() const {
     bool any_peg_id = false;
     for (const Feature& f : features_) if (f.isPeg()) { any_peg_id = true; break; }
     for (const Feature& f : features_) {
-        // GTO features are typed by their fid; a FASTA without fig-style ids is all proteins
-        if (any_peg_id ? f.isPeg() : true) out.push_back(&f);
+        // features are typed by their fid (Genome.getPegs()); only a protein FASTA without fig-style ids is all proteins
+        if (f.isPeg() || (fromFasta_ && !any_peg_id)) out.push_back(&f);
     }
     return out;
 }

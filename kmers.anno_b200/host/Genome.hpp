@@ -46,6 +46,7 @@ private:
     void loadFasta(const std::string& text, const std::string& stem);
     std::string id_, name_;
     std::vector<Feature> features_;
+    bool fromFasta_ = false;
 };
 
 /** Genome files of a directory, sorted by file name (GenomeDirectory keeps a sorted id set). */

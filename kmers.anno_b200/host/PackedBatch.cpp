@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstring>
 #include <thread>
 
@@ -128,6 +129,7 @@ void PackedBatch::load(const std::string* files, size_t n, int threads) {
         work();
         for (auto& t : th) t.join();
     };
+    const auto tp0 = std::chrono::steady_clock::now();
     // 1. parse: every file into its own staging (bytes) and peg table
     parallel([&](size_t i) {
         try { loadOne(files[i], genomes_[i]); }
@@ -143,6 +145,7 @@ void PackedBatch::load(const std::string* files, size_t n, int threads) {
     }
     if (nResidues_ >= 0xffffff00ull) throw IOException("A batch holds more than 2^32 residues; lower --batch.");
     reserve(nResidues_, nPegs_);
+    const auto tp1 = std::chrono::steady_clock::now();
     // 3. pack: every thread writes the whole stream bytes of its genomes (8 residues = 5 bytes); the group
     //    that straddles two genomes is completed afterwards
     parallel([&](size_t i) {
@@ -173,6 +176,8 @@ void PackedBatch::load(const std::string* files, size_t n, int threads) {
             engine_.packResidues(tmp, cnt, grp, codes_);
         }
     }
+    parseSeconds = std::chrono::duration<double>(tp1 - tp0).count();
+    packSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - tp1).count();
 }
 
 void PackedBatch::annotate(int minHits) {

@@ -43,6 +43,8 @@ public:
 
     /** Parse and pack files[0..n) with up to `threads` threads; throws IOException naming the bad file. */
     void load(const std::string* files, size_t n, int threads);
+    /** Size the pinned buffers ahead of the first load (cudaHostAlloc is slow: tens of ms per 100 MB). */
+    void reserve(uint64_t residues, size_t pegs);
     /** ka_annotate_packed on the whole batch; results in role() / hits() / flag(). */
     void annotate(int minHits);
 
@@ -55,10 +57,12 @@ public:
     const uint8_t* flag() const { return flag_; }
 
 private:
-    void reserve(uint64_t residues, size_t pegs);
     KmerEngine& engine_;
     std::vector<PackedGenome> genomes_;
     size_t nPegs_ = 0;
+public:
+    double parseSeconds = 0, packSeconds = 0;   // of the last load()
+private:
     uint64_t nResidues_ = 0;
     // pinned buffers, grown on demand and reused from batch to batch
     uint8_t* codes_ = nullptr; size_t codesCap_ = 0;

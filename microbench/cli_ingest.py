@@ -32,7 +32,8 @@ print(f"wrote {n_genomes} FASTA files ({total/1e6:.0f} M aa) and a {len(roles)}-
 cli = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "kmers.anno_b200", "bin", "kmers-anno")
 outs = []
 batch = sys.argv[3] if len(sys.argv) > 3 else "100"
-for threads in (1, 4, 16):
+os.environ["KA_CLI_TRACE"] = "1"
+for threads, batch in ((1, batch), (4, batch), (16, batch), (16, "25"), (16, "50")):
     t = time.time()
     r = subprocess.run([cli, "apply", "--threads", str(threads), "--batch", batch, os.path.join(root, "kmerdb.tbl"),
                         os.path.join(root, "roles.in.use"), gdir], capture_output=True)
@@ -42,5 +43,6 @@ for threads in (1, 4, 16):
     marks = [l for l in r.stderr.decode().splitlines() if "t=" in l]
     print("   ", " | ".join(m[-40:] for m in marks[:-1]))
     print("   ", marks[-1])
-    print(f"--threads {threads:2d}: {dt:.2f} s wall for the whole command ({n_genomes*4500/dt/1e3:.0f} k proteins/s incl. DB load), report {len(r.stdout)} bytes", flush=True)
+    print("   ", " | ".join(l for l in r.stderr.decode().splitlines() if l.startswith("[ingest]"))[-600:])
+    print(f"--threads {threads:2d} --batch {batch}: {dt:.2f} s wall for the whole command ({n_genomes*4500/dt/1e3:.0f} k proteins/s incl. DB load), report {len(r.stdout)} bytes", flush=True)
 print("reports identical:", all(o == outs[0] for o in outs))
