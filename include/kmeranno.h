@@ -90,7 +90,10 @@ const char* ka_last_error(const ka_engine* e);
  *                   over the engine's 2/4/8 devices, probes load remote sectors through NVLink
  *                   peer memory inside the probe kernel (for tables beyond one GPU); 2 = same sharding,
  *                   but the k-mer keys are ROUTED: NCCL send/recv all-to-all of 8-byte keys to the
- *                   owning GPU, local probe there, 8-byte answers back in request order, rounds pipelined
+ *                   owning GPU, local probe there, 8-byte answers back in request order, rounds pipelined;
+ *                   3 = the same routing with the exchanges FUSED into the kernels: the bucket-scatter kernel
+ *                   stores the keys straight into the owner's receive buffer and the owner's lookup kernel
+ *                   stores the answers straight into the requester's buffer (NVLink peer stores, no NCCL)
  *   "wide"          1 = use the wide-table kernels (64-bit sector indices, the mixed key as de-dup
  *                   token) on any sector-class table; 0 (default) = only beyond 2^32 - 16 slots
  *   "tile_span"     residues of sequence starts per CTA tile, default 1536

@@ -510,6 +510,7 @@ void ka_destroy(ka_engine* e) {
                             (void*)ln.r_small, (void*)ln.r_pos}) if (q) cudaFree(q);
             if (ln.h_cnt) cudaFreeHost(ln.h_cnt);
             if (ln.ev_counts) cudaEventDestroy(ln.ev_counts);
+            for (cudaEvent_t ev : {ln.ev_scatter, ln.ev_lookup, ln.ev_tally}) if (ev) cudaEventDestroy(ev);
         }
         if (d.ev_route0) cudaEventDestroy(d.ev_route0);
         if (d.ev_route1) cudaEventDestroy(d.ev_route1);
@@ -552,7 +553,8 @@ int ka_set_option(ka_engine* e, const char* name, double v) {
     } else if (n == "l2_persist") {
         l2_persist = v != 0;
     } else if (n == "table_mode") {
-        if (v != 0 && v != 1 && v != 2) return fail(e, KA_ERR_INVALID, "table_mode must be 0 (replicated), 1 (sharded, peer loads) or 2 (sharded, routed)");
+        if (v != 0 && v != 1 && v != 2 && v != 3)
+            return fail(e, KA_ERR_INVALID, "table_mode must be 0 (replicated), 1 (sharded, peer loads), 2 (sharded, NCCL routed) or 3 (sharded, routed by peer stores)");
         table_mode = (int)v;
     } else if (n == "wide") {
         wide = v != 0;
@@ -608,13 +610,30 @@ static int annotate_impl(ka_engine* e, const BatchIn& in, uint64_t N, int32_t mi
         cut[i] = std::min<uint64_t>(std::max<uint64_t>(lo, cut[i - 1]), N);
     }
     int rc;
-    if (e->db_table_mode == 2) {
-        if (in.packed()) return fail(e, KA_ERR_INVALID, "%s: the routed table (table_mode 2) takes byte residues (ka_annotate)", who);
-        if (!e->nccl_ready || e->geom.n_shards <= 1) return fail(e, KA_ERR_INVALID, "%s: the loaded table is not a routed table", who);
+    if (e->db_table_mode >= 2) {
+        if ((e->db_table_mode == 2 && !e->nccl_ready) || e->geom.n_shards <= 1) return fail(e, KA_ERR_INVALID, "%s: the loaded table is not a routed table", who);
+        // the key-extraction kernels of the routed path read residue bytes: a packed batch is expanded on the host
+        // first (the routed table is the capacity configuration, not the ingest-bound one)
+        std::vector<uint8_t> bytes;
+        std::vector<uint64_t> off64;
+        const uint8_t* residues = in.residues;
+        const uint64_t* offsets = in.off64;
+        if (in.packed()) {
+            const uint64_t r0 = in.off(0), r1 = in.off(N);
+            bytes.resize(r1);
+            off64.resize(N + 1);
+            for (uint64_t i = 0; i <= N; i++) off64[i] = in.off32[i];
+            for (uint64_t r = r0; r < r1; r++) {
+                const uint64_t bit = 5 * r;
+                const uint32_t two = (uint32_t)in.codes[bit >> 3] | ((uint32_t)in.codes[(bit >> 3) + 1] << 8);   // (the stream has slack bytes)
+                bytes[r] = e->inv32[(two >> (bit & 7)) & 31u];
+            }
+            residues = bytes.data(); offsets = off64.data();
+        }
         // routed sharded table: every device must walk every round, even with an empty range
         RouteShared shared((int)nd);
         rc = for_each_device(e, [&](Device& d, int i) {
-            return annotate_routed_range(e, d, i, shared, in.residues, in.off64, cut[i], cut[i + 1], min_hits, out_role, out_hits, out_flag);
+            return annotate_routed_range(e, d, i, shared, residues, offsets, cut[i], cut[i + 1], min_hits, out_role, out_hits, out_flag);
         });
     } else {
         rc = for_each_device(e, [&](Device& d, int i) {
@@ -700,7 +719,7 @@ int ka_batch_upload(ka_engine* e, int dev_index, const uint8_t* residues, const 
     std::lock_guard<std::mutex> lk(e->mu);
     if (!e->have_db) return fail(e, KA_ERR_NO_DB, "ka_batch_upload: load the k-mer database first");
     if (dev_index < 0 || dev_index >= (int)e->devs.size()) return fail(e, KA_ERR_INVALID, "ka_batch_upload: bad device index");
-    if (e->db_table_mode == 2) return fail(e, KA_ERR_INVALID, "ka_batch_upload: resident batches are not available with the routed table (table_mode 2)");
+    if (e->db_table_mode >= 2) return fail(e, KA_ERR_INVALID, "ka_batch_upload: resident batches are not available with the routed table (table_mode 2 / 3)");
     if (N == 0 || !offsets) return fail(e, KA_ERR_INVALID, "ka_batch_upload: empty batch");
     if (N > 0xfffffff0ull) return fail(e, KA_ERR_TOO_BIG, "ka_batch_upload: too many sequences");
     Device& d = e->devs[dev_index];

@@ -68,6 +68,7 @@ struct Device {
         size_t r_cap_pos = 0, r_cap_recv = 0;
         unsigned long long* h_cnt = nullptr;   // pinned: per-owner key counts of the round
         cudaEvent_t ev_counts = nullptr;
+        cudaEvent_t ev_scatter = nullptr, ev_lookup = nullptr, ev_tally = nullptr;   // peer-store transport
     } lane[2];
     cudaEvent_t ev_route0 = nullptr, ev_route1 = nullptr;
     uint8_t* lut = nullptr;
@@ -226,7 +227,15 @@ struct RouteShared {
     std::vector<std::array<unsigned long long, 8>> counts;   // counts[d][o]: keys device d sends to owner o this round
     std::vector<size_t> n_chunks;
     std::atomic<int> abort{0};                                // a device could not size its receive buffers
-    explicit RouteShared(int n) : bar(n), counts(n), n_chunks(n, 0) {}
+    // peer-store transport (table_mode 3): every device publishes, per lane, its receive and answer buffers and the
+    // events other devices order their kernels against
+    struct Pub {
+        unsigned long long* recv[2] = {nullptr, nullptr};
+        unsigned long long* ans[2] = {nullptr, nullptr};
+        cudaEvent_t scatter_done[2] = {nullptr, nullptr}, lookup_done[2] = {nullptr, nullptr}, tally_done[2] = {nullptr, nullptr};
+    };
+    std::vector<Pub> pub;
+    explicit RouteShared(int n) : bar(n), counts(n), n_chunks(n, 0), pub(n) {}
 };
 
 int route_init_comms(ka_engine* e);      // dlopen libnccl, one communicator per device (idempotent)

@@ -607,7 +607,7 @@ cudaError_t launch_route_count(const unsigned long long* keys, unsigned long lon
 // keys at (range + rank inside the CTA).
 __global__ void __launch_bounds__(256) route_scatter_kernel(const unsigned long long* __restrict__ keys, unsigned long long n,
                                      TableView tab, const unsigned long long* __restrict__ offsets,
-                                     unsigned long long* cursor, unsigned long long* send_keys, uint32_t* slot_of_pos) {
+                                     unsigned long long* cursor, RouteDst dst, uint32_t* slot_of_pos) {
     constexpr int PER = 16;                       // keys per thread, strided by 256 inside the tile
     __shared__ uint32_t s_cnt[8][8];              // [warp][owner]
     __shared__ unsigned long long s_base[8][8];   // [warp][owner] first output index
@@ -644,7 +644,7 @@ __global__ void __launch_bounds__(256) route_scatter_kernel(const unsigned long 
                 const unsigned b = __ballot_sync(0xffffffffu, own[k] == o);
                 if (own[k] == o) {
                     const unsigned long long w = s_base[warp][o] + done[o] + __popc(b & ((1u << lane) - 1));
-                    send_keys[w] = m[k];
+                    dst.p[o][w] = m[k];                // the local send buffer, or straight into the owner's receive buffer (NVLink store)
                     slot_of_pos[i] = (uint32_t)w;      // answers come back in send order: position i reads slot w
                 }
                 done[o] += __popc(b);
@@ -656,10 +656,10 @@ __global__ void __launch_bounds__(256) route_scatter_kernel(const unsigned long 
 
 cudaError_t launch_route_scatter(const unsigned long long* keys, unsigned long long n, TableView tab,
                                  const unsigned long long* offsets, unsigned long long* cursor,
-                                 unsigned long long* send_keys, uint32_t* slot_of_pos, cudaStream_t st) {
+                                 const RouteDst& dst, uint32_t* slot_of_pos, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     unsigned long long want = (n + 256ull * 16 - 1) / (256ull * 16);
-    route_scatter_kernel<<<(unsigned)(want < 148ull * 8 ? want : 148ull * 8), 256, 0, st>>>(keys, n, tab, offsets, cursor, send_keys, slot_of_pos);
+    route_scatter_kernel<<<(unsigned)(want < 148ull * 8 ? want : 148ull * 8), 256, 0, st>>>(keys, n, tab, offsets, cursor, dst, slot_of_pos);
     return cudaGetLastError();
 }
 
@@ -667,7 +667,7 @@ cudaError_t launch_route_scatter(const unsigned long long* keys, unsigned long l
 template <int CLS>
 __global__ void __launch_bounds__(256) route_lookup_kernel(const unsigned long long* __restrict__ keys,
                                                            unsigned long long n, TableView tab,
-                                                           unsigned long long* ans) {
+                                                           unsigned long long* ans, RouteAns ra) {
     constexpr int S = slots_per_sector<CLS>();
     constexpr int U = 4;
     typedef typename rem_type<CLS>::type rem_t;
@@ -713,19 +713,28 @@ __global__ void __launch_bounds__(256) route_lookup_kernel(const unsigned long l
                         s = (s + 1) & mask;
                     }
                 }
-                ans[i] = role >= 0 ? (((unsigned long long)(uint32_t)role << 32) | tok) : ROUTE_MISS;
+                const unsigned long long v = role >= 0 ? (((unsigned long long)(uint32_t)role << 32) | tok) : ROUTE_MISS;
+                if (ra.n_regions == 0) ans[i] = v;
+                else {
+                    // key i came from the sender whose region holds i: its answer goes straight into that GPU's
+                    // answer buffer, in its send order (NVLink store)
+                    uint32_t sdr = 0;
+#pragma unroll
+                    for (uint32_t q = 1; q < 8; q++) sdr += (q < ra.n_regions && i >= ra.first[q]) ? 1u : 0u;
+                    ra.p[sdr][i] = v;
+                }
             }
         }
     }
 }
 
 cudaError_t launch_route_lookup(const unsigned long long* keys, unsigned long long n, TableView tab,
-                                unsigned long long* ans, cudaStream_t st) {
+                                unsigned long long* ans, const RouteAns& ra, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
     unsigned long long want = (n + 256ull * 4 - 1) / (256ull * 4);
     unsigned blocks = (unsigned)(want < 148ull * 16 ? want : 148ull * 16);
-    if (tab.cls == 32) route_lookup_kernel<32><<<blocks, 256, 0, st>>>(keys, n, tab, ans);
-    else if (tab.cls == 64) route_lookup_kernel<64><<<blocks, 256, 0, st>>>(keys, n, tab, ans);
+    if (tab.cls == 32) route_lookup_kernel<32><<<blocks, 256, 0, st>>>(keys, n, tab, ans, ra);
+    else if (tab.cls == 64) route_lookup_kernel<64><<<blocks, 256, 0, st>>>(keys, n, tab, ans, ra);
     else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }

@@ -65,16 +65,23 @@ constexpr unsigned long long ROUTE_MISS = ~0ull;          // answer of a key tha
 // also the entry of every launch on a wide table)
 cudaError_t launch_tiles_mode(const AnnotParams& p, int variant, int mode, size_t smem, cudaStream_t st);
 cudaError_t tile_kernel_mode_set_smem(size_t bytes);
+// Where the bucketed keys go: p[o] is indexed with the sender's send slot w (offsets[o] <= w < offsets[o] + count[o]):
+// the local send buffer for every owner (NCCL transport), or the owner's receive buffer shifted so that slot w
+// lands in this sender's region of it (peer-store transport: the scatter kernel IS the key exchange).
+struct RouteDst { unsigned long long* p[8]; };
+// Where the owner's answers go: n_regions = 0: ans[i]; else region q = keys first[q] .. first[q+1) came from sender q
+// and p[q] is that sender's answer buffer shifted so that received key i lands at its send slot (peer store).
+struct RouteAns { unsigned long long* p[8]; unsigned long long first[8]; uint32_t n_regions; };
 // per-owner counts of the valid keys of keys[0..n) (owner = sector >> shard_shift); counts[8] accumulates
 cudaError_t launch_route_count(const unsigned long long* keys, unsigned long long n, TableView tab,
                                unsigned long long* counts, cudaStream_t st);
 // bucket the valid keys by owner: send_keys at offsets[o] + running cursor[o]; slot_of_pos[i] = that index
 cudaError_t launch_route_scatter(const unsigned long long* keys, unsigned long long n, TableView tab,
                                  const unsigned long long* offsets, unsigned long long* cursor,
-                                 unsigned long long* send_keys, uint32_t* slot_of_pos, cudaStream_t st);
+                                 const RouteDst& dst, uint32_t* slot_of_pos, cudaStream_t st);
 // owner side: answer every received key from the local shard
 cudaError_t launch_route_lookup(const unsigned long long* keys, unsigned long long n, TableView tab,
-                                unsigned long long* ans, cudaStream_t st);
+                                unsigned long long* ans, const RouteAns& ra, cudaStream_t st);
 
 cudaError_t launch_plan(const AnnotParams& p, cudaStream_t st);
 cudaError_t launch_tiles(const AnnotParams& p, int variant, size_t smem, cudaStream_t st);

@@ -92,6 +92,8 @@ int route_reserve(Device& dev, Device::RouteLane& d, size_t n_pos, size_t n_recv
     if (!d.r_small && cudaMalloc((void**)&d.r_small, 24 * 8) != cudaSuccess) return dev_fail(dev, KA_ERR_OOM, "routing counters", cudaErrorMemoryAllocation);
     if (!d.h_cnt && cudaHostAlloc((void**)&d.h_cnt, 64, cudaHostAllocDefault) != cudaSuccess) return dev_fail(dev, KA_ERR_OOM, "routing counters (pinned)", cudaErrorMemoryAllocation);
     if (!d.ev_counts && cudaEventCreateWithFlags(&d.ev_counts, cudaEventDisableTiming) != cudaSuccess) return dev_fail(dev, KA_ERR_CUDA, "routing event", cudaErrorUnknown);
+    for (cudaEvent_t* ev : {&d.ev_scatter, &d.ev_lookup, &d.ev_tally})
+        if (!*ev && cudaEventCreateWithFlags(ev, cudaEventDisableTiming) != cudaSuccess) return dev_fail(dev, KA_ERR_CUDA, "routing event", cudaErrorUnknown);
     return KA_OK;
 }
 
@@ -144,6 +146,7 @@ int annotate_routed_range(ka_engine* e, Device& d, int idx, RouteShared& sh, con
     ensure_tile_smem(d);   // a failure is recorded in d.err and turns the rounds of this device into empty ones
     if (!d.ev_route0) { cuda_ok(cudaEventCreate(&d.ev_route0), "event"); cuda_ok(cudaEventCreate(&d.ev_route1), "event"); }
 
+    const bool peer = e->db_table_mode == 3;     // keys and answers travel as NVLink stores of the scatter / lookup kernels
     const bool serial = getenv("KA_ROUTE_SERIAL") != nullptr;
     const bool trace = serial && idx == 0 && getenv("KA_ROUTE_TRACE") != nullptr;
     const int n_lanes = serial ? 1 : 2;
@@ -175,12 +178,11 @@ int annotate_routed_range(ka_engine* e, Device& d, int idx, RouteShared& sh, con
         if (R.has) {
             R.cs = chunks[r].first; R.ce = chunks[r].second; R.n = R.ce - R.cs;
             if (!scan_offsets(bin, R.cs, R.ce, e->long_seq, e->mid_seq, e->info.K, R.shp)) { d.err = KA_ERR_OFFSETS; d.errmsg = "offsets are not monotone"; R.has = false; }
-            else if (R.shp.n_long) { d.err = KA_ERR_TOO_BIG; d.errmsg = "routed table mode: a sequence is longer than mid_seq (raise the mid_seq option)"; R.has = false; }
             else if (R.shp.n_res > 0x7fffffffull) { d.err = KA_ERR_TOO_BIG; d.errmsg = "chunk exceeds 2^31 residues"; R.has = false; }
         }
         if (R.has) {
             d.probes += R.shp.probes;
-            if (pipe_reserve(d, p, R.shp.n_res, R.n, R.shp.n_res / e->tile_span + 1, 0, 0, R.shp.n_mid, e->geom.wide != 0, true, false) ||
+            if (pipe_reserve(d, p, R.shp.n_res, R.n, R.shp.n_res / e->tile_span + 1, R.shp.n_long, R.shp.long_res, R.shp.n_mid, e->geom.wide != 0, true, false) ||
                 route_reserve(d, ln, R.shp.n_res + 64, 0)) R.has = false;
         }
         if (ln.h_cnt) memset(ln.h_cnt, 0, 64);
@@ -236,19 +238,73 @@ int annotate_routed_range(ka_engine* e, Device& d, int idx, RouteShared& sh, con
         const unsigned long long total_recv = recv_off[nd];
         bool recv_ok = route_reserve(d, ln, 0, total_recv + 64) == KA_OK && ln.r_small;
         if (!recv_ok) { sh.abort.store(1); if (d.err == KA_OK) d.err = KA_ERR_OOM; }
+        if (peer) {
+            RouteShared::Pub& pb = sh.pub[idx];
+            pb.recv[L] = ln.r_recv; pb.ans[L] = ln.r_ans_sorted;
+            pb.scatter_done[L] = ln.ev_scatter; pb.lookup_done[L] = ln.ev_lookup; pb.tally_done[L] = ln.ev_tally;
+        }
+        // column sums: where my keys start inside every owner's receive buffer, where every sender's keys start in my send order
+        unsigned long long recv_base[8] = {0}, their_send_off[8] = {0};
+        for (int o = 0; o < nd; o++) {
+            for (int s2 = 0; s2 < idx; s2++) recv_base[o] += sh.counts[s2][o];          // my region in owner o's receive buffer
+            for (int o2 = 0; o2 < idx; o2++) their_send_off[o] += sh.counts[o][o2];     // send slot of sender o's first key for me
+        }
         sh.bar.wait();                     // nobody overwrites counts before everyone has read them
         if (sh.abort.load()) {
             // a peer cannot receive: every device skips the exchange of this and all later rounds
             if (d.err == KA_OK) { d.err = KA_ERR_OOM; d.errmsg = "routed table mode: a peer device ran out of memory"; }
             recv_ok = false; R.has = false;
         }
-        if (R.has) {
+        if (peer && !sh.abort.load()) {
+            // ---- peer-store transport: three kernels per round, ordered across the GPUs by events ----
+            // (an event must be RECORDED before another device waits on it, hence the host barriers)
+            if (R.has) {
+                RouteDst dst;
+                for (int o = 0; o < 8; o++) dst.p[o] = nullptr;
+                for (int o = 0; o < nd; o++) {
+                    // the owner's lookup of the previous round on this lane must have drained its receive buffer
+                    if (sh.pub[o].lookup_done[L]) cuda_ok(cudaStreamWaitEvent(st, sh.pub[o].lookup_done[L], 0), "wait lookup");
+                    dst.p[o] = sh.pub[o].recv[L] + recv_base[o] - send_off[o];
+                }
+                cuda_ok(cudaMemcpyAsync(ln.r_small + 8, send_off, 64, cudaMemcpyHostToDevice, st), "H2D offsets");
+                mark(3);
+                cuda_ok(launch_route_scatter(ln.r_keys, R.shp.n_res, R.ap.tab, ln.r_small + 8, ln.r_small + 16, dst, ln.r_pos, st), "route scatter");
+                mark(4);
+                d.launches += 1;
+            }
+            cuda_ok(cudaEventRecord(ln.ev_scatter, st), "event");
+            sh.bar.wait();                 // every scatter of this round is enqueued and its event recorded
+            {
+                RouteAns ra;
+                ra.n_regions = (uint32_t)nd;
+                for (int s2 = 0; s2 < 8; s2++) { ra.p[s2] = nullptr; ra.first[s2] = ~0ull; }
+                for (int s2 = 0; s2 < nd; s2++) {
+                    cuda_ok(cudaStreamWaitEvent(st, sh.pub[s2].scatter_done[L], 0), "wait scatter");
+                    // the requester's tally of the previous round on this lane must have read its answers
+                    if (sh.pub[s2].tally_done[L]) cuda_ok(cudaStreamWaitEvent(st, sh.pub[s2].tally_done[L], 0), "wait tally");
+                    ra.first[s2] = recv_off[s2];
+                    ra.p[s2] = sh.pub[s2].ans[L] + their_send_off[s2] - recv_off[s2];
+                }
+                TableView tab = e->geom;
+                tab.sectors = d.table; tab.ovf = d.ovf; tab.my_shard = (uint32_t)idx;
+                mark(5);
+                if (total_recv) { cuda_ok(launch_route_lookup(ln.r_recv, total_recv, tab, nullptr, ra, st), "route lookup"); d.launches += 1; }
+                mark(6);
+            }
+            cuda_ok(cudaEventRecord(ln.ev_lookup, st), "event");
+            sh.bar.wait();                 // every lookup of this round is enqueued and its event recorded
+            for (int o = 0; o < nd; o++) cuda_ok(cudaStreamWaitEvent(st, sh.pub[o].lookup_done[L], 0), "wait answers");
+            recv_ok = false;               // (the NCCL exchange below is not used)
+        } else if (R.has) {
+            RouteDst dst;
+            for (int o = 0; o < 8; o++) dst.p[o] = ln.r_send;
             cuda_ok(cudaMemcpyAsync(ln.r_small + 8, send_off, 64, cudaMemcpyHostToDevice, st), "H2D offsets");
             mark(3);
-            cuda_ok(launch_route_scatter(ln.r_keys, R.shp.n_res, R.ap.tab, ln.r_small + 8, ln.r_small + 16, ln.r_send, ln.r_pos, st), "route scatter");
+            cuda_ok(launch_route_scatter(ln.r_keys, R.shp.n_res, R.ap.tab, ln.r_small + 8, ln.r_small + 16, dst, ln.r_pos, st), "route scatter");
             mark(4);
             d.launches += 1;
         }
+        if (peer && sh.abort.load()) { sh.bar.wait(); sh.bar.wait(); }   // keep the barrier count of the round
         if (recv_ok) {
             // keys to their owners
             NCK(d, g_nccl.GroupStart());
@@ -263,7 +319,9 @@ int annotate_routed_range(ka_engine* e, Device& d, int idx, RouteShared& sh, con
             TableView tab = e->geom;
             tab.sectors = d.table; tab.ovf = d.ovf; tab.my_shard = (uint32_t)idx;
             mark(5);
-            cuda_ok(launch_route_lookup(ln.r_recv, total_recv, tab, ln.r_ans_recv, st), "route lookup");
+            RouteAns none;
+            none.n_regions = 0;
+            cuda_ok(launch_route_lookup(ln.r_recv, total_recv, tab, ln.r_ans_recv, none, st), "route lookup");
             mark(6);
             d.launches += 1;
             // answers back to the requesters, in request order
@@ -283,6 +341,12 @@ int annotate_routed_range(ka_engine* e, Device& d, int idx, RouteShared& sh, con
             if (R.shp.n_mid) cuda_ok(launch_tiles_mode(R.am, 1, 2, R.smem_mid, st), "tally mid tiles");
             mark(9);
             d.launches += 1 + (R.shp.n_mid ? 1 : 0);
+            if (R.shp.n_long) {
+                // sequences beyond the tile sizes: the long-sequence kernel probes the shards through NVLink peer loads
+                cuda_ok(launch_big(R.ap, (int)std::min<uint64_t>(R.shp.n_long, (uint64_t)d.sm_count * 4), st), "long sequences");
+                d.launches += 1;
+            }
+            if (peer) cuda_ok(cudaEventRecord(ln.ev_tally, st), "event");
             cuda_ok(cudaMemcpyAsync(out_role + R.cs, p.role, R.n * 4, cudaMemcpyDeviceToHost, st), "D2H role");
             cuda_ok(cudaMemcpyAsync(out_hits + R.cs, p.hits, R.n * 4, cudaMemcpyDeviceToHost, st), "D2H hits");
             d.d2h += R.n * 8;

@@ -458,7 +458,7 @@ int db_load_impl(ka_engine* e, const uint8_t* kmers, const int32_t* role_ids, ui
         }
     }
     // communicators first: NCCL sets up its buffers before the table takes most of the HBM
-    if (e->table_mode == 2) { int nrc = route_init_comms(e); if (nrc) return nrc; }
+    if (e->table_mode == 2) { int nrc = route_init_comms(e); if (nrc) return nrc; }   // (table_mode 3 routes with peer stores: no NCCL)
     if (!choose_geometry(n, K, max_role, e->load_factor > 0 ? e->load_factor : 0.4, e->slot_bits == 16 ? 0 : e->slot_bits, n_shards, e->wide != 0, geom))
         return fail(e, KA_ERR_TOO_BIG, "ka_db_load: %llu k-mers (K=%d, max role %d) do not fit %s",
                     (unsigned long long)n, K, max_role, e->slot_bits ? "the forced slot width" : "any slot class of this build");

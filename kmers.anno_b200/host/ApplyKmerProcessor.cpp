@@ -34,7 +34,7 @@ int parseInt(const std::string& opt, const std::string& v) {
 }  // namespace
 
 void ApplyKmerProcessor::usage(std::ostream& os) {
-    os << "apply [--format VERIFY|APPLY] [-m|--min N] [--devices 0,1,..] [--table-mode 0|1|2] [--batch N] kmerdb.tbl roles.in.use gtoDir\n"
+    os << "apply [--format VERIFY|APPLY] [-m|--min N] [--devices 0,1,..] [--table-mode 0|1|2|3] [--batch N] kmerdb.tbl roles.in.use gtoDir\n"
           " kmerdb.tbl     discriminating kmer database\n"
           " roles.in.use   list of roles in use\n"
           " gtoDir         input genome directory\n"
@@ -70,7 +70,7 @@ bool ApplyKmerProcessor::parseCommand(const std::vector<std::string>& args) {
             else if (a == "--threads") loadThreads_ = parseInt(a, value());
             else if (a == "--table-mode") {
                 tableMode_ = parseInt(a, value());
-                if (tableMode_ < 0 || tableMode_ > 2) throw ParseFailureException("--table-mode must be 0 (replicated), 1 (sharded, peer loads) or 2 (sharded, NCCL routed).");
+                if (tableMode_ < 0 || tableMode_ > 3) throw ParseFailureException("--table-mode must be 0 (replicated), 1 (sharded, peer loads), 2 (sharded, NCCL routed) or 3 (sharded, routed by peer stores).");
             }
             else if (a == "--devices") {
                 devices_.clear();

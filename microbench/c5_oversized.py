@@ -21,48 +21,12 @@ from kmers_anno_b200.engine import pinned_array
 n_dev = int(sys.argv[1])
 n_keys = int(float(sys.argv[2])) if len(sys.argv) > 2 else int(1.2e10)
 n_prot = int(float(sys.argv[3])) if len(sys.argv) > 3 else 1_000_000
-modes = [int(m) for m in (sys.argv[4] if len(sys.argv) > 4 else "1,2").split(",")]
+modes = [int(m) for m in (sys.argv[4] if len(sys.argv) > 4 else "1,2,3").split(",")]
 K, n_roles, seed = 12, 30000, 20261018
 
-# ---- planted proteins (vectorised) ----
 t0 = time.time()
-rng = np.random.default_rng(5)
-h = rng.integers(1, 12, n_prot)                      # planted k-mers per protein
-role = rng.integers(0, n_roles, n_prot)
-ambiguous = (np.arange(n_prot) % 7) == 0
-n_seg = h + ambiguous                                # + one k-mer of another role
-seg_prot = np.repeat(np.arange(n_prot), n_seg)
-seg_first = np.concatenate([[0], np.cumsum(n_seg)])[:-1]
-is_extra = np.zeros(seg_prot.shape[0], bool)
-is_extra[(seg_first + n_seg - 1)[ambiguous]] = True
-seg_role = role[seg_prot].copy()
-seg_role[is_extra] = (seg_role[is_extra] + 1 + rng.integers(0, n_roles - 1, int(is_extra.sum()))) % n_roles
-lines_per_role = n_keys // n_roles
-seg_line = (seg_role + n_roles * rng.integers(0, lines_per_role, seg_prot.shape[0])).astype(np.uint64)
-seg_kmers, seg_roles_chk = synth.synthetic_db_lines(seg_line, K, n_roles, seed)
-assert np.array_equal(seg_roles_chk, seg_role.astype(np.int32))
-spacer = rng.integers(0, 60, seg_prot.shape[0])
-seg_len = K + spacer
-seg_start = np.concatenate([[0], np.cumsum(seg_len)])
-total = int(seg_start[-1])
-res = pinned_array(total, np.uint8)
-res[:] = np.frombuffer(b"ACDEFGHIKLMNPQRSTVWY", np.uint8)[rng.integers(0, 20, total)]
-pos = (seg_start[:-1, None] + np.arange(K)[None, :]).reshape(-1)
-res[pos] = seg_kmers.reshape(-1)
-off = pinned_array(n_prot + 1, np.uint64)
-off[:] = np.concatenate([[0], seg_start[1:][np.cumsum(n_seg) - 1]])
-# expectation: distinct planted k-mers of the protein's role (duplicate picks count once)
-key = np.zeros(seg_prot.shape[0], np.uint64)
-for j in range(K):
-    key = key * np.uint64(32) + seg_kmers[:, j].astype(np.uint64)
-order = np.lexsort((key, seg_prot))
-sp, sk = seg_prot[order], key[order]
-first = np.ones(sp.shape[0], bool)
-first[1:] = (sp[1:] != sp[:-1]) | (sk[1:] != sk[:-1])
-distinct = np.bincount(sp[first], minlength=n_prot)
-exp_hits = np.where(ambiguous, 0, distinct).astype(np.int32)
-exp_role = np.where(ambiguous | (distinct < 5), -1, role).astype(np.int32)
-probes = int(np.maximum((off[1:] - off[:-1]).astype(np.int64) - K + 1, 0).sum())
+res, off, exp_role, exp_hits, ambiguous, probes = synth.planted_batch(n_keys, n_prot, K, n_roles, seed, alloc=pinned_array)
+total = int(off[-1])
 print(f"[c5] {n_prot} planted proteins, {total/1e6:.1f} M residues, {probes/1e6:.1f} M probes, built in {time.time()-t0:.1f}s", flush=True)
 
 out = (pinned_array(n_prot, np.int32), pinned_array(n_prot, np.int32), pinned_array(n_prot, np.uint8))
@@ -70,6 +34,8 @@ results = {}
 for mode in modes:
     eng = ka.Engine(list(range(n_dev)))
     eng.set_option("table_mode", mode)
+    if os.environ.get("KA_C5_CHUNK"):
+        eng.set_option("chunk_residues", int(os.environ["KA_C5_CHUNK"]))
     t = time.time(); eng.db_load_synthetic(n_keys, K, n_roles, seed); tl = time.time() - t
     info = eng.db_info()
     best = 1e9
@@ -80,15 +46,15 @@ for mode in modes:
     results[mode] = tuple(a.copy() for a in out)
     role_ok = float((out[0] == exp_role).mean()); hits_ok = float((out[1] == exp_hits).mean())
     amb_ok = float((out[2][ambiguous] == 2).mean())
-    print(f"[c5] mode {mode} ({('', 'sharded / NVLink peer loads', 'sharded / NCCL all-to-all')[mode]}) on {n_dev} GPUs: "
+    print(f"[c5] mode {mode} ({('', 'sharded / NVLink peer loads', 'sharded / NCCL all-to-all', 'sharded / routed by peer stores')[mode]}) on {n_dev} GPUs: "
           f"{info['n_lines']:.3e} lines -> {info['n_keys']:.4e} keys, {info['slot_bits']}-bit slots, 2^{int(np.log2(info['n_buckets']))} sectors, "
           f"table {info['table_bytes']/1e9:.1f} GB total ({info['table_bytes']/1e9/n_dev:.1f} GB/GPU), load {tl:.1f}s | "
           f"annotate e2e {best:.1f} ms = {probes/best/1e6:.2f} G probes/s, {n_prot/best/1e3:.2f} M seq/s, kernel max {st['kernel_ms']:.1f} ms | "
           f"planted role match {role_ok:.6f}, hits match {hits_ok:.6f}, ambiguous flagged {amb_ok:.6f}", flush=True)
     eng.close()
-if len(results) == 2:
-    a, b = results[modes[0]], results[modes[1]]
-    same = all(np.array_equal(x, y) for x, y in zip(a, b))
-    print(f"[c5] modes {modes[0]} and {modes[1]} identical on all {n_prot} proteins: {same}", flush=True)
+if len(results) >= 2:
+    a = results[modes[0]]
+    same = all(np.array_equal(x, y) for m in modes[1:] for x, y in zip(a, results[m]))
+    print(f"[c5] modes {modes} identical on all {n_prot} proteins: {same}", flush=True)
     if not same:
         sys.exit(1)

@@ -166,7 +166,7 @@ def test_genes_copies_aliases_of_the_closest_feature(tmp_path):
         assert f"with {updates} updates" in r.stderr and updates > 20
 
 
-@pytest.mark.parametrize("mode", ["1", "2"])
+@pytest.mark.parametrize("mode", ["1", "2", "3"])
 def test_apply_with_a_sharded_table(tmp_path, mode):
     """`apply --devices 0,1 --table-mode 1|2`: the table sharded over two GPUs gives the same reports."""
     import kmers_anno_b200 as ka

@@ -303,11 +303,13 @@ def test_sharded_table_peer_loads(ka, oracle, slot_bits, lf, wide):
     assert_same(got, want, f"sharded table over {n_dev} GPUs slot_bits={slot_bits}")
 
 
+@pytest.mark.parametrize("mode", [2, 3])
 @pytest.mark.parametrize("slot_bits,lf,chunk,wide", [(0, 0.4, 32 << 20, 0), (32, 0.9, 300000, 0), (64, 0.9, 1 << 20, 0),
                                                      (0, 0.4, 32 << 20, 1), (32, 0.9, 300000, 1)])
-def test_routed_table_nccl_all_to_all(ka, oracle, slot_bits, lf, chunk, wide):
+def test_routed_table_nccl_all_to_all(ka, oracle, slot_bits, lf, chunk, wide, mode):
     """table_mode=2: same sharding, but the keys are routed to the owning GPU with NCCL send/recv
-    (all-to-all), probed there and the answers come back in request order."""
+    (all-to-all), probed there and the answers come back in request order.  table_mode=3: the same routing
+    with the exchanges fused into the scatter / lookup kernels as NVLink peer stores."""
     n_dev = 0
     for n in (8, 4, 2):
         try:
@@ -325,7 +327,7 @@ def test_routed_table_nccl_all_to_all(ka, oracle, slot_bits, lf, chunk, wide):
     # uneven ranges: a long tail of empty sequences gives the last device fewer rounds than the first
     off = np.concatenate([off, np.full(5000, off[-1], np.uint64)])
     with ka.Engine(list(range(n_dev))) as eng:
-        eng.set_option("table_mode", 2)
+        eng.set_option("table_mode", mode)
         eng.set_option("wide", wide)
         eng.set_option("slot_bits", slot_bits)
         eng.set_option("load_factor", lf)
@@ -333,12 +335,17 @@ def test_routed_table_nccl_all_to_all(ka, oracle, slot_bits, lf, chunk, wide):
         eng.db_load(kmers, roles, 8)
         got = eng.annotate(res, off, 5)
         got2 = eng.annotate(res, off, 1)
-        with pytest.raises(ka.KmerAnnoError):           # longer than mid_seq: rejected in this mode, no hang
-            eng.annotate(np.full(9000, 65, np.uint8), np.asarray([0, 9000], np.uint64), 5)
+        # sequences longer than mid_seq (the reference annotates proteins of any length): their keys are not routed, the
+        # long-sequence kernel reads the shards through peer loads
+        lres = np.concatenate([res[: int(off[40])], res[: int(off[120])], res[: int(off[3])]])
+        loff = np.asarray([0, int(off[40]), int(off[40]) + int(off[120]), len(lres)], np.uint64)
+        assert int(off[120]) > 8192
+        glong = eng.annotate(lres, loff, 5)
         again = eng.annotate(res, off, 5)               # the engine stays usable
     want = oracle.OracleDb(kmers, roles, 8, threads=8).apply(res, off, 5, threads=8)
     assert_same(got, want, f"routed table over {n_dev} GPUs slot_bits={slot_bits}")
     assert_same(again, want, "routed table, second call")
+    assert_same(glong, oracle.OracleDb(kmers, roles, 8, threads=8).apply(lres, loff, 5, threads=8), "routed table, long sequences")
     assert_same(got2, oracle.OracleDb(kmers, roles, 8, threads=8).apply(res, off, 1, threads=8), "routed, min_hits 1")
 
 
@@ -387,7 +394,7 @@ def test_synthetic_db_matches_host_lines(ka, oracle, K, n, n_roles, opts):
         assert set(np.unique(got[2])) >= {1, 2}
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 def test_synthetic_db_sharded(ka, oracle, mode):
     """The oversized-table path at test size: device-generated lines, sharded wide table."""
     n_dev = 0
