@@ -612,28 +612,10 @@ static int annotate_impl(ka_engine* e, const BatchIn& in, uint64_t N, int32_t mi
     int rc;
     if (e->db_table_mode >= 2) {
         if ((e->db_table_mode == 2 && !e->nccl_ready) || e->geom.n_shards <= 1) return fail(e, KA_ERR_INVALID, "%s: the loaded table is not a routed table", who);
-        // the key-extraction kernels of the routed path read residue bytes: a packed batch is expanded on the host
-        // first (the routed table is the capacity configuration, not the ingest-bound one)
-        std::vector<uint8_t> bytes;
-        std::vector<uint64_t> off64;
-        const uint8_t* residues = in.residues;
-        const uint64_t* offsets = in.off64;
-        if (in.packed()) {
-            const uint64_t r0 = in.off(0), r1 = in.off(N);
-            bytes.resize(r1);
-            off64.resize(N + 1);
-            for (uint64_t i = 0; i <= N; i++) off64[i] = in.off32[i];
-            for (uint64_t r = r0; r < r1; r++) {
-                const uint64_t bit = 5 * r;
-                const uint32_t two = (uint32_t)in.codes[bit >> 3] | ((uint32_t)in.codes[(bit >> 3) + 1] << 8);   // (the stream has slack bytes)
-                bytes[r] = e->inv32[(two >> (bit & 7)) & 31u];
-            }
-            residues = bytes.data(); offsets = off64.data();
-        }
         // routed sharded table: every device must walk every round, even with an empty range
         RouteShared shared((int)nd);
         rc = for_each_device(e, [&](Device& d, int i) {
-            return annotate_routed_range(e, d, i, shared, residues, offsets, cut[i], cut[i + 1], min_hits, out_role, out_hits, out_flag);
+            return annotate_routed_range(e, d, i, shared, in, cut[i], cut[i + 1], min_hits, out_role, out_hits, out_flag);
         });
     } else {
         rc = for_each_device(e, [&](Device& d, int i) {

@@ -240,8 +240,8 @@ struct RouteShared {
 
 int route_init_comms(ka_engine* e);      // dlopen libnccl, one communicator per device (idempotent)
 void route_destroy_comm(Device& d);
-int annotate_routed_range(ka_engine* e, Device& d, int idx, RouteShared& sh, const uint8_t* residues,
-                          const uint64_t* offsets, uint64_t s_begin, uint64_t s_end, int32_t min_hits,
+int annotate_routed_range(ka_engine* e, Device& d, int idx, RouteShared& sh, const BatchIn& in,
+                          uint64_t s_begin, uint64_t s_end, int32_t min_hits,
                           int32_t* out_role, int32_t* out_hits, uint8_t* out_flag);
 
 template <typename F>

@@ -262,7 +262,7 @@ size_t tile_smem_bytes(uint32_t ext_max, uint32_t* res_bytes_out, bool wide) {
 template <int CLS, int C, int THREADS, int MINB, int MODE = 0, bool WIDE = false, bool PACKED = false>
 __global__ void __launch_bounds__(THREADS, MINB) tile_kernel(AnnotParams p) {
     static_assert(!WIDE || CLS != 128, "wide tables are quotiented");
-    static_assert(!PACKED || (MODE == 0 && !WIDE), "packed staging: plain probe kernels only");
+    static_assert(!PACKED || !(MODE == 0 && WIDE), "packed staging: narrow probe kernels and the routed extract / tally kernels");
     typedef typename std::conditional<WIDE, unsigned long long, uint32_t>::type tok_t;
     typedef typename std::conditional<WIDE, unsigned long long, typename rem_type<CLS>::type>::type rem_t;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -535,14 +535,19 @@ cudaError_t launch_tiles_mode(const AnnotParams& p, int variant, int mode, size_
     if (p.n_tiles == 0) return cudaSuccess;
     if (p.tab.cls == 128) return cudaErrorInvalidValue;   // routed and wide tables are quotiented
     if (variant > 1) variant = 1;                          // shapes 0 (4 x 128) and 1 (4 x 256)
+    const bool packed = p.pk != nullptr && mode != 0;      // routed extract / tally kernels stage the 5-bit stream
 #define KA_MODE_LAUNCH(CLS, W)                                                                          \
     if (variant == 0) {                                                                                 \
         if (mode == 0)      tile_kernel<CLS, 4, 128, 6, 0, W><<<p.n_tiles, 128, smem, st>>>(p);          \
+        else if (mode == 1 && packed) tile_kernel<CLS, 4, 128, 6, 1, W, true><<<p.n_tiles, 128, smem, st>>>(p);  \
         else if (mode == 1) tile_kernel<CLS, 4, 128, 6, 1, W><<<p.n_tiles, 128, smem, st>>>(p);          \
+        else if (packed)    tile_kernel<CLS, 4, 128, 6, 2, W, true><<<p.n_tiles, 128, smem, st>>>(p);    \
         else                tile_kernel<CLS, 4, 128, 6, 2, W><<<p.n_tiles, 128, smem, st>>>(p);          \
     } else {                                                                                            \
         if (mode == 0)      tile_kernel<CLS, 4, 256, 3, 0, W><<<p.n_tiles, 256, smem, st>>>(p);          \
+        else if (mode == 1 && packed) tile_kernel<CLS, 4, 256, 3, 1, W, true><<<p.n_tiles, 256, smem, st>>>(p);  \
         else if (mode == 1) tile_kernel<CLS, 4, 256, 3, 1, W><<<p.n_tiles, 256, smem, st>>>(p);          \
+        else if (packed)    tile_kernel<CLS, 4, 256, 3, 2, W, true><<<p.n_tiles, 256, smem, st>>>(p);    \
         else                tile_kernel<CLS, 4, 256, 3, 2, W><<<p.n_tiles, 256, smem, st>>>(p);          \
     }
     if (p.tab.wide) { if (p.tab.cls == 32) { KA_MODE_LAUNCH(32, true) } else { KA_MODE_LAUNCH(64, true) } }
@@ -559,7 +564,9 @@ cudaError_t tile_kernel_mode_set_smem(size_t bytes) {
 #define KA_MODE_ATTR6(CLS, W)                                                                   \
     KA_MODE_ATTR((tile_kernel<CLS, 4, 128, 6, 0, W>)) KA_MODE_ATTR((tile_kernel<CLS, 4, 256, 3, 0, W>))   \
     KA_MODE_ATTR((tile_kernel<CLS, 4, 128, 6, 1, W>)) KA_MODE_ATTR((tile_kernel<CLS, 4, 256, 3, 1, W>))   \
-    KA_MODE_ATTR((tile_kernel<CLS, 4, 128, 6, 2, W>)) KA_MODE_ATTR((tile_kernel<CLS, 4, 256, 3, 2, W>))
+    KA_MODE_ATTR((tile_kernel<CLS, 4, 128, 6, 2, W>)) KA_MODE_ATTR((tile_kernel<CLS, 4, 256, 3, 2, W>))   \
+    KA_MODE_ATTR((tile_kernel<CLS, 4, 128, 6, 1, W, true>)) KA_MODE_ATTR((tile_kernel<CLS, 4, 256, 3, 1, W, true>))   \
+    KA_MODE_ATTR((tile_kernel<CLS, 4, 128, 6, 2, W, true>)) KA_MODE_ATTR((tile_kernel<CLS, 4, 256, 3, 2, W, true>))
     KA_MODE_ATTR6(32, false) KA_MODE_ATTR6(64, false) KA_MODE_ATTR6(32, true) KA_MODE_ATTR6(64, true)
 #undef KA_MODE_ATTR6
 #undef KA_MODE_ATTR
@@ -602,30 +609,33 @@ cudaError_t launch_route_count(const unsigned long long* keys, unsigned long lon
     return cudaGetLastError();
 }
 
-// One CTA buckets a tile of 256 x 16 keys: owners are counted with ballots into shared memory,
-// ONE global atomicAdd per owner and CTA reserves the output ranges, then every warp writes its
-// keys at (range + rank inside the CTA).
+// One CTA buckets a tile of 256 x 16 keys.  __match_any_sync groups the lanes of a warp by owner in one
+// instruction whatever the number of shards: the lowest lane of a group adds the group's size to the warp's
+// shared-memory count of that owner; ONE global atomicAdd per owner and CTA reserves the output ranges; then
+// every lane writes its key at (range of its warp + keys of earlier rounds + rank inside its group).
 __global__ void __launch_bounds__(256) route_scatter_kernel(const unsigned long long* __restrict__ keys, unsigned long long n,
                                      TableView tab, const unsigned long long* __restrict__ offsets,
                                      unsigned long long* cursor, RouteDst dst, uint32_t* slot_of_pos) {
-    constexpr int PER = 16;                       // keys per thread, strided by 256 inside the tile
+    constexpr int PER = 16;                       // keys per thread, strided by 32 inside the warp's part of the tile
     __shared__ uint32_t s_cnt[8][8];              // [warp][owner]
-    __shared__ unsigned long long s_base[8][8];   // [warp][owner] first output index
+    __shared__ unsigned long long s_base[8][8];   // [warp][owner] next output index
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
     const unsigned long long tile = 256ull * PER;
     for (unsigned long long t0 = (unsigned long long)blockIdx.x * tile; t0 < n; t0 += (unsigned long long)gridDim.x * tile) {
         unsigned long long m[PER];
         uint32_t own[PER];
-        uint32_t wcnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (lane < 8) s_cnt[warp][lane] = 0;
+        __syncwarp();
 #pragma unroll
         for (int k = 0; k < PER; k++) {
             // a warp reads 32 consecutive keys at a time: ranks follow the position order inside a warp
             const unsigned long long i = t0 + (unsigned long long)warp * (32 * PER) + k * 32 + lane;
             m[k] = i < n ? keys[i] : ROUTE_INVALID;
             own[k] = m[k] == ROUTE_INVALID ? 0xffffffffu : route_owner(tab, m[k]);
-            for (uint32_t o = 0; o < tab.n_shards; o++) wcnt[o] += __popc(__ballot_sync(0xffffffffu, own[k] == o));
+            const unsigned grp = __match_any_sync(0xffffffffu, own[k]);
+            if (own[k] != 0xffffffffu && (grp & lt) == 0u) atomicAdd(&s_cnt[warp][own[k]], (uint32_t)__popc(grp));
         }
-        if (lane < 8) s_cnt[warp][lane] = wcnt[lane];
         __syncthreads();
         if (threadIdx.x < 8) {
             const uint32_t o = threadIdx.x;
@@ -636,19 +646,23 @@ __global__ void __launch_bounds__(256) route_scatter_kernel(const unsigned long 
             for (int w = 0; w < 8; w++) { s_base[w][o] = base; base += s_cnt[w][o]; }
         }
         __syncthreads();
-        uint32_t done[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
         for (int k = 0; k < PER; k++) {
             const unsigned long long i = t0 + (unsigned long long)warp * (32 * PER) + k * 32 + lane;
-            for (uint32_t o = 0; o < tab.n_shards; o++) {
-                const unsigned b = __ballot_sync(0xffffffffu, own[k] == o);
-                if (own[k] == o) {
-                    const unsigned long long w = s_base[warp][o] + done[o] + __popc(b & ((1u << lane) - 1));
-                    dst.p[o][w] = m[k];                // the local send buffer, or straight into the owner's receive buffer (NVLink store)
-                    slot_of_pos[i] = (uint32_t)w;      // answers come back in send order: position i reads slot w
-                }
-                done[o] += __popc(b);
+            const unsigned grp = __match_any_sync(0xffffffffu, own[k]);
+            const int leader = __ffs(grp) - 1;
+            unsigned long long first = 0;
+            if (own[k] != 0xffffffffu && (int)lane == leader) {
+                first = s_base[warp][own[k]];
+                s_base[warp][own[k]] = first + (unsigned)__popc(grp);
             }
+            first = __shfl_sync(grp, first, leader);
+            if (own[k] != 0xffffffffu) {
+                const unsigned long long w = first + (unsigned)__popc(grp & lt);
+                dst.p[own[k]][w] = m[k];           // the local send buffer, or straight into the owner's receive buffer (NVLink store)
+                slot_of_pos[i] = (uint32_t)w;      // answers come back in send order: position i reads slot w
+            }
+            __syncwarp();
         }
         __syncthreads();
     }

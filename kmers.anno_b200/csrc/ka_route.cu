@@ -118,19 +118,20 @@ int route_reserve(Device& dev, Device::RouteLane& d, size_t n_pos, size_t n_recv
 // point-to-point calls always match.  A failure on one device is remembered but the device keeps
 // taking part with empty rounds: nobody is left waiting in a collective.
 // KA_ROUTE_SERIAL=1 runs one lane with a sync per round (and KA_ROUTE_TRACE=1 then prints the phases).
-int annotate_routed_range(ka_engine* e, Device& d, int idx, RouteShared& sh, const uint8_t* residues,
-                          const uint64_t* offsets, uint64_t s_begin, uint64_t s_end, int32_t min_hits,
+int annotate_routed_range(ka_engine* e, Device& d, int idx, RouteShared& sh, const BatchIn& bin,
+                          uint64_t s_begin, uint64_t s_end, int32_t min_hits,
                           int32_t* out_role, int32_t* out_hits, uint8_t* out_flag) {
     const int nd = (int)e->devs.size();
     cudaSetDevice(d.id);
     d.kernel_ms = d.tile_ms = 0; d.launches = 0; d.h2d = d.d2h = 0; d.probes = 0;
     d.err = KA_OK; d.errmsg.clear();
-    BatchIn bin;
-    bin.residues = residues; bin.off64 = offsets;
+    const bool packed = bin.packed();
     std::vector<std::pair<uint64_t, uint64_t>> chunks;
     for (uint64_t cs = s_begin; cs < s_end;) {
-        uint64_t lim = offsets[cs] + e->chunk_residues;
-        uint64_t ce = std::upper_bound(offsets + cs + 1, offsets + s_end + 1, lim) - offsets - 1;
+        const uint64_t lim = bin.off(cs) + e->chunk_residues;
+        uint64_t lo = cs + 1, hi = s_end + 1;            // last sequence boundary at or below the limit
+        while (lo < hi) { const uint64_t mid = lo + ((hi - lo) >> 1); if (bin.off(mid) <= lim) lo = mid + 1; else hi = mid; }
+        uint64_t ce = lo - 1;
         if (ce <= cs) ce = cs + 1;
         chunks.push_back({cs, ce});
         cs = ce;
@@ -182,15 +183,28 @@ int annotate_routed_range(ka_engine* e, Device& d, int idx, RouteShared& sh, con
         }
         if (R.has) {
             d.probes += R.shp.probes;
-            if (pipe_reserve(d, p, R.shp.n_res, R.n, R.shp.n_res / e->tile_span + 1, R.shp.n_long, R.shp.long_res, R.shp.n_mid, e->geom.wide != 0, true, false) ||
+            if (pipe_reserve(d, p, R.shp.n_res, R.n, R.shp.n_res / e->tile_span + 1, R.shp.n_long, R.shp.long_res, R.shp.n_mid, e->geom.wide != 0, !packed || R.shp.n_long, packed) ||
                 route_reserve(d, ln, R.shp.n_res + 64, 0)) R.has = false;
         }
         if (ln.h_cnt) memset(ln.h_cnt, 0, 64);
         if (R.has) {
-            if (R.shp.n_res) cuda_ok(cudaMemcpyAsync(p.res, residues + offsets[R.cs], R.shp.n_res, cudaMemcpyHostToDevice, st), "H2D residues");
-            cuda_ok(cudaMemcpyAsync(p.off, offsets + R.cs, (R.n + 1) * 8, cudaMemcpyHostToDevice, st), "H2D offsets");
-            d.h2d += R.shp.n_res + (R.n + 1) * 8;
-            fill_params(e, d, p, offsets[R.cs], R.shp.n_res, R.n, min_hits, R.ap);
+            const uint64_t r_begin = bin.off(R.cs), r_end = bin.off(R.ce);
+            const uint64_t origin = r_begin & ~127ull;
+            if (packed) {
+                // the extract and tally kernels stage the 5-bit stream themselves; the long-sequence kernel reads bytes
+                const uint64_t byte0 = origin * 5 / 8, byte1 = (r_end * 5 + 7) / 8;
+                if (byte1 > byte0) cuda_ok(cudaMemcpyAsync(p.pk, bin.codes + byte0, byte1 - byte0, cudaMemcpyHostToDevice, st), "H2D codes");
+                cuda_ok(cudaMemcpyAsync(p.off32_in, bin.off32 + R.cs, (R.n + 1) * 4, cudaMemcpyHostToDevice, st), "H2D offsets");
+                cuda_ok(launch_widen_offsets(p.off32_in, R.n + 1, p.off, st), "widen offsets");
+                if (R.shp.n_long) cuda_ok(launch_unpack(p.pk, (uint32_t)(r_begin - origin), R.shp.n_res, d.inv32, p.res, st), "unpack");
+                d.h2d += (byte1 - byte0) + (R.n + 1) * 4;
+            } else {
+                if (R.shp.n_res) cuda_ok(cudaMemcpyAsync(p.res, bin.residues + r_begin, R.shp.n_res, cudaMemcpyHostToDevice, st), "H2D residues");
+                cuda_ok(cudaMemcpyAsync(p.off, bin.off64 + R.cs, (R.n + 1) * 8, cudaMemcpyHostToDevice, st), "H2D offsets");
+                d.h2d += R.shp.n_res + (R.n + 1) * 8;
+            }
+            fill_params(e, d, p, r_begin, R.shp.n_res, R.n, min_hits, R.ap);
+            if (packed) { R.ap.pk = p.pk; R.ap.pk_lead = (uint32_t)(r_begin - origin); }
             R.ap.route_keys = ln.r_keys;
             R.ap.route_ans = ln.r_ans_sorted;
             R.ap.route_slot = ln.r_pos;

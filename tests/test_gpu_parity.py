@@ -342,10 +342,17 @@ def test_routed_table_nccl_all_to_all(ka, oracle, slot_bits, lf, chunk, wide, mo
         assert int(off[120]) > 8192
         glong = eng.annotate(lres, loff, 5)
         again = eng.annotate(res, off, 5)               # the engine stays usable
+        # the packed input form: the extract and tally kernels stage the 5-bit stream themselves
+        codes, off32 = eng.pack(res, off)
+        gpacked = eng.annotate_packed(codes, off32, 5)
+        lcodes, loff32 = eng.pack(lres, loff)
+        glong_packed = eng.annotate_packed(lcodes, loff32, 5)
     want = oracle.OracleDb(kmers, roles, 8, threads=8).apply(res, off, 5, threads=8)
     assert_same(got, want, f"routed table over {n_dev} GPUs slot_bits={slot_bits}")
     assert_same(again, want, "routed table, second call")
     assert_same(glong, oracle.OracleDb(kmers, roles, 8, threads=8).apply(lres, loff, 5, threads=8), "routed table, long sequences")
+    assert_same(gpacked, want, "routed table, packed input")
+    assert_same(glong_packed, glong, "routed table, long sequences, packed input")
     assert_same(got2, oracle.OracleDb(kmers, roles, 8, threads=8).apply(res, off, 1, threads=8), "routed, min_hits 1")
 
 
