@@ -95,6 +95,7 @@ def parse():
     ap.add_argument("--no-cpu-best", action="store_true", help="skip the packed-integer 'best CPU' line")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cli", action="store_true", help="skip the file-to-report run of the C++ apply command and the build record")
+    ap.add_argument("--no-ingest-via", action="store_true", help="N >= 4: do not re-route the H2D copies of ranks with a slow host path")
     ap.add_argument("--no-multi", action="store_true", help="N > 1: skip the one-engine-over-N-devices records")
     ap.add_argument("--c5-keys-per-gpu", type=float, default=1.5e9, help="lines of the sharded config-5 table per GPU")
     ap.add_argument("--c5-proteins-per-gpu", type=int, default=125000)
@@ -528,6 +529,38 @@ def main():
     total_seq = sum_over_ranks(float(n_seq))
     total_probes = sum_over_ranks(float(probes))
 
+    # ---- ingest paths: on some boxes a group of GPUs shares a slower host path (microbench/pcie_concurrent.py) ----
+    ingest = None
+    if dist and world >= 4 and not a.no_e2e and not a.no_ingest_via:
+        import torch
+        hbuf = torch.empty(256 << 20, dtype=torch.uint8, pin_memory=True)
+        dbuf = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
+        dbuf.copy_(hbuf, non_blocking=True)
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(4):
+            dbuf.copy_(hbuf, non_blocking=True)
+        torch.cuda.synchronize()
+        rate = 4 * hbuf.numel() / (time.perf_counter() - t0) / 1e9
+        rates = [torch.zeros(1, dtype=torch.float64, device=f"cuda:{local}") for _ in range(world)]
+        dist.all_gather(rates, torch.tensor([rate], dtype=torch.float64, device=f"cuda:{local}"))
+        rates = [float(r.item()) for r in rates]
+        del hbuf, dbuf
+        # ranks whose concurrent H2D rate is well below the best land their batches on a fast rank's GPU
+        # (its PCIe path) and forward them over NVLink: engine option "ingest_via"
+        best = max(rates)
+        slow = sorted([r for r in range(world) if rates[r] < 0.8 * best], key=lambda r: rates[r])
+        fast = sorted([r for r in range(world) if rates[r] >= 0.8 * best], key=lambda r: -rates[r])
+        via = {}
+        if slow and len(slow) <= len(fast):
+            via = {s: f for s, f in zip(slow, fast)}
+        if rank in via:
+            eng.set_option("ingest_via", via[rank])
+        ingest = {"concurrent_h2d_GBps_per_rank": [round(r, 1) for r in rates], "ingest_via": {str(k): v for k, v in via.items()},
+                  "note": "256 MiB pinned copies on all ranks at once; a rank below 80 % of the best rate sends its H2D copies through "
+                          "the GPU of a fast rank and on over NVLink (ka_set_option ingest_via)"}
+
     # ---- e2e loops: the public calls with pinned host buffers -----------------------------
     e2e = e2e_bytes = host_pack = None
     codes = off32 = None
@@ -666,7 +699,7 @@ def main():
                        "table_keys": int(info["n_keys"]), "parallelism": f"replicated table, {world} shard(s)",
                        "l2": "table (>> 126 MB L2) probed at random and batch residues > L2: no flush needed",
                        "setup_s": round(t_setup, 1), "host_affinity": numa},
-            "e2e": e2e, "e2e_bytes": e2e_bytes, "host_pack": host_pack, "gpu_launches": int(launches) * world, "clocks": clocks,
+            "e2e": e2e, "e2e_bytes": e2e_bytes, "host_pack": host_pack, "ingest_paths": ingest, "gpu_launches": int(launches) * world, "clocks": clocks,
             "roofline": roofline, "rand_roofline": rand, "cpu_baseline": cpu, "c2_single_proteome": c2,
         }
         if cli:

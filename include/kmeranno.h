@@ -84,6 +84,10 @@ const char* ka_last_error(const ka_engine* e);
  *                   most 25 bits); 0 (default) = the narrowest sector class that holds the DB
  *   "filter"        line table only: 1 (default) = probe the L2-resident presence filter first, 0 = always read
  *                   the table (measurement knob)
+ *   "ingest_via"    single-device engines: CUDA device id whose PCIe path carries the H2D copies of ka_annotate /
+ *                   ka_annotate_packed (the chunk lands in a staging buffer there and crosses NVLink to the engine's
+ *                   GPU); -1 (default) = the engine's own path.  For boxes where some GPUs share a slower host path
+ *                   (microbench/pcie_concurrent.py; bench.py probes and pairs the ranks at N = 8)
  *   "resident_packed" 1 (default) = ka_batch_upload keeps the batch as the 5-bit stream where the tile kernels can stage
  *                   it (what ka_annotate_packed ships), 0 = as residue bytes (measurement knob)
  *   "table_mode"    0 = table replicated on every device (default); 1 = table sharded by sector range

@@ -64,6 +64,12 @@ void pipe_free(Pipe& p) {
     if (p.ev_k1) cudaEventDestroy(p.ev_k1);
     if (p.done) cudaEventDestroy(p.done);
     if (p.st) cudaStreamDestroy(p.st);
+    if (p.via_buf || p.via_st || p.via_ev) {
+        // (allocated on the via device; cudaFree / destroy work from any current device)
+        if (p.via_buf) cudaFree(p.via_buf);
+        if (p.via_st) cudaStreamDestroy(p.via_st);
+        if (p.via_ev) cudaEventDestroy(p.via_ev);
+    }
     p = Pipe();
 }
 
@@ -323,6 +329,36 @@ int enqueue_line_kernels(ka_engine* e, Device& d, Pipe& p, const LineParams& lp,
     return KA_OK;
 }
 
+// Host -> device copy of a chunk, directly or through the via device: H2D into a staging buffer on the via GPU
+// (its PCIe path), then a peer copy over NVLink on the pipe's stream.
+static int h2d_chunk(ka_engine* e, Device& d, Pipe& p, void* dst, const void* src, size_t bytes) {
+    if (bytes == 0) return KA_OK;
+    if (e->ingest_via < 0 || e->ingest_via == d.id) {
+        DCK(d, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, p.st));
+        return KA_OK;
+    }
+    const int via = e->ingest_via;
+    if (!p.via_st || bytes > p.via_cap) {
+        DCK(d, cudaSetDevice(via));
+        if (!p.via_st) { DCK(d, cudaStreamCreateWithFlags(&p.via_st, cudaStreamNonBlocking)); DCK(d, cudaEventCreateWithFlags(&p.via_ev, cudaEventDisableTiming)); }
+        if (bytes > p.via_cap) {
+            if (p.via_buf) cudaFree(p.via_buf);
+            p.via_buf = nullptr; p.via_cap = 0;
+            const size_t want = bytes + bytes / 8 + 4096;
+            cudaError_t ce = cudaMalloc((void**)&p.via_buf, want);
+            if (ce != cudaSuccess) { cudaSetDevice(d.id); return dev_fail(d, KA_ERR_OOM, "ingest_via staging buffer", ce); }
+            p.via_cap = want;
+        }
+        DCK(d, cudaSetDevice(d.id));
+    }
+    // (the staging buffer of this pipe is free: the pipe's previous chunk has completed, see p.busy)
+    DCK(d, cudaMemcpyAsync(p.via_buf, src, bytes, cudaMemcpyHostToDevice, p.via_st));
+    DCK(d, cudaEventRecord(p.via_ev, p.via_st));
+    DCK(d, cudaStreamWaitEvent(p.st, p.via_ev, 0));
+    DCK(d, cudaMemcpyPeerAsync(dst, d.id, p.via_buf, via, bytes, p.st));
+    return KA_OK;
+}
+
 template <typename OffT>
 static uint64_t chunk_end(const OffT* off, uint64_t cs, uint64_t s_end, uint64_t chunk_residues) {
     const uint64_t lim = (uint64_t)off[cs] + chunk_residues;
@@ -379,13 +415,11 @@ int annotate_range(ka_engine* e, Device& d, const BatchIn& in, uint64_t s_begin,
         const uint32_t lead = (uint32_t)(r_begin - origin);
         if (packed) {
             const uint64_t byte0 = origin * 5 / 8, byte1 = (r_end * 5 + 7) / 8;
-            if (byte1 > byte0)
-                DCK(d, cudaMemcpyAsync(p.pk, in.codes + byte0, byte1 - byte0, cudaMemcpyHostToDevice, p.st));
+            if ((rc = h2d_chunk(e, d, p, p.pk, in.codes + byte0, byte1 - byte0))) return rc;
             DCK(d, cudaMemcpyAsync(p.off32_in, in.off32 + cs, (n + 1) * 4, cudaMemcpyHostToDevice, p.st));
             d.h2d += (byte1 - byte0) + (n + 1) * 4;
         } else {
-            if (sh.n_res)
-                DCK(d, cudaMemcpyAsync(p.res, in.residues + r_begin, sh.n_res, cudaMemcpyHostToDevice, p.st));
+            if ((rc = h2d_chunk(e, d, p, p.res, in.residues + r_begin, sh.n_res))) return rc;
             DCK(d, cudaMemcpyAsync(p.off, in.off64 + cs, (n + 1) * 8, cudaMemcpyHostToDevice, p.st));
             d.h2d += sh.n_res + (n + 1) * 8;
         }
@@ -532,7 +566,7 @@ int ka_set_option(ka_engine* e, const char* name, double v) {
     uint32_t tile_span = e->tile_span, long_seq = e->long_seq, mid_seq = e->mid_seq;
     uint64_t chunk_residues = e->chunk_residues;
     int l2_persist = e->l2_persist, table_mode = e->table_mode, wide = e->wide, filter = e->filter, slot_bits = e->slot_bits;
-    int resident_packed = e->resident_packed;
+    int resident_packed = e->resident_packed, ingest_via = e->ingest_via;
     if (n == "load_factor") {
         if (!(v > 0.0 && v <= 0.9)) return fail(e, KA_ERR_INVALID, "load_factor must be in (0, 0.9]");
         load_factor = v;
@@ -562,6 +596,21 @@ int ka_set_option(ka_engine* e, const char* name, double v) {
         filter = v != 0;
     } else if (n == "resident_packed") {
         resident_packed = v != 0;
+    } else if (n == "ingest_via") {
+        int count = 0;
+        cudaGetDeviceCount(&count);
+        if (v != -1 && !(v >= 0 && v < count && v == (int)v)) return fail(e, KA_ERR_INVALID, "ingest_via must be -1 or a CUDA device id");
+        if (v >= 0 && e->devs.size() != 1) return fail(e, KA_ERR_INVALID, "ingest_via applies to a single-device engine");
+        if (v >= 0 && (int)v != e->devs[0].id) {
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, e->devs[0].id, (int)v);
+            if (!can) return fail(e, KA_ERR_NO_DEVICE, "ingest_via: device %d cannot reach device %d over NVLink / P2P", e->devs[0].id, (int)v);
+            cudaSetDevice(e->devs[0].id);
+            cudaError_t pe = cudaDeviceEnablePeerAccess((int)v, 0);
+            if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) return fail(e, KA_ERR_CUDA, "ingest_via: cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(pe));
+            cudaGetLastError();
+        }
+        ingest_via = (int)v;
     } else if (n == "slot_bits") {
         if (v != 0 && v != 16 && v != 32 && v != 64 && v != 128) return fail(e, KA_ERR_INVALID, "slot_bits must be 0, 16, 32, 64 or 128");
         slot_bits = (int)v;
@@ -574,7 +623,7 @@ int ka_set_option(ka_engine* e, const char* name, double v) {
         return fail(e, KA_ERR_INVALID, "tile_span + long_seq (or mid_seq) needs more than 227 KB of shared memory");
     e->load_factor = load_factor; e->tile_span = tile_span; e->long_seq = long_seq; e->mid_seq = mid_seq;
     e->chunk_residues = chunk_residues; e->l2_persist = l2_persist; e->table_mode = table_mode; e->wide = wide;
-    e->filter = filter; e->slot_bits = slot_bits; e->resident_packed = resident_packed;
+    e->filter = filter; e->slot_bits = slot_bits; e->resident_packed = resident_packed; e->ingest_via = ingest_via;
     return KA_OK;
 }
 

@@ -47,6 +47,10 @@ struct Pipe {
     uint32_t* scratch = nullptr; size_t scratch_cap = 0;
     cudaEvent_t ev_k0 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_k1 = nullptr, done = nullptr;
     bool busy = false;
+    // option "ingest_via": the chunk lands on another GPU with a faster host path and crosses NVLink from there
+    uint8_t* via_buf = nullptr; size_t via_cap = 0;      // staging buffer ON the via device
+    cudaStream_t via_st = nullptr;                       // stream on the via device
+    cudaEvent_t via_ev = nullptr;
 };
 
 struct Device {
@@ -106,6 +110,7 @@ struct ka_engine {
     int l2_persist = 1;
     int slot_bits = 0;  // 0 = choose automatically; 16 = the 128-byte-line table (ka_line.cuh)
     int filter = 1;     // line table: 1 = L2-resident presence filter in front of it (measurement knob)
+    int ingest_via = -1;      // CUDA device id whose PCIe path carries the H2D copies of a single-device engine (-1 = its own)
     int resident_packed = 1;  // resident batches of narrow sector tables are kept as the 5-bit stream (measurement knob)
     int table_mode = 0; // next ka_db_load: 0 = replicated, 1 = sharded by sector range (peer loads), 2 = sharded + NCCL routing
     int wide = 0;       // next ka_db_load: 1 = force the wide-table kernels (64-bit sector indices and tokens)
