@@ -313,9 +313,11 @@ __global__ void __launch_bounds__(LT_THREADS, KA_LT_MINB) line_tile_kernel(LineP
         __syncthreads();
         if (nbytes) { mbar_wait(&s_bar, parity); parity ^= 1; }
 
-        // this warp's quarter of the positions
-        const uint32_t wq = (ext + LT_WARPS - 1) / LT_WARPS;
-        const uint32_t wbeg = min(ext, warp * wq), wend = min(ext, wbeg + wq);
+        // The positions are cut into equal passes of at most 32 * A, a multiple of the warp count of them, dealt
+        // round-robin to the warps: every warp samples the whole tile, so sequences with many hits (family members)
+        // and sequences with none spread over all warps instead of loading one of them.
+        const uint32_t n_pass = LT_WARPS * ((ext + LT_WARPS * 32 * A - 1) / (LT_WARPS * 32 * A));
+        const uint32_t plen = (ext + n_pass - 1) / n_pass;              // <= 32 * A
         uint32_t qn = 0;                                                // queue fill (warp-uniform)
 
         uint32_t q2n = 0;                                               // second-stage queue fill (warp-uniform)
@@ -419,9 +421,9 @@ __global__ void __launch_bounds__(LT_THREADS, KA_LT_MINB) line_tile_kernel(LineP
                 if (32u * k < count) consume(e[k], sa[k], sb2[k], lane + 32u * k < count);
         };
 
-        for (uint32_t pb = wbeg; pb < wend; pb += 32 * A) {
+        for (uint32_t pb = warp * plen; pb < ext; pb += LT_WARPS * plen) {
             // ---- phase A: keys + filter for a run of <= A positions per lane ----
-            const uint32_t pend = min(wend, pb + 32 * A);
+            const uint32_t pend = min(ext, pb + plen);
             const uint32_t run = (pend - pb + 31) >> 5;                 // <= A
             const uint32_t P0 = pb + lane * run;
             const uint32_t nrun = P0 < pend ? min(run, pend - P0) : 0u;
