@@ -440,8 +440,6 @@ def multi_gpu_records(a, world, fam, kmers, roles, res, off, codes, off32, singl
             eng.db_load_synthetic(n_keys, K5, a.roles, SEED)
             t_load = time.time() - t0
             info = eng.db_info()
-            if mode >= 2:
-                eng.set_option("chunk_residues", 32 << 20)      # more rounds per device: the H2D of one overlaps the kernels of the other
             if p_codes is None:
                 p_codes, p_off32 = eng.pack(p_res, p_off, alloc=pinned_array)
             best_b = 1e30

@@ -103,7 +103,7 @@ const char* ka_last_error(const ka_engine* e);
  *   "tile_span"     residues of sequence starts per CTA tile, default 1536
  *   "long_seq"      sequences longer than this get a tile of their own (second tile launch), default 2048
  *   "mid_seq"       sequences longer than this use the global-scratch long-sequence kernel, default 8192
- *   "chunk_residues" residues per pipelined H2D chunk, default 64 Mi (4 chunks in flight per device)
+ *   "chunk_residues" residues per pipelined H2D chunk; 0 (default) = 64 Mi, 32 Mi on a routed table (table_mode 2/3)
  *   "l2_persist"    sector classes: 1 = L2 persisting access-policy window on the table (default 1)
  */
 int ka_set_option(ka_engine* e, const char* name, double value);

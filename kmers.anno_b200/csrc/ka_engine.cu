@@ -385,7 +385,7 @@ int annotate_range(ka_engine* e, Device& d, const BatchIn& in, uint64_t s_begin,
     uint64_t cs = s_begin;
     while (cs < s_end) {
         // chunk = as many whole sequences as fit in chunk_residues (at least one)
-        uint64_t ce = in.off64 ? chunk_end(in.off64, cs, s_end, e->chunk_residues) : chunk_end(in.off32, cs, s_end, e->chunk_residues);
+        uint64_t ce = in.off64 ? chunk_end(in.off64, cs, s_end, chunk_of(e, false)) : chunk_end(in.off32, cs, s_end, chunk_of(e, false));
         if (ce <= cs) ce = cs + 1;
         if (ce - cs > 0xfffffff0ull) ce = cs + 0xfffffff0ull;
         ChunkShape sh;
@@ -582,7 +582,7 @@ int ka_set_option(ka_engine* e, const char* name, double v) {
         if (!(v >= 256 && v <= 49152)) return fail(e, KA_ERR_INVALID, "mid_seq must be in [256, 49152]");
         mid_seq = (uint32_t)v;
     } else if (n == "chunk_residues") {
-        if (!(v >= 4096 && v <= (double)(1ull << 30))) return fail(e, KA_ERR_INVALID, "chunk_residues must be in [4096, 2^30]");
+        if (!(v == 0 || (v >= 4096 && v <= (double)(1ull << 30)))) return fail(e, KA_ERR_INVALID, "chunk_residues must be 0 (automatic) or in [4096, 2^30]");
         chunk_residues = (uint64_t)v;
     } else if (n == "l2_persist") {
         l2_persist = v != 0;

@@ -106,7 +106,7 @@ struct ka_engine {
     uint32_t tile_span = 1536;
     uint32_t long_seq = 2048;
     uint32_t mid_seq = 8192;
-    uint64_t chunk_residues = 64ull << 20;
+    uint64_t chunk_residues = 0;       // 0 = automatic: 64 Mi, 32 Mi on a routed table (see chunk_of)
     int l2_persist = 1;
     int slot_bits = 0;  // 0 = choose automatically; 16 = the 128-byte-line table (ka_line.cuh)
     int filter = 1;     // line table: 1 = L2-resident presence filter in front of it (measurement knob)
@@ -182,6 +182,11 @@ int ensure_tile_smem(Device& d);
 int enqueue_kernels(ka_engine* e, Device& d, Pipe& p, const AnnotParams& ap, uint64_t n_long, uint64_t n_mid);
 int collect_times(Device& d, Pipe& p);
 void set_l2_window(ka_engine* e, Device& d, cudaStream_t st);
+// residues per pipelined chunk: the option, or the measured best of the mode (profiles/r02_summary.md D, G)
+static inline uint64_t chunk_of(const ka_engine* e, bool routed) {
+    return e->chunk_residues ? e->chunk_residues : (routed ? 32ull << 20 : 64ull << 20);
+}
+
 int annotate_range(ka_engine* e, Device& d, const BatchIn& in, uint64_t s_begin, uint64_t s_end, int32_t min_hits,
                    int32_t* out_role, int32_t* out_hits, uint8_t* out_flag);
 void fill_line_params(ka_engine* e, Device& d, Pipe& p, uint64_t n_res, uint64_t n_seq, int32_t min_hits, LineParams& lp);

@@ -611,14 +611,19 @@ cudaError_t launch_route_count(const unsigned long long* keys, unsigned long lon
 
 // One CTA buckets a tile of 256 x 16 keys.  __match_any_sync groups the lanes of a warp by owner in one
 // instruction whatever the number of shards: the lowest lane of a group adds the group's size to the warp's
-// shared-memory count of that owner; ONE global atomicAdd per owner and CTA reserves the output ranges; then
-// every lane writes its key at (range of its warp + keys of earlier rounds + rank inside its group).
+// shared-memory count of that owner; ONE global atomicAdd per owner and CTA reserves the output ranges.  The keys
+// are first ordered by owner in shared memory and then written out linearly, so that consecutive threads store
+// consecutive addresses: whole 128-byte segments per owner instead of 32-byte pieces — what matters when the
+// destination is another GPU's memory behind NVLink (table_mode 3).
 __global__ void __launch_bounds__(256) route_scatter_kernel(const unsigned long long* __restrict__ keys, unsigned long long n,
                                      TableView tab, const unsigned long long* __restrict__ offsets,
                                      unsigned long long* cursor, RouteDst dst, uint32_t* slot_of_pos) {
     constexpr int PER = 16;                       // keys per thread, strided by 32 inside the warp's part of the tile
+    __shared__ unsigned long long s_keys[256 * PER];   // the tile's valid keys, ordered by owner
     __shared__ uint32_t s_cnt[8][8];              // [warp][owner]
-    __shared__ unsigned long long s_base[8][8];   // [warp][owner] next output index
+    __shared__ uint32_t s_next[8][8];             // [warp][owner] next index into s_keys
+    __shared__ uint32_t s_start[9];               // first index of every owner in s_keys
+    __shared__ unsigned long long s_gbase[8];     // first send slot of every owner for this CTA
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt = (1u << lane) - 1u;
     const unsigned long long tile = 256ull * PER;
@@ -637,13 +642,18 @@ __global__ void __launch_bounds__(256) route_scatter_kernel(const unsigned long 
             if (own[k] != 0xffffffffu && (grp & lt) == 0u) atomicAdd(&s_cnt[warp][own[k]], (uint32_t)__popc(grp));
         }
         __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t run = 0;
+            for (uint32_t o = 0; o < 8; o++) {
+                s_start[o] = run;
+                for (int w = 0; w < 8; w++) { s_next[w][o] = run; run += s_cnt[w][o]; }
+            }
+            s_start[8] = run;
+        }
+        __syncthreads();
         if (threadIdx.x < 8) {
-            const uint32_t o = threadIdx.x;
-            uint32_t tot = 0;
-            for (int w = 0; w < 8; w++) tot += s_cnt[w][o];
-            unsigned long long base = tot ? atomicAdd(&cursor[o], (unsigned long long)tot) : 0ull;
-            base += offsets[o];
-            for (int w = 0; w < 8; w++) { s_base[w][o] = base; base += s_cnt[w][o]; }
+            const uint32_t o = threadIdx.x, tot = s_start[o + 1] - s_start[o];
+            s_gbase[o] = (tot ? atomicAdd(&cursor[o], (unsigned long long)tot) : 0ull) + offsets[o];
         }
         __syncthreads();
 #pragma unroll
@@ -651,18 +661,28 @@ __global__ void __launch_bounds__(256) route_scatter_kernel(const unsigned long 
             const unsigned long long i = t0 + (unsigned long long)warp * (32 * PER) + k * 32 + lane;
             const unsigned grp = __match_any_sync(0xffffffffu, own[k]);
             const int leader = __ffs(grp) - 1;
-            unsigned long long first = 0;
+            uint32_t first = 0;
             if (own[k] != 0xffffffffu && (int)lane == leader) {
-                first = s_base[warp][own[k]];
-                s_base[warp][own[k]] = first + (unsigned)__popc(grp);
+                first = s_next[warp][own[k]];
+                s_next[warp][own[k]] = first + (uint32_t)__popc(grp);
             }
             first = __shfl_sync(grp, first, leader);
             if (own[k] != 0xffffffffu) {
-                const unsigned long long w = first + (unsigned)__popc(grp & lt);
-                dst.p[own[k]][w] = m[k];           // the local send buffer, or straight into the owner's receive buffer (NVLink store)
-                slot_of_pos[i] = (uint32_t)w;      // answers come back in send order: position i reads slot w
+                const uint32_t si = first + (uint32_t)__popc(grp & lt);
+                s_keys[si] = m[k];
+                // answers come back in send order: position i reads send slot (first slot of its owner + rank in the CTA)
+                slot_of_pos[i] = (uint32_t)(s_gbase[own[k]] + (si - s_start[own[k]]));
             }
             __syncwarp();
+        }
+        __syncthreads();
+        const uint32_t total = s_start[8];
+        for (uint32_t idx = threadIdx.x; idx < total; idx += 256) {
+            uint32_t o = 0;
+#pragma unroll
+            for (uint32_t q = 1; q < 8; q++) o += (idx >= s_start[q]) ? 1u : 0u;
+            // the local send buffer, or straight into the owner's receive buffer (NVLink store)
+            dst.p[o][s_gbase[o] + (idx - s_start[o])] = s_keys[idx];
         }
         __syncthreads();
     }

@@ -128,7 +128,7 @@ int annotate_routed_range(ka_engine* e, Device& d, int idx, RouteShared& sh, con
     const bool packed = bin.packed();
     std::vector<std::pair<uint64_t, uint64_t>> chunks;
     for (uint64_t cs = s_begin; cs < s_end;) {
-        const uint64_t lim = bin.off(cs) + e->chunk_residues;
+        const uint64_t lim = bin.off(cs) + chunk_of(e, true);
         uint64_t lo = cs + 1, hi = s_end + 1;            // last sequence boundary at or below the limit
         while (lo < hi) { const uint64_t mid = lo + ((hi - lo) >> 1); if (bin.off(mid) <= lim) lo = mid + 1; else hi = mid; }
         uint64_t ce = lo - 1;

@@ -46,7 +46,7 @@ def test_idempotent_and_chunk_invariant(world):
     for chunk in (1 << 16, 3_000_000):
         eng.set_option("chunk_residues", chunk)
         assert same(eng.annotate(world["res"], world["off"], 5), world["base"])
-    eng.set_option("chunk_residues", 32 << 20)
+    eng.set_option("chunk_residues", 0)
 
 
 def test_concatenation_of_shards_equals_whole(world):
