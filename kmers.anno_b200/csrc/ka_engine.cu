@@ -51,6 +51,8 @@ void pipe_free(Pipe& p) {
     if (p.off32_in) cudaFree(p.off32_in);
     if (p.off32) cudaFree(p.off32);
     if (p.first) cudaFree(p.first);
+    if (p.surv) cudaFree(p.surv);
+    if (p.surv_cnt) cudaFree(p.surv_cnt);
     if (p.role) cudaFree(p.role);
     if (p.hits) cudaFree(p.hits);
     if (p.flag) cudaFree(p.flag);
@@ -75,7 +77,8 @@ void pipe_free(Pipe& p) {
 
 // size the per-chunk device buffers
 int pipe_reserve(Device& d, Pipe& p, uint64_t n_res, uint64_t n_seq, uint64_t n_tiles,
-                 uint64_t n_long, uint64_t long_res, uint64_t n_mid, bool wide, bool need_bytes, bool need_codes) {
+                 uint64_t n_long, uint64_t long_res, uint64_t n_mid, bool wide, bool need_bytes, bool need_codes,
+                 bool need_surv) {
     int rc;
     if (need_bytes && (rc = ensure(d, p.res, p.res_cap, n_res + 64, "residues"))) return rc;
     // 5-bit codes of up to 127 lead residues + the chunk, in groups of 32 residues = 5 words, + over-read slack
@@ -102,6 +105,8 @@ int pipe_reserve(Device& d, Pipe& p, uint64_t n_res, uint64_t n_seq, uint64_t n_
         p.seq_cap = n;
     }
     if ((rc = ensure(d, p.first, p.first_cap, n_tiles + 2, "tile index"))) return rc;
+    if (need_surv && ((rc = ensure(d, p.surv, p.surv_cap, n_res + 128 + 64, "survivor list")) ||
+                      (rc = ensure(d, p.surv_cnt, p.surv_cnt_cap, n_seq + 2, "survivor counts")))) return rc;
     if ((rc = ensure(d, p.big, p.big_cap, n_long + 1, "long-sequence list"))) return rc;
     if ((rc = ensure(d, p.mid, p.mid_cap, n_mid + 1, "mid-sequence tiles"))) return rc;
     if ((rc = ensure(d, p.scratch, p.scratch_cap, (wide ? 2 : 1) * (2 * long_res + 4), "long-sequence tokens")))
@@ -280,6 +285,8 @@ void fill_line_params(ka_engine* e, Device& d, Pipe& p, uint64_t n_res, uint64_t
     lp.ext_max = e->tile_span + e->long_seq;
     line_tile_smem_bytes(lp.ext_max, &lp.stage_bytes);
     lp.first = p.first;
+    lp.surv = p.surv;
+    lp.surv_cnt = p.surv_cnt;
     lp.mid_desc = p.mid;
     lp.mid_count = p.ctr + 1;
     lp.big_count = p.ctr;
@@ -307,8 +314,8 @@ int enqueue_line_kernels(ka_engine* e, Device& d, Pipe& p, const LineParams& lp,
     DCK(d, cudaEventRecord(p.ev_k0, p.st));
     DCK(d, launch_line_plan(lp, off_is_64 ? p.off : nullptr, p.off32_in, origin, p.st));
     DCK(d, cudaEventRecord(p.ev_t0, p.st));
-    DCK(d, launch_line_tiles(lp, smem, p.st));
-    d.launches += 2;
+    DCK(d, launch_line_tiles(lp, p.st));
+    d.launches += 3;
     if (n_mid) {
         LineParams lm = lp;
         lm.first = p.mid;
@@ -316,8 +323,8 @@ int enqueue_line_kernels(ka_engine* e, Device& d, Pipe& p, const LineParams& lp,
         lm.ext_max = lp.mid_seq;
         const size_t smem_mid = line_tile_smem_bytes(lm.ext_max, &lm.stage_bytes);
         if (smem_mid > d.smem_set) return dev_fail(d, KA_ERR_INVALID, "mid tile shared memory exceeds the device limit", cudaErrorInvalidValue);
-        DCK(d, launch_line_tiles(lm, smem_mid, p.st));
-        d.launches += 1;
+        DCK(d, launch_line_tiles(lm, p.st));
+        d.launches += 2;
     }
     DCK(d, cudaEventRecord(p.ev_t1, p.st));
     if (n_long) {
@@ -408,7 +415,7 @@ int annotate_range(ka_engine* e, Device& d, const BatchIn& in, uint64_t s_begin,
         const uint64_t n = ce - cs;
         const uint64_t n_tiles = sh.n_res / e->tile_span + 1;
         int rc = pipe_reserve(d, p, sh.n_res, n, n_tiles, sh.n_long, sh.long_res, sh.n_mid, e->geom.wide != 0,
-                              !packed || !line, packed || line);
+                              !packed || !line, packed || line, line);
         if (rc) return rc;
         const uint64_t r_begin = in.off(cs), r_end = in.off(ce);
         const uint64_t origin = r_begin & ~127ull;          // chunk-relative residue 0 (5 * 128 bits = 80 bytes: byte aligned)
@@ -769,7 +776,7 @@ int ka_batch_upload(ka_engine* e, int dev_index, const uint8_t* residues, const 
     // resident form: the 5-bit stream wherever the tile kernels can stage it (line table; narrow unsharded sector tables)
     const bool keep_codes = e->line || (!e->geom.wide && e->geom.n_shards <= 1 && e->resident_packed);
     if (rc == KA_OK) rc = pipe_reserve(d, b->p, sh.n_res, N, sh.n_res / e->tile_span + 1, sh.n_long, sh.long_res, sh.n_mid, e->geom.wide != 0,
-                                       true, keep_codes);
+                                       true, keep_codes, e->line);
     cudaError_t ce = cudaSuccess;
     if (rc == KA_OK && sh.n_res) ce = cudaMemcpy(b->p.res, residues + offsets[0], sh.n_res, cudaMemcpyHostToDevice);
     if (rc == KA_OK && ce == cudaSuccess) ce = cudaMemcpy(b->p.off, offsets, (N + 1) * 8, cudaMemcpyHostToDevice);

@@ -40,6 +40,8 @@ struct Pipe {
     uint32_t* off32_in = nullptr;                        // absolute 32-bit offsets as given to ka_annotate_packed
     uint32_t* off32 = nullptr;                           // chunk-relative offsets written by line_plan_kernel
     uint4* first = nullptr; size_t first_cap = 0;
+    uint2* surv = nullptr; size_t surv_cap = 0;          // line table: survivors of the filter pass (one slot per residue position)
+    uint32_t* surv_cnt = nullptr; size_t surv_cnt_cap = 0;
     int32_t* role = nullptr; int32_t* hits = nullptr; uint8_t* flag = nullptr;
     uint32_t* ctr = nullptr;  // 16 bytes: [0] big_count, [2..3] token cursor (u64)
     BigItem* big = nullptr; size_t big_cap = 0;
@@ -173,7 +175,8 @@ struct ChunkShape {
 int pipe_init(Device& d, Pipe& p);
 void pipe_free(Pipe& p);
 int pipe_reserve(Device& d, Pipe& p, uint64_t n_res, uint64_t n_seq, uint64_t n_tiles,
-                 uint64_t n_long, uint64_t long_res, uint64_t n_mid, bool wide, bool need_bytes, bool need_codes);
+                 uint64_t n_long, uint64_t long_res, uint64_t n_mid, bool wide, bool need_bytes, bool need_codes,
+                 bool need_surv = false);
 bool scan_offsets(const BatchIn& in, uint64_t cs, uint64_t ce, uint32_t long_seq, uint32_t mid_seq, int K,
                   ChunkShape& s);
 void fill_params(ka_engine* e, Device& d, Pipe& p, uint64_t base, uint64_t n_res, uint64_t n_seq,

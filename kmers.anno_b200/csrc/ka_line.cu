@@ -227,263 +227,145 @@ cudaError_t launch_line_plan(const LineParams& p, const unsigned long long* off6
 }
 
 // ------------------------------------------------------------------------------------
-// tile kernel
+// tile kernels: filter pass, then probe pass
 // ------------------------------------------------------------------------------------
-constexpr int LT_THREADS = 128, LT_WARPS = LT_THREADS / 32;
-constexpr int LT_A = 8;        // window positions per lane and pass
-#ifndef KA_LT_PB
-#define KA_LT_PB 2
+// The work of a tile is two kernels with a global-memory list of survivors between them, because the two halves
+// want opposite things from the SM.  The filter pass is arithmetic over a stream (rolling keys, one L2-resident
+// filter word per window): every lane busy, no HBM access besides the 0.625 B per residue of the codes.  The probe
+// pass is nothing but random 128-byte lines: with the survivors already compacted, every lane of every warp has a
+// sector load in flight (PB per thread), which a kernel that discovers its survivors as it goes cannot arrange
+// (profiles/r02_summary.md C: 10-15 active lanes per instruction and a third of the time at the tile barrier).
+// The list costs 8 bytes per SURVIVOR written and read once — ~5 B per window against the 128-byte line saved for
+// every window the filter rejects.  Survivors of the tile (sub-batch) whose first position is chunk residue g0 live
+// at surv[g0 ...), their number at surv_cnt[first sequence of the sub-batch]: no prefix sum, no zeroing.
+constexpr int LF_A = 8;        // window positions per lane and pass
+constexpr int LP_THREADS = 128;
+#ifndef KA_LP_PB
+#define KA_LP_PB 4
 #endif
-constexpr int LT_PB = KA_LT_PB; // sector loads in flight per lane in phase B
-constexpr int LT_QCAP = 32 * LT_A + 32 * LT_PB;
-constexpr int LT_Q2CAP = 32 + 4 * 32;     // second-stage queue: < 32 left over + at most 4 entries per lane of one sector round
+constexpr int LP_PB = KA_LP_PB;   // sector loads in flight per thread of the probe pass
 
-// dynamic shared memory (bytes), fixed-size parts first so that their addresses are compile-time constants:
-//   [0, 4*(LINE_MAX_SEQ+4))               s_off: sequence starts relative to the tile's first residue
-//   [+3*4*LINE_MAX_SEQ)                   s_cnt, s_min, s_max
-//   [+8*LT_WARPS*(LT_QCAP+LT_Q2CAP))      survivor queues and second-stage queues, one pair per warp
-//   [+stage_bytes)                        packed stage (TMA destination, 16-byte aligned) + over-read slack
-//   [+4*(tok_cap(ext_max)+4*LINE_MAX_SEQ+8))  token set, region of sequence q at tok_cap(start) + 4q
-constexpr uint32_t LT_OFF_CNT = 4 * (LINE_MAX_SEQ + 4);
-constexpr uint32_t LT_OFF_Q = LT_OFF_CNT + 3 * 4 * LINE_MAX_SEQ;
-constexpr uint32_t LT_OFF_Q2 = LT_OFF_Q + 8 * LT_WARPS * LT_QCAP;
-constexpr uint32_t LT_OFF_PK = LT_OFF_Q2 + 8 * LT_WARPS * LT_Q2CAP;
-static_assert(LT_OFF_PK % 16 == 0 && LT_OFF_Q % 8 == 0, "alignment of the shared-memory parts");
+// dynamic shared memory of the probe pass: s_off, s_cnt/s_min/s_max, then the token set (region of sequence q at tok_cap(start) + 4q)
+constexpr uint32_t LP_OFF_CNT = 4 * (LINE_MAX_SEQ + 4);
+constexpr uint32_t LP_OFF_TOK = LP_OFF_CNT + 3 * 4 * LINE_MAX_SEQ;
+static_assert(LP_OFF_TOK % 16 == 0, "alignment of the shared-memory parts");
 
+size_t line_probe_smem_bytes(uint32_t ext_max) {
+    return (size_t)LP_OFF_TOK + 4 * ((size_t)tok_cap(ext_max) + 4 * LINE_MAX_SEQ + 8);
+}
 size_t line_tile_smem_bytes(uint32_t ext_max, uint32_t* stage_bytes_out) {
-    const uint32_t stage = (((ext_max * 5u + 7u) >> 3) + 16u + 16u + 32u + 15u) & ~15u;   // lead alignment, rounding, over-read
-    if (stage_bytes_out) *stage_bytes_out = stage;
-    return (size_t)LT_OFF_PK + stage + 4 * ((size_t)tok_cap(ext_max) + 4 * LINE_MAX_SEQ + 8);
+    if (stage_bytes_out) *stage_bytes_out = 0;
+    return line_probe_smem_bytes(ext_max);
 }
 
-#ifndef KA_LT_MINB
-#define KA_LT_MINB 6
-#endif
-template <bool FILTER>
-__global__ void __launch_bounds__(LT_THREADS, KA_LT_MINB) line_tile_kernel(LineParams p) {
-    constexpr int A = LT_A, PB = LT_PB;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t s_bar;
+namespace {
+// 5-bit code number J (compile time) of a 96-bit window held in three registers
+template <int J>
+__device__ __forceinline__ uint32_t wcode(uint32_t u0, uint32_t u1, uint32_t u2) {
+    constexpr int bit = 5 * J, w = bit >> 5, sh = bit & 31;
+    static_assert(bit + 5 <= 96, "code outside the window");
+    const uint32_t lo = w == 0 ? u0 : (w == 1 ? u1 : u2);
+    if (sh + 5 <= 32) return (lo >> sh) & 31u;
+    const uint32_t hi = w == 0 ? u1 : u2;
+    return __funnelshift_r(lo, hi, sh) & 31u;
+}
+}  // namespace
 
-    uint32_t* const s_off = reinterpret_cast<uint32_t*>(smem_raw);
-    int* const s_cnt = reinterpret_cast<int*>(smem_raw + LT_OFF_CNT);
-    int* const s_min = s_cnt + LINE_MAX_SEQ;
-    int* const s_max = s_min + LINE_MAX_SEQ;
-    uint2* const s_q = reinterpret_cast<uint2*>(smem_raw + LT_OFF_Q) + (threadIdx.x >> 5) * LT_QCAP;
-    uint2* const s_q2 = reinterpret_cast<uint2*>(smem_raw + LT_OFF_Q2) + (threadIdx.x >> 5) * LT_Q2CAP;
-    uint32_t* const s_pk = reinterpret_cast<uint32_t*>(smem_raw + LT_OFF_PK);
-    uint32_t* const s_tok = reinterpret_cast<uint32_t*>(smem_raw + LT_OFF_PK + p.stage_bytes);
-
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// Filter pass.  ONE WARP per tile, no shared memory, no barrier, no atomic: the kernel is a chain of dependent
+// latencies (offsets -> codes -> filter words), so what it needs is many independent warps, not co-operation.  The
+// tile's positions are cut into passes of <= 32 * A; in a pass a lane rolls the two key halves over a run of <= A
+// consecutive positions (K is a compile-time constant: every code of the lane's 96-bit window sits at a fixed bit),
+// issues the filter loads of the whole run, tests them, and the warp appends its survivors (H | seq << 26, Lo) to
+// the tile's list — one ballot per step, the running count in a register.
+template <int K, bool FILTER>
+__global__ void __launch_bounds__(32, 32) line_filter_kernel(LineParams p) {
+    constexpr int A = LF_A;
+    constexpr int Kh = K / 2;
+    static_assert(A + K - 1 <= 19, "the lane's window holds 19 codes");
+    const uint32_t lane = threadIdx.x;
+    const uint32_t lt = (1u << lane) - 1u;
     const uint4 desc = p.first[blockIdx.x];
     const uint32_t s0 = desc.x, s1 = desc.x + desc.y;
     if (desc.y == 0) return;
-    if (tid == 0) mbar_init(&s_bar, 1);
-    __syncthreads();
 
-    const LineTable tab = p.tab;
-    const int K = tab.K;
-    const uint32_t radix = tab.radix, Kh = tab.Kh, pw_h = tab.pw_h, pw_l = tab.pw_l;
-    const unsigned long long pol_first = policy_evict_first(), pol_last = policy_evict_last();
-    uint32_t parity = 0;
+    const uint32_t radix = p.tab.radix, npw_h = 0u - p.tab.pw_h, npw_l = 0u - p.tab.pw_l, n_filt = p.tab.n_filt;
+    const uint32_t* const filt = p.tab.filt;
+    const uint32_t* __restrict__ const off = p.off;
+    const unsigned long long pol_last = policy_evict_last();
 
     for (uint32_t sb = s0; sb < s1; sb += LINE_MAX_SEQ) {
         const uint32_t ns = min((uint32_t)LINE_MAX_SEQ, s1 - sb);
-        const uint32_t g0 = (sb == s0) ? desc.z : p.off[sb];
-        const uint32_t g1 = (sb + ns == s1) ? desc.w : p.off[sb + ns];
+        const uint32_t g0 = (sb == s0) ? desc.z : off[sb];
+        const uint32_t g1 = (sb + ns == s1) ? desc.w : off[sb + ns];
         const uint32_t ext = g1 - g0;                                   // window positions of the sub-batch
-        const unsigned long long bit_g0 = 5ull * g0;
-        const unsigned long long bt = (bit_g0 >> 3) & ~15ull;           // 16-byte aligned start of the copy
-        const uint32_t leadbits = (uint32_t)(bit_g0 - 8ull * bt);       // stage bit of tile position 0
-        const uint32_t nbytes = (uint32_t)((((5ull * g1 + 7ull) >> 3) - bt + 15ull) & ~15ull);
-        KA_CHECK(nbytes + 32u <= p.stage_bytes, 1u);
-        KA_CHECK(tok_cap(ext) + 4u * ns + 8u <= tok_cap(p.ext_max) + 4u * LINE_MAX_SEQ + 8u, 2u);
+        const uint32_t n_pass = (ext + 32 * A - 1) / (32 * A);
+        const uint32_t plen = n_pass ? (ext + n_pass - 1) / n_pass : 0;  // <= 32 * A
+        uint2* const out = p.surv + g0;
+        uint32_t cnt = 0;                                               // survivors so far (warp-uniform)
+        uint32_t sw = sb;                                               // a sequence at or before the pass's first position
 
-        if (tid == 0 && nbytes) {
-            mbar_expect_tx(&s_bar, nbytes);
-            bulk_g2s(s_pk, reinterpret_cast<const unsigned char*>(p.pk) + bt, nbytes, &s_bar);
-        }
-        for (uint32_t i = tid; i <= ns; i += LT_THREADS) s_off[i] = p.off[sb + i] - g0;
-        for (uint32_t i = tid; i < ns; i += LT_THREADS) { s_cnt[i] = 0; s_min[i] = 0x7fffffff; s_max[i] = -1; }
-        {
-            const uint32_t ntok = tok_cap(ext) + 4u * ns + 4u;
-            const uint4 z = make_uint4(0, 0, 0, 0);
-            for (uint32_t i = tid * 4; i < ntok; i += LT_THREADS * 4) *reinterpret_cast<uint4*>(s_tok + i) = z;
-        }
-        __syncthreads();
-        if (nbytes) { mbar_wait(&s_bar, parity); parity ^= 1; }
-
-        // The positions are cut into equal passes of at most 32 * A, a multiple of the warp count of them, dealt
-        // round-robin to the warps: every warp samples the whole tile, so sequences with many hits (family members)
-        // and sequences with none spread over all warps instead of loading one of them.
-        const uint32_t n_pass = LT_WARPS * ((ext + LT_WARPS * 32 * A - 1) / (LT_WARPS * 32 * A));
-        const uint32_t plen = (ext + n_pass - 1) / n_pass;              // <= 32 * A
-        uint32_t qn = 0;                                                // queue fill (warp-uniform)
-
-        uint32_t q2n = 0;                                               // second-stage queue fill (warp-uniform)
-
-        // ---- phase B ----
-        // a hit: de-duplicate against the sequence's token set, then one lane per sequence updates the
-        // shared tallies (survivors of neighbouring positions mostly belong to one sequence)
-        auto hit = [&](int role, uint32_t tok, uint32_t si) {
-            int q = -1;
-            if (role >= 0) {
-                q = (int)si;
-                const uint32_t sa = s_off[q], se = s_off[q + 1];
-                KA_CHECK(q < (int)ns && se >= sa, 8u);
-                if (!line_token_insert(s_tok + tok_cap(sa) + 4u * (uint32_t)q, tok_cap(se - sa) + 4u, tok)) q = -1;
-            }
-            if (__any_sync(0xffffffffu, q >= 0)) {
-                const unsigned grp = __match_any_sync(0xffffffffu, q);
-                const int gmin = __reduce_min_sync(grp, q >= 0 ? role : 0x7fffffff);
-                const int gmax = __reduce_max_sync(grp, q >= 0 ? role : -1);
-                if (q >= 0 && lane == (uint32_t)(__ffs(grp) - 1)) {
-                    atomicAdd(&s_cnt[q], __popc(grp));
-                    atomicMin(&s_min[q], gmin);
-                    atomicMax(&s_max[q], gmax);
-                }
-            }
-        };
-        // second stage (a key outside its home sector): entries (sector of the same line, tag | seq << 16), or
-        // (home sector, tag | seq << 16 | 1 << 31) for the overflow table; popped a full warp at a time
-        auto second = [&](uint32_t first, uint32_t count) {
-            int role = -1;
-            uint32_t tok = 0, si = 0;
-            if (lane < count) {
-                const uint2 e = s_q2[first + lane];
-                si = (e.y >> 16) & 63u;
-                if (e.y >> 31) {
-                    role = line_ovf_lookup(tab, e.x, e.y & 0xFFFFu, tok);
-                } else {
-                    uint4 a, b;
-                    load_line_sector(tab.lines + 2 * (size_t)e.x, pol_first, a, b);   // L2 hit: the line was just fetched
-                    uint32_t j = 0;
-                    const uint32_t tag = e.y & 0xFFFFu;
-                    role = match16(a, b, tag | (tag << 16), j);
-                    tok = e.x * 8u + j + 1u;
-                }
-            }
-            hit(role, tok, si);
-        };
-        // first stage: the home sector is loaded; a miss in a sector whose flags name other places queues them
-        auto consume = [&](const uint2& e, const uint4& a, const uint4& b, bool live) {
-            int role = -1;
-            uint32_t tok = 0, flags = 0;
-            if (live) {
-                uint32_t j = 0;
-                const uint32_t tag = e.y & 0xFFFFu;
-                role = match16(a, b, tag | (tag << 16), j);
-                tok = e.x * 8u + j + 1u;
-                if (role < 0) flags = sector_flags(a);
-            }
-            if (__any_sync(0xffffffffu, flags != 0u)) {
-                const uint32_t mine = __popc(flags);
-                uint32_t incl = mine;
-#pragma unroll
-                for (int dlt = 1; dlt < 32; dlt <<= 1) {
-                    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, dlt);
-                    if ((int)lane >= dlt) incl += up;
-                }
-                uint2* w = s_q2 + q2n + (incl - mine);
-                const uint32_t line0 = e.x & ~3u, home = e.x & 3u;
-#pragma unroll
-                for (uint32_t alt = 1; alt < 4; alt++)
-                    if (flags & (1u << (alt - 1))) *w++ = make_uint2(line0 | (home ^ alt), e.y & 0x3FFFFFu);
-                if (flags & 8u) *w++ = make_uint2(e.x, (e.y & 0x3FFFFFu) | 0x80000000u);
-                q2n += __shfl_sync(0xffffffffu, incl, 31);
-                __syncwarp();
-            }
-            hit(role, tok, e.y >> 16);
-            while (q2n >= 32u) {
-                q2n -= 32u;
-                second(q2n, 32u);
-            }
-        };
-
-        // PB survivors per lane with all their sector loads in flight before the first use
-        auto pop = [&](uint32_t first, uint32_t count) {
-            uint2 e[PB];
-            uint4 sa[PB], sb2[PB];
-#pragma unroll
-            for (int k = 0; k < PB; k++) {
-                e[k] = make_uint2(0, 0);
-                sa[k] = make_uint4(0, 0, 0, 0); sb2[k] = sa[k];
-                if (lane + 32u * k < count) {
-                    const uint2 kq = s_q[first + lane + 32u * k];       // (H | seq << 26, Lo)
-                    uint32_t tag;
-                    line_locate(tab, kq.x & 0x3FFFFFFu, kq.y, e[k].x, tag);
-                    e[k].y = tag | ((kq.x >> 26) << 16);
-                    load_line_sector(tab.lines + 2 * (size_t)e[k].x, pol_first, sa[k], sb2[k]);
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < PB; k++)
-                if (32u * k < count) consume(e[k], sa[k], sb2[k], lane + 32u * k < count);
-        };
-
-        for (uint32_t pb = warp * plen; pb < ext; pb += LT_WARPS * plen) {
-            // ---- phase A: keys + filter for a run of <= A positions per lane ----
-            const uint32_t pend = min(ext, pb + plen);
+        for (uint32_t pass = 0; pass < n_pass; pass++) {
+            const uint32_t pb = pass * plen, pend = min(ext, pb + plen);
             const uint32_t run = (pend - pb + 31) >> 5;                 // <= A
             const uint32_t P0 = pb + lane * run;
             const uint32_t nrun = P0 < pend ? min(run, pend - P0) : 0u;
+            // sequence containing the lane's first position: walk on from the warp's (sequences are mostly longer
+            // than a run, so this is one or two cached loads; lanes past the end look at the last position)
+            const uint32_t Pc = g0 + min(P0, pend - 1u);
+            uint32_t si = sw;
+            uint32_t nb = off[si + 1];
+            while (Pc >= nb) { si++; nb = off[si + 1]; }
+            KA_CHECK(si < sb + ns, 32u);
+
             uint32_t qh[A], ql[A], fw[A];
             unsigned okm = 0;
             if (nrun) {
-                // sequence containing P0: last i with s_off[i] <= P0 (P0 < ext = s_off[ns])
-                int lo = 0, hi = (int)ns + 1;
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (s_off[mid] <= P0) lo = mid + 1; else hi = mid;
-                }
-                uint32_t si = (uint32_t)(lo - 1);
-                KA_CHECK(si < ns, 32u);
-                uint32_t nb = s_off[si + 1];
+                // the 96 stream bits from the run's first position: code J of the window at a fixed bit
+                const unsigned long long bit0 = 5ull * (g0 + P0);
+                const uint32_t* w = p.pk + (bit0 >> 5);
+                const uint32_t sh = (uint32_t)bit0 & 31u, w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
+                const uint32_t u0 = __funnelshift_r(w0, w1, sh), u1 = __funnelshift_r(w1, w2, sh), u2 = __funnelshift_r(w2, w3, sh);
+                const uint32_t G0 = g0 + P0;                            // chunk residue of the run's first position
 
-                // Three 64-bit code windows: u at the run's first position (warm-up codes and the digit
-                // leaving H), m at +Kh-1 (the digit moving from Lo to H), v at +K-1 (the digit entering Lo);
-                // code I of each window then sits at a compile-time bit position.
-                const uint32_t bit0 = leadbits + 5u * P0;
-                uint32_t u0, u1, m0, m1, v0, v1;
-                load_window(s_pk, bit0, u0, u1);
-                load_window(s_pk, bit0 + 5u * (Kh - 1u), m0, m1);
-                load_window(s_pk, bit0 + 5u * (uint32_t)(K - 1), v0, v1);
                 // warm-up over the K-1 codes in front of the first window end: H complete, Lo short of one digit
                 uint32_t H = 0, Lo = 0;
                 int okc = 0;                                            // consecutive codes inside the alphabet
-                {
-                    uint32_t t0 = u0, t1 = u1;
-                    for (uint32_t j = 0; j + 1 < (uint32_t)K; j++) {
-                        const uint32_t c = t0 & 31u;
-                        t0 = __funnelshift_r(t0, t1, 5);
-                        t1 >>= 5;
-                        if (j < Kh) H = H * radix + c; else Lo = Lo * radix + c;
+                auto warm = [&](auto J_) {
+                    constexpr int J = decltype(J_)::value;
+                    if (J < K - 1) {
+                        const uint32_t c = wcode<(J < K - 1 ? J : 0)>(u0, u1, u2);
+                        if (J < Kh) H = H * radix + c; else Lo = Lo * radix + c;
                         okc = (c == CODE_INVALID) ? 0 : okc + 1;
                     }
-                }
+                };
+                warm(std::integral_constant<int, 0>()); warm(std::integral_constant<int, 1>());
+                warm(std::integral_constant<int, 2>()); warm(std::integral_constant<int, 3>());
+                warm(std::integral_constant<int, 4>()); warm(std::integral_constant<int, 5>());
+                warm(std::integral_constant<int, 6>()); warm(std::integral_constant<int, 7>());
+                warm(std::integral_constant<int, 8>());
+                static_assert(K <= 10, "warm-up unrolled for K - 1 <= 9 codes");
+
                 auto step = [&](auto I_) {
                     constexpr int I = decltype(I_)::value;
-                    if (I < (int)nrun) {
-                        const uint32_t pos = P0 + I;
-                        const uint32_t cnew = window_code<I>(v0, v1);
-                        if (I > 0) {
-                            const uint32_t cmid = window_code<I>(m0, m1);
-                            H = (H - window_code<(I > 0 ? I - 1 : 0)>(u0, u1) * pw_h) * radix + cmid;
-                            Lo = (Lo - cmid * pw_l) * radix + cnew;
-                        } else {
-                            Lo = Lo * radix + cnew;
-                        }
-                        okc = (cnew == CODE_INVALID) ? 0 : okc + 1;
-                        if (pos >= nb) {                                // rare: the run crosses into the next sequence(s)
-                            do { si++; KA_CHECK(si < ns, 4u); nb = s_off[si + 1]; } while (pos >= nb);
-                        }
-                        if (pos + (uint32_t)K <= nb && okc >= K) {
-                            qh[I] = H | (si << 26);                     // H < 31^5 < 2^25, si < 64
-                            ql[I] = Lo;
-                            okm |= 1u << I;
-                            if (FILTER)
-                                fw[I] = load_filter_word(tab.filt + line_filter_word(line_filter_hash(H, Lo), tab.n_filt), pol_last);
-                        }
+                    const uint32_t pos = G0 + I;
+                    const uint32_t cnew = wcode<I + K - 1>(u0, u1, u2);
+                    if (I > 0) {
+                        const uint32_t cmid = wcode<I + Kh - 1>(u0, u1, u2);
+                        H = (H + wcode<(I > 0 ? I - 1 : 0)>(u0, u1, u2) * npw_h) * radix + cmid;
+                        Lo = (Lo + cmid * npw_l) * radix + cnew;
+                    } else {
+                        Lo = Lo * radix + cnew;
+                    }
+                    okc = (cnew == CODE_INVALID) ? 0 : okc + 1;
+                    if (pos >= nb && I < (int)nrun) {                   // rare: the run crosses into the next sequence(s)
+                        do { si++; KA_CHECK(si < sb + ns, 4u); nb = off[si + 1]; } while (pos >= nb);
+                    }
+                    // (positions past the lane's run belong to the next lane: never valid here)
+                    if (pos + (uint32_t)K <= nb && okc >= K && I < (int)nrun) {
+                        qh[I] = H | ((si - sb) << 26);                  // H < 31^5 < 2^25, si - sb < 64
+                        ql[I] = Lo;
+                        okm |= 1u << I;
+                        if (FILTER) fw[I] = load_filter_word(filt + __umulhi(line_filter_hash(H, Lo), n_filt), pol_last);
                     }
                 };
                 step(std::integral_constant<int, 0>()); step(std::integral_constant<int, 1>());
@@ -491,58 +373,160 @@ __global__ void __launch_bounds__(LT_THREADS, KA_LT_MINB) line_tile_kernel(LineP
                 step(std::integral_constant<int, 4>()); step(std::integral_constant<int, 5>());
                 step(std::integral_constant<int, 6>()); step(std::integral_constant<int, 7>());
                 static_assert(A == 8, "unrolled for 8 positions per lane");
-                if (FILTER) {
+            }
+            // the next pass starts at or after the last lane's sequence
+            sw = __shfl_sync(0xffffffffu, si, 31);
+            // test and append: the survivors of step i of all lanes go to consecutive list slots
 #pragma unroll
-                    for (int i = 0; i < A; i++)
-                        if (okm & (1u << i)) {
-                            const uint32_t need = line_filter_bits(line_filter_hash(qh[i] & 0x3FFFFFFu, ql[i]));
-                            if ((fw[i] & need) != need) okm &= ~(1u << i);
-                        }
+            for (int i = 0; i < A; i++) {
+                bool ok = (okm >> i) & 1u;
+                if (FILTER && ok) {
+                    const uint32_t need = line_filter_bits(line_filter_hash(qh[i] & 0x3FFFFFFu, ql[i]));
+                    ok = (fw[i] & need) == need;
                 }
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                if (ok) out[cnt + __popc(m & lt)] = make_uint2(qh[i], ql[i]);
+                cnt += __popc(m);
             }
-            // compact the survivors of the warp into its queue: one warp scan of the per-lane counts, then
-            // every lane writes its own survivors back to back
-            {
-                const uint32_t mine = __popc(okm);
-                uint32_t incl = mine;
-#pragma unroll
-                for (int dlt = 1; dlt < 32; dlt <<= 1) {
-                    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, dlt);
-                    if ((int)lane >= dlt) incl += up;
-                }
-                uint2* w = s_q + qn + (incl - mine);
-#pragma unroll
-                for (int i = 0; i < A; i++)
-                    if ((okm >> i) & 1u) *w++ = make_uint2(qh[i], ql[i]);
-                qn += __shfl_sync(0xffffffffu, incl, 31);
-            }
-            __syncwarp();
-            while (qn >= 32u * PB) {
-                qn -= 32u * PB;
-                pop(qn, 32u * PB);
-            }
-            __syncwarp();
         }
-        if (qn > 0) pop(0, qn);                                         // drain (qn < 32 * PB)
-        if (q2n > 0) second(0, q2n);                                    // (q2n < 32)
+        if (lane == 0) p.surv_cnt[sb] = cnt;
+    }
+}
+
+#ifndef KA_LP_MINB
+#define KA_LP_MINB 6
+#endif
+// Probe pass.  One CTA per tile: the survivors are read densely, PB per thread with all their sector loads (the only
+// HBM access of a probe) in flight before the first use; eight tags matched SIMD-in-register; a miss in a sector
+// whose flags name other places follows them (L2 hits on the line just fetched, or the overflow table); a hit is
+// de-duplicated against the sequence's token set and tallied (warp match + redux, one shared atomic per sequence).
+__global__ void __launch_bounds__(LP_THREADS, KA_LP_MINB) line_probe_kernel(LineParams p) {
+    constexpr int PB = LP_PB;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t* const s_off = reinterpret_cast<uint32_t*>(smem_raw);
+    int* const s_cnt = reinterpret_cast<int*>(smem_raw + LP_OFF_CNT);
+    int* const s_min = s_cnt + LINE_MAX_SEQ;
+    int* const s_max = s_min + LINE_MAX_SEQ;
+    uint32_t* const s_tok = reinterpret_cast<uint32_t*>(smem_raw + LP_OFF_TOK);
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint4 desc = p.first[blockIdx.x];
+    const uint32_t s0 = desc.x, s1 = desc.x + desc.y;
+    if (desc.y == 0) return;
+    const LineTable tab = p.tab;
+    const unsigned long long pol_first = policy_evict_first();
+
+    for (uint32_t sb = s0; sb < s1; sb += LINE_MAX_SEQ) {
+        const uint32_t ns = min((uint32_t)LINE_MAX_SEQ, s1 - sb);
+        const uint32_t g0 = (sb == s0) ? desc.z : p.off[sb];
+        const uint32_t n = p.surv_cnt[sb];
+        const uint2* const q = p.surv + g0;
+        // the first round's entries before anything else: their latency overlaps the shared-memory set-up
+        uint2 kq[PB];
+#pragma unroll
+        for (int k = 0; k < PB; k++) kq[k] = (tid + k * LP_THREADS < n) ? q[tid + k * LP_THREADS] : make_uint2(0, 0);
+
+        if (n == 0) {                                                   // (uniform) nothing survived: no call for these sequences
+            for (uint32_t i = tid; i < ns; i += LP_THREADS) line_emit(p, sb + i, 0, 0, 0);
+            continue;
+        }
+        const uint32_t g1 = (sb + ns == s1) ? desc.w : p.off[sb + ns];
+        const uint32_t ext = g1 - g0;
+        KA_CHECK(n <= ext, 16u);
+        KA_CHECK(tok_cap(ext) + 4u * ns + 8u <= tok_cap(p.ext_max) + 4u * LINE_MAX_SEQ + 8u, 2u);
+        for (uint32_t i = tid; i <= ns; i += LP_THREADS) s_off[i] = p.off[sb + i] - g0;
+        for (uint32_t i = tid; i < ns; i += LP_THREADS) { s_cnt[i] = 0; s_min[i] = 0x7fffffff; s_max[i] = -1; }
+        {
+            const uint32_t ntok = tok_cap(ext) + 4u * ns + 4u;
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            for (uint32_t i = tid * 4; i < ntok; i += LP_THREADS * 4) *reinterpret_cast<uint4*>(s_tok + i) = z;
+        }
         __syncthreads();
-        for (uint32_t i = tid; i < ns; i += LT_THREADS) line_emit(p, sb + i, s_cnt[i], s_min[i], s_max[i]);
+
+        for (uint32_t base = 0; base < n; base += LP_THREADS * PB) {
+            uint32_t sec[PB], tg[PB];
+            uint4 sa[PB], sb2[PB];
+#pragma unroll
+            for (int k = 0; k < PB; k++) {
+                sec[k] = 0; tg[k] = 0;
+                sa[k] = make_uint4(0, 0, 0, 0); sb2[k] = sa[k];
+                if (base + tid + k * LP_THREADS < n) {
+                    line_locate(tab, kq[k].x & 0x3FFFFFFu, kq[k].y, sec[k], tg[k]);
+                    load_line_sector(tab.lines + 2 * (size_t)sec[k], pol_first, sa[k], sb2[k]);
+                }
+            }
+            // the next round's entries travel while this round's sectors do
+            uint2 nx[PB];
+#pragma unroll
+            for (int k = 0; k < PB; k++) {
+                const uint32_t i = base + LP_THREADS * PB + tid + k * LP_THREADS;
+                nx[k] = i < n ? q[i] : make_uint2(0, 0);
+            }
+#pragma unroll
+            for (int k = 0; k < PB; k++) {
+                if (base + (tid & ~31u) + k * LP_THREADS >= n) break;  // (warp-uniform) the whole warp is past the end
+                int role = -1;
+                uint32_t tok = 0;
+                if (base + tid + k * LP_THREADS < n) role = line_resolve(tab, pol_first, sec[k], tg[k], sa[k], sb2[k], tok);
+                // a hit: de-duplicate against the sequence's token set, then one lane per sequence updates the tallies
+                int sq = -1;
+                if (role >= 0) {
+                    sq = (int)(kq[k].x >> 26);
+                    const uint32_t a0 = s_off[sq], a1 = s_off[sq + 1];
+                    KA_CHECK(sq < (int)ns && a1 >= a0, 8u);
+                    if (!line_token_insert(s_tok + tok_cap(a0) + 4u * (uint32_t)sq, tok_cap(a1 - a0) + 4u, tok)) sq = -1;
+                }
+                if (__any_sync(0xffffffffu, sq >= 0)) {
+                    const unsigned grp = __match_any_sync(0xffffffffu, sq);
+                    const int gmin = __reduce_min_sync(grp, sq >= 0 ? role : 0x7fffffff);
+                    const int gmax = __reduce_max_sync(grp, sq >= 0 ? role : -1);
+                    if (sq >= 0 && lane == (uint32_t)(__ffs(grp) - 1)) {
+                        atomicAdd(&s_cnt[sq], __popc(grp));
+                        atomicMin(&s_min[sq], gmin);
+                        atomicMax(&s_max[sq], gmax);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < PB; k++) kq[k] = nx[k];
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < ns; i += LP_THREADS) line_emit(p, sb + i, s_cnt[i], s_min[i], s_max[i]);
         __syncthreads();
     }
 }
 
+namespace {
+template <int K> void filter_launch(const LineParams& p, cudaStream_t st) {
+    if (p.tab.filt) line_filter_kernel<K, true><<<p.n_tiles, 32, 0, st>>>(p);
+    else line_filter_kernel<K, false><<<p.n_tiles, 32, 0, st>>>(p);
+}
+}  // namespace
+
 cudaError_t line_tile_set_smem(size_t bytes) {
-    cudaError_t ce = cudaFuncSetAttribute(line_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(line_tile_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(line_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(line_tile_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaError_t ce = cudaFuncSetAttribute(line_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(line_probe_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     return ce;
 }
 
-cudaError_t launch_line_tiles(const LineParams& p, size_t smem, cudaStream_t st) {
+cudaError_t launch_line_tiles(const LineParams& p, cudaStream_t st) {
     if (p.n_tiles == 0) return cudaSuccess;
-    if (p.tab.filt) line_tile_kernel<true><<<p.n_tiles, LT_THREADS, smem, st>>>(p);
-    else line_tile_kernel<false><<<p.n_tiles, LT_THREADS, smem, st>>>(p);
+    const size_t smem_p = line_probe_smem_bytes(p.ext_max);
+    switch (p.tab.K) {
+        case 2: filter_launch<2>(p, st); break;
+        case 3: filter_launch<3>(p, st); break;
+        case 4: filter_launch<4>(p, st); break;
+        case 5: filter_launch<5>(p, st); break;
+        case 6: filter_launch<6>(p, st); break;
+        case 7: filter_launch<7>(p, st); break;
+        case 8: filter_launch<8>(p, st); break;
+        case 9: filter_launch<9>(p, st); break;
+        case 10: filter_launch<10>(p, st); break;
+        default: return cudaErrorInvalidValue;
+    }
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) return ce;
+    line_probe_kernel<<<p.n_tiles, LP_THREADS, smem_p, st>>>(p);
     return cudaGetLastError();
 }
 
