@@ -239,7 +239,6 @@ cudaError_t launch_line_plan(const LineParams& p, const unsigned long long* off6
 // every window the filter rejects.  Survivors of the tile (sub-batch) whose first position is chunk residue g0 live
 // at surv[g0 ...), their number at surv_cnt[first sequence of the sub-batch]: no prefix sum, no zeroing.
 constexpr int LF_A = 8;        // window positions per lane and pass
-constexpr int LP_THREADS = 128;
 #ifndef KA_LP_PB
 #define KA_LP_PB 4
 #endif
@@ -284,15 +283,14 @@ __global__ void __launch_bounds__(32, 32) line_filter_kernel(LineParams p) {
     static_assert(A + K - 1 <= 19, "the lane's window holds 19 codes");
     const uint32_t lane = threadIdx.x;
     const uint32_t lt = (1u << lane) - 1u;
-    const uint4 desc = p.first[blockIdx.x];
-    const uint32_t s0 = desc.x, s1 = desc.x + desc.y;
-    if (desc.y == 0) return;
-
     const uint32_t radix = p.tab.radix, npw_h = 0u - p.tab.pw_h, npw_l = 0u - p.tab.pw_l, n_filt = p.tab.n_filt;
     const uint32_t* const filt = p.tab.filt;
     const uint32_t* __restrict__ const off = p.off;
     const unsigned long long pol_last = policy_evict_last();
 
+    for (uint32_t tile = p.tile0 + blockIdx.x; tile < p.tile1; tile += gridDim.x) {
+    const uint4 desc = p.first[tile];
+    const uint32_t s0 = desc.x, s1 = desc.x + desc.y;
     for (uint32_t sb = s0; sb < s1; sb += LINE_MAX_SEQ) {
         const uint32_t ns = min((uint32_t)LINE_MAX_SEQ, s1 - sb);
         const uint32_t g0 = (sb == s0) ? desc.z : off[sb];
@@ -391,17 +389,74 @@ __global__ void __launch_bounds__(32, 32) line_filter_kernel(LineParams p) {
         }
         if (lane == 0) p.surv_cnt[sb] = cnt;
     }
+    }
 }
 
-#ifndef KA_LP_MINB
-#define KA_LP_MINB 6
-#endif
-// Probe pass.  One CTA per tile: the survivors are read densely, PB per thread with all their sector loads (the only
-// HBM access of a probe) in flight before the first use; eight tags matched SIMD-in-register; a miss in a sector
-// whose flags name other places follows them (L2 hits on the line just fetched, or the overflow table); a hit is
-// de-duplicated against the sequence's token set and tallied (warp match + redux, one shared atomic per sequence).
-__global__ void __launch_bounds__(LP_THREADS, KA_LP_MINB) line_probe_kernel(LineParams p) {
+// Probe pass.  One warp per tile, again without shared memory or barriers: the survivors are read densely, PB per
+// lane with all their sector loads (the only HBM access of a probe) in flight before the first use; eight tags
+// matched SIMD-in-register; a miss in a sector whose flags name other places follows them (L2 hits on the line just
+// fetched, or the overflow table).  The hits (de-dup token, role | seq << 16) are written back compacted over the
+// front of the tile's list — the warp has consumed an entry before a hit can land on it — and counted in hit_cnt.
+__global__ void __launch_bounds__(32, 32) line_probe_kernel(LineParams p) {
     constexpr int PB = LP_PB;
+    const uint32_t lane = threadIdx.x;
+    const uint32_t lt = (1u << lane) - 1u;
+    const LineTable tab = p.tab;
+    const unsigned long long pol_first = policy_evict_first();
+
+    for (uint32_t tile = p.tile0 + blockIdx.x; tile < p.tile1; tile += gridDim.x) {
+    const uint4 desc = p.first[tile];
+    const uint32_t s0 = desc.x, s1 = desc.x + desc.y;
+    for (uint32_t sb = s0; sb < s1; sb += LINE_MAX_SEQ) {
+        const uint32_t g0 = (sb == s0) ? desc.z : p.off[sb];
+        const uint32_t n = p.surv_cnt[sb];
+        uint2* const q = p.surv + g0;
+        uint32_t hcnt = 0;
+        uint2 kq[PB];
+#pragma unroll
+        for (int k = 0; k < PB; k++) kq[k] = (lane + k * 32 < n) ? q[lane + k * 32] : make_uint2(0, 0);
+        for (uint32_t base = 0; base < n; base += 32 * PB) {
+            uint32_t sec[PB], tg[PB];
+            uint4 sa[PB], sb2[PB];
+#pragma unroll
+            for (int k = 0; k < PB; k++) {
+                sec[k] = 0; tg[k] = 0;
+                sa[k] = make_uint4(0, 0, 0, 0); sb2[k] = sa[k];
+                if (base + lane + k * 32 < n) {
+                    line_locate(tab, kq[k].x & 0x3FFFFFFu, kq[k].y, sec[k], tg[k]);
+                    load_line_sector(tab.lines + 2 * (size_t)sec[k], pol_first, sa[k], sb2[k]);
+                }
+            }
+            // the next round's entries travel while this round's sectors do (they lie behind everything this round writes)
+            uint2 nx[PB];
+#pragma unroll
+            for (int k = 0; k < PB; k++) {
+                const uint32_t i = base + 32 * PB + lane + k * 32;
+                nx[k] = i < n ? q[i] : make_uint2(0, 0);
+            }
+#pragma unroll
+            for (int k = 0; k < PB; k++) {
+                if (base + k * 32 >= n) break;                          // (warp-uniform)
+                int role = -1;
+                uint32_t tok = 0;
+                if (base + lane + k * 32 < n) role = line_resolve(tab, pol_first, sec[k], tg[k], sa[k], sb2[k], tok);
+                const unsigned m = __ballot_sync(0xffffffffu, role >= 0);
+                if (role >= 0) q[hcnt + __popc(m & lt)] = make_uint2(tok, (uint32_t)role | ((kq[k].x >> 26) << 16));
+                hcnt += __popc(m);
+            }
+#pragma unroll
+            for (int k = 0; k < PB; k++) kq[k] = nx[k];
+        }
+        if (lane == 0) p.hit_cnt[sb] = hcnt;
+    }
+    }
+}
+
+// Tally pass.  One CTA per tile: every hit is de-duplicated against its sequence's token set (a protein contributes
+// the SET of its k-mers, ApplyKmerProcessor.java:123) and tallied (warp match + redux, one shared atomic per
+// sequence and warp), then the calls of the tile's sequences are written (:131-147).
+constexpr int LY_THREADS = 128;
+__global__ void __launch_bounds__(LY_THREADS, 8) line_tally_kernel(LineParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t* const s_off = reinterpret_cast<uint32_t*>(smem_raw);
     int* const s_cnt = reinterpret_cast<int*>(smem_raw + LP_OFF_CNT);
@@ -410,123 +465,103 @@ __global__ void __launch_bounds__(LP_THREADS, KA_LP_MINB) line_probe_kernel(Line
     uint32_t* const s_tok = reinterpret_cast<uint32_t*>(smem_raw + LP_OFF_TOK);
 
     const uint32_t tid = threadIdx.x, lane = tid & 31;
-    const uint4 desc = p.first[blockIdx.x];
-    const uint32_t s0 = desc.x, s1 = desc.x + desc.y;
-    if (desc.y == 0) return;
-    const LineTable tab = p.tab;
-    const unsigned long long pol_first = policy_evict_first();
 
+    for (uint32_t tile = p.tile0 + blockIdx.x; tile < p.tile1; tile += gridDim.x) {
+    const uint4 desc = p.first[tile];
+    const uint32_t s0 = desc.x, s1 = desc.x + desc.y;
     for (uint32_t sb = s0; sb < s1; sb += LINE_MAX_SEQ) {
         const uint32_t ns = min((uint32_t)LINE_MAX_SEQ, s1 - sb);
         const uint32_t g0 = (sb == s0) ? desc.z : p.off[sb];
-        const uint32_t n = p.surv_cnt[sb];
+        const uint32_t n = p.hit_cnt[sb];
         const uint2* const q = p.surv + g0;
-        // the first round's entries before anything else: their latency overlaps the shared-memory set-up
-        uint2 kq[PB];
-#pragma unroll
-        for (int k = 0; k < PB; k++) kq[k] = (tid + k * LP_THREADS < n) ? q[tid + k * LP_THREADS] : make_uint2(0, 0);
-
-        if (n == 0) {                                                   // (uniform) nothing survived: no call for these sequences
-            for (uint32_t i = tid; i < ns; i += LP_THREADS) line_emit(p, sb + i, 0, 0, 0);
+        if (n == 0) {                                                   // (uniform) no hit: no call for these sequences
+            for (uint32_t i = tid; i < ns; i += LY_THREADS) line_emit(p, sb + i, 0, 0, 0);
             continue;
         }
+        const uint2 first = tid < n ? q[tid] : make_uint2(0, 0);       // in flight during the set-up
         const uint32_t g1 = (sb + ns == s1) ? desc.w : p.off[sb + ns];
         const uint32_t ext = g1 - g0;
         KA_CHECK(n <= ext, 16u);
         KA_CHECK(tok_cap(ext) + 4u * ns + 8u <= tok_cap(p.ext_max) + 4u * LINE_MAX_SEQ + 8u, 2u);
-        for (uint32_t i = tid; i <= ns; i += LP_THREADS) s_off[i] = p.off[sb + i] - g0;
-        for (uint32_t i = tid; i < ns; i += LP_THREADS) { s_cnt[i] = 0; s_min[i] = 0x7fffffff; s_max[i] = -1; }
+        for (uint32_t i = tid; i <= ns; i += LY_THREADS) s_off[i] = p.off[sb + i] - g0;
+        for (uint32_t i = tid; i < ns; i += LY_THREADS) { s_cnt[i] = 0; s_min[i] = 0x7fffffff; s_max[i] = -1; }
         {
             const uint32_t ntok = tok_cap(ext) + 4u * ns + 4u;
             const uint4 z = make_uint4(0, 0, 0, 0);
-            for (uint32_t i = tid * 4; i < ntok; i += LP_THREADS * 4) *reinterpret_cast<uint4*>(s_tok + i) = z;
+            for (uint32_t i = tid * 4; i < ntok; i += LY_THREADS * 4) *reinterpret_cast<uint4*>(s_tok + i) = z;
         }
         __syncthreads();
-
-        for (uint32_t base = 0; base < n; base += LP_THREADS * PB) {
-            uint32_t sec[PB], tg[PB];
-            uint4 sa[PB], sb2[PB];
-#pragma unroll
-            for (int k = 0; k < PB; k++) {
-                sec[k] = 0; tg[k] = 0;
-                sa[k] = make_uint4(0, 0, 0, 0); sb2[k] = sa[k];
-                if (base + tid + k * LP_THREADS < n) {
-                    line_locate(tab, kq[k].x & 0x3FFFFFFu, kq[k].y, sec[k], tg[k]);
-                    load_line_sector(tab.lines + 2 * (size_t)sec[k], pol_first, sa[k], sb2[k]);
+        for (uint32_t base = 0; base < n; base += LY_THREADS) {
+            if (base + (tid & ~31u) >= n) break;                        // (warp-uniform) the whole warp is past the end
+            const uint32_t i = base + tid;
+            const uint2 h = base == 0 ? first : (i < n ? q[i] : make_uint2(0, 0));
+            int sq = -1;
+            const int role = (int)(h.y & 0xFFFFu);
+            if (i < n) {
+                sq = (int)(h.y >> 16);
+                const uint32_t a0 = s_off[sq], a1 = s_off[sq + 1];
+                KA_CHECK(sq < (int)ns && a1 >= a0, 8u);
+                if (!line_token_insert(s_tok + tok_cap(a0) + 4u * (uint32_t)sq, tok_cap(a1 - a0) + 4u, h.x)) sq = -1;
+            }
+            if (__any_sync(0xffffffffu, sq >= 0)) {
+                const unsigned grp = __match_any_sync(0xffffffffu, sq);
+                const int gmin = __reduce_min_sync(grp, sq >= 0 ? role : 0x7fffffff);
+                const int gmax = __reduce_max_sync(grp, sq >= 0 ? role : -1);
+                if (sq >= 0 && lane == (uint32_t)(__ffs(grp) - 1)) {
+                    atomicAdd(&s_cnt[sq], __popc(grp));
+                    atomicMin(&s_min[sq], gmin);
+                    atomicMax(&s_max[sq], gmax);
                 }
             }
-            // the next round's entries travel while this round's sectors do
-            uint2 nx[PB];
-#pragma unroll
-            for (int k = 0; k < PB; k++) {
-                const uint32_t i = base + LP_THREADS * PB + tid + k * LP_THREADS;
-                nx[k] = i < n ? q[i] : make_uint2(0, 0);
-            }
-#pragma unroll
-            for (int k = 0; k < PB; k++) {
-                if (base + (tid & ~31u) + k * LP_THREADS >= n) break;  // (warp-uniform) the whole warp is past the end
-                int role = -1;
-                uint32_t tok = 0;
-                if (base + tid + k * LP_THREADS < n) role = line_resolve(tab, pol_first, sec[k], tg[k], sa[k], sb2[k], tok);
-                // a hit: de-duplicate against the sequence's token set, then one lane per sequence updates the tallies
-                int sq = -1;
-                if (role >= 0) {
-                    sq = (int)(kq[k].x >> 26);
-                    const uint32_t a0 = s_off[sq], a1 = s_off[sq + 1];
-                    KA_CHECK(sq < (int)ns && a1 >= a0, 8u);
-                    if (!line_token_insert(s_tok + tok_cap(a0) + 4u * (uint32_t)sq, tok_cap(a1 - a0) + 4u, tok)) sq = -1;
-                }
-                if (__any_sync(0xffffffffu, sq >= 0)) {
-                    const unsigned grp = __match_any_sync(0xffffffffu, sq);
-                    const int gmin = __reduce_min_sync(grp, sq >= 0 ? role : 0x7fffffff);
-                    const int gmax = __reduce_max_sync(grp, sq >= 0 ? role : -1);
-                    if (sq >= 0 && lane == (uint32_t)(__ffs(grp) - 1)) {
-                        atomicAdd(&s_cnt[sq], __popc(grp));
-                        atomicMin(&s_min[sq], gmin);
-                        atomicMax(&s_max[sq], gmax);
-                    }
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < PB; k++) kq[k] = nx[k];
         }
         __syncthreads();
-        for (uint32_t i = tid; i < ns; i += LP_THREADS) line_emit(p, sb + i, s_cnt[i], s_min[i], s_max[i]);
+        for (uint32_t i = tid; i < ns; i += LY_THREADS) line_emit(p, sb + i, s_cnt[i], s_min[i], s_max[i]);
         __syncthreads();
+    }
     }
 }
 
 namespace {
-template <int K> void filter_launch(const LineParams& p, cudaStream_t st) {
-    if (p.tab.filt) line_filter_kernel<K, true><<<p.n_tiles, 32, 0, st>>>(p);
-    else line_filter_kernel<K, false><<<p.n_tiles, 32, 0, st>>>(p);
+template <int K> void filter_launch(const LineParams& p, unsigned grid, cudaStream_t st) {
+    if (p.tab.filt) line_filter_kernel<K, true><<<grid, 32, 0, st>>>(p);
+    else line_filter_kernel<K, false><<<grid, 32, 0, st>>>(p);
 }
 }  // namespace
 
 cudaError_t line_tile_set_smem(size_t bytes) {
-    cudaError_t ce = cudaFuncSetAttribute(line_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(line_probe_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaError_t ce = cudaFuncSetAttribute(line_tally_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(line_tally_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     return ce;
 }
 
-cudaError_t launch_line_tiles(const LineParams& p, cudaStream_t st) {
-    if (p.n_tiles == 0) return cudaSuccess;
-    const size_t smem_p = line_probe_smem_bytes(p.ext_max);
+// the three passes over tiles [p.tile0, p.tile1), each with `grid` CTAs striding over them
+cudaError_t launch_line_filter(const LineParams& p, unsigned grid, cudaStream_t st) {
+    if (p.tile1 <= p.tile0) return cudaSuccess;
+    grid = grid < p.tile1 - p.tile0 ? grid : p.tile1 - p.tile0;
     switch (p.tab.K) {
-        case 2: filter_launch<2>(p, st); break;
-        case 3: filter_launch<3>(p, st); break;
-        case 4: filter_launch<4>(p, st); break;
-        case 5: filter_launch<5>(p, st); break;
-        case 6: filter_launch<6>(p, st); break;
-        case 7: filter_launch<7>(p, st); break;
-        case 8: filter_launch<8>(p, st); break;
-        case 9: filter_launch<9>(p, st); break;
-        case 10: filter_launch<10>(p, st); break;
+        case 2: filter_launch<2>(p, grid, st); break;
+        case 3: filter_launch<3>(p, grid, st); break;
+        case 4: filter_launch<4>(p, grid, st); break;
+        case 5: filter_launch<5>(p, grid, st); break;
+        case 6: filter_launch<6>(p, grid, st); break;
+        case 7: filter_launch<7>(p, grid, st); break;
+        case 8: filter_launch<8>(p, grid, st); break;
+        case 9: filter_launch<9>(p, grid, st); break;
+        case 10: filter_launch<10>(p, grid, st); break;
         default: return cudaErrorInvalidValue;
     }
-    cudaError_t ce = cudaGetLastError();
-    if (ce != cudaSuccess) return ce;
-    line_probe_kernel<<<p.n_tiles, LP_THREADS, smem_p, st>>>(p);
+    return cudaGetLastError();
+}
+cudaError_t launch_line_probe(const LineParams& p, unsigned grid, cudaStream_t st) {
+    if (p.tile1 <= p.tile0) return cudaSuccess;
+    grid = grid < p.tile1 - p.tile0 ? grid : p.tile1 - p.tile0;
+    line_probe_kernel<<<grid, 32, 0, st>>>(p);
+    return cudaGetLastError();
+}
+cudaError_t launch_line_tally(const LineParams& p, unsigned grid, cudaStream_t st) {
+    if (p.tile1 <= p.tile0) return cudaSuccess;
+    grid = grid < p.tile1 - p.tile0 ? grid : p.tile1 - p.tile0;
+    line_tally_kernel<<<grid, LY_THREADS, line_probe_smem_bytes(p.ext_max), st>>>(p);
     return cudaGetLastError();
 }
 

@@ -106,11 +106,13 @@ struct LineParams {
     const uint32_t* pk;               // packed codes of the chunk: chunk-relative residue g at bits [5g, 5g+5)
     uint32_t* off;                    // chunk-relative offsets (n_seq + 1), written by the plan kernel
     uint32_t n_seq, n_tiles;
+    uint32_t tile0, tile1;            // tiles of this launch of the filter / probe / tally passes
     uint32_t tile_span, long_seq, mid_seq, ext_max;
     uint32_t stage_bytes;             // shared-memory bytes reserved for the packed stage
     uint4* first;                     // n_tiles descriptors {first seq, n seqs, g0, g1}
     uint2* surv;                      // survivors of the filter pass: (H | seq in tile << 26, Lo), the tile's at surv[g0 ...)
     uint32_t* surv_cnt;               // ... and their number, at the index of the tile's (sub-batch's) first sequence
+    uint32_t* hit_cnt;                // hits of the probe pass (token, role | seq << 16), compacted over the front of the tile's list
     uint4* mid_desc;
     uint32_t* mid_count;
     uint32_t* big_count;
@@ -133,7 +135,10 @@ cudaError_t line_tile_set_smem(size_t bytes);
 // residue index of chunk-relative residue 0.
 cudaError_t launch_line_plan(const LineParams& p, const unsigned long long* off64, const uint32_t* off32,
                              unsigned long long origin, cudaStream_t st);
-cudaError_t launch_line_tiles(const LineParams& p, cudaStream_t st);   // filter pass + probe pass
+// the three passes over tiles [p.tile0, p.tile1): `grid` CTAs stride over them (32, 32 and 128 threads)
+cudaError_t launch_line_filter(const LineParams& p, unsigned grid, cudaStream_t st);
+cudaError_t launch_line_probe(const LineParams& p, unsigned grid, cudaStream_t st);
+cudaError_t launch_line_tally(const LineParams& p, unsigned grid, cudaStream_t st);
 cudaError_t launch_line_big(const LineParams& p, int grid, cudaStream_t st);
 
 // residue bytes -> 5-bit codes.  bytes[0] is chunk-relative residue `lead`; residues outside
