@@ -48,6 +48,7 @@ struct Pipe {
     uint4* mid = nullptr; size_t mid_cap = 0;
     uint32_t* scratch = nullptr; size_t scratch_cap = 0;
     cudaEvent_t ev_k0 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr, ev_k1 = nullptr, done = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;       // line table: hand-over to and from the device's compute stream
     bool busy = false;
     // option "ingest_via": the chunk lands on another GPU with a faster host path and crosses NVLink from there
     uint8_t* via_buf = nullptr; size_t via_cap = 0;      // staging buffer ON the via device
@@ -61,6 +62,7 @@ struct Device {
     uint4* table = nullptr;
     uint4* ovf = nullptr;     // overflow table (cls 32/64)
     uint32_t* filt = nullptr; // presence filter of the line table: one word per sector
+    cudaStream_t line_st = nullptr;  // line table: the passes of all chunks run on ONE stream (see enqueue_line_kernels)
     uint8_t* lut5 = nullptr;  // 256-byte residue -> radix digit table (31 = not in the DB alphabet)
     uint8_t* inv32 = nullptr; // 32-byte digit -> residue byte table (entry 31 = a byte outside the alphabet)
     const uint4** shard_sectors = nullptr;  // sharded mode: device array of peer pointers, one per shard

@@ -289,7 +289,8 @@ __global__ void __launch_bounds__(32, 32) line_filter_kernel(LineParams p) {
     const unsigned long long pol_last = policy_evict_last();
 
     for (uint32_t tile = p.tile0 + blockIdx.x; tile < p.tile1; tile += gridDim.x) {
-    const uint4 desc = p.first[tile];
+    // single-sequence (mid) tiles first: the longest items of the launch start earliest
+    const uint4 desc = tile < p.n_mid_tiles ? p.mid_desc[tile] : p.first[tile - p.n_mid_tiles];
     const uint32_t s0 = desc.x, s1 = desc.x + desc.y;
     for (uint32_t sb = s0; sb < s1; sb += LINE_MAX_SEQ) {
         const uint32_t ns = min((uint32_t)LINE_MAX_SEQ, s1 - sb);
@@ -405,7 +406,8 @@ __global__ void __launch_bounds__(32, 32) line_probe_kernel(LineParams p) {
     const unsigned long long pol_first = policy_evict_first();
 
     for (uint32_t tile = p.tile0 + blockIdx.x; tile < p.tile1; tile += gridDim.x) {
-    const uint4 desc = p.first[tile];
+    // single-sequence (mid) tiles first: the longest items of the launch start earliest
+    const uint4 desc = tile < p.n_mid_tiles ? p.mid_desc[tile] : p.first[tile - p.n_mid_tiles];
     const uint32_t s0 = desc.x, s1 = desc.x + desc.y;
     for (uint32_t sb = s0; sb < s1; sb += LINE_MAX_SEQ) {
         const uint32_t g0 = (sb == s0) ? desc.z : p.off[sb];

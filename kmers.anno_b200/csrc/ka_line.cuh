@@ -107,6 +107,7 @@ struct LineParams {
     uint32_t* off;                    // chunk-relative offsets (n_seq + 1), written by the plan kernel
     uint32_t n_seq, n_tiles;
     uint32_t tile0, tile1;            // tiles of this launch of the filter / probe / tally passes
+    uint32_t n_mid_tiles;             // filter / probe passes: tiles [0, n_mid_tiles) are mid_desc[], the others first[tile - n_mid_tiles]
     uint32_t tile_span, long_seq, mid_seq, ext_max;
     uint32_t stage_bytes;             // shared-memory bytes reserved for the packed stage
     uint4* first;                     // n_tiles descriptors {first seq, n seqs, g0, g1}
