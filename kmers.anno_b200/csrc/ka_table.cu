@@ -386,10 +386,11 @@ int db_load_impl(ka_engine* e, const uint8_t* kmers, const int32_t* role_ids, ui
             return fail(e, KA_ERR_TOO_BIG, "ka_db_load: %llu lines with role ids up to %d exceed the 64-bit (line, role) word",
                         (unsigned long long)n, max_role);
     }
-    // line table (slot class 16): option slot_bits = 16 only.  It halves the DRAM traffic per probe (51 B against
-    // 95 B, profiles/r02_summary.md) but its queue-based kernel reaches 38 G probes/s against 52 for the sector
-    // kernel on the C3 batch, so it is never chosen automatically.
-    if (e->slot_bits == 16) {
+    // line table (slot class 16): the default of a replicated table whenever its layout fits (K <= 10, role ids
+    // below 65536), or forced by slot_bits = 16.  57 B of DRAM traffic per probe against 95 B, 64 against 53 G probes/s
+    // on the C3 batch and 112 against 54 on genomes unrelated to the DB (profiles/r02_summary.md); K = 11, 12, wide
+    // and sharded tables use the sector classes.
+    if (e->slot_bits == 16 || (e->slot_bits == 0 && e->table_mode == 0 && !e->wide && max_role <= 0xFFFF)) {
         LineTable lg;
         const bool forced = e->slot_bits == 16;
         if (forced && (e->table_mode != 0 || e->wide || max_role > 0xFFFF))

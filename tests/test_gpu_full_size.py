@@ -18,7 +18,7 @@ def world():
     eng = ka.Engine([0])
     eng.db_load(kmers, roles, 8)
     info = eng.db_info()
-    assert info["n_keys"] == int(1e8) and info["slot_bits"] == 32
+    assert info["n_keys"] == int(1e8) and info["slot_bits"] == 16
     base = eng.annotate(res, off, 5)
     yield {"ka": ka, "eng": eng, "kmers": kmers, "roles": roles, "res": res, "off": off, "true": true_role,
            "base": base, "fam": fam}
