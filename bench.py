@@ -20,8 +20,10 @@ ranks share nothing on the data path (no collective), results are gathered by th
                        per-sequence results are all inside the timed region; the packing itself is
                        timed separately (`host_pack`) and `e2e_bytes` is the same loop through
                        ka_annotate() on raw residue bytes + 64-bit offsets.
-  roofline             dominant kernel = tile_kernel; achieved = 33 B/probe x probes per
-                       launch / its mean CUDA-event duration; peak = MEASURED_PEAKS.json.
+  roofline             the kernels of the probe path: the three passes of the line table (filter,
+                       probe, tally: one launch group) or the sector tile kernel; achieved = 33 B/probe
+                       x probes per launch / the group's mean CUDA-event duration; peak =
+                       MEASURED_PEAKS.json; traffic = the passes' DRAM bytes from the committed ncu export.
   rand_roofline        the graded denominator of BASELINE.md §3: R_rand = independent random
                        32-byte sector loads over a buffer the size of the table, measured
                        live in this run by ka_probe_roofline.
@@ -51,30 +53,39 @@ sys.path.insert(0, ROOT)
 SEED = 20261018
 N_PROT = 4500
 BYTES_PER_PROBE = 33.0  # 32-byte bucket sector + 1 residue byte
-# DRAM traffic per probe of the dominant kernel comes from the committed ncu export of this round
-# (profiles/r02_tile_kernel_raw.csv + its capture note), never from a constant in this file.
-NCU_RAW = os.path.join(ROOT, "profiles", "r02_tile_kernel_raw.csv")
-NCU_NOTE = os.path.join(ROOT, "profiles", "r02_tile_kernel_capture.json")
+# DRAM traffic per probe of the probe-path kernels comes from the committed ncu exports of this round
+# (profiles/r02_line_passes_raw.csv or r02_tile_kernel_raw.csv + their capture notes), never from a constant here.
+NCU_FILES = {16: ("r02_line_passes_raw.csv", "r02_line_passes_capture.json"),
+             32: ("r02_tile_kernel_raw.csv", "r02_tile_kernel_capture.json")}
 
 
-def ncu_dram_bytes_per_probe():
-    """(bytes per probe, description) from the committed `ncu --page raw --csv` export; loud if missing."""
+def ncu_dram_bytes_per_probe(slot_bits):
+    """(bytes per probe, description, per-kernel shares) from the committed `ncu --page raw --csv` export of the
+    table layout in use; loud if missing."""
     import csv
-    if not (os.path.exists(NCU_RAW) and os.path.exists(NCU_NOTE)):
-        raise SystemExit(f"bench.py: {NCU_RAW} / {NCU_NOTE} are missing: the roofline's DRAM traffic must come from a "
+    raw_name, note_name = NCU_FILES[16 if slot_bits == 16 else 32]
+    raw, note_path = os.path.join(ROOT, "profiles", raw_name), os.path.join(ROOT, "profiles", note_name)
+    if not (os.path.exists(raw) and os.path.exists(note_path)):
+        raise SystemExit(f"bench.py: {raw} / {note_path} are missing: the roofline's DRAM traffic must come from a "
                          "committed ncu capture (see profiles/r02_summary.md)")
-    note = json.load(open(NCU_NOTE))
-    rows = list(csv.reader(open(NCU_RAW)))
+    note = json.load(open(note_path))
+    rows = list(csv.reader(open(raw)))
     hdr, units = rows[0], rows[1]
-    row = rows[2 + int(note.get("row", 0))]
 
-    def metric(name):
+    def metric(row, name):
         i = hdr.index(name)
-        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[units[i]]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12,
+                 "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}[units[i]]
         return float(row[i]) * scale
-    total = metric("dram__bytes_read.sum") + metric("dram__bytes_write.sum")
+    total, parts = 0.0, []
+    for r in note.get("rows", [note.get("row", 0)]):
+        row = rows[2 + int(r)]
+        b = metric(row, "dram__bytes_read.sum") + metric(row, "dram__bytes_write.sum")
+        total += b
+        parts.append({"kernel": row[hdr.index("Kernel Name")].split("(")[0].strip(), "ncu_ms": metric(row, "gpu__time_duration.sum"),
+                      "dram_bytes_per_probe": b / float(note["probes"])})
     return total / float(note["probes"]), (f"ncu dram__bytes_read.sum + dram__bytes_write.sum of {note['kernel']} = {total / 1e9:.3f} GB for "
-                                           f"{note['probes']:.4g} probes ({note['command']}; profiles/r02_tile_kernel_raw.csv)")
+                                           f"{note['probes']:.4g} probes ({note['command']}; profiles/{raw_name})"), parts
 
 
 def parse():
@@ -341,6 +352,42 @@ def cli_e2e(a, fam, n_genomes=200, n_kmers=5_000_000):
                         "one-off reservation of the pinned buffers (both logged by the command)"}
     finally:
         shutil.rmtree(root, ignore_errors=True)
+
+
+def layout_comparison(a, ka, kmers, roles, res, off, genomes=300):
+    """Probe-path kernel rate of the two table layouts on the first `genomes` proteomes of the C3 batch (same protein
+    families as the DB: ~35 % of the windows hit) and on as many proteomes of UNRELATED families (nearly all windows
+    miss — what annotating a new genome against a role DB mostly looks like): resident inputs, best of 4."""
+    from kmers_anno_b200 import synth
+    genomes = min(genomes, a.genomes)
+    n_seq = genomes * N_PROT
+    batches = {"c3_families": (res[: int(off[n_seq])], off[: n_seq + 1])}
+    cres, coff, _ = synth.Families(a.roles, SEED + 7).batch(0, genomes, n_prot=N_PROT, K=a.K)
+    batches["unrelated_families"] = (cres, coff)
+    out = {"proteomes": genomes}
+    for name, bits in (("line_table", 16), ("sector_table", 32)):
+        with ka.Engine([0]) as eng:
+            eng.set_option("slot_bits", bits)
+            try:
+                eng.db_load(kmers, roles, a.K)
+            except Exception as err:  # noqa: BLE001 — a K or role range the line layout does not take
+                out[name] = {"unavailable": str(err)}
+                continue
+            info = eng.db_info()
+            rec = {"slot_bits": int(info["slot_bits"]), "table_bytes": int(info["table_bytes"]) + int(info.get("filter_bytes", 0))}
+            for bname, (r, o) in batches.items():
+                b = eng.upload(r, o)
+                best, st = 1e30, None
+                for _ in range(4):
+                    eng.annotate_resident(b, a.min_hits)
+                    st = eng.stats()
+                    best = min(best, st["tile_kernel_ms"])
+                calls = eng.download(b)
+                b.free()
+                rec[bname] = {"kernel_ms": best, "probes_per_s": st["probes"] / (best * 1e-3), "probes": int(st["probes"]),
+                              "called": int((calls[2] == 1).sum())}
+            out[name] = rec
+    return out
 
 
 def build_record(a, eng_cls, fam):
@@ -667,10 +714,12 @@ def main():
     # ---- roofline of the dominant kernel ----------------------------------------------
     peak, peak_src = measured_peak()
     achieved = BYTES_PER_PROBE * probes / (tile_ms * 1e-3) / 1e9
-    dram_per_probe, dram_note = ncu_dram_bytes_per_probe()
-    roofline = {"bound": "hbm", "kernel": "tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    dram_per_probe, dram_note, ncu_parts = ncu_dram_bytes_per_probe(int(info["slot_bits"]))
+    kernel_name = ("line_filter_kernel + line_probe_kernel + line_tally_kernel (the three passes of the line table, one launch group; "
+                   "the probe pass is the HBM-bound one)") if int(info["slot_bits"]) == 16 else "tile_kernel"
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": dram_per_probe * probes,
-                "traffic_bytes_per_probe": dram_per_probe,
+                "traffic_bytes_per_probe": dram_per_probe, "ncu_passes": ncu_parts,
                 "traffic_note": dram_note + " x probes of this launch",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_probe": BYTES_PER_PROBE, "probes_per_launch": int(probes),
@@ -694,10 +743,11 @@ def main():
         cpu["gpu_matches_oracle_on_sample"] = bool(all(np.array_equal(x, y) for x, y in zip(g, cpu_out)))
     eng.close()
 
-    cli = build = None
+    cli = build = layouts = None
     if rank == 0 and world == 1 and not a.no_cli:
         cli = cli_e2e(a, fam)
         build = build_record(a, ka.Engine, fam)
+        layouts = layout_comparison(a, ka, kmers, roles, res, off)
 
     multi = None
     if world > 1 and not a.no_multi and not a.no_e2e:
@@ -733,6 +783,8 @@ def main():
             line["cli_e2e"] = cli
         if build:
             line["build"] = build
+        if layouts:
+            line["layout_comparison"] = layouts
         if multi:
             line.update(multi)
         print(json.dumps(line), flush=True)
