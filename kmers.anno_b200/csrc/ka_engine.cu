@@ -110,7 +110,7 @@ int pipe_reserve(Device& d, Pipe& p, uint64_t n_res, uint64_t n_seq, uint64_t n_
     }
     if ((rc = ensure(d, p.first, p.first_cap, n_tiles + 2, "tile index"))) return rc;
     if (need_surv && ((rc = ensure(d, p.surv, p.surv_cap, n_res + 128 + 64, "survivor list")) ||
-                      (rc = ensure(d, p.surv_cnt, p.surv_cnt_cap, 2 * (n_seq + 2), "survivor counts")))) return rc;
+                      (rc = ensure(d, p.surv_cnt, p.surv_cnt_cap, 2 * (n_seq + 2 + n_mid), "survivor counts")))) return rc;
     if ((rc = ensure(d, p.big, p.big_cap, n_long + 1, "long-sequence list"))) return rc;
     if ((rc = ensure(d, p.mid, p.mid_cap, n_mid + 1, "mid-sequence tiles"))) return rc;
     if ((rc = ensure(d, p.scratch, p.scratch_cap, (wide ? 2 : 1) * (2 * long_res + 4), "long-sequence tokens")))
@@ -127,7 +127,7 @@ static bool scan_offsets_t(const OffT* off, uint64_t cs, uint64_t ce, uint32_t l
         if (off[i + 1] < off[i]) return false;
         uint64_t L = (uint64_t)off[i + 1] - (uint64_t)off[i];
         if (L > mid_seq) { s.n_long++; s.long_res += L; }
-        else if (L > long_seq) s.n_mid++;
+        else if (L > long_seq) { s.n_mid++; s.n_mid_seg += (L + LINE_MID_SEG - 1) / LINE_MID_SEG; }
         if (L >= (uint64_t)K) s.probes += L - K + 1;
     }
     s.n_res = (uint64_t)off[ce] - (uint64_t)off[cs];
@@ -289,11 +289,11 @@ void fill_line_params(ka_engine* e, Device& d, Pipe& p, uint64_t n_res, uint64_t
     lp.pk = p.pk;
     lp.off = p.off32;
     lp.n_seq = (uint32_t)n_seq;
-    lp.n_tiles = (uint32_t)(n_res / e->tile_span + 1);
-    lp.tile_span = e->tile_span;
+    lp.tile_span = line_span(e, d, n_res);
+    lp.n_tiles = (uint32_t)(n_res / lp.tile_span + 1);
     lp.long_seq = e->long_seq;
     lp.mid_seq = std::max(e->mid_seq, e->long_seq);
-    lp.ext_max = e->tile_span + e->long_seq;
+    lp.ext_max = lp.tile_span + e->long_seq;
     line_tile_smem_bytes(lp.ext_max, &lp.stage_bytes);
     lp.first = p.first;
     lp.surv = p.surv;
@@ -321,15 +321,18 @@ void fill_line_params(ka_engine* e, Device& d, Pipe& p, uint64_t n_res, uint64_t
 // chunks never run side by side — the probe pass of one would evict the filter words the filter pass of the other
 // needs from L2 (measured: 29.9 -> 32.7-38 ms end to end when every pipe launched on its own stream).
 int enqueue_line_kernels(ka_engine* e, Device& d, Pipe& p, const LineParams& lp, bool off_is_64, uint64_t origin,
-                         uint64_t n_long, uint64_t n_mid) {
+                         uint64_t n_long, uint64_t n_mid, bool solo) {
     const size_t smem = line_tile_smem_bytes(lp.ext_max, nullptr);
     { int rc = ensure_tile_smem(d); if (rc) return rc; }
     if (smem > d.smem_set) return dev_fail(d, KA_ERR_INVALID, "tile shared memory exceeds the device limit", cudaErrorInvalidValue);
-    if (!d.line_st) DCK(d, cudaStreamCreateWithFlags(&d.line_st, cudaStreamNonBlocking));
-    cudaStream_t st = d.line_st;
+    // (a call that is a single chunk on this device has nothing to be kept apart from: it stays on the pipe's stream)
+    if (!solo && !d.line_st) DCK(d, cudaStreamCreateWithFlags(&d.line_st, cudaStreamNonBlocking));
+    cudaStream_t st = solo ? p.st : d.line_st;
     DCK(d, cudaMemsetAsync(p.ctr, 0, 16, p.st));
-    DCK(d, cudaEventRecord(p.ev_in, p.st));
-    DCK(d, cudaStreamWaitEvent(st, p.ev_in, 0));
+    if (!solo) {
+        DCK(d, cudaEventRecord(p.ev_in, p.st));
+        DCK(d, cudaStreamWaitEvent(st, p.ev_in, 0));
+    }
     DCK(d, cudaEventRecord(p.ev_k0, st));
     DCK(d, launch_line_plan(lp, off_is_64 ? p.off : nullptr, p.off32_in, origin, st));
     d.launches += 1;
@@ -339,23 +342,40 @@ int enqueue_line_kernels(ka_engine* e, Device& d, Pipe& p, const LineParams& lp,
     // scheduler balances tiles of very different cost (a grid of resident warps striding over the tiles measured
     // 0.95 against 0.75 ms for the probe pass of 60 proteomes).
     const unsigned all = 0x7fffffffu;
+    static const bool trace = getenv("KA_LINE_TRACE") != nullptr;     // debugging aid: per-pass times on stderr (synchronises)
+    cudaEvent_t tv[5] = {};
+    if (trace) for (auto& ev : tv) { cudaEventCreate(&ev); }
+    if (trace) cudaEventRecord(tv[0], st);
     LineParams q = lp;
-    q.n_mid_tiles = (uint32_t)n_mid;
+    q.n_mid_tiles = (uint32_t)n_mid; q.tally_mid = 0;   // (n_mid counts SEGMENTS of mid sequences here)
     q.tile0 = 0; q.tile1 = (uint32_t)n_mid + lp.n_tiles;
     DCK(d, launch_line_filter(q, all, st));
+    if (trace) cudaEventRecord(tv[1], st);
     DCK(d, launch_line_probe(q, all, st));
-    q.n_mid_tiles = 0; q.tile1 = lp.n_tiles;
+    if (trace) cudaEventRecord(tv[2], st);
+    q.n_mid_tiles = 0; q.tally_mid = 0; q.tile1 = lp.n_tiles;
     DCK(d, launch_line_tally(q, all, st));
+    if (trace) cudaEventRecord(tv[3], st);
     d.launches += 3;
     if (n_mid) {
         LineParams lm = lp;
         lm.first = p.mid;
-        lm.n_mid_tiles = 0; lm.tile0 = 0; lm.tile1 = (uint32_t)n_mid;
+        lm.n_mid_tiles = 0; lm.tally_mid = 1; lm.tile0 = 0; lm.tile1 = (uint32_t)n_mid;
         lm.ext_max = lp.mid_seq;
         const size_t smem_mid = line_tile_smem_bytes(lm.ext_max, &lm.stage_bytes);
         if (smem_mid > d.smem_set) return dev_fail(d, KA_ERR_INVALID, "mid tile shared memory exceeds the device limit", cudaErrorInvalidValue);
         DCK(d, launch_line_tally(lm, all, st));
         d.launches += 1;
+    }
+    if (trace) {
+        cudaEventRecord(tv[4], st);
+        cudaEventSynchronize(tv[4]);
+        float f = 0, pr = 0, ta = 0, tm = 0;
+        cudaEventElapsedTime(&f, tv[0], tv[1]); cudaEventElapsedTime(&pr, tv[1], tv[2]);
+        cudaEventElapsedTime(&ta, tv[2], tv[3]); cudaEventElapsedTime(&tm, tv[3], tv[4]);
+        fprintf(stderr, "[line trace dev%d] %u tiles of %u + %llu mid segments: filter %.1f us, probe %.1f us, tally %.1f us, mid tally %.1f us\n",
+                d.id, lp.n_tiles, lp.tile_span, (unsigned long long)n_mid, f * 1e3, pr * 1e3, ta * 1e3, tm * 1e3);
+        for (auto& ev : tv) cudaEventDestroy(ev);
     }
     DCK(d, cudaEventRecord(p.ev_t1, st));
     if (n_long) {
@@ -364,8 +384,10 @@ int enqueue_line_kernels(ka_engine* e, Device& d, Pipe& p, const LineParams& lp,
         d.launches += 1;
     }
     DCK(d, cudaEventRecord(p.ev_k1, st));
-    DCK(d, cudaEventRecord(p.ev_out, st));
-    DCK(d, cudaStreamWaitEvent(p.st, p.ev_out, 0));
+    if (!solo) {
+        DCK(d, cudaEventRecord(p.ev_out, st));
+        DCK(d, cudaStreamWaitEvent(p.st, p.ev_out, 0));
+    }
     return KA_OK;
 }
 
@@ -446,8 +468,8 @@ int annotate_range(ka_engine* e, Device& d, const BatchIn& in, uint64_t s_begin,
             p.busy = false;
         }
         const uint64_t n = ce - cs;
-        const uint64_t n_tiles = sh.n_res / e->tile_span + 1;
-        int rc = pipe_reserve(d, p, sh.n_res, n, n_tiles, sh.n_long, sh.long_res, sh.n_mid, e->geom.wide != 0,
+        const uint64_t n_tiles = tiles_of(e, d, sh.n_res);
+        int rc = pipe_reserve(d, p, sh.n_res, n, n_tiles, sh.n_long, sh.long_res, line ? sh.n_mid_seg : sh.n_mid, e->geom.wide != 0,
                               !packed || !line, packed || line, line);
         if (rc) return rc;
         const uint64_t r_begin = in.off(cs), r_end = in.off(ce);
@@ -467,7 +489,7 @@ int annotate_range(ka_engine* e, Device& d, const BatchIn& in, uint64_t s_begin,
             if (!packed) { DCK(d, launch_pack(p.res, lead, sh.n_res, d.lut5, p.pk, p.st)); d.launches += 1; }
             LineParams lp;
             fill_line_params(e, d, p, sh.n_res, n, min_hits, lp);
-            rc = enqueue_line_kernels(e, d, p, lp, !packed, origin, sh.n_long, sh.n_mid);
+            rc = enqueue_line_kernels(e, d, p, lp, !packed, origin, sh.n_long, sh.n_mid_seg, cs == s_begin && ce == s_end);
         } else {
             // packed input: the narrow probe kernels stage the code stream themselves; the wide / sharded forms and
             // the long-sequence kernel read residue bytes, so those chunks are expanded first
@@ -803,13 +825,13 @@ int ka_batch_upload(ka_engine* e, int dev_index, const uint8_t* residues, const 
     if (e->line && sh.n_res > 0x7fffff00ull) return fail(e, KA_ERR_TOO_BIG, "ka_batch_upload: more than 2^31 residues in one resident batch");
     ka_batch* b = new ka_batch();
     b->dev_index = dev_index; b->n_seq = N; b->n_res = sh.n_res; b->base = offsets[0];
-    b->long_res = sh.long_res; b->n_long = sh.n_long; b->n_mid = sh.n_mid;
+    b->long_res = sh.long_res; b->n_long = sh.n_long; b->n_mid = e->line ? sh.n_mid_seg : sh.n_mid;
     b->origin = offsets[0] & ~127ull;
     b->tile_span = e->tile_span; b->long_seq = e->long_seq; b->mid_seq = e->mid_seq; b->db_serial = e->db_serial;
     int rc = pipe_init(d, b->p);
     // resident form: the 5-bit stream wherever the tile kernels can stage it (line table; narrow unsharded sector tables)
     const bool keep_codes = e->line || (!e->geom.wide && e->geom.n_shards <= 1 && e->resident_packed);
-    if (rc == KA_OK) rc = pipe_reserve(d, b->p, sh.n_res, N, sh.n_res / e->tile_span + 1, sh.n_long, sh.long_res, sh.n_mid, e->geom.wide != 0,
+    if (rc == KA_OK) rc = pipe_reserve(d, b->p, sh.n_res, N, tiles_of(e, d, sh.n_res), sh.n_long, sh.long_res, e->line ? sh.n_mid_seg : sh.n_mid, e->geom.wide != 0,
                                        true, keep_codes, e->line);
     cudaError_t ce = cudaSuccess;
     if (rc == KA_OK && sh.n_res) ce = cudaMemcpy(b->p.res, residues + offsets[0], sh.n_res, cudaMemcpyHostToDevice);
@@ -850,7 +872,7 @@ int ka_annotate_resident(ka_engine* e, ka_batch* b, int32_t min_hits) {
     if (e->line) {
         LineParams lp;
         fill_line_params(e, d, b->p, b->n_res, b->n_seq, min_hits, lp);
-        rc = enqueue_line_kernels(e, d, b->p, lp, true, b->origin, b->n_long, b->n_mid);
+        rc = enqueue_line_kernels(e, d, b->p, lp, true, b->origin, b->n_long, b->n_mid, true);
     } else {
         AnnotParams ap;
         fill_params(e, d, b->p, b->base, b->n_res, b->n_seq, min_hits, ap);

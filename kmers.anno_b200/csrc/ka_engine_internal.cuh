@@ -171,6 +171,7 @@ struct BatchIn {
 
 struct ChunkShape {
     uint64_t n_res = 0, n_long = 0, long_res = 0, probes = 0, n_mid = 0;
+    uint64_t n_mid_seg = 0;    // line table: segments of the mid sequences (ka_line.cuh LINE_MID_SEG)
 };
 
 
@@ -192,11 +193,21 @@ static inline uint64_t chunk_of(const ka_engine* e, bool routed) {
     return e->chunk_residues ? e->chunk_residues : (routed ? 32ull << 20 : 64ull << 20);
 }
 
+// Tile span of the line passes for a chunk of n_res residues: one tile is one warp of the filter and probe passes,
+// so a chunk with fewer tiles than the GPU holds warps (a single proteome: config 2) is cut into smaller tiles.
+static inline uint32_t line_span(const ka_engine* e, const Device& d, uint64_t n_res) {
+    const uint64_t want = (n_res / ((uint64_t)d.sm_count * 32) + 127) & ~127ull;
+    return (uint32_t)std::min<uint64_t>(e->tile_span, std::max<uint64_t>(256, want));
+}
+static inline uint64_t tiles_of(const ka_engine* e, const Device& d, uint64_t n_res) {
+    return n_res / (e->line ? line_span(e, d, n_res) : e->tile_span) + 1;
+}
+
 int annotate_range(ka_engine* e, Device& d, const BatchIn& in, uint64_t s_begin, uint64_t s_end, int32_t min_hits,
                    int32_t* out_role, int32_t* out_hits, uint8_t* out_flag);
 void fill_line_params(ka_engine* e, Device& d, Pipe& p, uint64_t n_res, uint64_t n_seq, int32_t min_hits, LineParams& lp);
 int enqueue_line_kernels(ka_engine* e, Device& d, Pipe& p, const LineParams& lp, bool off_is_64, uint64_t origin,
-                         uint64_t n_long, uint64_t n_mid);
+                         uint64_t n_long, uint64_t n_mid, bool solo);
 
 // ---- ka_table.cu ----
 // Source of the DB lines: host arrays, or the synthetic generator (kmers == NULL).

@@ -206,12 +206,18 @@ __global__ void line_plan_kernel(LineParams p, const OffT* __restrict__ off, uns
             BigItem it; it.seq = (uint32_t)gid; it.pad = 0; it.tok_base = tb;
             reinterpret_cast<BigItem*>(p.big_list)[idx] = it;
         } else if (L > p.long_seq) {
-            const uint32_t idx = atomicAdd(p.mid_count, 1u);
-            uint4 d;
-            d.x = (uint32_t)gid; d.y = 1;
-            d.z = (uint32_t)((unsigned long long)off[gid] - origin);
-            d.w = (uint32_t)((unsigned long long)off[gid + 1] - origin);
-            p.mid_desc[idx] = d;
+            // a sequence with tiles of its own: equal segments of <= LINE_MID_SEG positions, one warp each in the
+            // filter and probe passes; segment k of the sequence has count slot idx + k
+            const uint32_t nseg = ((uint32_t)L + LINE_MID_SEG - 1) / LINE_MID_SEG, seglen = ((uint32_t)L + nseg - 1) / nseg;
+            const uint32_t idx = atomicAdd(p.mid_count, nseg);
+            const uint32_t a0 = (uint32_t)((unsigned long long)off[gid] - origin), a1 = a0 + (uint32_t)L;
+            for (uint32_t k = 0; k < nseg; k++) {
+                uint4 d;
+                d.x = (uint32_t)gid; d.y = idx + k;
+                d.z = a0 + k * seglen;
+                d.w = min(a1, d.z + seglen);
+                p.mid_desc[idx + k] = d;
+            }
         }
     }
 }
@@ -243,6 +249,10 @@ constexpr int LF_A = 8;        // window positions per lane and pass
 #define KA_LP_PB 4
 #endif
 constexpr int LP_PB = KA_LP_PB;   // sector loads in flight per thread of the probe pass
+#ifndef KA_LP_MINW
+#define KA_LP_MINW 32            // resident warps per SM of the probe pass (batching the flag-path loads of the PB probes
+                                 // at 80 registers / 24 warps measured slower: 59.3 against 64.0 G probes/s)
+#endif
 
 // dynamic shared memory of the probe pass: s_off, s_cnt/s_min/s_max, then the token set (region of sequence q at tok_cap(start) + 4q)
 constexpr uint32_t LP_OFF_CNT = 4 * (LINE_MAX_SEQ + 4);
@@ -289,9 +299,10 @@ __global__ void __launch_bounds__(32, 32) line_filter_kernel(LineParams p) {
     const unsigned long long pol_last = policy_evict_last();
 
     for (uint32_t tile = p.tile0 + blockIdx.x; tile < p.tile1; tile += gridDim.x) {
-    // single-sequence (mid) tiles first: the longest items of the launch start earliest
-    const uint4 desc = tile < p.n_mid_tiles ? p.mid_desc[tile] : p.first[tile - p.n_mid_tiles];
-    const uint32_t s0 = desc.x, s1 = desc.x + desc.y;
+    // segments of single-sequence (mid) tiles first: the longest items of the launch start earliest
+    const bool mid = tile < p.n_mid_tiles;
+    const uint4 desc = mid ? p.mid_desc[tile] : p.first[tile - p.n_mid_tiles];
+    const uint32_t s0 = desc.x, s1 = mid ? desc.x + 1u : desc.x + desc.y;
     for (uint32_t sb = s0; sb < s1; sb += LINE_MAX_SEQ) {
         const uint32_t ns = min((uint32_t)LINE_MAX_SEQ, s1 - sb);
         const uint32_t g0 = (sb == s0) ? desc.z : off[sb];
@@ -388,7 +399,7 @@ __global__ void __launch_bounds__(32, 32) line_filter_kernel(LineParams p) {
                 cnt += __popc(m);
             }
         }
-        if (lane == 0) p.surv_cnt[sb] = cnt;
+        if (lane == 0) p.surv_cnt[mid ? p.n_seq + 2u + desc.y : sb] = cnt;
     }
     }
 }
@@ -398,7 +409,7 @@ __global__ void __launch_bounds__(32, 32) line_filter_kernel(LineParams p) {
 // matched SIMD-in-register; a miss in a sector whose flags name other places follows them (L2 hits on the line just
 // fetched, or the overflow table).  The hits (de-dup token, role | seq << 16) are written back compacted over the
 // front of the tile's list — the warp has consumed an entry before a hit can land on it — and counted in hit_cnt.
-__global__ void __launch_bounds__(32, 32) line_probe_kernel(LineParams p) {
+__global__ void __launch_bounds__(32, KA_LP_MINW) line_probe_kernel(LineParams p) {
     constexpr int PB = LP_PB;
     const uint32_t lane = threadIdx.x;
     const uint32_t lt = (1u << lane) - 1u;
@@ -406,12 +417,14 @@ __global__ void __launch_bounds__(32, 32) line_probe_kernel(LineParams p) {
     const unsigned long long pol_first = policy_evict_first();
 
     for (uint32_t tile = p.tile0 + blockIdx.x; tile < p.tile1; tile += gridDim.x) {
-    // single-sequence (mid) tiles first: the longest items of the launch start earliest
-    const uint4 desc = tile < p.n_mid_tiles ? p.mid_desc[tile] : p.first[tile - p.n_mid_tiles];
-    const uint32_t s0 = desc.x, s1 = desc.x + desc.y;
+    // segments of single-sequence (mid) tiles first: the longest items of the launch start earliest
+    const bool mid = tile < p.n_mid_tiles;
+    const uint4 desc = mid ? p.mid_desc[tile] : p.first[tile - p.n_mid_tiles];
+    const uint32_t s0 = desc.x, s1 = mid ? desc.x + 1u : desc.x + desc.y;
     for (uint32_t sb = s0; sb < s1; sb += LINE_MAX_SEQ) {
         const uint32_t g0 = (sb == s0) ? desc.z : p.off[sb];
-        const uint32_t n = p.surv_cnt[sb];
+        const uint32_t slot = mid ? p.n_seq + 2u + desc.y : sb;
+        const uint32_t n = p.surv_cnt[slot];
         uint2* const q = p.surv + g0;
         uint32_t hcnt = 0;
         uint2 kq[PB];
@@ -449,7 +462,7 @@ __global__ void __launch_bounds__(32, 32) line_probe_kernel(LineParams p) {
 #pragma unroll
             for (int k = 0; k < PB; k++) kq[k] = nx[k];
         }
-        if (lane == 0) p.hit_cnt[sb] = hcnt;
+        if (lane == 0) p.hit_cnt[slot] = hcnt;
     }
     }
 }
@@ -458,6 +471,7 @@ __global__ void __launch_bounds__(32, 32) line_probe_kernel(LineParams p) {
 // the SET of its k-mers, ApplyKmerProcessor.java:123) and tallied (warp match + redux, one shared atomic per
 // sequence and warp), then the calls of the tile's sequences are written (:131-147).
 constexpr int LY_THREADS = 128;
+template <bool MID>
 __global__ void __launch_bounds__(LY_THREADS, 8) line_tally_kernel(LineParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t* const s_off = reinterpret_cast<uint32_t*>(smem_raw);
@@ -470,20 +484,33 @@ __global__ void __launch_bounds__(LY_THREADS, 8) line_tally_kernel(LineParams p)
 
     for (uint32_t tile = p.tile0 + blockIdx.x; tile < p.tile1; tile += gridDim.x) {
     const uint4 desc = p.first[tile];
-    const uint32_t s0 = desc.x, s1 = desc.x + desc.y;
+    const uint32_t s0 = desc.x;
+    // an ordinary tile has one list of hits per sub-batch; a single-sequence tile one per segment of the sequence,
+    // all tallied by the CTA of the first segment
+    uint32_t s1 = s0 + desc.y, nlist = 1, seglen = 0, mid_slot = 0;
+    if (MID) {
+        const uint32_t a0 = p.off[s0], L = p.off[s0 + 1] - a0;
+        if (desc.z != a0) continue;                                     // (uniform) not the sequence's first segment
+        s1 = s0 + 1;
+        nlist = (L + LINE_MID_SEG - 1) / LINE_MID_SEG;
+        seglen = (L + nlist - 1) / nlist;
+        mid_slot = p.n_seq + 2u + desc.y;
+    }
     for (uint32_t sb = s0; sb < s1; sb += LINE_MAX_SEQ) {
         const uint32_t ns = min((uint32_t)LINE_MAX_SEQ, s1 - sb);
         const uint32_t g0 = (sb == s0) ? desc.z : p.off[sb];
-        const uint32_t n = p.hit_cnt[sb];
-        const uint2* const q = p.surv + g0;
-        if (n == 0) {                                                   // (uniform) no hit: no call for these sequences
+        const uint32_t slot0 = MID ? mid_slot : sb;
+        const uint32_t n0 = p.hit_cnt[slot0];
+        uint32_t total = n0;
+        if (MID) for (uint32_t k = 1; k < nlist; k++) total += p.hit_cnt[slot0 + k];
+        if (total == 0) {                                               // (uniform) no hit: no call for these sequences
             for (uint32_t i = tid; i < ns; i += LY_THREADS) line_emit(p, sb + i, 0, 0, 0);
             continue;
         }
-        const uint2 first = tid < n ? q[tid] : make_uint2(0, 0);       // in flight during the set-up
-        const uint32_t g1 = (sb + ns == s1) ? desc.w : p.off[sb + ns];
+        const uint2 first = tid < n0 ? p.surv[g0 + tid] : make_uint2(0, 0);   // in flight during the set-up
+        const uint32_t g1 = MID ? p.off[s0 + 1] : ((sb + ns == s1) ? desc.w : p.off[sb + ns]);
         const uint32_t ext = g1 - g0;
-        KA_CHECK(n <= ext, 16u);
+        KA_CHECK(total <= ext, 16u);
         KA_CHECK(tok_cap(ext) + 4u * ns + 8u <= tok_cap(p.ext_max) + 4u * LINE_MAX_SEQ + 8u, 2u);
         for (uint32_t i = tid; i <= ns; i += LY_THREADS) s_off[i] = p.off[sb + i] - g0;
         for (uint32_t i = tid; i < ns; i += LY_THREADS) { s_cnt[i] = 0; s_min[i] = 0x7fffffff; s_max[i] = -1; }
@@ -493,26 +520,30 @@ __global__ void __launch_bounds__(LY_THREADS, 8) line_tally_kernel(LineParams p)
             for (uint32_t i = tid * 4; i < ntok; i += LY_THREADS * 4) *reinterpret_cast<uint4*>(s_tok + i) = z;
         }
         __syncthreads();
-        for (uint32_t base = 0; base < n; base += LY_THREADS) {
-            if (base + (tid & ~31u) >= n) break;                        // (warp-uniform) the whole warp is past the end
-            const uint32_t i = base + tid;
-            const uint2 h = base == 0 ? first : (i < n ? q[i] : make_uint2(0, 0));
-            int sq = -1;
-            const int role = (int)(h.y & 0xFFFFu);
-            if (i < n) {
-                sq = (int)(h.y >> 16);
-                const uint32_t a0 = s_off[sq], a1 = s_off[sq + 1];
-                KA_CHECK(sq < (int)ns && a1 >= a0, 8u);
-                if (!line_token_insert(s_tok + tok_cap(a0) + 4u * (uint32_t)sq, tok_cap(a1 - a0) + 4u, h.x)) sq = -1;
-            }
-            if (__any_sync(0xffffffffu, sq >= 0)) {
-                const unsigned grp = __match_any_sync(0xffffffffu, sq);
-                const int gmin = __reduce_min_sync(grp, sq >= 0 ? role : 0x7fffffff);
-                const int gmax = __reduce_max_sync(grp, sq >= 0 ? role : -1);
-                if (sq >= 0 && lane == (uint32_t)(__ffs(grp) - 1)) {
-                    atomicAdd(&s_cnt[sq], __popc(grp));
-                    atomicMin(&s_min[sq], gmin);
-                    atomicMax(&s_max[sq], gmax);
+        for (uint32_t k = 0; k < (MID ? nlist : 1u); k++) {
+            const uint32_t n = (MID && k) ? p.hit_cnt[slot0 + k] : n0;
+            const uint2* const q = p.surv + g0 + (MID ? k * seglen : 0u);
+            for (uint32_t base = 0; base < n; base += LY_THREADS) {
+                if (base + (tid & ~31u) >= n) break;                    // (warp-uniform) the whole warp is past the end
+                const uint32_t i = base + tid;
+                const uint2 h = (base == 0 && k == 0) ? first : (i < n ? q[i] : make_uint2(0, 0));
+                int sq = -1;
+                const int role = (int)(h.y & 0xFFFFu);
+                if (i < n) {
+                    sq = (int)(h.y >> 16);
+                    const uint32_t a0 = s_off[sq], a1 = s_off[sq + 1];
+                    KA_CHECK(sq < (int)ns && a1 >= a0, 8u);
+                    if (!line_token_insert(s_tok + tok_cap(a0) + 4u * (uint32_t)sq, tok_cap(a1 - a0) + 4u, h.x)) sq = -1;
+                }
+                if (__any_sync(0xffffffffu, sq >= 0)) {
+                    const unsigned grp = __match_any_sync(0xffffffffu, sq);
+                    const int gmin = __reduce_min_sync(grp, sq >= 0 ? role : 0x7fffffff);
+                    const int gmax = __reduce_max_sync(grp, sq >= 0 ? role : -1);
+                    if (sq >= 0 && lane == (uint32_t)(__ffs(grp) - 1)) {
+                        atomicAdd(&s_cnt[sq], __popc(grp));
+                        atomicMin(&s_min[sq], gmin);
+                        atomicMax(&s_max[sq], gmax);
+                    }
                 }
             }
         }
@@ -531,8 +562,10 @@ template <int K> void filter_launch(const LineParams& p, unsigned grid, cudaStre
 }  // namespace
 
 cudaError_t line_tile_set_smem(size_t bytes) {
-    cudaError_t ce = cudaFuncSetAttribute(line_tally_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(line_tally_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaError_t ce = cudaFuncSetAttribute(line_tally_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(line_tally_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(line_tally_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(line_tally_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     return ce;
 }
 
@@ -563,7 +596,8 @@ cudaError_t launch_line_probe(const LineParams& p, unsigned grid, cudaStream_t s
 cudaError_t launch_line_tally(const LineParams& p, unsigned grid, cudaStream_t st) {
     if (p.tile1 <= p.tile0) return cudaSuccess;
     grid = grid < p.tile1 - p.tile0 ? grid : p.tile1 - p.tile0;
-    line_tally_kernel<<<grid, LY_THREADS, line_probe_smem_bytes(p.ext_max), st>>>(p);
+    if (p.tally_mid) line_tally_kernel<true><<<grid, LY_THREADS, line_probe_smem_bytes(p.ext_max), st>>>(p);
+    else line_tally_kernel<false><<<grid, LY_THREADS, line_probe_smem_bytes(p.ext_max), st>>>(p);
     return cudaGetLastError();
 }
 

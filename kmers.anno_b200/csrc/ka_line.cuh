@@ -47,6 +47,7 @@ constexpr uint32_t TAG_FLAG = 0x4000u;      // per-slot flag bit, ignored by the
 constexpr uint32_t TAG_CMP = 0xBFFFu;
 constexpr uint32_t TAG_REM_BITS = 14;
 constexpr int LINE_MAX_SEQ = 64;            // sequences per tile sub-batch of the line kernels
+constexpr uint32_t LINE_MID_SEG = 1024;   // a single-sequence (mid) tile is cut into segments of at most this many positions
 constexpr int LINE_KMAX = 10;               // the three 64-bit code windows of a lane hold K + 7 <= 17 codes... (Kh <= 5)
 
 struct LineTable {
@@ -107,7 +108,9 @@ struct LineParams {
     uint32_t* off;                    // chunk-relative offsets (n_seq + 1), written by the plan kernel
     uint32_t n_seq, n_tiles;
     uint32_t tile0, tile1;            // tiles of this launch of the filter / probe / tally passes
-    uint32_t n_mid_tiles;             // filter / probe passes: tiles [0, n_mid_tiles) are mid_desc[], the others first[tile - n_mid_tiles]
+    uint32_t n_mid_tiles;             // filter / probe passes: tiles [0, n_mid_tiles) are mid_desc[] (segments of single
+                                      // sequences: {seq, count slot, g0, g1}), the others first[tile - n_mid_tiles]
+    uint32_t tally_mid;               // tally pass: first[] holds such segments; the CTA of a sequence's first segment tallies all of them
     uint32_t tile_span, long_seq, mid_seq, ext_max;
     uint32_t stage_bytes;             // shared-memory bytes reserved for the packed stage
     uint4* first;                     // n_tiles descriptors {first seq, n seqs, g0, g1}
