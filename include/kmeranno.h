@@ -78,10 +78,10 @@ const char* ka_last_error(const ka_engine* e);
  * tiling options is rejected by ka_annotate_resident: upload it again).
  *   "load_factor"   table load factor in (0,0.9]; default: 0.68 for the line table, 0.4 for the sector classes
  *   "slot_bits"     force the table layout: 32 / 64 / 128 = sector classes with slots of that width; 16 = the
- *                   128-byte-line table (16-bit tags + 16-bit roles, spill inside the line, L2-resident
- *                   presence filter: half the DRAM traffic per probe, but a slower kernel — measured, not the
- *                   default; needs a replicated table, role ids < 65536 and 2 <= K <= 10 with key halves of at
- *                   most 25 bits); 0 (default) = the narrowest sector class that holds the DB
+ *                   128-byte-line table (16-bit tags + 16-bit roles, spill inside the line, presence filter in
+ *                   L2; needs a replicated table, role ids < 65536 and 2 <= K <= 10 with key halves of at
+ *                   most 25 bits); 0 (default) = the line table when those conditions hold and its layout fits
+ *                   the key space without padding, else the narrowest sector class that holds the DB
  *   "filter"        line table only: 1 (default) = probe the L2-resident presence filter first, 0 = always read
  *                   the table (measurement knob)
  *   "ingest_via"    single-device engines: CUDA device id whose PCIe path carries the H2D copies of ka_annotate /

@@ -3,16 +3,16 @@
 // ApplyKmerProcessor.java:122-148 (distinct K-windows of a peg :123, kmerRoleMap.get :130,
 // unanimous-role tally :131-144, thresholded call :146-147) and :99-110 (HashMap.put, last line wins).
 //
-//   line_plan_kernel    chunk-relative 32-bit offsets, one descriptor per residue tile, lists of the
-//                       sequences that get a tile of their own (mid) or the long-sequence kernel (big)
-//   line_tile_kernel    one CTA per tile: the tile's 5-bit codes are staged with one TMA bulk copy;
-//                       every warp owns a quarter of the tile's window positions.  Phase A: a lane
-//                       rolls the radix-n key over a run of <= A consecutive positions, mixes it and
-//                       issues the filter loads (L2) of the whole run; survivors are compacted
-//                       into the warp's shared-memory queue.  Phase B: whenever the queue holds a
-//                       full warp of survivors, every lane pops one, loads its home sector (the
-//                       only HBM access of the probe), matches the eight tags SIMD-in-register and
-//                       on a hit de-duplicates (token set) and tallies (warp match + redux).
+//   line_plan_kernel    chunk-relative 32-bit offsets, one descriptor per residue tile, segment descriptors of the
+//                       sequences that get tiles of their own (mid), list of those for the long-sequence kernel (big)
+//   line_filter_kernel  one warp per tile: a lane rolls the radix-n key halves over a run of <= 8 consecutive
+//                       positions (codes read straight from the packed stream), issues the filter loads (L2) of
+//                       the whole run, and the warp appends the survivors to the tile's list in global memory
+//   line_probe_kernel   one warp per tile: survivors read densely, 4 per lane with all their sector loads (the only
+//                       HBM access of a probe) in flight; eight tags matched SIMD-in-register; hits compacted
+//                       over the front of the list
+//   line_tally_kernel   one CTA per tile: hits de-duplicated per sequence (token set in shared memory), tallied
+//                       (warp match + redux), calls written
 //   line_big_kernel     sequences beyond the shared-memory tile sizes
 //   line_insert/finalize, pack/unpack: table build and stream conversion
 #include "ka_line.cuh"

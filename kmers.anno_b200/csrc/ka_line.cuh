@@ -28,13 +28,18 @@
 //           overflow table (flag bit of slot 3) under (sector index : rem) + 1.
 //   filter  a Bloom filter of n_filt 32-bit words (one per table sector: B*16 bytes, 75 MB for 1e8
 //           8-mers), two bits per key in ONE word chosen by a cheap hash of the raw halves
-//           (two multiplies and a xor — no mixer, no table geometry), so the ~65 % of the windows
-//           that are absent cost a few instructions and one L2 access; only the survivors pay
-//           the mixer, the line arithmetic and the HBM access.  No false negatives; L2 resident
-//           next to a table whose lines are read with an evict-first hint.
+//           (two multiplies and a xor — no mixer, no table geometry), so the windows that are
+//           absent cost a few instructions and one L2 access; only the survivors pay
+//           the mixer, the line arithmetic and the HBM access.  No false negatives.
 //   stream  residues travel and are staged as 5-bit codes (digit 0..n-1, 31 = byte not in the DB
 //           alphabet): residue r of the batch occupies bits [5r, 5r+5) of a little-endian byte
 //           stream — 0.625 bytes per residue over PCIe instead of 1.
+//   passes  a chunk is annotated by three kernels with a list in global memory between them
+//           (ka_line.cu): FILTER (one warp per tile: rolling keys, filter words, survivors appended to the
+//           tile's list), PROBE (one warp per tile: the survivors' home sectors — the only HBM access of a
+//           probe —, hits written back over the front of the list), TALLY (one CTA per tile: distinct
+//           k-mers per sequence, unanimous-role call).  Each pass is bound by something else (issue
+//           slots / HBM lines / shared-memory atomics) and none waits for another inside a kernel.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
