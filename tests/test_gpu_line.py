@@ -134,6 +134,29 @@ def test_line_table_tiny_sequences_and_long_ones(ka, oracle):
     run_line(ka, oracle, seqs, kmers, roles, 8, options={"tile_span": 256, "long_seq": 256, "mid_seq": 512}, form="packed")
 
 
+def test_line_table_segments_of_one_sequence_share_one_kmer_set(ka, oracle):
+    """A sequence with tiles of its own is cut into segments that are filtered and probed by different warps and
+    tallied together: a k-mer that occurs in several segments counts once, and windows that straddle a segment
+    boundary are looked up like any other (here every window of the periodic sequences is in the DB)."""
+    rng = np.random.default_rng(11)
+    K = 8
+    motifs = [random_seq(rng, 50), random_seq(rng, 37), random_seq(rng, 64)]
+    seqs = [motifs[0] * 120, random_seq(rng, 400), motifs[1] * 100 + random_seq(rng, 900) + motifs[1] * 60,
+            motifs[2] * 128, random_seq(rng, 3000) + motifs[0] * 20]           # 6000, 400, 6820, 8192, 4000 residues
+    kmers, roles = [], []
+    for r, m in enumerate(motifs):
+        mm = m + m[: K - 1]
+        for i in range(len(m)):
+            kmers.append(mm[i:i + K]); roles.append(3 + r)
+    roles = np.asarray(roles, np.int32)
+    for form in ("bytes", "packed", "resident"):
+        got, _ = run_line(ka, oracle, seqs, kmers, roles, K, min_hits=5, form=form)
+        assert got[1][0] == 50 and got[0][0] == 3 and got[2][0] == 1          # 50 distinct k-mers, however often they recur
+        assert got[1][3] == 64 and got[0][3] == 5
+        assert got[2][4] == 1 and got[0][4] == 3
+    run_line(ka, oracle, seqs, kmers, roles, K, min_hits=5, options={"tile_span": 256, "long_seq": 512, "mid_seq": 8192}, form="packed")
+
+
 def test_packed_form_on_every_layout(ka, oracle):
     """ka_annotate_packed == ka_annotate on sector-class tables too (device unpack), with a batch whose
     first offset is not zero and with several chunks; ka_pack_residues from several threads."""
