@@ -246,7 +246,7 @@ cudaError_t launch_line_plan(const LineParams& p, const unsigned long long* off6
 // at surv[g0 ...), their number at surv_cnt[first sequence of the sub-batch]: no prefix sum, no zeroing.
 constexpr int LF_A = 8;        // window positions per lane and pass
 #ifndef KA_LP_PB
-#define KA_LP_PB 4
+#define KA_LP_PB 3
 #endif
 constexpr int LP_PB = KA_LP_PB;   // sector loads in flight per thread of the probe pass
 #ifndef KA_LP_MINW
