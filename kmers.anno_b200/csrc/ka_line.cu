@@ -35,6 +35,11 @@ __device__ __forceinline__ unsigned long long policy_evict_first() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
+__device__ __forceinline__ unsigned long long policy_evict_normal() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ unsigned long long policy_evict_last() {
     unsigned long long pol;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
@@ -414,7 +419,9 @@ __global__ void __launch_bounds__(32, KA_LP_MINW) line_probe_kernel(LineParams p
     const uint32_t lane = threadIdx.x;
     const uint32_t lt = (1u << lane) - 1u;
     const LineTable tab = p.tab;
-    const unsigned long long pol_first = policy_evict_first();
+        // (no filter word is read in this pass: table lines are cached like anything else — 65.8 against 65.3 G probes/s
+    // with an evict-first hint)
+    const unsigned long long pol_first = policy_evict_normal();
 
     for (uint32_t tile = p.tile0 + blockIdx.x; tile < p.tile1; tile += gridDim.x) {
     // segments of single-sequence (mid) tiles first: the longest items of the launch start earliest
