@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(32, 32) line_filter_kernel(LineParams p) {
                 // the 96 stream bits from the run's first position: code J of the window at a fixed bit
                 const unsigned long long bit0 = 5ull * (g0 + P0);
                 const uint32_t* w = p.pk + (bit0 >> 5);
-                const uint32_t sh = (uint32_t)bit0 & 31u, w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
+                const uint32_t sh = (uint32_t)bit0 & 31u, w0 = __ldcs(w), w1 = __ldcs(w + 1), w2 = __ldcs(w + 2), w3 = __ldcs(w + 3);
                 const uint32_t u0 = __funnelshift_r(w0, w1, sh), u1 = __funnelshift_r(w1, w2, sh), u2 = __funnelshift_r(w2, w3, sh);
                 const uint32_t G0 = g0 + P0;                            // chunk residue of the run's first position
 
@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(32, 32) line_filter_kernel(LineParams p) {
                     ok = (fw[i] & need) == need;
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, ok);
-                if (ok) out[cnt + __popc(m & lt)] = make_uint2(qh[i], ql[i]);
+                if (ok) __stcs(out + cnt + __popc(m & lt), make_uint2(qh[i], ql[i]));   // streaming: keep L2 for the filter words
                 cnt += __popc(m);
             }
         }
