@@ -1,6 +1,8 @@
 """Property-based GPU parity (hypothesis): arbitrary byte alphabets, K, ragged sequences and DBs
 with duplicate / conflicting lines — the engine must equal the pure-Python statement of
 ApplyKmerProcessor.java:122-148 on every generated case."""
+import os
+
 import numpy as np
 import pytest
 from hypothesis import HealthCheck, given, settings, strategies as st
@@ -39,7 +41,7 @@ def case(draw):
     return K, seqs, kmers, roles, min_hits, wide, layout, packed
 
 
-@settings(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@settings(max_examples=int(os.environ.get("KA_HYP_EXAMPLES", 150)), deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
 @given(case())
 def test_engine_equals_python_statement(engine, c):
     import kmers_anno_b200 as ka
@@ -52,8 +54,10 @@ def test_engine_equals_python_statement(engine, c):
     try:
         engine.db_load(kmers, np.asarray(roles, np.int32), K)
     except ka.KmerAnnoError as err:
-        # keys of more than 39 bits (or a one-letter alphabet) do not fit the line table: loud error, then the default layout
-        assert layout == 16 and err.code == -10, err
+        # keys of more than 39 bits (or a one-letter alphabet) do not fit the line table (KA_ERR_TOO_BIG), and a forced
+        # narrow slot under 12-mers needs a table of ~100 GB + its build scratch, which the HBM left by the other
+        # fixtures of the session may not hold (KA_ERR_OOM): a loud error either way, then the default layout
+        assert (layout == 16 and err.code == -10) or (layout in (32, 64) and K >= 11 and err.code == -7), err
         engine.set_option("slot_bits", 0)
         engine.db_load(kmers, np.asarray(roles, np.int32), K)
     else:
@@ -82,7 +86,7 @@ def distance_case(draw):
     return K, seqs, groups
 
 
-@settings(max_examples=100, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+@settings(max_examples=int(os.environ.get("KA_HYP_EXAMPLES", 100)), deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
 @given(distance_case())
 def test_distance_equals_python_sets(engine, c):
     """ka_kmer_distance against Python sets (GeneCopyProcessor.java:137-142, recalled ProteinKmers.distance)."""
