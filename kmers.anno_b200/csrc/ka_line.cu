@@ -8,7 +8,7 @@
 //   line_filter_kernel  one warp per tile: a lane rolls the radix-n key halves over a run of <= 8 consecutive
 //                       positions (codes read straight from the packed stream), issues the filter loads (L2) of
 //                       the whole run, and the warp appends the survivors to the tile's list in global memory
-//   line_probe_kernel   one warp per tile: survivors read densely, 4 per lane with all their sector loads (the only
+//   line_probe_kernel   one warp per tile: survivors read densely, 3 per lane with all their sector loads (the only
 //                       HBM access of a probe) in flight; eight tags matched SIMD-in-register; hits compacted
 //                       over the front of the list
 //   line_tally_kernel   one CTA per tile: hits de-duplicated per sequence (token set in shared memory), tallied
