@@ -294,7 +294,6 @@ void fill_line_params(ka_engine* e, Device& d, Pipe& p, uint64_t n_res, uint64_t
     lp.long_seq = e->long_seq;
     lp.mid_seq = std::max(e->mid_seq, e->long_seq);
     lp.ext_max = lp.tile_span + e->long_seq;
-    line_tile_smem_bytes(lp.ext_max, &lp.stage_bytes);
     lp.first = p.first;
     lp.surv = p.surv;
     lp.surv_cnt = p.surv_cnt;
@@ -322,7 +321,7 @@ void fill_line_params(ka_engine* e, Device& d, Pipe& p, uint64_t n_res, uint64_t
 // needs from L2 (measured: 29.9 -> 32.7-38 ms end to end when every pipe launched on its own stream).
 int enqueue_line_kernels(ka_engine* e, Device& d, Pipe& p, const LineParams& lp, bool off_is_64, uint64_t origin,
                          uint64_t n_long, uint64_t n_mid, bool solo) {
-    const size_t smem = line_tile_smem_bytes(lp.ext_max, nullptr);
+    const size_t smem = line_tile_smem_bytes(lp.ext_max);
     { int rc = ensure_tile_smem(d); if (rc) return rc; }
     if (smem > d.smem_set) return dev_fail(d, KA_ERR_INVALID, "tile shared memory exceeds the device limit", cudaErrorInvalidValue);
     // (a call that is a single chunk on this device has nothing to be kept apart from: it stays on the pipe's stream)
@@ -362,7 +361,7 @@ int enqueue_line_kernels(ka_engine* e, Device& d, Pipe& p, const LineParams& lp,
         lm.first = p.mid;
         lm.n_mid_tiles = 0; lm.tally_mid = 1; lm.tile0 = 0; lm.tile1 = (uint32_t)n_mid;
         lm.ext_max = lp.mid_seq;
-        const size_t smem_mid = line_tile_smem_bytes(lm.ext_max, &lm.stage_bytes);
+        const size_t smem_mid = line_tile_smem_bytes(lm.ext_max);
         if (smem_mid > d.smem_set) return dev_fail(d, KA_ERR_INVALID, "mid tile shared memory exceeds the device limit", cudaErrorInvalidValue);
         DCK(d, launch_line_tally(lm, all, st));
         d.launches += 1;
@@ -694,7 +693,7 @@ int ka_set_option(ka_engine* e, const char* name, double v) {
     }
     const uint32_t mid_eff = std::max(mid_seq, long_seq);
     if (tile_smem_bytes(tile_span + long_seq, nullptr, true) > 225 * 1024 || tile_smem_bytes(mid_eff, nullptr, true) > 225 * 1024 ||
-        line_tile_smem_bytes(tile_span + long_seq, nullptr) > 225 * 1024 || line_tile_smem_bytes(mid_eff, nullptr) > 225 * 1024)
+        line_tile_smem_bytes(tile_span + long_seq) > 225 * 1024 || line_tile_smem_bytes(mid_eff) > 225 * 1024)
         return fail(e, KA_ERR_INVALID, "tile_span + long_seq (or mid_seq) needs more than 227 KB of shared memory");
     e->load_factor = load_factor; e->tile_span = tile_span; e->long_seq = long_seq; e->mid_seq = mid_seq;
     e->chunk_residues = chunk_residues; e->l2_persist = l2_persist; e->table_mode = table_mode; e->wide = wide;

@@ -238,17 +238,18 @@ cudaError_t launch_line_plan(const LineParams& p, const unsigned long long* off6
 }
 
 // ------------------------------------------------------------------------------------
-// tile kernels: filter pass, then probe pass
+// tile kernels: filter pass, probe pass, tally pass
 // ------------------------------------------------------------------------------------
-// The work of a tile is two kernels with a global-memory list of survivors between them, because the two halves
-// want opposite things from the SM.  The filter pass is arithmetic over a stream (rolling keys, one L2-resident
-// filter word per window): every lane busy, no HBM access besides the 0.625 B per residue of the codes.  The probe
-// pass is nothing but random 128-byte lines: with the survivors already compacted, every lane of every warp has a
-// sector load in flight (PB per thread), which a kernel that discovers its survivors as it goes cannot arrange
-// (profiles/r02_summary.md C: 10-15 active lanes per instruction and a third of the time at the tile barrier).
-// The list costs 8 bytes per SURVIVOR written and read once — ~5 B per window against the 128-byte line saved for
-// every window the filter rejects.  Survivors of the tile (sub-batch) whose first position is chunk residue g0 live
-// at surv[g0 ...), their number at surv_cnt[first sequence of the sub-batch]: no prefix sum, no zeroing.
+// The work of a tile is three kernels with a list in global memory between them, because its parts want opposite
+// things from the SM.  The filter pass is arithmetic over a stream (rolling keys, one L2-resident filter word per
+// window): every lane busy, no HBM access besides the 0.625 B per residue of the codes.  The probe pass is nothing
+// but random 128-byte lines: with the survivors already compacted, every lane of every warp has PB sector loads in
+// flight, which a kernel that discovers its survivors as it goes cannot arrange (profiles/r02_summary.md C: 10-15
+// active lanes per instruction and a third of the time at the tile barrier when all of it was one kernel).  The
+// tally pass is shared-memory atomics on the hits only.  The list costs 8 bytes per SURVIVOR written and read once
+// — ~7 B per window against the 128-byte line saved for every window the filter rejects.  Survivors of the tile
+// (sub-batch) whose first position is chunk residue g0 live at surv[g0 ...), their number at surv_cnt[first sequence
+// of the sub-batch]; the probe pass writes the hits over the front of the same list: no prefix sum, no zeroing.
 constexpr int LF_A = 8;        // window positions per lane and pass
 #ifndef KA_LP_PB
 #define KA_LP_PB 3
@@ -259,18 +260,15 @@ constexpr int LP_PB = KA_LP_PB;   // sector loads in flight per thread of the pr
                                  // at 80 registers / 24 warps measured slower: 59.3 against 64.0 G probes/s)
 #endif
 
-// dynamic shared memory of the probe pass: s_off, s_cnt/s_min/s_max, then the token set (region of sequence q at tok_cap(start) + 4q)
-constexpr uint32_t LP_OFF_CNT = 4 * (LINE_MAX_SEQ + 4);
-constexpr uint32_t LP_OFF_TOK = LP_OFF_CNT + 3 * 4 * LINE_MAX_SEQ;
-static_assert(LP_OFF_TOK % 16 == 0, "alignment of the shared-memory parts");
+// dynamic shared memory of the tally pass: s_off, s_cnt/s_min/s_max, then the token set (region of sequence q at tok_cap(start) + 4q)
+constexpr uint32_t LY_OFF_CNT = 4 * (LINE_MAX_SEQ + 4);
+constexpr uint32_t LY_OFF_TOK = LY_OFF_CNT + 3 * 4 * LINE_MAX_SEQ;
+static_assert(LY_OFF_TOK % 16 == 0, "alignment of the shared-memory parts");
 
-size_t line_probe_smem_bytes(uint32_t ext_max) {
-    return (size_t)LP_OFF_TOK + 4 * ((size_t)tok_cap(ext_max) + 4 * LINE_MAX_SEQ + 8);
+size_t line_tally_smem_bytes(uint32_t ext_max) {
+    return (size_t)LY_OFF_TOK + 4 * ((size_t)tok_cap(ext_max) + 4 * LINE_MAX_SEQ + 8);
 }
-size_t line_tile_smem_bytes(uint32_t ext_max, uint32_t* stage_bytes_out) {
-    if (stage_bytes_out) *stage_bytes_out = 0;
-    return line_probe_smem_bytes(ext_max);
-}
+size_t line_tile_smem_bytes(uint32_t ext_max) { return line_tally_smem_bytes(ext_max); }
 
 namespace {
 // 5-bit code number J (compile time) of a 96-bit window held in three registers
@@ -482,10 +480,10 @@ template <bool MID>
 __global__ void __launch_bounds__(LY_THREADS, 8) line_tally_kernel(LineParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t* const s_off = reinterpret_cast<uint32_t*>(smem_raw);
-    int* const s_cnt = reinterpret_cast<int*>(smem_raw + LP_OFF_CNT);
+    int* const s_cnt = reinterpret_cast<int*>(smem_raw + LY_OFF_CNT);
     int* const s_min = s_cnt + LINE_MAX_SEQ;
     int* const s_max = s_min + LINE_MAX_SEQ;
-    uint32_t* const s_tok = reinterpret_cast<uint32_t*>(smem_raw + LP_OFF_TOK);
+    uint32_t* const s_tok = reinterpret_cast<uint32_t*>(smem_raw + LY_OFF_TOK);
 
     const uint32_t tid = threadIdx.x, lane = tid & 31;
 
@@ -603,8 +601,8 @@ cudaError_t launch_line_probe(const LineParams& p, unsigned grid, cudaStream_t s
 cudaError_t launch_line_tally(const LineParams& p, unsigned grid, cudaStream_t st) {
     if (p.tile1 <= p.tile0) return cudaSuccess;
     grid = grid < p.tile1 - p.tile0 ? grid : p.tile1 - p.tile0;
-    if (p.tally_mid) line_tally_kernel<true><<<grid, LY_THREADS, line_probe_smem_bytes(p.ext_max), st>>>(p);
-    else line_tally_kernel<false><<<grid, LY_THREADS, line_probe_smem_bytes(p.ext_max), st>>>(p);
+    if (p.tally_mid) line_tally_kernel<true><<<grid, LY_THREADS, line_tally_smem_bytes(p.ext_max), st>>>(p);
+    else line_tally_kernel<false><<<grid, LY_THREADS, line_tally_smem_bytes(p.ext_max), st>>>(p);
     return cudaGetLastError();
 }
 

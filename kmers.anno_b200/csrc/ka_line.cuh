@@ -117,7 +117,6 @@ struct LineParams {
                                       // sequences: {seq, count slot, g0, g1}), the others first[tile - n_mid_tiles]
     uint32_t tally_mid;               // tally pass: first[] holds such segments; the CTA of a sequence's first segment tallies all of them
     uint32_t tile_span, long_seq, mid_seq, ext_max;
-    uint32_t stage_bytes;             // shared-memory bytes reserved for the packed stage
     uint4* first;                     // n_tiles descriptors {first seq, n seqs, g0, g1}
     uint2* surv;                      // survivors of the filter pass: (H | seq in tile << 26, Lo), the tile's at surv[g0 ...)
     uint32_t* surv_cnt;               // ... and their number, at the index of the tile's (sub-batch's) first sequence
@@ -136,7 +135,7 @@ struct LineParams {
     uint32_t* dbg;
 };
 
-size_t line_tile_smem_bytes(uint32_t ext_max, uint32_t* stage_bytes_out);
+size_t line_tile_smem_bytes(uint32_t ext_max);     // dynamic shared memory of the tally pass for tiles of <= ext_max positions
 cudaError_t line_tile_set_smem(size_t bytes);
 
 // offsets -> chunk-relative u32 offsets + tile descriptors + lists of mid / long sequences.
