@@ -261,3 +261,18 @@ def test_genes_cli_validation_and_no_candidates(tmp_path):
     norm = lambda s: subprocess.run([st, "--norm", s], capture_output=True, text=True).stdout.rstrip("\n")
     assert norm("DNA polymerase III  alpha subunit (EC 2.7.7.7) # frameshift") == "dna polymerase iii alpha subunit ec 2 7 7 7"
     assert norm("Hypothetical protein ! truncated") == norm("hypothetical  PROTEIN")
+
+
+def test_committed_ncu_exports_feed_the_bench_roofline():
+    """bench.py takes roofline.traffic from the committed `ncu --page raw --csv` exports (and refuses to run without
+    them): both exports parse, name the kernels of their layout and give plausible DRAM bytes per probe."""
+    sys.path.insert(0, ROOT)
+    import bench
+    per_probe, note, parts = bench.ncu_dram_bytes_per_probe(16)
+    assert [p["kernel"].split("<")[0].split()[-1] for p in parts] == ["line_filter_kernel", "line_probe_kernel", "line_tally_kernel"]
+    assert 40.0 < per_probe < 70.0 and abs(sum(p["dram_bytes_per_probe"] for p in parts) - per_probe) < 1e-6
+    assert max(parts, key=lambda p: p["ncu_ms"])["kernel"].startswith("line_probe_kernel")      # the HBM-bound pass dominates
+    assert "profiles/r02_line_passes_raw.csv" in note
+    per_probe32, note32, parts32 = bench.ncu_dram_bytes_per_probe(32)
+    assert len(parts32) == 1 and "tile_kernel" in parts32[0]["kernel"] and 85.0 < per_probe32 < 105.0
+    assert per_probe < 0.6 * per_probe32              # the point of the line table
