@@ -276,3 +276,15 @@ def test_committed_ncu_exports_feed_the_bench_roofline():
     per_probe32, note32, parts32 = bench.ncu_dram_bytes_per_probe(32)
     assert len(parts32) == 1 and "tile_kernel" in parts32[0]["kernel"] and 85.0 < per_probe32 < 105.0
     assert per_probe < 0.6 * per_probe32              # the point of the line table
+
+
+def test_line_table_key_arithmetic_on_the_host(tmp_path):
+    """The key arithmetic of the line table (csrc/ka_line.cuh: Feistel mixer, c-way split of the top bits,
+    line_locate, filter hash) is host + device code: tests/native/line_geom_check.cu checks exhaustively on small
+    key spaces that the mixer and the split are bijections and that (line, tag) identifies the key."""
+    exe = tmp_path / "line_geom_check"
+    src = os.path.join(ROOT, "tests", "native", "line_geom_check.cu")
+    subprocess.run(["nvcc", "-std=c++17", "-O2", "-gencode", "arch=compute_100a,code=sm_100a",
+                    "-I" + os.path.join(ROOT, "kmers.anno_b200", "csrc"), "-o", str(exe), src], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert out.strip() == "ok", out
