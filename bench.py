@@ -643,9 +643,14 @@ def main():
         # product: by the FASTA / GTO parser while it touches the residues anyway) — outside the timed region
         t0 = time.perf_counter()
         codes, off32 = eng.pack(res, off, alloc=pinned_array)
-        pack_ms = (time.perf_counter() - t0) * 1e3
+        first_pack_ms = (time.perf_counter() - t0) * 1e3        # includes cudaHostAlloc of the pinned stream
+        t0 = time.perf_counter()
+        eng.pack(res, off, out=(codes, off32))
+        pack_ms = (time.perf_counter() - t0) * 1e3              # into the buffers a service would reuse
         host_pack = {"ms": pack_ms, "GB_per_s": int(off[-1]) / pack_ms / 1e6, "threads": min(os.cpu_count() or 1, 32),
-                     "note": "ka_pack_residues over the whole batch (includes first touch of the pinned stream), outside the timed region"}
+                     "first_call_ms": first_pack_ms,
+                     "note": "ka_pack_residues over the whole batch into pinned buffers that already exist, outside the timed region; "
+                             "first_call_ms includes cudaHostAlloc of the stream"}
 
         def timed(call):
             for _ in range(a.warmup):

@@ -198,18 +198,23 @@ class Engine:
         self._check(self._lib.ka_db_get_alphabet(self._h, _ptr(lut)))
         return lut
 
-    def pack(self, residues, offsets, alloc=None, threads=None):
+    def pack(self, residues, offsets, alloc=None, threads=None, out=None):
         """The packed form of a CSR batch for annotate_packed: (codes u8 stream, offsets u32).  The
         stream is indexed like `residues` (residue r at bits [5r, 5r+5)); ka_pack_residues on
-        8-aligned slices, one per thread."""
+        8-aligned slices, one per thread.  `out` = (codes, offsets32) of an earlier call to write into."""
         residues = np.ascontiguousarray(residues, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         total = int(offsets[-1]) if offsets.shape[0] else 0
         if total >= 1 << 32:
             raise KmerAnnoError(-10, "annotate_packed takes at most 2^32 - 1 residues per call")
         alloc = alloc or (lambda shape, dtype: np.empty(shape, dtype))
-        codes = alloc((total * 5 + 7) // 8 + 16, np.uint8)
-        off32 = alloc(offsets.shape[0], np.uint32)
+        if out is not None:
+            codes, off32 = out
+            if codes.shape[0] < (total * 5 + 7) // 8 + 16 or off32.shape[0] != offsets.shape[0]:
+                raise ValueError("pack: `out` does not fit this batch")
+        else:
+            codes = alloc((total * 5 + 7) // 8 + 16, np.uint8)
+            off32 = alloc(offsets.shape[0], np.uint32)
         off32[:] = offsets
         threads = threads or min(os.cpu_count() or 1, 32)
         step = max(1 << 20, -(-total // threads) + 7 & ~7)
